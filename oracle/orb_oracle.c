@@ -1,0 +1,584 @@
+/*
+ * oracle/orb_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see orb_oracle.h).
+ *
+ * Scalar restatement of the reference ORB front end.  Citations are to the
+ * reference tree (src/ORBextractor.cc unless another file is named).  Build with
+ * -ffp-contract=off so every float expression rounds where the source says.
+ */
+#include "orb_oracle.h"
+#include "cvprim.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+enum { PATCH_SIZE = 31, HALF_PATCH_SIZE = 15, EDGE_THRESHOLD = 19 };      /* :72-74 */
+
+static const int8_t kPattern[512 * 2] = {
+#include "orb_pattern.inc"
+};
+
+struct orbo_extractor {
+    int nfeatures, nlevels, ini_th, min_th;
+    double scale_factor;                      /* include/ORBextractor.h:98 stores the float as double */
+    float scale[ORBO_MAX_LEVELS], inv_scale[ORBO_MAX_LEVELS], sigma2[ORBO_MAX_LEVELS], inv_sigma2[ORBO_MAX_LEVELS];
+    int nfeat[ORBO_MAX_LEVELS];
+    int umax[HALF_PATCH_SIZE + 2];
+    /* stage outputs of the last call */
+    int lw[ORBO_MAX_LEVELS], lh[ORBO_MAX_LEVELS];
+    uint8_t *img[ORBO_MAX_LEVELS], *blur[ORBO_MAX_LEVELS];
+    size_t img_cap[ORBO_MAX_LEVELS];
+    int has_blur[ORBO_MAX_LEVELS];
+    orbo_cand *cand[ORBO_MAX_LEVELS];
+    int ncand[ORBO_MAX_LEVELS], cand_cap[ORBO_MAX_LEVELS];
+    int min_cells[ORBO_MAX_LEVELS], cells[ORBO_MAX_LEVELS];
+    orbo_keypoint *lkp[ORBO_MAX_LEVELS];
+    int nlkp[ORBO_MAX_LEVELS], lkp_cap[ORBO_MAX_LEVELS];
+};
+
+/* ------------------------------------------------------------ constructor */
+
+orbo_extractor *orbo_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th)
+{
+    if (nlevels < 1 || nlevels > ORBO_MAX_LEVELS) return NULL;
+    orbo_extractor *e = (orbo_extractor *)calloc(1, sizeof(*e));
+    e->nfeatures = nfeatures; e->nlevels = nlevels; e->ini_th = ini_th; e->min_th = min_th;
+    e->scale_factor = (double)scale_factor;
+    /* :415-431 -- float * double -> double -> float */
+    e->scale[0] = 1.0f; e->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; ++i) {
+        e->scale[i] = (float)(e->scale[i - 1] * e->scale_factor);
+        e->sigma2[i] = e->scale[i] * e->scale[i];
+    }
+    for (int i = 0; i < nlevels; ++i) {
+        e->inv_scale[i] = 1.0f / e->scale[i];
+        e->inv_sigma2[i] = 1.0f / e->sigma2[i];
+    }
+    /* :435-447 -- geometric split of nfeatures over the levels */
+    float factor = (float)(1.0f / e->scale_factor);
+    float n_desired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int level = 0; level < nlevels - 1; ++level) {
+        e->nfeat[level] = cvp_round_f(n_desired);
+        sum += e->nfeat[level];
+        n_desired *= factor;
+    }
+    e->nfeat[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    /* :453-469 -- row ends of the circular patch */
+    int v, v0;
+    int vmax = cvp_floor_d(HALF_PATCH_SIZE * sqrtf(2.f) / 2 + 1);
+    int vmin = cvp_ceil_d(HALF_PATCH_SIZE * sqrtf(2.f) / 2);
+    const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+    for (v = 0; v <= vmax; ++v) e->umax[v] = cvp_round_d(sqrt(hp2 - v * v));
+    for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+    return e;
+}
+
+void orbo_destroy(orbo_extractor *e)
+{
+    if (!e) return;
+    for (int l = 0; l < ORBO_MAX_LEVELS; ++l) { free(e->img[l]); free(e->blur[l]); free(e->cand[l]); free(e->lkp[l]); }
+    free(e);
+}
+
+int orbo_tables(const orbo_extractor *e, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                int *nfeat, int *umax16)
+{
+    for (int i = 0; i < e->nlevels; ++i) {
+        if (scale) scale[i] = e->scale[i];
+        if (inv_scale) inv_scale[i] = e->inv_scale[i];
+        if (sigma2) sigma2[i] = e->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = e->inv_sigma2[i];
+        if (nfeat) nfeat[i] = e->nfeat[i];
+    }
+    if (umax16) for (int i = 0; i < 16; ++i) umax16[i] = e->umax[i];
+    return e->nlevels;
+}
+
+/* ----------------------------------------------------------------- octree */
+/* DistributeOctTree / ExtractorNode::DivideNode, :481-763, canonical tie-break. */
+
+typedef struct {
+    int ulx, uly, brx, bry;      /* UL and BR corners (UR.x = brx, BL.y = bry) */
+    int *keys; int nkeys;        /* indices into the candidate array, parent order kept (:519-534) */
+    int no_more;
+    long seq;                    /* creation sequence number (canonical tie-break) */
+    int prev, next;              /* list links; the std::list of :545 */
+} onode;
+
+typedef struct {
+    onode *n; int count, cap;
+    int head, tail, size;
+    long seq_counter;
+} olist;
+
+static int ol_new(olist *L)
+{
+    if (L->count == L->cap) { L->cap = L->cap ? L->cap * 2 : 256; L->n = (onode *)realloc(L->n, sizeof(onode) * (size_t)L->cap); }
+    memset(&L->n[L->count], 0, sizeof(onode));
+    L->n[L->count].prev = L->n[L->count].next = -1;
+    return L->count++;
+}
+static void ol_push_back(olist *L, int i)
+{
+    L->n[i].seq = L->seq_counter++;
+    L->n[i].prev = L->tail; L->n[i].next = -1;
+    if (L->tail >= 0) L->n[L->tail].next = i; else L->head = i;
+    L->tail = i; L->size++;
+}
+static void ol_push_front(olist *L, int i)
+{
+    L->n[i].seq = L->seq_counter++;
+    L->n[i].next = L->head; L->n[i].prev = -1;
+    if (L->head >= 0) L->n[L->head].prev = i; else L->tail = i;
+    L->head = i; L->size++;
+}
+static int ol_erase(olist *L, int i)       /* returns the following element */
+{
+    const int p = L->n[i].prev, q = L->n[i].next;
+    if (p >= 0) L->n[p].next = q; else L->head = q;
+    if (q >= 0) L->n[q].prev = p; else L->tail = p;
+    L->size--;
+    free(L->n[i].keys); L->n[i].keys = NULL;
+    return q;
+}
+
+/* DivideNode (:481-537).  Children are created in the node pool; returns their ids. */
+static void divide_node(olist *L, int p, const orbo_cand *c, int ch[4])
+{
+    const int ulx = L->n[p].ulx, uly = L->n[p].uly, brx = L->n[p].brx, bry = L->n[p].bry;
+    const int halfX = (int)ceil((double)((float)(brx - ulx) / 2));
+    const int halfY = (int)ceil((double)((float)(bry - uly) / 2));
+    const int nk = L->n[p].nkeys;
+    for (int k = 0; k < 4; ++k) {
+        ch[k] = ol_new(L);
+        L->n[ch[k]].keys = (int *)malloc(sizeof(int) * (size_t)(nk ? nk : 1));
+    }
+    onode *n1 = &L->n[ch[0]], *n2 = &L->n[ch[1]], *n3 = &L->n[ch[2]], *n4 = &L->n[ch[3]];
+    const int midx = ulx + halfX, midy = uly + halfY;
+    n1->ulx = ulx;  n1->uly = uly;  n1->brx = midx; n1->bry = midy;
+    n2->ulx = midx; n2->uly = uly;  n2->brx = brx;  n2->bry = midy;
+    n3->ulx = ulx;  n3->uly = midy; n3->brx = midx; n3->bry = bry;
+    n4->ulx = midx; n4->uly = midy; n4->brx = brx;  n4->bry = bry;
+    const int *keys = L->n[p].keys;
+    for (int i = 0; i < nk; ++i) {
+        const orbo_cand *kp = &c[keys[i]];
+        onode *dst;
+        if (kp->x < midx) dst = kp->y < midy ? n1 : n3;
+        else dst = kp->y < midy ? n2 : n4;
+        dst->keys[dst->nkeys++] = keys[i];
+    }
+    for (int k = 0; k < 4; ++k) if (L->n[ch[k]].nkeys == 1) L->n[ch[k]].no_more = 1;
+}
+
+typedef struct { int size; int node; long seq; } size_node;
+static int cmp_size_node(const void *a, const void *b)
+{
+    const size_node *x = (const size_node *)a, *y = (const size_node *)b;
+    if (x->size != y->size) return x->size < y->size ? -1 : 1;
+    return x->seq < y->seq ? -1 : (x->seq > y->seq ? 1 : 0);       /* canonical: seq instead of pointer */
+}
+
+/* push non-empty children to the front in order n1..n4 and record the splittable ones */
+static void adopt_children(olist *L, const int ch[4], size_node **rec, int *nrec, int *caprec, int *n_to_expand)
+{
+    for (int k = 0; k < 4; ++k) {
+        const int c = ch[k];
+        if (L->n[c].nkeys > 0) {
+            ol_push_front(L, c);
+            if (L->n[c].nkeys > 1) {
+                if (n_to_expand) (*n_to_expand)++;
+                if (*nrec == *caprec) { *caprec = *caprec ? *caprec * 2 : 256; *rec = (size_node *)realloc(*rec, sizeof(size_node) * (size_t)*caprec); }
+                (*rec)[*nrec].size = L->n[c].nkeys; (*rec)[*nrec].node = c; (*rec)[*nrec].seq = L->n[c].seq;
+                (*nrec)++;
+            }
+        } else {
+            free(L->n[c].keys); L->n[c].keys = NULL;
+        }
+    }
+}
+
+int orbo_distribute(const orbo_cand *cands, int n, int minX, int maxX, int minY, int maxY, int N,
+                    orbo_cand *out, int cap)
+{
+    /* :543-546 */
+    const int nIni = (int)roundf((float)(maxX - minX) / (maxY - minY));
+    if (nIni < 1) return 0;                      /* the reference divides by zero here; callers reject such shapes */
+    const float hX = (float)(maxX - minX) / nIni;
+
+    olist L; memset(&L, 0, sizeof(L)); L.head = L.tail = -1;
+    int *roots = (int *)malloc(sizeof(int) * (size_t)nIni);
+    for (int i = 0; i < nIni; ++i) {                                   /* :553-563 */
+        const int id = ol_new(&L);
+        L.n[id].ulx = (int)(hX * (float)i);
+        L.n[id].brx = (int)(hX * (float)(i + 1));
+        L.n[id].uly = 0; L.n[id].bry = maxY - minY;
+        L.n[id].keys = (int *)malloc(sizeof(int) * (size_t)(n ? n : 1));
+        ol_push_back(&L, id);
+        roots[i] = id;
+    }
+    for (int i = 0; i < n; ++i) {                                      /* :566-570 */
+        int r = (int)((float)cands[i].x / hX);
+        if (r >= nIni) r = nIni - 1;             /* unreachable for FAST candidates (x <= width-4) */
+        onode *nd = &L.n[roots[r]];
+        nd->keys[nd->nkeys++] = i;
+    }
+    for (int it = L.head; it >= 0;) {                                  /* :572-585 */
+        if (L.n[it].nkeys == 1) { L.n[it].no_more = 1; it = L.n[it].next; }
+        else if (L.n[it].nkeys == 0) it = ol_erase(&L, it);
+        else it = L.n[it].next;
+    }
+
+    int finish = 0;
+    size_node *rec = NULL; int nrec = 0, caprec = 0;
+    while (!finish) {                                                  /* :594-737 */
+        int prev_size = L.size;
+        int n_to_expand = 0;
+        nrec = 0;
+        for (int it = L.head; it >= 0;) {
+            if (L.n[it].no_more) { it = L.n[it].next; continue; }
+            int ch[4];
+            divide_node(&L, it, cands, ch);
+            adopt_children(&L, ch, &rec, &nrec, &caprec, &n_to_expand);
+            it = ol_erase(&L, it);
+        }
+        if (L.size >= N || L.size == prev_size) {
+            finish = 1;
+        } else if (L.size + n_to_expand * 3 > N) {
+            while (!finish) {                                          /* :676-735 */
+                prev_size = L.size;
+                size_node *prev = (size_node *)malloc(sizeof(size_node) * (size_t)(nrec ? nrec : 1));
+                const int nprev = nrec;
+                memcpy(prev, rec, sizeof(size_node) * (size_t)nrec);
+                nrec = 0;
+                qsort(prev, (size_t)nprev, sizeof(size_node), cmp_size_node);
+                for (int j = nprev - 1; j >= 0; --j) {
+                    int ch[4];
+                    divide_node(&L, prev[j].node, cands, ch);
+                    adopt_children(&L, ch, &rec, &nrec, &caprec, NULL);
+                    ol_erase(&L, prev[j].node);
+                    if (L.size >= N) break;
+                }
+                free(prev);
+                if (L.size >= N || L.size == prev_size) finish = 1;
+            }
+        }
+    }
+    /* :740-760 -- first strictly greatest response per node, list order */
+    int m = 0;
+    for (int it = L.head; it >= 0; it = L.n[it].next) {
+        const onode *nd = &L.n[it];
+        int best = nd->keys[0];
+        for (int k = 1; k < nd->nkeys; ++k)
+            if (cands[nd->keys[k]].score > cands[best].score) best = nd->keys[k];
+        if (m < cap) out[m] = cands[best];
+        ++m;
+    }
+    for (int i = 0; i < L.count; ++i) free(L.n[i].keys);
+    free(L.n); free(rec); free(roots);
+    return m;
+}
+
+/* ---------------------------------------------------------- orientation */
+
+static float ic_angle(const uint8_t *img, int stride, float ptx, float pty, const int *umax)   /* :77-104 */
+{
+    int m_01 = 0, m_10 = 0;
+    const uint8_t *center = img + (size_t)cvp_round_f(pty) * stride + cvp_round_f(ptx);
+    for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+    for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        int v_sum = 0;
+        const int d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            const int val_plus = center[u + v * stride], val_minus = center[u - v * stride];
+            v_sum += (val_plus - val_minus);
+            m_10 += u * (val_plus + val_minus);
+        }
+        m_01 += v * v_sum;
+    }
+    return cvp_fast_atan2((float)m_01, (float)m_10);
+}
+
+/* ------------------------------------------------------------ descriptor */
+
+static void orb_descriptor(const orbo_keypoint *kpt, const uint8_t *img, int stride, uint8_t *desc)   /* :108-147 */
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float angle = kpt->angle * factorPI;
+    const float a = cosf(angle), b = sinf(angle);
+    const uint8_t *center = img + (size_t)cvp_round_f(kpt->y) * stride + cvp_round_f(kpt->x);
+    const int8_t *p = kPattern;
+    for (int i = 0; i < 32; ++i, p += 32) {
+        int val = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int x0 = p[4 * k], y0 = p[4 * k + 1], x1 = p[4 * k + 2], y1 = p[4 * k + 3];
+            const int t0 = center[cvp_round_f(x0 * b + y0 * a) * stride + cvp_round_f(x0 * a - y0 * b)];
+            const int t1 = center[cvp_round_f(x1 * b + y1 * a) * stride + cvp_round_f(x1 * a - y1 * b)];
+            val |= (t0 < t1) << k;
+        }
+        desc[i] = (uint8_t)val;
+    }
+}
+
+/* ------------------------------------------------------------- operator() */
+
+static void ensure_img(orbo_extractor *e, int l, size_t bytes)
+{
+    if (e->img_cap[l] < bytes) {
+        free(e->img[l]); free(e->blur[l]);
+        e->img[l] = (uint8_t *)malloc(bytes); e->blur[l] = (uint8_t *)malloc(bytes);
+        e->img_cap[l] = bytes;
+    }
+}
+
+static void cand_push(orbo_extractor *e, int l, int x, int y, int s)
+{
+    if (e->ncand[l] == e->cand_cap[l]) {
+        e->cand_cap[l] = e->cand_cap[l] ? e->cand_cap[l] * 2 : 4096;
+        e->cand[l] = (orbo_cand *)realloc(e->cand[l], sizeof(orbo_cand) * (size_t)e->cand_cap[l]);
+    }
+    orbo_cand *c = &e->cand[l][e->ncand[l]++];
+    c->x = x; c->y = y; c->score = s;
+}
+
+int orbo_extract(orbo_extractor *e, const uint8_t *gray, int w, int h, int stride,
+                 orbo_keypoint *kps, uint8_t *desc, int cap)
+{
+    const int L = e->nlevels;
+    for (int l = 0; l < L; ++l) { e->ncand[l] = 0; e->nlkp[l] = 0; e->has_blur[l] = 0; e->lw[l] = e->lh[l] = 0; }
+    if (!gray || w <= 0 || h <= 0) return 0;                           /* :1049 */
+
+    /* ComputePyramid :1111-1136 (levels kept un-padded; the border is synthesised on demand) */
+    for (int l = 0; l < L; ++l) {
+        const float s = e->inv_scale[l];
+        const int lw = cvp_round_f((float)w * s), lh = cvp_round_f((float)h * s);
+        e->lw[l] = lw; e->lh[l] = lh;
+        if (lw <= 0 || lh <= 0) { e->lw[l] = e->lh[l] = 0; continue; }
+        ensure_img(e, l, (size_t)lw * (size_t)lh);
+        if (l == 0) for (int y = 0; y < h; ++y) memcpy(e->img[0] + (size_t)y * w, gray + (size_t)y * stride, (size_t)w);
+        else cvp_resize_linear_u8(e->img[l - 1], e->lw[l - 1], e->lh[l - 1], e->lw[l - 1], e->img[l], lw, lh, lw);
+    }
+
+    /* ComputeKeyPointsOctTree :765-853 */
+    const float W = 30;
+    cvp_corner *cell_buf = (cvp_corner *)malloc(sizeof(cvp_corner) * 4096);
+    int cell_cap = 4096;
+    for (int level = 0; level < L; ++level) {
+        const int cols = e->lw[level], rows = e->lh[level];
+        const int minBorderX = EDGE_THRESHOLD - 3, minBorderY = minBorderX;
+        const int maxBorderX = cols - EDGE_THRESHOLD + 3, maxBorderY = rows - EDGE_THRESHOLD + 3;
+        e->min_cells[level] = e->cells[level] = 0;
+        const float width = (float)(maxBorderX - minBorderX), height = (float)(maxBorderY - minBorderY);
+        const int nCols = (int)(width / W), nRows = (int)(height / W);
+        if (nCols < 1 || nRows < 1) continue;       /* the reference divides by zero for such tiny levels */
+        const int wCell = (int)ceil((double)(width / nCols)), hCell = (int)ceil((double)(height / nRows));
+        const uint8_t *img = e->img[level];
+        for (int i = 0; i < nRows; ++i) {
+            const float iniY = (float)(minBorderY + i * hCell);
+            float maxY = iniY + hCell + 6;
+            if (iniY >= maxBorderY - 3) continue;
+            if (maxY > maxBorderY) maxY = (float)maxBorderY;
+            for (int j = 0; j < nCols; ++j) {
+                const float iniX = (float)(minBorderX + j * wCell);
+                float maxX = iniX + wCell + 6;
+                if (iniX >= maxBorderX - 6) continue;
+                if (maxX > maxBorderX) maxX = (float)maxBorderX;
+                const int x0 = (int)iniX, y0 = (int)iniY, cw = (int)maxX - x0, chh = (int)maxY - y0;
+                if (cw * chh > cell_cap) { cell_cap = cw * chh; cell_buf = (cvp_corner *)realloc(cell_buf, sizeof(cvp_corner) * (size_t)cell_cap); }
+                const uint8_t *roi = img + (size_t)y0 * cols + x0;
+                e->cells[level]++;
+                int nk = cvp_fast9_16(roi, cw, chh, cols, e->ini_th, 1, cell_buf, cell_cap);      /* :809 */
+                if (nk == 0) {
+                    nk = cvp_fast9_16(roi, cw, chh, cols, e->min_th, 1, cell_buf, cell_cap);      /* :814 */
+                    e->min_cells[level]++;
+                }
+                for (int k = 0; k < nk; ++k)                                                       /* :820-825 */
+                    cand_push(e, level, cell_buf[k].x + j * wCell, cell_buf[k].y + i * hCell, cell_buf[k].score);
+            }
+        }
+        /* :834 DistributeOctTree, :837-847 */
+        const int capk = e->nfeat[level] + 64 > e->ncand[level] ? e->ncand[level] + 1 : e->nfeat[level] + 64;
+        orbo_cand *sel = (orbo_cand *)malloc(sizeof(orbo_cand) * (size_t)(capk > 0 ? capk : 1));
+        int nsel = orbo_distribute(e->cand[level], e->ncand[level], minBorderX, maxBorderX, minBorderY, maxBorderY,
+                                   e->nfeat[level], sel, capk);
+        if (nsel > capk) nsel = capk;               /* cannot happen: the list never exceeds N+3 */
+        if (e->lkp_cap[level] < nsel) { free(e->lkp[level]); e->lkp[level] = (orbo_keypoint *)malloc(sizeof(orbo_keypoint) * (size_t)nsel); e->lkp_cap[level] = nsel; }
+        const int scaledPatchSize = (int)(PATCH_SIZE * e->scale[level]);
+        for (int i = 0; i < nsel; ++i) {
+            orbo_keypoint *k = &e->lkp[level][i];
+            k->x = (float)sel[i].x + minBorderX; k->y = (float)sel[i].y + minBorderY;
+            k->size = (float)scaledPatchSize; k->angle = -1.f; k->response = (float)sel[i].score;
+            k->octave = level; k->class_id = -1;
+        }
+        e->nlkp[level] = nsel;
+        free(sel);
+    }
+    free(cell_buf);
+    for (int level = 0; level < L; ++level)                                                         /* :851-852 */
+        for (int i = 0; i < e->nlkp[level]; ++i)
+            e->lkp[level][i].angle = ic_angle(e->img[level], e->lw[level], e->lkp[level][i].x, e->lkp[level][i].y, e->umax);
+
+    /* :1062-1108 */
+    int n = 0;
+    for (int level = 0; level < L; ++level) n += e->nlkp[level];
+    const int write = kps && desc && n <= cap;
+    int offset = 0;
+    for (int level = 0; level < L; ++level) {
+        const int nl = e->nlkp[level];
+        if (nl == 0) continue;
+        cvp_gaussian7x7_s2_u8(e->img[level], e->lw[level], e->lh[level], e->lw[level], e->blur[level], e->lw[level]);
+        e->has_blur[level] = 1;
+        if (write) {
+            for (int i = 0; i < nl; ++i) {
+                orbo_keypoint k = e->lkp[level][i];
+                orb_descriptor(&k, e->blur[level], e->lw[level], desc + 32 * (size_t)(offset + i));
+                if (level != 0) { const float s = e->scale[level]; k.x = k.x * s; k.y = k.y * s; }
+                kps[offset + i] = k;
+            }
+        }
+        offset += nl;
+    }
+    return (kps && desc && n > cap) ? -n : n;
+}
+
+int orbo_level_size(const orbo_extractor *e, int level, int *w, int *h)
+{
+    if (level < 0 || level >= e->nlevels) return -1;
+    *w = e->lw[level]; *h = e->lh[level];
+    return 0;
+}
+const uint8_t *orbo_level_image(const orbo_extractor *e, int level) { return e->img[level]; }
+const uint8_t *orbo_level_blurred(const orbo_extractor *e, int level) { return e->has_blur[level] ? e->blur[level] : NULL; }
+int orbo_level_candidates(const orbo_extractor *e, int level, const orbo_cand **out) { *out = e->cand[level]; return e->ncand[level]; }
+int orbo_level_min_cells(const orbo_extractor *e, int level, int *cells) { if (cells) *cells = e->cells[level]; return e->min_cells[level]; }
+int orbo_level_nkeypoints(const orbo_extractor *e, int level) { return e->nlkp[level]; }
+int orbo_level_padded(const orbo_extractor *e, int level, uint8_t *dst, int dst_stride)
+{
+    if (level < 0 || level >= e->nlevels || !e->lw[level]) return -1;
+    cvp_border_reflect101_u8(e->img[level], e->lw[level], e->lh[level], e->lw[level], dst, dst_stride,
+                             EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- matcher */
+
+int orbo_hamming256(const uint8_t *a, const uint8_t *b)        /* src/ORBmatcher.cc:2279-2295 */
+{
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        memcpy(&x, a + 4 * i, 4); memcpy(&y, b + 4 * i, 4);
+        uint32_t v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+static int match_rows(const uint8_t *A, int i0, int i1, const uint8_t *B, int nB, int th, float ratio,
+                      int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept)
+{
+    int acc = 0;
+    for (int i = i0; i < i1; ++i) {                            /* src/ORBmatcher.cc:574-605 */
+        int best1 = 256, best2 = 256, bi = -1;
+        for (int j = 0; j < nB; ++j) {
+            const int d = orbo_hamming256(A + 32 * (size_t)i, B + 32 * (size_t)j);
+            if (d < best1) { best2 = best1; best1 = d; bi = j; }
+            else if (d < best2) best2 = d;
+        }
+        idx[i] = bi; d1[i] = best1; d2[i] = best2;
+        const int ok = bi >= 0 && best1 <= th && (float)best1 < ratio * (float)best2;
+        if (accept) accept[i] = (uint8_t)ok;
+        acc += ok;
+    }
+    return acc;
+}
+
+int orbo_match(const uint8_t *A, int nA, const uint8_t *B, int nB, int th, float ratio,
+               int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept)
+{
+    return match_rows(A, 0, nA, B, nB, th, ratio, idx, d1, d2, accept);
+}
+
+typedef struct { const uint8_t *A, *B; int i0, i1, nB, th; float ratio; int32_t *idx, *d1, *d2; uint8_t *accept; int acc; } match_job;
+static void *match_worker(void *p)
+{
+    match_job *j = (match_job *)p;
+    j->acc = match_rows(j->A, j->i0, j->i1, j->B, j->nB, j->th, j->ratio, j->idx, j->d1, j->d2, j->accept);
+    return NULL;
+}
+
+int orbo_match_mt(const uint8_t *A, int nA, const uint8_t *B, int nB, int th, float ratio,
+                  int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > nA) threads = nA > 0 ? nA : 1;
+    pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    match_job *jobs = (match_job *)malloc(sizeof(match_job) * (size_t)threads);
+    for (int k = 0; k < threads; ++k) {
+        match_job j = {A, B, (int)((long)nA * k / threads), (int)((long)nA * (k + 1) / threads), nB, th, ratio, idx, d1, d2, accept, 0};
+        jobs[k] = j;
+        pthread_create(&t[k], NULL, match_worker, &jobs[k]);
+    }
+    int acc = 0;
+    for (int k = 0; k < threads; ++k) { pthread_join(t[k], NULL); acc += jobs[k].acc; }
+    free(t); free(jobs);
+    return acc;
+}
+
+/* ----------------------------------------------------------- CPU baseline */
+
+typedef struct {
+    int nfeatures, nlevels, ini_th, min_th; float sf;
+    const uint8_t *frames; int nframes, w, h;
+    int *next; pthread_mutex_t *mu; long kps;
+} many_job;
+
+static void *many_worker(void *p)
+{
+    many_job *j = (many_job *)p;
+    orbo_extractor *e = orbo_create(j->nfeatures, j->sf, j->nlevels, j->ini_th, j->min_th);
+    const int cap = j->nfeatures + 4 * j->nlevels + 64;
+    orbo_keypoint *k = (orbo_keypoint *)malloc(sizeof(orbo_keypoint) * (size_t)cap);
+    uint8_t *d = (uint8_t *)malloc(32 * (size_t)cap);
+    for (;;) {
+        pthread_mutex_lock(j->mu);
+        const int f = (*j->next)++;
+        pthread_mutex_unlock(j->mu);
+        if (f >= j->nframes) break;
+        const int n = orbo_extract(e, j->frames + (size_t)f * j->w * j->h, j->w, j->h, j->w, k, d, cap);
+        j->kps += n > 0 ? n : 0;
+    }
+    free(k); free(d); orbo_destroy(e);
+    return NULL;
+}
+
+double orbo_extract_many(int nfeatures, float sf, int nlevels, int ini_th, int min_th,
+                         const uint8_t *frames, int nframes, int w, int h, int threads, long *total_kps)
+{
+    if (threads < 1) threads = 1;
+    pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    many_job *jobs = (many_job *)malloc(sizeof(many_job) * (size_t)threads);
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    int next = 0;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int k = 0; k < threads; ++k) {
+        many_job j = {nfeatures, nlevels, ini_th, min_th, sf, frames, nframes, w, h, &next, &mu, 0};
+        jobs[k] = j;
+        pthread_create(&t[k], NULL, many_worker, &jobs[k]);
+    }
+    long kps = 0;
+    for (int k = 0; k < threads; ++k) { pthread_join(t[k], NULL); kps += jobs[k].kps; }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (total_kps) *total_kps = kps;
+    free(t); free(jobs);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

@@ -1,0 +1,87 @@
+/*
+ * oracle/orb_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement ("port") of the reference's ORB front end:
+ *   ORBextractor   src/ORBextractor.cc:77-147,410-853,1034-1136
+ *   ORBmatcher     src/ORBmatcher.cc:41-43,574-605,2279-2295
+ * with the canonical octree tie-break of SURVEY.md section 8c (creation
+ * sequence number instead of heap address).  Pinned against
+ *   - oracle/_ref/liborbref_canon.so : the reference's own ORBextractor.cc compiled
+ *     from /root/reference with only that tie-break edit (tests/test_oracle_vs_ref.py),
+ *   - cv2 4.13.0 for the OpenCV primitives (tests/test_oracle_cvprim.py),
+ *   - committed golden vectors (tests/golden/, scripts/make_golden.py).
+ * The reference itself ships no tests or golden vectors.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * legs may use this.  The CUDA product path never does.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBO_MAX_LEVELS 32
+
+/* cv::KeyPoint layout (28 bytes). */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbo_keypoint;
+
+/* FAST candidate, coordinates relative to (minBorderX, minBorderY) = (16,16). */
+typedef struct { int32_t x, y, score; } orbo_cand;
+
+typedef struct orbo_extractor orbo_extractor;
+
+orbo_extractor *orbo_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th);
+void orbo_destroy(orbo_extractor *e);
+
+/* ORBextractor::operator().  Returns the keypoint count n (kps/desc may be NULL to
+ * just run the stages), or -n if cap < n. */
+int orbo_extract(orbo_extractor *e, const uint8_t *gray, int w, int h, int stride,
+                 orbo_keypoint *kps, uint8_t *desc, int cap);
+
+/* Constructor tables (src/ORBextractor.cc:410-470). umax16 gets 16 ints. */
+int orbo_tables(const orbo_extractor *e, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                int *nfeat_per_level, int *umax16);
+
+/* Stage outputs of the last orbo_extract call. */
+int orbo_level_size(const orbo_extractor *e, int level, int *w, int *h);
+const uint8_t *orbo_level_image(const orbo_extractor *e, int level);    /* un-padded, stride = w */
+const uint8_t *orbo_level_blurred(const orbo_extractor *e, int level);  /* NULL if the level had no keypoints */
+int orbo_level_candidates(const orbo_extractor *e, int level, const orbo_cand **out);
+int orbo_level_min_cells(const orbo_extractor *e, int level, int *cells_visited); /* cells that fell back to minTh */
+int orbo_level_nkeypoints(const orbo_extractor *e, int level);
+/* copy the padded (w+38)x(h+38) level like mvImagePyramid's parent buffer */
+int orbo_level_padded(const orbo_extractor *e, int level, uint8_t *dst, int dst_stride);
+
+/* DistributeOctTree alone (canonical tie-break). cands relative coords; out gets selected
+ * candidates in list order.  Returns count. */
+int orbo_distribute(const orbo_cand *cands, int n, int minX, int maxX, int minY, int maxY, int N,
+                    orbo_cand *out, int cap);
+
+/* ORBmatcher core. */
+int orbo_hamming256(const uint8_t *a, const uint8_t *b);           /* SWAR popcount, 8 x int32 */
+/* All-pairs best / second-best scan in index order (src/ORBmatcher.cc:574-605).
+ * idx[i] = best j or -1 when nB == 0; d1/d2 = best / second-best distance (256 if none);
+ * accept[i] = d1 <= th && (float)d1 < ratio*(float)d2.  Returns the number accepted. */
+int orbo_match(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int th, float ratio,
+               int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept);
+/* Same, query rows split over `threads` pthreads (CPU baseline). */
+int orbo_match_mt(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int th, float ratio,
+                  int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept, int threads);
+
+/* CPU baseline: extract `nframes` frames (contiguous, w*h each) with `threads` worker
+ * threads, one extractor instance and one frame at a time per thread.  Returns wall
+ * seconds; *total_kps = sum of keypoint counts. */
+double orbo_extract_many(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                         const uint8_t *frames, int nframes, int w, int h, int threads, long *total_kps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
