@@ -1,0 +1,214 @@
+/*
+ * include/orbx.h -- C ABI of the B200-native ORB front end (liborbx.so).
+ *
+ * This is the drop-in boundary for the reference's feature front end
+ * (MultMotTracking / ORB-SLAM2): everything below replaces work the reference
+ * does on the CPU inside
+ *
+ *   ORBextractor::operator()(image, mask, keypoints, descriptors)
+ *                                   src/ORBextractor.cc:1046-1109, include/ORBextractor.h:56-61
+ *   ORBmatcher::DescriptorDistance  src/ORBmatcher.cc:2279-2295, include/ORBmatcher.h:44
+ *   the best / second-best / ratio loop shared by every SearchBy* matcher
+ *                                   src/ORBmatcher.cc:574-605 (also :807-836, :941-975)
+ *
+ * Plain C: POD structs, raw pointers and sizes, integer status codes, no C++
+ * exceptions, no OpenCV or torch types.  The C++ adapter that keeps the
+ * reference's class surface (multimot_track_b200/adapter/ORBextractor.{h,cc}) and the
+ * Python mirror (multimot_track_b200/extractor.py) are thin layers over these entry
+ * points; INTEGRATION.md shows the binding a maintainer of the reference adds.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device
+ * (sm_100a) and returns ORBX_ERR_CUDA when none is usable.
+ *
+ * Threading: a handle owns one CUDA stream and all of its scratch memory.  One
+ * handle must not be used from two threads at once; different handles may run
+ * concurrently (the reference's stereo Frame constructor runs two extractor
+ * instances on two threads, src/Frame.cc:96-99).  orbx_hamming256 is re-entrant.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK               0
+#define ORBX_ERR_BAD_ARG     -1   /* NULL pointer, non-positive size, nlevels out of range ... */
+#define ORBX_ERR_CAPACITY    -2   /* output buffer too small (see orbx_max_keypoints)          */
+#define ORBX_ERR_CUDA        -3   /* CUDA runtime error or no usable device                     */
+#define ORBX_ERR_OOM         -4   /* host or device allocation failed                           */
+#define ORBX_ERR_UNSUPPORTED -5   /* shape the reference itself cannot process (see below)      */
+#define ORBX_ERR_STATE       -6   /* collect without a pending submit, stage read before extract */
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_TH_LOW   50          /* ORBmatcher::TH_LOW,  src/ORBmatcher.cc:42 */
+#define ORBX_TH_HIGH 100          /* ORBmatcher::TH_HIGH, src/ORBmatcher.cc:41 */
+#define ORBX_HISTO_LENGTH 30      /* ORBmatcher::HISTO_LENGTH, src/ORBmatcher.cc:43 */
+
+typedef struct orbx_handle orbx_handle;
+
+/* The five ORBextractor constructor arguments (src/ORBextractor.cc:410-414,
+ * read from ORBextractor.* in the settings yaml by src/Tracking.cc:202-208)
+ * plus sizing hints.  max_* may be 0: buffers then grow on first use. */
+typedef struct {
+    int32_t nfeatures;
+    float   scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t max_width;
+    int32_t max_height;
+    int32_t max_batch;
+    int32_t device_id;       /* CUDA device ordinal; -1 = current device */
+} orbx_config;
+
+/* Binary layout of cv::KeyPoint (28 bytes), so a std::vector<cv::KeyPoint> can be
+ * filled by memcpy.  Fields as the reference sets them (src/ORBextractor.cc:837-847,
+ * :1098-1104): pt in level-0 pixels, size = (int)(31*scale[octave]), angle in
+ * degrees [0,360) from fastAtan2, response = FAST score, class_id = -1. */
+typedef struct {
+    float   x, y;
+    float   size;
+    float   angle;
+    float   response;
+    int32_t octave;
+    int32_t class_id;
+} orbx_keypoint;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Replaces `new ORBextractor(nFeatures, fScaleFactor, nLevels, fIniThFAST, fMinThFAST)`
+ * (src/Tracking.cc:208).  Builds the constructor tables with the reference's exact
+ * float/double arithmetic (src/ORBextractor.cc:415-469). */
+int orbx_create(const orbx_config *cfg, orbx_handle **out);
+void orbx_destroy(orbx_handle *h);
+
+/* Message for the last failing call on this handle (h may be NULL: last
+ * orbx_create failure of the calling thread).  Never NULL. */
+const char *orbx_last_error(const orbx_handle *h);
+
+/* ---- constructor tables (the getters Frame reads, src/Frame.cc:87-93) ---- */
+
+/* GetLevels / GetScaleFactor(s) / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:63-85) and mnFeaturesPerLevel.
+ * Any pointer may be NULL.  Returns nlevels (>0) or a negative status. */
+int orbx_get_tables(const orbx_handle *h, float *scale, float *inv_scale, float *sigma2,
+                    float *inv_sigma2, int32_t *nfeatures_per_level);
+
+/* Upper bound on keypoints per frame for a width x height image (each level may
+ * exceed its quota by at most 3: src/ORBextractor.cc:669,730).  Output buffers
+ * passed to the extract calls must hold at least this many rows per frame. */
+int orbx_max_keypoints(orbx_handle *h, int width, int height);
+
+/* Host-only planning (no CUDA device needed): the constructor tables and the
+ * per-level geometry the front end will use for a width x height image -- level
+ * sizes (:1116), FAST cell grid (:771-806), feature quota per level (:435-447),
+ * initial octree nodes (:543), and the keypoint capacity per frame.  Lets a caller
+ * size its buffers, and lets the host arithmetic be checked without a GPU. */
+typedef struct {
+    int32_t nlevels;
+    int32_t max_keypoints;                       /* == orbx_max_keypoints(width, height) */
+    int32_t level_width[ORBX_MAX_LEVELS], level_height[ORBX_MAX_LEVELS];
+    int32_t nfeatures_per_level[ORBX_MAX_LEVELS];
+    int32_t cell_cols[ORBX_MAX_LEVELS], cell_rows[ORBX_MAX_LEVELS];   /* cells actually visited */
+    int32_t cell_w[ORBX_MAX_LEVELS], cell_h[ORBX_MAX_LEVELS];         /* wCell, hCell */
+    int32_t octree_roots[ORBX_MAX_LEVELS];       /* nIni */
+    int32_t max_candidates[ORBX_MAX_LEVELS];     /* worst-case FAST candidates of the level */
+    float   scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS];
+    float   sigma2[ORBX_MAX_LEVELS], inv_sigma2[ORBX_MAX_LEVELS];
+    float   keypoint_size[ORBX_MAX_LEVELS];      /* cv::KeyPoint::size per octave */
+    int32_t umax[16];                            /* circular patch row ends (:453-469) */
+} orbx_plan;
+int orbx_make_plan(const orbx_config *cfg, int width, int height, orbx_plan *out);
+
+/* ---- ORBextractor::operator() ------------------------------------------ */
+
+/* One frame, host buffers, synchronous: the body of ORBextractor::operator().
+ * gray: 8-bit single channel (the reference asserts CV_8UC1, :1053), stride_bytes
+ * between rows.  kps[cap], desc[cap*32].  On return *n_out keypoints/descriptor rows
+ * are valid, in the reference's order (level-major, octree list order).  An empty
+ * image (NULL / zero size) returns ORBX_OK with *n_out = 0 and leaves the outputs
+ * untouched, mirroring the silent return at :1049. */
+int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int stride_bytes,
+                 orbx_keypoint *kps, uint8_t *desc, int cap, int *n_out);
+
+/* A batch of equally sized frames given as host pointers.  Outputs are laid out
+ * frame-major: frame f writes kps[f*cap_per_frame ...], desc[f*cap_per_frame*32 ...],
+ * n_out[f].  Pinned (page-locked) host buffers are used directly by the copy engine;
+ * pageable ones go through the handle's pinned staging area. */
+int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height,
+                       int stride_bytes, orbx_keypoint *kps, uint8_t *desc, int cap_per_frame, int *n_out);
+
+/* Same, with the frames already resident in device memory (frame f starts at
+ * d_frames + f*frame_stride_bytes).  Split into an asynchronous submit on the
+ * handle's stream and a collect that waits for it, so a caller can keep several
+ * handles in flight (results of batch i copy back while batch i+1 computes). */
+int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int nframes, int width, int height,
+                       int stride_bytes, size_t frame_stride_bytes);
+int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height,
+                     int stride_bytes);
+/* Waits for the pending submit, then fills the caller's arrays (frame-major as above). */
+int orbx_collect(orbx_handle *h, orbx_keypoint *kps, uint8_t *desc, int cap_per_frame, int *n_out);
+
+/* Zero-copy variant: waits for the pending submit and returns pointers into the
+ * handle's pinned result buffers (frame f at kps + f*cap, desc + f*cap*32, n[f]);
+ * they stay valid until the next submit on this handle.  Any pointer may be NULL. */
+int orbx_collect_view(orbx_handle *h, const orbx_keypoint **kps, const uint8_t **desc, const int **n_out,
+                      int *cap_per_frame);
+
+/* ---- mvImagePyramid and stage read-back -------------------------------- */
+
+/* Size of pyramid level `level` for the last processed shape. */
+int orbx_get_level_size(const orbx_handle *h, int level, int *width, int *height);
+
+/* Copies level `level` of frame `frame` of the last batch to host memory.
+ * with_border = 0: the w x h image (what mvImagePyramid[level] views);
+ * with_border = 1: the (w+38) x (h+38) parent buffer with the 19-pixel
+ * BORDER_REFLECT_101 frame of src/ORBextractor.cc:1126-1132, which
+ * Frame::ComputeStereoMatches may read around a keypoint (src/Frame.cc:960-977). */
+int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride, int with_border);
+
+/* The 7x7 sigma=2 blurred level the descriptors were sampled from (:1089-1090). */
+int orbx_get_blurred_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride);
+
+/* FAST candidates of one level before the octree (vToDistributeKeys, :820-825):
+ * xys[3*i..] = x, y (relative to (16,16) like the reference) and score.  The device
+ * emits them unordered; this call returns them sorted into the reference's order
+ * (cell row, cell column, y, x).  *n gets the count (may exceed cap). */
+int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t *xys, int cap, int *n);
+
+/* ---- ORBmatcher core ---------------------------------------------------- */
+
+/* ORBmatcher::DescriptorDistance on two 32-byte descriptors (host scalar: a
+ * one-pair GPU launch is meaningless; this keeps the static member's signature). */
+int orbx_hamming256(const void *a, const void *b);
+
+/* All-pairs nearest / second-nearest scan, queries descA[nA][32] against
+ * descB[nB][32] (host pointers), with the reference's update rule in index order:
+ *   if d < best1 { best2 = best1; best1 = d; idx = j } else if d < best2 { best2 = d }
+ * idx[i] = -1 and d1 = d2 = 256 when nB == 0.  accept[i] (may be NULL) =
+ *   best1 <= th && (float)best1 < ratio * (float)best2          (:601-603).
+ * Returns the number of accepted matches (>= 0) or a negative status. */
+int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const uint8_t *descB, int nB,
+               int th, float ratio, int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept);
+
+/* Same with all six arrays in device memory, asynchronous on the handle's stream
+ * (orbx_sync waits).  d_accept may be NULL.  Returns a status only. */
+int orbx_match_device(orbx_handle *h, const uint8_t *d_descA, int nA, const uint8_t *d_descB, int nB,
+                      int th, float ratio, int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept);
+
+/* ---- misc ---------------------------------------------------------------- */
+
+int orbx_sync(orbx_handle *h);                 /* waits for everything queued on the handle's stream */
+void *orbx_stream(orbx_handle *h);             /* the handle's cudaStream_t (for event timing by the caller) */
+/* Number of kernel launches issued by this handle since creation (bench bookkeeping). */
+long long orbx_launch_count(const orbx_handle *h);
+const char *orbx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

@@ -1,0 +1,61 @@
+// multimot_track_b200/csrc/kernels.cuh -- device-side parameter block and launch API.
+#ifndef ORBX_KERNELS_CUH
+#define ORBX_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orbx_internal.h"
+
+namespace orbx {
+
+// Lives in device memory (one per handle), rebuilt when the image shape changes.
+struct DevParams {
+    int nlevels, ini_th, min_th;
+    int kp_frame_cap;
+    long long pyr_frame_bytes;
+    long long cand_frame_elems;
+    LevelGeom lv[kMaxLevels];
+    int umax[16];
+    int xtab_off[kMaxLevels], ytab_off[kMaxLevels];
+    // buffers (batch-major: frame f at base + f*stride)
+    uint8_t *pyr;                 // [F][pyr_frame_bytes]   levels 0..L-1, un-padded, pitch = lv.pitch
+    uint8_t *blur;                // [F][pyr_frame_bytes]   7x7 sigma=2 blurred levels
+    uint32_t *cand;               // [F][cand_frame_elems]  packed x | y<<12 | score<<24 (relative to (16,16))
+    uint32_t *cand_count;         // [F][nlevels]
+    uint32_t *kp_stage;           // [F][kp_frame_cap]      octree winners, packed like cand, list order per level
+    uint32_t *kp_count;           // [F][nlevels]
+    unsigned long long *sort_scratch;   // [F][cand_frame_elems]  octree keys when a level does not fit shared memory
+    orbx_keypoint *out_kps;       // [F][kp_frame_cap]
+    uint8_t *out_desc;            // [F][kp_frame_cap][32]
+    int *out_n;                   // [F]
+    const ResizeTab *xtab, *ytab;
+    const uint32_t *fast_work;  int n_fast_work;
+    const uint32_t *blur_work;  int n_blur_work;
+    const int8_t *pattern;        // 512 x (x,y)
+};
+
+// Level-0 source of the current batch (either the caller's device frames used in
+// place, or the level-0 slot of DevParams::pyr).
+struct Src0 {
+    const uint8_t *ptr;
+    long long frame_stride;
+    int pitch;
+};
+
+struct LaunchStats { long long launches = 0; };
+
+cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, bool small_cells, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_pad_level(const uint8_t *src, int w, int h, int pitch, uint8_t *dst, int dst_pitch, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB, int th, float ratio,
+                         int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept, int *d_naccept,
+                         int4 *d_partial, int nchunks, cudaStream_t st, LaunchStats *ls);
+int match_chunks(int nA, int nB);       // number of B chunks launch_match will use (sizes d_partial: nchunks*nA)
+size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap);
+
+} // namespace orbx
+#endif

@@ -1,0 +1,565 @@
+// multimot_track_b200/csrc/orbx_api.cu -- the C ABI of include/orbx.h: handle, buffers,
+// stream orchestration.  No compute happens on the host: an entry point either
+// runs the CUDA kernels of kernels.cu or fails with ORBX_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace orbx;
+
+static const int8_t kPatternHost[1024] = {
+#include "orb_pattern.inc"
+};
+
+struct orbx_handle {
+    Tables tab;
+    Geometry geo;
+    bool geo_valid = false;
+    bool small_cells = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int batch_cap = 0;                  // frames the per-batch buffers hold
+    DevParams hp;                       // host copy of the device parameter block
+    DevParams *d_params = nullptr;
+    // geometry-sized device tables
+    ResizeTab *d_xtab = nullptr, *d_ytab = nullptr;
+    uint32_t *d_fast_work = nullptr, *d_blur_work = nullptr;
+    int8_t *d_pattern = nullptr;
+    // batch-sized device buffers
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+    uint32_t *d_cand = nullptr, *d_cand_count = nullptr, *d_kp_stage = nullptr, *d_kp_count = nullptr;
+    unsigned long long *d_sort = nullptr;
+    orbx_keypoint *d_out_kps = nullptr;
+    uint8_t *d_out_desc = nullptr;
+    int *d_out_n = nullptr;
+    uint8_t *d_pad = nullptr; size_t pad_bytes = 0;
+    // pinned host staging of the results
+    orbx_keypoint *p_kps = nullptr;
+    uint8_t *p_desc = nullptr;
+    int *p_n = nullptr;
+    // state of the last / pending batch
+    bool pending = false, have_batch = false;
+    int last_nframes = 0;
+    Src0 last_src0 = {nullptr, 0, 0};
+    // matcher scratch
+    uint32_t *m_A = nullptr, *m_B = nullptr; size_t m_capA = 0, m_capB = 0;
+    int32_t *m_out = nullptr; uint8_t *m_acc = nullptr; int *m_nacc = nullptr; size_t m_cap_out = 0;
+    int4 *m_partial = nullptr; size_t m_cap_partial = 0;
+    LaunchStats stats;
+    std::string err;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int fail(orbx_handle *h, int code, const std::string &msg) { if (h) h->err = msg; else g_create_error = msg; return code; }
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char b_[512];                                                                                \
+            std::snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? ORBX_ERR_OOM : ORBX_ERR_CUDA, b_);          \
+        }                                                                                                \
+    } while (0)
+
+template <typename T> void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+template <typename T> void hfree(T *&p) { if (p) cudaFreeHost(p); p = nullptr; }
+
+void free_batch_buffers(orbx_handle *h)
+{
+    dfree(h->d_pyr); dfree(h->d_blur); dfree(h->d_cand); dfree(h->d_cand_count); dfree(h->d_kp_stage);
+    dfree(h->d_kp_count); dfree(h->d_sort); dfree(h->d_out_kps); dfree(h->d_out_desc); dfree(h->d_out_n);
+    hfree(h->p_kps); hfree(h->p_desc); hfree(h->p_n);
+    h->batch_cap = 0;
+}
+
+void free_geo_tables(orbx_handle *h) { dfree(h->d_xtab); dfree(h->d_ytab); dfree(h->d_fast_work); dfree(h->d_blur_work); }
+
+int upload_params(orbx_handle *h)
+{
+    DevParams &P = h->hp;
+    P.pyr = h->d_pyr; P.blur = h->d_blur; P.cand = h->d_cand; P.cand_count = h->d_cand_count;
+    P.kp_stage = h->d_kp_stage; P.kp_count = h->d_kp_count; P.sort_scratch = h->d_sort;
+    P.out_kps = h->d_out_kps; P.out_desc = h->d_out_desc; P.out_n = h->d_out_n;
+    P.xtab = h->d_xtab; P.ytab = h->d_ytab; P.fast_work = h->d_fast_work; P.blur_work = h->d_blur_work;
+    P.pattern = h->d_pattern;
+    CU(cudaMemcpyAsync(h->d_params, &P, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));      // hp is reused; keep it simple: params change rarely
+    return ORBX_OK;
+}
+
+int ensure_batch(orbx_handle *h, int nframes)
+{
+    if (nframes <= h->batch_cap) return ORBX_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    free_batch_buffers(h);
+    const Geometry &g = h->geo;
+    const size_t F = (size_t)nframes, L = (size_t)g.nlevels;
+    CU(cudaMalloc(&h->d_pyr, F * g.pyr_frame_bytes));
+    CU(cudaMalloc(&h->d_blur, F * g.pyr_frame_bytes));
+    CU(cudaMalloc(&h->d_cand, F * g.cand_frame_elems * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_sort, F * g.cand_frame_elems * 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_cand_count, F * L * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_kp_count, F * L * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_kp_stage, F * g.kp_frame_cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_out_kps, F * g.kp_frame_cap * sizeof(orbx_keypoint)));
+    CU(cudaMalloc(&h->d_out_desc, F * g.kp_frame_cap * 32));
+    CU(cudaMalloc(&h->d_out_n, F * sizeof(int)));
+    CU(cudaMallocHost(&h->p_kps, F * g.kp_frame_cap * sizeof(orbx_keypoint)));
+    CU(cudaMallocHost(&h->p_desc, F * g.kp_frame_cap * 32));
+    CU(cudaMallocHost(&h->p_n, F * sizeof(int)));
+    // rows beyond a level's width are padding that kernels may write but never read as data;
+    // clear once so read-back of padded rows is deterministic
+    CU(cudaMemsetAsync(h->d_pyr, 0, F * g.pyr_frame_bytes, h->stream));
+    CU(cudaMemsetAsync(h->d_blur, 0, F * g.pyr_frame_bytes, h->stream));
+    h->batch_cap = nframes;
+    return upload_params(h);
+}
+
+int ensure_geometry(orbx_handle *h, int width, int height, int nframes)
+{
+    if (h->geo_valid && h->geo.width == width && h->geo.height == height) return ensure_batch(h, nframes);
+    CU(cudaStreamSynchronize(h->stream));
+    Geometry g;
+    std::string err;
+    const int rc = build_geometry(h->tab, width, height, &g, &err);
+    if (rc != ORBX_OK) return fail(h, rc, err);
+    if (g.max_node_cap > 8192) {
+        char b[160];
+        std::snprintf(b, sizeof b, "nfeatures too large: a level asks for %d octree nodes (limit 8192)", g.max_node_cap);
+        return fail(h, ORBX_ERR_UNSUPPORTED, b);
+    }
+    h->geo_valid = false; h->have_batch = false;
+    const int keep_cap = h->batch_cap;
+    free_batch_buffers(h);
+    free_geo_tables(h);
+    h->geo = g;
+    CU(cudaMalloc(&h->d_xtab, std::max<size_t>(g.xtab.size(), 4) * sizeof(ResizeTab)));
+    CU(cudaMalloc(&h->d_ytab, std::max<size_t>(g.ytab.size(), 4) * sizeof(ResizeTab)));
+    CU(cudaMalloc(&h->d_fast_work, std::max<size_t>(g.fast_work.size(), 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_blur_work, std::max<size_t>(g.blur_work.size(), 1) * sizeof(uint32_t)));
+    if (!g.xtab.empty()) CU(cudaMemcpy(h->d_xtab, g.xtab.data(), g.xtab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    if (!g.ytab.empty()) CU(cudaMemcpy(h->d_ytab, g.ytab.data(), g.ytab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    if (!g.fast_work.empty()) CU(cudaMemcpy(h->d_fast_work, g.fast_work.data(), g.fast_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!g.blur_work.empty()) CU(cudaMemcpy(h->d_blur_work, g.blur_work.data(), g.blur_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+    DevParams &P = h->hp;
+    std::memset(&P, 0, sizeof(P));
+    P.nlevels = g.nlevels; P.ini_th = h->tab.ini_th; P.min_th = h->tab.min_th;
+    P.kp_frame_cap = g.kp_frame_cap; P.pyr_frame_bytes = g.pyr_frame_bytes; P.cand_frame_elems = g.cand_frame_elems;
+    h->small_cells = true;
+    for (int l = 0; l < g.nlevels; ++l) {
+        P.lv[l] = g.lv[l]; P.xtab_off[l] = g.xtab_off[l]; P.ytab_off[l] = g.ytab_off[l];
+        if (g.lv[l].w_cell > 34 || g.lv[l].h_cell > 34) h->small_cells = false;
+    }
+    for (int i = 0; i < 16; ++i) P.umax[i] = h->tab.umax[i];
+    P.n_fast_work = (int)g.fast_work.size(); P.n_blur_work = (int)g.blur_work.size();
+    h->geo_valid = true;
+    return ensure_batch(h, std::max(nframes, keep_cap));
+}
+
+bool aligned16(const void *p, long long a, long long b) { return ((uintptr_t)p % 16 == 0) && a % 16 == 0 && b % 16 == 0; }
+
+// Queue the whole front end for a batch whose level-0 images are described by s0.
+int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
+{
+    const DevParams &P = h->hp;
+    cudaStream_t st = h->stream;
+    CU(cudaMemsetAsync(h->d_cand_count, 0, (size_t)nframes * P.nlevels * sizeof(uint32_t), st));
+    CU(launch_pyramid(h->d_params, P, s0, nframes, st, &h->stats));
+    CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
+    CU(launch_fast(h->d_params, P, s0, nframes, h->small_cells, st, &h->stats));
+    CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
+    CU(launch_orient_desc(h->d_params, P, s0, nframes, st, &h->stats));
+    const size_t cap = (size_t)P.kp_frame_cap;
+    CU(cudaMemcpyAsync(h->p_n, h->d_out_n, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->p_desc, h->d_out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, st));
+    h->pending = true; h->have_batch = true; h->last_nframes = nframes; h->last_src0 = s0;
+    return ORBX_OK;
+}
+
+int check_shape(orbx_handle *h, int nframes, int width, int height, int stride)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (nframes <= 0 || width <= 0 || height <= 0 || stride < width) return fail(h, ORBX_ERR_BAD_ARG, "bad frame shape / stride / count");
+    return ORBX_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ lifetime
+
+extern "C" int orbx_create(const orbx_config *cfg, orbx_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, ORBX_ERR_BAD_ARG, "orbx_create: NULL argument");
+    *out = nullptr;
+    if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAX_LEVELS || cfg->nfeatures < 1 || !(cfg->scale_factor >= 1.0f) ||
+        cfg->ini_th_fast < 1 || cfg->min_th_fast < 1 || cfg->ini_th_fast > 255 || cfg->min_th_fast > 255)
+        return fail(nullptr, ORBX_ERR_BAD_ARG, "orbx_create: nlevels in 1..16, nfeatures >= 1, scale_factor >= 1, thresholds in 1..255 required");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ORBX_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    orbx_handle *h = new (std::nothrow) orbx_handle();
+    if (!h) return fail(nullptr, ORBX_ERR_OOM, "host allocation failed");
+    int dev = cfg->device_id;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) { delete h; return fail(nullptr, ORBX_ERR_BAD_ARG, "device_id out of range"); }
+    h->device = dev;
+    build_tables(cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th_fast, cfg->min_th_fast, &h->tab);
+    int rc = ORBX_OK;
+    auto init = [&]() -> int {
+        CU(cudaSetDevice(dev));
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&h->d_params, sizeof(DevParams)));
+        CU(cudaMalloc(&h->d_pattern, sizeof(kPatternHost)));
+        CU(cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice));
+        if (cfg->max_width > 0 && cfg->max_height > 0)
+            return ensure_geometry(h, cfg->max_width, cfg->max_height, std::max(cfg->max_batch, 1));
+        return ORBX_OK;
+    };
+    rc = init();
+    if (rc != ORBX_OK) { g_create_error = h->err; orbx_destroy(h); return rc; }
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" void orbx_destroy(orbx_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_batch_buffers(h);
+    free_geo_tables(h);
+    dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad);
+    dfree(h->m_A); dfree(h->m_B); dfree(h->m_out); dfree(h->m_acc); dfree(h->m_nacc); dfree(h->m_partial);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *orbx_last_error(const orbx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" const char *orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
+
+extern "C" int orbx_get_tables(const orbx_handle *h, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2, int32_t *nfeat)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    for (int i = 0; i < h->tab.nlevels; ++i) {
+        if (scale) scale[i] = h->tab.scale[i];
+        if (inv_scale) inv_scale[i] = h->tab.inv_scale[i];
+        if (sigma2) sigma2[i] = h->tab.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->tab.inv_sigma2[i];
+        if (nfeat) nfeat[i] = h->tab.nfeat[i];
+    }
+    return h->tab.nlevels;
+}
+
+extern "C" int orbx_max_keypoints(orbx_handle *h, int width, int height)
+{
+    if (!h || width <= 0 || height <= 0) return ORBX_ERR_BAD_ARG;
+    if (h->geo_valid && h->geo.width == width && h->geo.height == height) return h->geo.kp_frame_cap;
+    Geometry g;
+    std::string err;
+    const int rc = build_geometry(h->tab, width, height, &g, &err);
+    if (rc != ORBX_OK) return fail(h, rc, err);
+    return g.kp_frame_cap;
+}
+
+extern "C" int orbx_make_plan(const orbx_config *cfg, int width, int height, orbx_plan *out)
+{
+    if (!cfg || !out || width <= 0 || height <= 0 || cfg->nlevels < 1 || cfg->nlevels > ORBX_MAX_LEVELS || cfg->nfeatures < 1 ||
+        !(cfg->scale_factor >= 1.0f))
+        return fail(nullptr, ORBX_ERR_BAD_ARG, "orbx_make_plan: bad argument");
+    Tables t;
+    build_tables(cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th_fast, cfg->min_th_fast, &t);
+    Geometry g;
+    std::string err;
+    const int rc = build_geometry(t, width, height, &g, &err);
+    if (rc != ORBX_OK) return fail(nullptr, rc, err);
+    std::memset(out, 0, sizeof(*out));
+    out->nlevels = g.nlevels; out->max_keypoints = g.kp_frame_cap;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom &L = g.lv[l];
+        out->level_width[l] = L.w; out->level_height[l] = L.h; out->nfeatures_per_level[l] = L.n_feat;
+        out->cell_cols[l] = L.cols_vis; out->cell_rows[l] = L.rows_vis; out->cell_w[l] = L.w_cell; out->cell_h[l] = L.h_cell;
+        out->octree_roots[l] = L.n_ini; out->max_candidates[l] = L.cand_cap;
+        out->scale[l] = t.scale[l]; out->inv_scale[l] = t.inv_scale[l]; out->sigma2[l] = t.sigma2[l]; out->inv_sigma2[l] = t.inv_sigma2[l];
+        out->keypoint_size[l] = L.kp_size;
+    }
+    for (int i = 0; i < 16; ++i) out->umax[i] = t.umax[i];
+    return ORBX_OK;
+}
+
+// ------------------------------------------------------------------ extract
+
+extern "C" int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int nframes, int width, int height,
+                                  int stride_bytes, size_t frame_stride_bytes)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!d_frames) return fail(h, ORBX_ERR_BAD_ARG, "NULL frame pointer");
+    int rc = check_shape(h, nframes, width, height, stride_bytes);
+    if (rc != ORBX_OK) return rc;
+    if (frame_stride_bytes < (size_t)stride_bytes * (size_t)(height - 1) + (size_t)width) return fail(h, ORBX_ERR_BAD_ARG, "frame_stride_bytes too small");
+    CU(cudaSetDevice(h->device));
+    if (h->pending) return fail(h, ORBX_ERR_STATE, "a batch is already pending on this handle: call orbx_collect first");
+    rc = ensure_geometry(h, width, height, nframes);
+    if (rc != ORBX_OK) return rc;
+    Src0 s0;
+    if (aligned16(d_frames, stride_bytes, (long long)frame_stride_bytes)) {
+        s0.ptr = d_frames; s0.pitch = stride_bytes; s0.frame_stride = (long long)frame_stride_bytes;   // used in place
+    } else {
+        const LevelGeom &L0 = h->geo.lv[0];
+        for (int f = 0; f < nframes; ++f)
+            CU(cudaMemcpy2DAsync(h->d_pyr + (size_t)f * h->geo.pyr_frame_bytes + L0.img_off, L0.pitch,
+                                 d_frames + (size_t)f * frame_stride_bytes, stride_bytes, width, height,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+        s0.ptr = h->d_pyr + L0.img_off; s0.pitch = L0.pitch; s0.frame_stride = h->geo.pyr_frame_bytes;
+    }
+    return enqueue_pipeline(h, s0, nframes);
+}
+
+extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height, int stride_bytes)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!frames) return fail(h, ORBX_ERR_BAD_ARG, "NULL frame array");
+    int rc = check_shape(h, nframes, width, height, stride_bytes);
+    if (rc != ORBX_OK) return rc;
+    for (int f = 0; f < nframes; ++f) if (!frames[f]) return fail(h, ORBX_ERR_BAD_ARG, "NULL frame pointer");
+    CU(cudaSetDevice(h->device));
+    if (h->pending) return fail(h, ORBX_ERR_STATE, "a batch is already pending on this handle: call orbx_collect first");
+    rc = ensure_geometry(h, width, height, nframes);
+    if (rc != ORBX_OK) return rc;
+    const LevelGeom &L0 = h->geo.lv[0];
+    for (int f = 0; f < nframes; ++f)
+        CU(cudaMemcpy2DAsync(h->d_pyr + (size_t)f * h->geo.pyr_frame_bytes + L0.img_off, L0.pitch, frames[f], stride_bytes,
+                             width, height, cudaMemcpyHostToDevice, h->stream));
+    Src0 s0;
+    s0.ptr = h->d_pyr + L0.img_off; s0.pitch = L0.pitch; s0.frame_stride = h->geo.pyr_frame_bytes;
+    return enqueue_pipeline(h, s0, nframes);
+}
+
+extern "C" int orbx_collect_view(orbx_handle *h, const orbx_keypoint **kps, const uint8_t **desc, const int **n_out, int *cap_per_frame)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!h->pending) return fail(h, ORBX_ERR_STATE, "orbx_collect without a pending submit");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    h->pending = false;
+    if (kps) *kps = h->p_kps;
+    if (desc) *desc = h->p_desc;
+    if (n_out) *n_out = h->p_n;
+    if (cap_per_frame) *cap_per_frame = h->geo.kp_frame_cap;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_collect(orbx_handle *h, orbx_keypoint *kps, uint8_t *desc, int cap_per_frame, int *n_out)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!kps || !desc || !n_out) return fail(h, ORBX_ERR_BAD_ARG, "NULL output pointer");
+    const int rc = orbx_collect_view(h, nullptr, nullptr, nullptr, nullptr);
+    if (rc != ORBX_OK) return rc;
+    const size_t cap = (size_t)h->geo.kp_frame_cap;
+    int status = ORBX_OK;
+    for (int f = 0; f < h->last_nframes; ++f) {
+        const int n = h->p_n[f];
+        n_out[f] = n;
+        if (n > cap_per_frame) { status = fail(h, ORBX_ERR_CAPACITY, "cap_per_frame smaller than the keypoint count (see orbx_max_keypoints)"); continue; }
+        std::memcpy(kps + (size_t)f * cap_per_frame, h->p_kps + f * cap, (size_t)n * sizeof(orbx_keypoint));
+        std::memcpy(desc + (size_t)f * cap_per_frame * 32, h->p_desc + f * cap * 32, (size_t)n * 32);
+    }
+    return status;
+}
+
+extern "C" int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height,
+                                  int stride_bytes, orbx_keypoint *kps, uint8_t *desc, int cap_per_frame, int *n_out)
+{
+    const int rc = orbx_submit_host(h, frames, nframes, width, height, stride_bytes);
+    if (rc != ORBX_OK) return rc;
+    return orbx_collect(h, kps, desc, cap_per_frame, n_out);
+}
+
+extern "C" int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int stride_bytes,
+                            orbx_keypoint *kps, uint8_t *desc, int cap, int *n_out)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!n_out) return fail(h, ORBX_ERR_BAD_ARG, "NULL n_out");
+    if (!gray || width <= 0 || height <= 0) { *n_out = 0; return ORBX_OK; }     // src/ORBextractor.cc:1049
+    const uint8_t *frames[1] = {gray};
+    return orbx_extract_batch(h, frames, 1, width, height, stride_bytes, kps, desc, cap, n_out);
+}
+
+// ----------------------------------------------------------- stage read-back
+
+static int stage_ready(orbx_handle *h, int frame, int level)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!h->have_batch || !h->geo_valid) return fail(h, ORBX_ERR_STATE, "no batch has been processed yet");
+    if (frame < 0 || frame >= h->last_nframes || level < 0 || level >= h->geo.nlevels) return fail(h, ORBX_ERR_BAD_ARG, "frame/level out of range");
+    return ORBX_OK;
+}
+
+extern "C" int orbx_get_level_size(const orbx_handle *h, int level, int *width, int *height)
+{
+    if (!h || !h->geo_valid || level < 0 || level >= h->geo.nlevels) return ORBX_ERR_BAD_ARG;
+    if (width) *width = h->geo.lv[level].w;
+    if (height) *height = h->geo.lv[level].h;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride, int with_border)
+{
+    int rc = stage_ready(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    if (!dst) return fail(h, ORBX_ERR_BAD_ARG, "NULL dst");
+    CU(cudaSetDevice(h->device));
+    const LevelGeom &L = h->geo.lv[level];
+    const uint8_t *src; int pitch;
+    if (level == 0) { src = h->last_src0.ptr + (size_t)frame * h->last_src0.frame_stride; pitch = h->last_src0.pitch; }
+    else { src = h->d_pyr + (size_t)frame * h->geo.pyr_frame_bytes + L.img_off; pitch = L.pitch; }
+    if (!with_border) {
+        if (dst_stride < L.w) return fail(h, ORBX_ERR_BAD_ARG, "dst_stride too small");
+        CU(cudaMemcpy2DAsync(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        const int W = L.w + 2 * kEdge, H = L.h + 2 * kEdge;
+        if (dst_stride < W) return fail(h, ORBX_ERR_BAD_ARG, "dst_stride too small");
+        const size_t need = (size_t)W * H;
+        if (need > h->pad_bytes) { dfree(h->d_pad); CU(cudaMalloc(&h->d_pad, need)); h->pad_bytes = need; }
+        CU(launch_pad_level(src, L.w, L.h, pitch, h->d_pad, W, h->stream, &h->stats));
+        CU(cudaMemcpy2DAsync(dst, dst_stride, h->d_pad, W, W, H, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_get_blurred_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride)
+{
+    int rc = stage_ready(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    const LevelGeom &L = h->geo.lv[level];
+    if (!dst || dst_stride < L.w) return fail(h, ORBX_ERR_BAD_ARG, "bad dst / dst_stride");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy2DAsync(dst, dst_stride, h->d_blur + (size_t)frame * h->geo.pyr_frame_bytes + L.img_off, L.pitch, L.w, L.h,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t *xys, int cap, int *n)
+{
+    int rc = stage_ready(h, frame, level);
+    if (rc != ORBX_OK) return rc;
+    if (!n) return fail(h, ORBX_ERR_BAD_ARG, "NULL n");
+    CU(cudaSetDevice(h->device));
+    const LevelGeom &L = h->geo.lv[level];
+    uint32_t cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, h->d_cand_count + (size_t)frame * h->geo.nlevels + level, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (cnt > (uint32_t)L.cand_cap) cnt = (uint32_t)L.cand_cap;
+    *n = (int)cnt;
+    if (!xys || cap <= 0 || cnt == 0) return ORBX_OK;
+    std::vector<uint32_t> raw(cnt);
+    CU(cudaMemcpyAsync(raw.data(), h->d_cand + (size_t)frame * h->geo.cand_frame_elems + L.cand_off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // reference emission order: cell row, cell column, then y, x inside the cell (:789-829)
+    auto key = [&](uint32_t c) {
+        const unsigned long long x = c & 0xfff, y = (c >> 12) & 0xfff;
+        return ((unsigned long long)((y - 3) / L.h_cell * L.n_cols + (x - 3) / L.w_cell) << 24) | y << 12 | x;
+    };
+    std::sort(raw.begin(), raw.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    for (int i = 0; i < (int)cnt && i < cap; ++i) {
+        xys[3 * i] = (int32_t)(raw[i] & 0xfff); xys[3 * i + 1] = (int32_t)((raw[i] >> 12) & 0xfff); xys[3 * i + 2] = (int32_t)(raw[i] >> 24);
+    }
+    return ORBX_OK;
+}
+
+// ------------------------------------------------------------------ matcher
+
+extern "C" int orbx_hamming256(const void *a, const void *b)
+{
+    uint64_t x[4], y[4];
+    std::memcpy(x, a, 32); std::memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) + __builtin_popcountll(x[2] ^ y[2]) +
+           __builtin_popcountll(x[3] ^ y[3]);
+}
+
+static int ensure_partial(orbx_handle *h, int nA, int nchunks)
+{
+    const size_t need = (size_t)nA * nchunks;
+    if (need > h->m_cap_partial) { dfree(h->m_partial); CU(cudaMalloc(&h->m_partial, need * sizeof(int4))); h->m_cap_partial = need; }
+    if (!h->m_nacc) CU(cudaMalloc(&h->m_nacc, sizeof(int)));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_match_device(orbx_handle *h, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int th, float ratio,
+                                 int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (nA < 0 || nB < 0 || (nA > 0 && (!dA || !d_idx || !d_d1 || !d_d2)) || (nB > 0 && !dB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_match_device: bad argument");
+    if (((uintptr_t)dA | (uintptr_t)dB) % 16) return fail(h, ORBX_ERR_BAD_ARG, "descriptor arrays must be 16-byte aligned");
+    if (nA == 0) return ORBX_OK;
+    CU(cudaSetDevice(h->device));
+    const int nchunks = match_chunks(nA, nB);
+    int rc = ensure_partial(h, nA, nchunks);
+    if (rc != ORBX_OK) return rc;
+    CU(launch_match((const uint32_t *)dA, nA, (const uint32_t *)dB, nB, th, ratio, d_idx, d_d1, d_d2, d_accept, nullptr,
+                    h->m_partial, nchunks, h->stream, &h->stats));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const uint8_t *descB, int nB, int th, float ratio,
+                          int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (nA < 0 || nB < 0 || (nA > 0 && (!descA || !idx || !d1 || !d2)) || (nB > 0 && !descB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_match: bad argument");
+    if (nA == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    if ((size_t)nA > h->m_capA) { dfree(h->m_A); CU(cudaMalloc(&h->m_A, (size_t)nA * 32)); h->m_capA = nA; }
+    if ((size_t)std::max(nB, 1) > h->m_capB) { dfree(h->m_B); CU(cudaMalloc(&h->m_B, (size_t)std::max(nB, 1) * 32)); h->m_capB = std::max(nB, 1); }
+    if ((size_t)nA > h->m_cap_out) {
+        dfree(h->m_out); dfree(h->m_acc);
+        CU(cudaMalloc(&h->m_out, (size_t)nA * 3 * sizeof(int32_t)));
+        CU(cudaMalloc(&h->m_acc, (size_t)nA));
+        h->m_cap_out = nA;
+    }
+    const int nchunks = match_chunks(nA, nB);
+    int rc = ensure_partial(h, nA, nchunks);
+    if (rc != ORBX_OK) return rc;
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(h->m_A, descA, (size_t)nA * 32, cudaMemcpyHostToDevice, st));
+    if (nB > 0) CU(cudaMemcpyAsync(h->m_B, descB, (size_t)nB * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->m_nacc, 0, sizeof(int), st));
+    CU(launch_match(h->m_A, nA, h->m_B, nB, th, ratio, h->m_out, h->m_out + nA, h->m_out + 2 * (size_t)nA, h->m_acc, h->m_nacc,
+                    h->m_partial, nchunks, st, &h->stats));
+    int nacc = 0;
+    CU(cudaMemcpyAsync(idx, h->m_out, (size_t)nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d1, h->m_out + nA, (size_t)nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d2, h->m_out + 2 * (size_t)nA, (size_t)nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (accept) CU(cudaMemcpyAsync(accept, h->m_acc, (size_t)nA, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&nacc, h->m_nacc, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return nacc;
+}
+
+// --------------------------------------------------------------------- misc
+
+extern "C" int orbx_sync(orbx_handle *h)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" long long orbx_launch_count(const orbx_handle *h) { return h ? h->stats.launches : 0; }

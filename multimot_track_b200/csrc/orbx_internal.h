@@ -1,0 +1,84 @@
+// multimot_track_b200/csrc/orbx_internal.h -- shared between the host-side geometry
+// builder (host_tables.cpp), the kernels (kernels.cu) and the C-ABI (orbx_api.cpp).
+#ifndef ORBX_INTERNAL_H
+#define ORBX_INTERNAL_H
+
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+
+namespace orbx {
+
+constexpr int kMaxLevels = ORBX_MAX_LEVELS;
+constexpr int kMaxRoots = 16;            // initial octree nodes (round(width/height)), :543
+constexpr int kEdge = 19;                // EDGE_THRESHOLD, src/ORBextractor.cc:74
+constexpr int kMinBorder = 16;           // EDGE_THRESHOLD-3, :772
+constexpr int kMaxDim = 4095 + 2 * kMinBorder;   // candidate coordinates are packed in 12 bits
+
+// Per-level geometry.  Everything that needs the reference's float arithmetic is
+// evaluated once on the host (host_tables.cpp) so the device code is integer-only
+// wherever the reference is.
+struct LevelGeom {
+    int w, h, pitch;                 // un-padded level image; pitch in bytes (multiple of 64)
+    long long img_off;               // byte offset of the level inside one frame's pyramid block
+    // per-cell FAST grid, src/ORBextractor.cc:771-806
+    int n_cols, n_rows;              // nCols, nRows as the reference computes them
+    int w_cell, h_cell;              // wCell, hCell
+    int cols_vis, rows_vis;          // cells actually visited (after the two `continue`s)
+    int x_end, y_end;                // exclusive end of the detection area in level coordinates
+    int cell_work_off;               // first entry of this level in the FAST work list
+    // DistributeOctTree, :539-763
+    int n_feat;                      // mnFeaturesPerLevel[level]
+    int n_ini;                       // initial nodes
+    float h_x;                       // hX
+    int root_ul[kMaxRoots], root_br[kMaxRoots];
+    int region_h;                    // maxY - minY
+    int depth;                       // splits until every node is one pixel
+    // buffers
+    int cand_cap;                    // worst-case FAST candidates of the level
+    long long cand_off;              // element offset inside one frame's candidate block
+    int kp_cap, kp_off;              // per-level slot in one frame's keypoint staging
+    int node_cap;                    // octree node array capacity
+    // output fields
+    float scale;                     // mvScaleFactor[level]
+    float kp_size;                   // (float)(int)(PATCH_SIZE*scale), :837
+};
+
+struct ResizeTab {                   // cv::resize INTER_LINEAR coefficients, one per dst column / row
+    uint16_t s0, s1;                 // source indices (s1 clamped)
+    int16_t c0, c1;                  // 11-bit fixed point weights
+};
+
+struct Geometry {
+    int width = 0, height = 0, nlevels = 0;
+    LevelGeom lv[kMaxLevels];
+    long long pyr_frame_bytes = 0;   // bytes of one frame's pyramid block (levels 1..L-1; level 0 too when copied)
+    long long cand_frame_elems = 0;  // candidate slots per frame
+    int kp_frame_cap = 0;            // keypoint staging slots per frame == output capacity per frame
+    int max_node_cap = 0, max_feat = 0, max_cand_cap = 0;
+    std::vector<uint32_t> fast_work; // (level<<24 | cell_row<<12 | cell_col), visited cells only
+    std::vector<ResizeTab> xtab, ytab;   // concatenated per level (level 0 unused)
+    int xtab_off[kMaxLevels], ytab_off[kMaxLevels];
+    std::vector<uint32_t> blur_work; // (level<<24 | tile_y<<12 | tile_x)
+};
+
+struct Tables {                      // ORBextractor constructor, :410-470
+    int nfeatures, nlevels, ini_th, min_th;
+    float scale_factor_f;
+    float scale[kMaxLevels], inv_scale[kMaxLevels], sigma2[kMaxLevels], inv_sigma2[kMaxLevels];
+    int nfeat[kMaxLevels];
+    int umax[16];
+};
+
+// host_tables.cpp
+void build_tables(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, Tables *t);
+// returns ORBX_OK / ORBX_ERR_UNSUPPORTED (+ message)
+int build_geometry(const Tables &t, int width, int height, Geometry *g, std::string *err);
+
+constexpr int kBlurTileW = 64, kBlurTileH = 16;
+
+} // namespace orbx
+
+#endif

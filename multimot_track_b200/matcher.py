@@ -1,0 +1,38 @@
+"""Python mirror of the hot core of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-109):
+`DescriptorDistance` (src/ORBmatcher.cc:2279-2295), the thresholds (:41-43) and the
+best / second-best / ratio scan every SearchBy* shares (:574-605), as an all-pairs
+brute-force match on the GPU (BASELINE.json config 4)."""
+import numpy as np
+
+from . import _lib
+
+
+class ORBmatcher:
+    TH_LOW = 50
+    TH_HIGH = 100
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio=0.6, checkOri=True, extractor=None):
+        """nnratio / checkOri as in ORBmatcher::ORBmatcher (src/ORBmatcher.cc:50).  `extractor`
+        lends its GPU handle (stream + scratch); a private one is created otherwise."""
+        from .extractor import ORBextractor
+        self.mfNNratio = float(np.float32(nnratio))
+        self.mbCheckOrientation = bool(checkOri)
+        self._ext = extractor if extractor is not None else ORBextractor(1000, 1.2, 1, 20, 7)
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        """256-bit Hamming distance of two 32-byte descriptors (host scalar, like the static member)."""
+        lib = _lib.load_library()
+        a = np.frombuffer(a, np.uint8) if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a, np.uint8).reshape(-1)
+        b = np.frombuffer(b, np.uint8) if isinstance(b, (bytes, bytearray)) else np.ascontiguousarray(b, np.uint8).reshape(-1)
+        if a.size != 32 or b.size != 32:
+            raise ValueError("descriptors are 32 bytes")
+        return int(lib.orbx_hamming256(a.ctypes.data, b.ctypes.data))
+
+    def match(self, descA, descB, th=None, ratio=None):
+        """All-pairs scan.  Returns idx[nA] (-1 if nB == 0), best[nA], second[nA], accept[nA] where
+        accept = best <= th and float(best) < ratio*float(second)."""
+        th = self.TH_LOW if th is None else th
+        ratio = self.mfNNratio if ratio is None else ratio
+        return self._ext.match(descA, descB, th, ratio)

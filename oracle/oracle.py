@@ -1,0 +1,236 @@
+"""ctypes bindings of the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+  Oracle      : oracle/liborb_oracle.so, our C restatement (orb_oracle.c + cvprim.c)
+  RefExtractor: oracle/_ref/liborbref_{canon,asis}.so, the reference's own
+                src/ORBextractor.cc compiled against oracle/minicv (built here from
+                /root/reference by `make -C oracle ref`; the .so travels to the GPU box)
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+_I, _VP, _F = ctypes.c_int, ctypes.c_void_p, ctypes.c_float
+
+
+def build(ref=True):
+    """Compile the port, and the reference-based libs when /root/reference is present."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    if ref and os.path.exists(os.environ.get("ORBX_REFERENCE", "/root/reference") + "/src/ORBextractor.cc"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def _load(path):
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return ctypes.CDLL(path)
+
+
+class Oracle:
+    """Our scalar C port of ORBextractor / ORBmatcher (canonical octree tie-break)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            path = os.path.join(HERE, "liborb_oracle.so")
+            if not os.path.exists(path):
+                build(ref=False)
+            L = _load(path)
+            L.orbo_create.restype = _VP
+            L.orbo_create.argtypes = [_I, _F, _I, _I, _I]
+            L.orbo_destroy.argtypes = [_VP]
+            L.orbo_extract.argtypes = [_VP, _VP, _I, _I, _I, _VP, _VP, _I]
+            L.orbo_tables.argtypes = [_VP] * 7
+            L.orbo_level_size.argtypes = [_VP, _I, _VP, _VP]
+            L.orbo_level_image.restype = _VP
+            L.orbo_level_image.argtypes = [_VP, _I]
+            L.orbo_level_blurred.restype = _VP
+            L.orbo_level_blurred.argtypes = [_VP, _I]
+            L.orbo_level_candidates.argtypes = [_VP, _I, _VP]
+            L.orbo_level_min_cells.argtypes = [_VP, _I, _VP]
+            L.orbo_level_nkeypoints.argtypes = [_VP, _I]
+            L.orbo_level_padded.argtypes = [_VP, _I, _VP, _I]
+            L.orbo_distribute.argtypes = [_VP, _I, _I, _I, _I, _I, _I, _VP, _I]
+            L.orbo_hamming256.argtypes = [_VP, _VP]
+            L.orbo_match.argtypes = [_VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP]
+            L.orbo_match_mt.argtypes = [_VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP, _I]
+            L.orbo_extract_many.restype = ctypes.c_double
+            L.orbo_extract_many.argtypes = [_I, _F, _I, _I, _I, _VP, _I, _I, _I, _I, _VP]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST):
+        self.L = self.lib()
+        self.params = (int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST))
+        self.h = self.L.orbo_create(*self.params)
+        if not self.h:
+            raise ValueError("orbo_create failed")
+        self.nlevels, self.nfeatures = int(nlevels), int(nfeatures)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orbo_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        L = self.nlevels
+        t = [np.zeros(L, np.float32) for _ in range(4)] + [np.zeros(L, np.int32), np.zeros(16, np.int32)]
+        self.L.orbo_tables(self.h, *[a.ctypes.data for a in t])
+        return dict(scale=t[0], inv_scale=t[1], sigma2=t[2], inv_sigma2=t[3], nfeat=t[4], umax=t[5])
+
+    def __call__(self, image):
+        a = np.ascontiguousarray(image, np.uint8)
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orbo_extract(self.h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], kps.ctypes.data, desc.ctypes.data, cap)
+        assert n >= 0
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_size(self, level):
+        w, h = _I(), _I()
+        self.L.orbo_level_size(self.h, level, ctypes.byref(w), ctypes.byref(h))
+        return w.value, h.value
+
+    def _img(self, ptr, level):
+        w, h = self.level_size(level)
+        if not ptr:
+            return None
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), (h, w)).copy()
+
+    def level_image(self, level):
+        return self._img(self.L.orbo_level_image(self.h, level), level)
+
+    def level_blurred(self, level):
+        return self._img(self.L.orbo_level_blurred(self.h, level), level)
+
+    def level_padded(self, level):
+        w, h = self.level_size(level)
+        out = np.zeros((h + 38, w + 38), np.uint8)
+        self.L.orbo_level_padded(self.h, level, out.ctypes.data, out.strides[0])
+        return out
+
+    def level_candidates(self, level):
+        p = _VP()
+        n = self.L.orbo_level_candidates(self.h, level, ctypes.byref(p))
+        if n == 0:
+            return np.zeros((0, 3), np.int32)
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_int32)), (n, 3)).copy()
+
+    def level_min_cells(self, level):
+        c = _I()
+        m = self.L.orbo_level_min_cells(self.h, level, ctypes.byref(c))
+        return m, c.value
+
+    def level_nkeypoints(self, level):
+        return self.L.orbo_level_nkeypoints(self.h, level)
+
+    @classmethod
+    def hamming256(cls, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return cls.lib().orbo_hamming256(a.ctypes.data, b.ctypes.data)
+
+    @classmethod
+    def match(cls, A, B, th, ratio, threads=1):
+        A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32); B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+        nA, nB = len(A), len(B)
+        idx = np.zeros(nA, np.int32); d1 = np.zeros(nA, np.int32); d2 = np.zeros(nA, np.int32); acc = np.zeros(nA, np.uint8)
+        if threads > 1:
+            cls.lib().orbo_match_mt(A.ctypes.data, nA, B.ctypes.data, nB, int(th), float(ratio), idx.ctypes.data, d1.ctypes.data,
+                                    d2.ctypes.data, acc.ctypes.data, int(threads))
+        else:
+            cls.lib().orbo_match(A.ctypes.data, nA, B.ctypes.data, nB, int(th), float(ratio), idx.ctypes.data, d1.ctypes.data,
+                                 d2.ctypes.data, acc.ctypes.data)
+        return idx, d1, d2, acc.astype(bool)
+
+    @classmethod
+    def extract_many(cls, params, frames, threads):
+        """CPU baseline: frames [F,H,W] uint8 contiguous; returns (seconds, total keypoints)."""
+        f = np.ascontiguousarray(frames, np.uint8)
+        tot = ctypes.c_long()
+        s = cls.lib().orbo_extract_many(int(params[0]), float(params[1]), int(params[2]), int(params[3]), int(params[4]),
+                                        f.ctypes.data, f.shape[0], f.shape[2], f.shape[1], int(threads), ctypes.byref(tot))
+        return s, tot.value
+
+
+class RefExtractor:
+    """The reference's own compiled ORBextractor (variant 'canon' or 'asis')."""
+    _libs = {}
+
+    @classmethod
+    def available(cls, variant="canon"):
+        return os.path.exists(os.path.join(HERE, "_ref", "liborbref_%s.so" % variant))
+
+    @classmethod
+    def lib(cls, variant):
+        if variant not in cls._libs:
+            L = _load(os.path.join(HERE, "_ref", "liborbref_%s.so" % variant))
+            L.orbref_create.restype = _VP
+            L.orbref_create.argtypes = [_I, _F, _I, _I, _I]
+            L.orbref_destroy.argtypes = [_VP]
+            L.orbref_extract.argtypes = [_VP, _VP, _I, _I, _I, _VP, _VP, _I]
+            L.orbref_pyramid_level.argtypes = [_VP, _I, _VP, _I, _VP, _VP, _I]
+            L.orbref_tables.argtypes = [_VP] * 7
+            L.orbref_distribute.argtypes = [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _I]
+            L.orbref_descriptor_distance.argtypes = [_VP, _VP]
+            L.orbref_thresholds.argtypes = [_VP, _VP, _VP]
+            if hasattr(L, "orbref_extract_many"):
+                L.orbref_extract_many.restype = ctypes.c_double
+                L.orbref_extract_many.argtypes = [_I, _F, _I, _I, _I, _VP, _I, _I, _I, _I, _VP]
+            cls._libs[variant] = L
+        return cls._libs[variant]
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, variant="canon"):
+        self.L = self.lib(variant)
+        self.h = self.L.orbref_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST))
+        self.nlevels, self.nfeatures = int(nlevels), int(nfeatures)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orbref_destroy(self.h)
+            self.h = None
+
+    def __call__(self, image):
+        a = np.ascontiguousarray(image, np.uint8)
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        k = np.zeros((cap, 7), np.float32)
+        d = np.zeros((cap, 32), np.uint8)
+        n = self.L.orbref_extract(self.h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], k.ctypes.data, d.ctypes.data, cap)
+        assert n >= 0
+        kps = np.zeros(n, KEYPOINT_DTYPE)
+        for i, name in enumerate(["x", "y", "size", "angle", "response"]):
+            kps[name] = k[:n, i]
+        kps["octave"] = k[:n, 5].astype(np.int32)
+        kps["class_id"] = k[:n, 6].astype(np.int32)
+        return kps, d[:n].copy()
+
+    def pyramid_level(self, level, with_border=False):
+        w, h = _I(), _I()
+        self.L.orbref_pyramid_level(self.h, level, None, 0, ctypes.byref(w), ctypes.byref(h), int(with_border))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.L.orbref_pyramid_level(self.h, level, out.ctypes.data, out.strides[0], ctypes.byref(w), ctypes.byref(h), int(with_border))
+        return out
+
+    def tables(self):
+        L = self.nlevels
+        t = [np.zeros(L, np.float32) for _ in range(4)] + [np.zeros(L, np.int32), np.zeros(16, np.int32)]
+        self.L.orbref_tables(self.h, *[a.ctypes.data for a in t])
+        return dict(scale=t[0], inv_scale=t[1], sigma2=t[2], inv_sigma2=t[3], nfeat=t[4], umax=t[5])
+
+    @classmethod
+    def descriptor_distance(cls, a, b, variant="canon"):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return cls.lib(variant).orbref_descriptor_distance(a.ctypes.data, b.ctypes.data)
+
+    @classmethod
+    def extract_many(cls, params, frames, threads, variant="asis"):
+        f = np.ascontiguousarray(frames, np.uint8)
+        tot = ctypes.c_long()
+        s = cls.lib(variant).orbref_extract_many(int(params[0]), float(params[1]), int(params[2]), int(params[3]), int(params[4]),
+                                                 f.ctypes.data, f.shape[0], f.shape[2], f.shape[1], int(threads), ctypes.byref(tot))
+        return s, tot.value

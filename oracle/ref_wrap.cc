@@ -129,3 +129,35 @@ void orbref_thresholds(int *th_low, int *th_high, int *histo_length)
 }
 
 } // extern "C"
+
+// CPU baseline runner: one ORBextractor instance and one frame at a time per thread
+// (the reference's own threading contract, src/Frame.cc:96-99).  Returns wall seconds.
+#include <atomic>
+#include <chrono>
+#include <thread>
+extern "C" double orbref_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                                      const uint8_t *frames, int nframes, int w, int h, int threads, long *total_kps)
+{
+    if (threads < 1) threads = 1;
+    std::atomic<int> next(0);
+    std::atomic<long> kps(0);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&]() {
+            RefExtractor e(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST);
+            for (;;) {
+                const int f = next.fetch_add(1);
+                if (f >= nframes) break;
+                cv::Mat img(h, w, CV_8UC1, (void *)(frames + (size_t)f * w * h), (size_t)w);
+                std::vector<cv::KeyPoint> keys;
+                cv::Mat d;
+                e(img, cv::Mat(), keys, d);
+                kps += (long)keys.size();
+            }
+        });
+    for (auto &th : pool) th.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (total_kps) *total_kps = kps.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}

@@ -1,0 +1,210 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes mirror in
+multimot_track_b200), against the CPU oracle on the same inputs and against the committed
+reference-derived goldens.  Bars (BASELINE.json north_star): pyramid, blur, FAST
+responses, post-octree keypoints and match indices/distances bit-exact; angles within
+1e-4 rad; descriptor bit mismatch rate <= 1e-4 (reported)."""
+import numpy as np
+import pytest
+
+from conftest import angle_diff_rad, crc32, desc_bit_mismatch, kps_equal_exact
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_RAD = 1e-4
+DESC_MISMATCH_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def orb():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    import multimot_track_b200
+    multimot_track_b200.load_library()          # raises when the CUDA extension is missing: no silent fallback
+    return multimot_track_b200
+
+
+def synth(seed, h, w):
+    from multimot_track_b200.synth import value_noise_frame
+    return value_noise_frame(seed, h, w)
+
+
+def check_frame(ext, oracle, img, tag=""):
+    """Full stage-by-stage comparison of one frame; returns (descriptor bits differing, total bits)."""
+    kps, desc = ext(img)
+    okps, odesc = oracle(img)
+    L = oracle.nlevels
+    for l in range(L):
+        assert ext.level_size(l) == oracle.level_size(l), (tag, l)
+        assert np.array_equal(ext.pyramid_level(l), oracle.level_image(l)), "%s pyramid level %d" % (tag, l)
+        cand, ocand = ext.candidates(l), oracle.level_candidates(l)
+        assert cand.shape == ocand.shape and np.array_equal(cand, ocand), "%s FAST candidates level %d: %d vs %d" % (tag, l, len(cand), len(ocand))
+        ob = oracle.level_blurred(l)
+        if ob is not None:
+            assert np.array_equal(ext.blurred_level(l), ob), "%s blur level %d" % (tag, l)
+    assert len(kps) == len(okps), "%s keypoint count %d vs %d" % (tag, len(kps), len(okps))
+    assert kps_equal_exact(kps, okps), "%s keypoint set/order" % tag
+    assert angle_diff_rad(kps["angle"], okps["angle"]).max(initial=0) <= ANGLE_TOL_RAD
+    bad, total = desc_bit_mismatch(desc, odesc)
+    assert bad <= DESC_MISMATCH_TOL * total, "%s descriptor mismatch %d/%d" % (tag, bad, total)
+    return bad, total
+
+
+def test_kitti_golden_reference(orb, golden_kitti, kitti_frames):
+    """Config 1: kitti_sample frames with kitti03.yaml's (4000,1.2,8,20,7) and the benchmark's 2000,
+    against the outputs of the reference's own ORBextractor.cc (tests/golden/golden_kitti.npz)."""
+    bad_total = bits_total = 0
+    for nfeat in (4000, 2000):
+        ext = orb.ORBextractor(nfeat, 1.2, 8, 20, 7)
+        for f in (0, 1):
+            tag = "f%d_n%d" % (f, nfeat)
+            kps, desc = ext(kitti_frames[f])
+            ref_k, ref_d = golden_kitti["kps_" + tag], golden_kitti["desc_" + tag]
+            assert [crc32(ext.pyramid_level(l)) for l in range(8)] == golden_kitti["pyr_crc_" + tag].tolist()
+            assert [crc32(ext.pyramid_level(l, with_border=True)) for l in range(8)] == golden_kitti["pyr_border_crc_" + tag].tolist()
+            assert [crc32(ext.blurred_level(l)) for l in range(8)] == golden_kitti["blur_crc_" + tag].tolist()
+            assert [len(ext.candidates(l)) for l in range(8)] == golden_kitti["ncand_" + tag].tolist()
+            assert kps_equal_exact(kps, ref_k), tag
+            assert angle_diff_rad(kps["angle"], ref_k["angle"]).max() <= ANGLE_TOL_RAD
+            bad, total = desc_bit_mismatch(desc, ref_d)
+            bad_total += bad; bits_total += total
+    print("descriptor bit mismatch vs reference: %d / %d = %.2e" % (bad_total, bits_total, bad_total / bits_total))
+    assert bad_total <= DESC_MISMATCH_TOL * bits_total
+
+
+def test_kitti_stages_vs_oracle(orb, oracle_mod, kitti_frames):
+    ext = orb.ORBextractor(4000, 1.2, 8, 20, 7)
+    o = oracle_mod.Oracle(4000, 1.2, 8, 20, 7)
+    for f in (0, 1):
+        check_frame(ext, o, kitti_frames[f], "kitti%d" % f)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_synthetic_k1_vs_oracle(orb, oracle_mod, seed):
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
+    check_frame(ext, o, synth(seed, 375, 1242), "syn%d" % seed)
+
+
+def test_synthetic_golden_reference(orb, golden_synth):
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    for seed in (0, 1):
+        kps, desc = ext(synth(seed, 375, 1242))
+        assert kps_equal_exact(kps, golden_synth["kps_1242x375_seed%d" % seed])
+        bad, total = desc_bit_mismatch(desc, golden_synth["desc_1242x375_seed%d" % seed])
+        assert bad <= DESC_MISMATCH_TOL * total
+
+
+def test_uniform_noise_stress(orb, oracle_mod):
+    """~40k candidates on level 0: the octree keys do not fit shared memory (global scratch path)."""
+    from multimot_track_b200.synth import uniform_noise_frame
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
+    check_frame(ext, o, uniform_noise_frame(5, 375, 1242), "noise")
+
+
+@pytest.mark.parametrize("shape,params", [((480, 640), (1000, 1.2, 8, 20, 7)), ((240, 320), (500, 1.2, 4, 20, 7)),
+                                          ((300, 700), (500, 1.5, 4, 25, 10)), ((230, 231), (300, 1.2, 8, 20, 7)),
+                                          ((128, 400), (256, 1.3, 3, 15, 5)), ((600, 333), (1500, 1.2, 6, 20, 7))])
+def test_other_shapes_and_parameters(orb, oracle_mod, shape, params):
+    ext = orb.ORBextractor(*params)
+    o = oracle_mod.Oracle(*params)
+    check_frame(ext, o, synth(40, *shape), "shape%s" % (shape,))
+
+
+def test_edge_inputs(orb, oracle_mod):
+    ext = orb.ORBextractor(1000, 1.2, 8, 20, 7)
+    o = oracle_mod.Oracle(1000, 1.2, 8, 20, 7)
+    # empty image: silent return (src/ORBextractor.cc:1049)
+    k, d = ext(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # flat image: no corners anywhere
+    k, d = ext(np.full((375, 1242), 128, np.uint8))
+    assert len(k) == 0
+    # a single bright blob: a handful of candidates, fewer than the per-level quota
+    img = np.full((375, 1242), 30, np.uint8); img[180:190, 600:612] = 220
+    check_frame(ext, o, img, "blob")
+    # non-CV_8UC1 input asserts like the reference (:1053)
+    with pytest.raises(AssertionError):
+        ext(np.zeros((375, 1242), np.float32))
+    # strided view (every row padded) and a shape change on the same handle
+    big = synth(8, 375, 1300)
+    check_frame(ext, o, big[:, :1242], "strided")
+    check_frame(ext, o, synth(9, 480, 640), "reshape")
+
+
+def test_capacity_error(orb):
+    import ctypes
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    img = synth(0, 375, 1242)
+    kps = np.zeros(10, orb.KEYPOINT_DTYPE); desc = np.zeros((10, 32), np.uint8); n = ctypes.c_int()
+    rc = ext._lib.orbx_extract(ext._h, img.ctypes.data, 1242, 375, 1242, kps.ctypes.data, desc.ctypes.data, 10, ctypes.byref(n))
+    assert rc == -2 and n.value > 10 and b"cap" in ext._lib.orbx_last_error(ext._h)
+
+
+def test_batch_equals_single_and_is_deterministic(orb):
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    frames = [synth(s, 375, 1242) for s in range(6)]
+    singles = [ext(f) for f in frames]
+    for rep in range(2):
+        batch = ext.extract_batch(frames)
+        for (k1, d1), (k2, d2) in zip(singles, batch):
+            assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+
+
+def test_device_resident_paths(orb):
+    """Frames already in HBM: aligned stride (used in place) and odd stride (copied) give identical results."""
+    import torch
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    frames = np.stack([synth(s, 375, 1242) for s in range(4)])
+    ref = ext.extract_batch(list(frames))
+    for pitch in (1242, 1280):
+        buf = torch.zeros((4, 375, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, :, :1242] = torch.from_numpy(frames).cuda()
+        torch.cuda.synchronize()
+        ext.submit_device(buf.data_ptr(), 4, 1242, 375, pitch, 375 * pitch)
+        kps, desc, n = ext.collect_view()
+        for f in range(4):
+            assert np.array_equal(kps[f, :n[f]], ref[f][0]) and np.array_equal(desc[f, :n[f]], ref[f][1]), (pitch, f)
+
+
+def test_matcher_vs_oracle(orb, oracle_mod):
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    (_, dA), (_, dB) = ext.extract_batch([synth(0, 375, 1242), synth(1, 375, 1242)])
+    m = orb.ORBmatcher(0.9, extractor=ext)
+    rng = np.random.default_rng(1)
+    rnd = rng.integers(0, 256, (777, 32), dtype=np.uint8)
+    near = dA.copy(); flip = rng.integers(0, 256, len(near)); near[np.arange(len(near)), flip % 32] ^= 1 << (flip % 8).astype(np.uint8)
+    for A, B in ((dA, dB), (dA, dA), (dA, near), (rnd, rnd[::-1].copy()), (dA[:1], dB), (dA, dB[:1]), (dA[:130], dB[:129])):
+        for th in (orb.ORBmatcher.TH_LOW, orb.ORBmatcher.TH_HIGH):
+            idx, d1, d2, acc = m.match(A, B, th, 0.9)
+            oi, o1, o2, oa = oracle_mod.Oracle.match(A, B, th, 0.9)
+            assert np.array_equal(idx, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2) and np.array_equal(acc, oa)
+    idx, d1, d2, acc = m.match(dA, dA, 50, 0.9)
+    assert np.array_equal(idx[d1 == 0][:5], np.arange(len(dA))[d1 == 0][:5])      # self-match: distance 0 at the own (lowest) index
+    idx, d1, d2, acc = m.match(dA, np.zeros((0, 32), np.uint8), 50, 0.9)
+    assert (idx == -1).all() and (d1 == 256).all() and not acc.any()
+
+
+def test_full_size_properties(orb, oracle_mod):
+    """BASELINE configs 3 and 5 at full size: one frame each against the oracle (seconds on the CPU),
+    and size-independent properties on the batch: determinism, self-match, level-major ordering, bounds."""
+    for (h, w), params in (((1080, 1920), (5000, 1.2, 8, 20, 7)), ((2160, 3840), (10000, 1.2, 12, 20, 7))):
+        ext = orb.ORBextractor(*params)
+        o = oracle_mod.Oracle(*params)
+        img = synth(0, h, w)
+        bad, total = check_frame(ext, o, img, "%dx%d" % (w, h))
+        print("%dx%d descriptor mismatch %d/%d" % (w, h, bad, total))
+        kps, desc = ext(img)
+        k2, d2 = ext(img)
+        assert np.array_equal(kps, k2) and np.array_equal(desc, d2)                       # idempotent
+        assert (np.diff(kps["octave"]) >= 0).all()                                           # level-major order
+        sc = ext.GetScaleFactors()
+        lx, ly = kps["x"] / sc[kps["octave"]], kps["y"] / sc[kps["octave"]]
+        for l in range(params[2]):
+            lw, lh = ext.level_size(l)
+            sel = kps["octave"] == l
+            assert sel.sum() <= ext.mnFeaturesPerLevel[l] + 3
+            assert (lx[sel] >= 19 - 1e-3).all() and (lx[sel] <= lw - 19).all() and (ly[sel] >= 19 - 1e-3).all() and (ly[sel] <= lh - 19).all()
+        m = orb.ORBmatcher(0.9, extractor=ext)
+        idx, d1, _, _ = m.match(desc, desc, 100, 0.9)
+        assert (d1 == 0).all() and (idx <= np.arange(len(desc))).all()

@@ -1,0 +1,108 @@
+"""Pins the oracle port (oracle/orb_oracle.c) to the reference:
+  * golden outputs of the reference's own ORBextractor.cc (canonical tie-break build)
+    on the two committed KITTI sample frames, both parameter sets (tests/golden/);
+  * live, when oracle/_ref/*.so is present (built from /root/reference here; shipped
+    to the GPU box), on synthetic frames too, incl. DescriptorDistance."""
+import numpy as np
+import pytest
+
+from conftest import crc32, desc_bit_mismatch, kps_equal_exact
+
+
+@pytest.mark.parametrize("frame", [0, 1])
+@pytest.mark.parametrize("nfeat", [2000, 4000])
+def test_port_matches_reference_golden(oracle_mod, golden_kitti, kitti_frames, frame, nfeat):
+    tag = "f%d_n%d" % (frame, nfeat)
+    o = oracle_mod.Oracle(nfeat, 1.2, 8, 20, 7)
+    kps, desc = o(kitti_frames[frame])
+    ref_k, ref_d = golden_kitti["kps_" + tag], golden_kitti["desc_" + tag]
+    assert kps_equal_exact(kps, ref_k)
+    assert np.array_equal(kps["angle"].view(np.uint32), ref_k["angle"].view(np.uint32))      # same fastAtan2 polynomial
+    bad, total = desc_bit_mismatch(desc, ref_d)
+    assert bad == 0, "descriptor bits differing from the reference: %d of %d" % (bad, total)
+    assert [crc32(o.level_image(l)) for l in range(8)] == golden_kitti["pyr_crc_" + tag].tolist()
+    assert [crc32(o.level_padded(l)) for l in range(8)] == golden_kitti["pyr_border_crc_" + tag].tolist()
+    assert [len(o.level_candidates(l)) for l in range(8)] == golden_kitti["ncand_" + tag].tolist()
+
+
+def test_survey_anchors(golden_kitti):
+    """Appendix B of SURVEY.md (measured with cv2 during the survey) agrees with the reference-derived goldens."""
+    assert "%08x" % int(golden_kitti["gray_crc_0"]) == "afa276f3"
+    assert ["%08x" % v for v in golden_kitti["pyr_crc_f0_n2000"]] == \
+        ["afa276f3", "69c746e0", "6c793fe7", "a1c81c73", "a30f55d4", "d2064ff0", "0e9b1e9b", "bfb93a19"]
+    assert ["%08x" % v for v in golden_kitti["blur_crc_f0_n2000"]] == \
+        ["fe8ec1e9", "e84cd204", "d6186819", "dad34ae4", "7cf9a9ec", "bbad43fe", "30bf3a11", "98e84fec"]
+    assert golden_kitti["ncand_f0_n2000"].tolist() == [7507, 5158, 3539, 2461, 1682, 1148, 794, 533]
+    assert golden_kitti["mincells_f0_n2000"].tolist() == [109, 69, 31, 18, 6, 0, 0, 0]
+    assert np.bincount(golden_kitti["kps_f0_n2000"]["octave"]).tolist() == [436, 364, 303, 251, 211, 176, 145, 122]
+
+
+def test_constructor_tables(oracle_mod, golden_kitti):
+    t = oracle_mod.Oracle(2000, 1.2, 8, 20, 7).tables()
+    for k in ("scale", "inv_scale", "sigma2", "inv_sigma2"):
+        assert np.array_equal(t[k].view(np.uint32), golden_kitti["tables2000_" + k].view(np.uint32)), k
+    assert t["nfeat"].tolist() == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert t["umax"].tolist() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    t12 = oracle_mod.Oracle(10000, 1.2, 12, 20, 7).tables()
+    assert np.array_equal(t12["nfeat"], golden_kitti["tables10000x12_nfeat"])
+    assert np.array_equal(t12["scale"].view(np.uint32), golden_kitti["tables10000x12_scale"].view(np.uint32))
+
+
+def test_synthetic_golden(oracle_mod, golden_synth):
+    pytest.importorskip("cv2")
+    from multimot_track_b200.synth import value_noise_frame
+    for (h, w) in ((375, 1242), (1080, 1920)):
+        assert crc32(value_noise_frame(0, h, w)) == int(golden_synth["crc_%dx%d_seed0" % (w, h)])
+    assert "%08x" % int(golden_synth["crc_1242x375_seed0"]) == "dc51c799"
+    o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
+    for seed in (0, 1):
+        kps, desc = o(value_noise_frame(seed, 375, 1242))
+        assert kps_equal_exact(kps, golden_synth["kps_1242x375_seed%d" % seed])
+        assert np.array_equal(desc, golden_synth["desc_1242x375_seed%d" % seed])
+
+
+def test_port_matches_live_reference(oracle_mod):
+    if not oracle_mod.RefExtractor.available("canon"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(11)
+    frames = [rng.integers(0, 256, (240, 320), dtype=np.uint8)]
+    try:
+        from multimot_track_b200.synth import value_noise_frame
+        frames += [value_noise_frame(21, 300, 500), value_noise_frame(22, 480, 640)]
+    except ImportError:
+        pass
+    for img in frames:
+        for nfeat, L in ((1000, 5), (300, 3)):
+            ref = oracle_mod.RefExtractor(nfeat, 1.2, L, 20, 7, "canon")
+            o = oracle_mod.Oracle(nfeat, 1.2, L, 20, 7)
+            rk, rd = ref(img)
+            ok, od = o(img)
+            assert kps_equal_exact(ok, rk) and np.array_equal(ok["angle"].view(np.uint32), rk["angle"].view(np.uint32))
+            assert np.array_equal(od, rd)
+            for l in range(L):
+                assert np.array_equal(o.level_image(l), ref.pyramid_level(l))
+                assert np.array_equal(o.level_padded(l), ref.pyramid_level(l, True))
+
+
+def test_hamming_and_matcher_rule(oracle_mod):
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (55, 32), dtype=np.uint8)
+    B[7] = A[3]; B[20] = A[3]                        # duplicate minimum: second-best equals best
+    d = np.unpackbits(A[:, None, :] ^ B[None, :, :], axis=2).sum(axis=2)
+    for i in range(5):
+        for j in range(5):
+            assert oracle_mod.Oracle.hamming256(A[i], B[j]) == d[i, j]
+            if oracle_mod.RefExtractor.available("canon"):
+                assert oracle_mod.RefExtractor.descriptor_distance(A[i], B[j]) == d[i, j]
+    idx, d1, d2, acc = oracle_mod.Oracle.match(A, B, 100, 0.9)
+    assert np.array_equal(idx, d.argmin(axis=1))     # argmin returns the lowest index on ties
+    assert np.array_equal(d1, d.min(axis=1))
+    assert np.array_equal(d2, np.sort(d, axis=1)[:, 1])
+    assert idx[3] == 7 and d1[3] == 0 and d2[3] == 0 and not acc[3]      # 0 < 0.9*0 is false
+    exp = (d1 <= 100) & (d1.astype(np.float32) < np.float32(0.9) * d2.astype(np.float32))
+    assert np.array_equal(acc, exp)
+    i2, a1, a2, ac2 = oracle_mod.Oracle.match(A, B, 100, 0.9, threads=3)
+    assert np.array_equal(i2, idx) and np.array_equal(a1, d1) and np.array_equal(a2, d2) and np.array_equal(ac2, acc)
+    e_idx, e_d1, e_d2, e_acc = oracle_mod.Oracle.match(A, np.zeros((0, 32), np.uint8), 100, 0.9)
+    assert (e_idx == -1).all() and (e_d1 == 256).all() and not e_acc.any()
