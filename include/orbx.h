@@ -200,6 +200,18 @@ int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const uint8_t *desc
 int orbx_match_device(orbx_handle *h, const uint8_t *d_descA, int nA, const uint8_t *d_descB, int nB,
                       int th, float ratio, int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept);
 
+/* ---- per-stage device timing ---------------------------------------------- */
+
+/* With profiling on, every submit brackets its stages with CUDA events on the
+ * handle's stream; after the matching collect, orbx_get_stage_ms returns the device
+ * time of each stage of that batch in milliseconds (stage i named orbx_stage_name(i):
+ * "input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h").  Returns the
+ * number of stages.  Off by default (the events cost a few microseconds per batch). */
+#define ORBX_NUM_STAGES 7
+int orbx_set_profiling(orbx_handle *h, int on);
+int orbx_get_stage_ms(orbx_handle *h, float *ms, int cap);
+const char *orbx_stage_name(int stage);
+
 /* ---- misc ---------------------------------------------------------------- */
 
 int orbx_sync(orbx_handle *h);                 /* waits for everything queued on the handle's stream */

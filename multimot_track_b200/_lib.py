@@ -57,6 +57,9 @@ SIGNATURES = {
     "orbx_hamming256": (_I, [_VP, _VP]),
     "orbx_match": (_I, [_VP, _VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP]),
     "orbx_match_device": (_I, [_VP, _VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP]),
+    "orbx_set_profiling": (_I, [_VP, _I]),
+    "orbx_get_stage_ms": (_I, [_VP, _VP, _I]),
+    "orbx_stage_name": (ctypes.c_char_p, [_I]),
     "orbx_sync": (_I, [_VP]),
     "orbx_stream": (_VP, [_VP]),
     "orbx_launch_count": (ctypes.c_longlong, [_VP]),

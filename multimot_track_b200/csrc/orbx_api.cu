@@ -53,6 +53,9 @@ struct orbx_handle {
     int32_t *m_out = nullptr; uint8_t *m_acc = nullptr; int *m_nacc = nullptr; size_t m_cap_out = 0;
     int4 *m_partial = nullptr; size_t m_cap_partial = 0;
     LaunchStats stats;
+    bool profiling = false;
+    cudaEvent_t ev[ORBX_NUM_STAGES + 1] = {};
+    bool ev_valid = false;
     std::string err;
 };
 
@@ -175,16 +178,27 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
 {
     const DevParams &P = h->hp;
     cudaStream_t st = h->stream;
+    const bool prof = h->profiling;
+#define MARK(i) do { if (prof) CU(cudaEventRecord(h->ev[i], st)); } while (0)
+    MARK(1);                                     // ev[0] was recorded by the caller before the input copies
     CU(cudaMemsetAsync(h->d_cand_count, 0, (size_t)nframes * P.nlevels * sizeof(uint32_t), st));
     CU(launch_pyramid(h->d_params, P, s0, nframes, st, &h->stats));
+    MARK(2);
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
+    MARK(3);
     CU(launch_fast(h->d_params, P, s0, nframes, h->small_cells, st, &h->stats));
+    MARK(4);
     CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
+    MARK(5);
     CU(launch_orient_desc(h->d_params, P, s0, nframes, st, &h->stats));
+    MARK(6);
     const size_t cap = (size_t)P.kp_frame_cap;
     CU(cudaMemcpyAsync(h->p_n, h->d_out_n, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_desc, h->d_out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, st));
+    MARK(7);
+#undef MARK
+    h->ev_valid = prof;
     h->pending = true; h->have_batch = true; h->last_nframes = nframes; h->last_src0 = s0;
     return ORBX_OK;
 }
@@ -244,6 +258,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     free_geo_tables(h);
     dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad);
     dfree(h->m_A); dfree(h->m_B); dfree(h->m_out); dfree(h->m_acc); dfree(h->m_nacc); dfree(h->m_partial);
+    for (int i = 0; i <= ORBX_NUM_STAGES; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -315,6 +330,7 @@ extern "C" int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int n
     if (h->pending) return fail(h, ORBX_ERR_STATE, "a batch is already pending on this handle: call orbx_collect first");
     rc = ensure_geometry(h, width, height, nframes);
     if (rc != ORBX_OK) return rc;
+    if (h->profiling) CU(cudaEventRecord(h->ev[0], h->stream));
     Src0 s0;
     if (aligned16(d_frames, stride_bytes, (long long)frame_stride_bytes)) {
         s0.ptr = d_frames; s0.pitch = stride_bytes; s0.frame_stride = (long long)frame_stride_bytes;   // used in place
@@ -340,6 +356,7 @@ extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, in
     if (h->pending) return fail(h, ORBX_ERR_STATE, "a batch is already pending on this handle: call orbx_collect first");
     rc = ensure_geometry(h, width, height, nframes);
     if (rc != ORBX_OK) return rc;
+    if (h->profiling) CU(cudaEventRecord(h->ev[0], h->stream));
     const LevelGeom &L0 = h->geo.lv[0];
     for (int f = 0; f < nframes; ++f)
         CU(cudaMemcpy2DAsync(h->d_pyr + (size_t)f * h->geo.pyr_frame_bytes + L0.img_off, L0.pitch, frames[f], stride_bytes,
@@ -549,6 +566,32 @@ extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const ui
     CU(cudaMemcpyAsync(&nacc, h->m_nacc, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return nacc;
+}
+
+// ---------------------------------------------------------------- profiling
+
+static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h"};
+
+extern "C" const char *orbx_stage_name(int stage) { return stage >= 0 && stage < ORBX_NUM_STAGES ? kStageNames[stage] : ""; }
+
+extern "C" int orbx_set_profiling(orbx_handle *h, int on)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    CU(cudaSetDevice(h->device));
+    if (on && !h->ev[0])
+        for (int i = 0; i <= ORBX_NUM_STAGES; ++i) CU(cudaEventCreate(&h->ev[i]));
+    h->profiling = on != 0;
+    h->ev_valid = false;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_get_stage_ms(orbx_handle *h, float *ms, int cap)
+{
+    if (!h || !ms) return ORBX_ERR_BAD_ARG;
+    if (!h->ev_valid || h->pending) return fail(h, ORBX_ERR_STATE, "no profiled batch has completed (enable profiling, submit, collect)");
+    CU(cudaSetDevice(h->device));
+    for (int i = 0; i < ORBX_NUM_STAGES && i < cap; ++i) CU(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    return ORBX_NUM_STAGES;
 }
 
 // --------------------------------------------------------------------- misc

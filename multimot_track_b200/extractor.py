@@ -166,6 +166,15 @@ class ORBextractor:
         n = np.frombuffer(nb, dtype=np.int32)
         return kps, desc, n
 
+    def set_profiling(self, on=True):
+        self._ck(self._lib.orbx_set_profiling(self._h, int(bool(on))))
+
+    def stage_ms(self):
+        """Device milliseconds per stage of the last collected batch (profiling must be on): dict name -> ms."""
+        ms = (ctypes.c_float * 16)()
+        n = self._ck(self._lib.orbx_get_stage_ms(self._h, ms, 16))
+        return {self._lib.orbx_stage_name(i).decode(): float(ms[i]) for i in range(n)}
+
     def sync(self):
         self._ck(self._lib.orbx_sync(self._h))
 
