@@ -104,7 +104,8 @@ def test_uniform_noise_stress(orb, oracle_mod):
 
 @pytest.mark.parametrize("shape,params", [((480, 640), (1000, 1.2, 8, 20, 7)), ((240, 320), (500, 1.2, 4, 20, 7)),
                                           ((300, 700), (500, 1.5, 4, 25, 10)), ((230, 231), (300, 1.2, 8, 20, 7)),
-                                          ((128, 400), (256, 1.3, 3, 15, 5)), ((600, 333), (1500, 1.2, 6, 20, 7))])
+                                          ((128, 400), (256, 1.3, 3, 15, 5)), ((500, 333), (1500, 1.2, 6, 20, 7)),
+                                          ((720, 1280), (3000, 1.2, 8, 12, 4))])
 def test_other_shapes_and_parameters(orb, oracle_mod, shape, params):
     ext = orb.ORBextractor(*params)
     o = oracle_mod.Oracle(*params)
@@ -130,6 +131,18 @@ def test_edge_inputs(orb, oracle_mod):
     big = synth(8, 375, 1300)
     check_frame(ext, o, big[:, :1242], "strided")
     check_frame(ext, o, synth(9, 480, 640), "reshape")
+
+
+def test_unsupported_shapes_fail_loudly(orb):
+    """Shapes the reference itself cannot process (division by zero there) are refused, not guessed."""
+    ext = orb.ORBextractor(1500, 1.2, 6, 20, 7)
+    with pytest.raises(orb.OrbxError) as e:
+        ext(synth(1, 600, 333))                      # level 5 is 134x241: round(102/209) = 0 initial octree nodes
+    assert e.value.code == -5
+    with pytest.raises(orb.OrbxError):
+        orb.ORBextractor(1000, 1.2, 8, 20, 7)(synth(1, 200, 200))       # level 7 is 56x56 < 62
+    k, d = ext(synth(2, 480, 640))                   # the handle stays usable
+    assert len(k) > 100
 
 
 def test_capacity_error(orb):
