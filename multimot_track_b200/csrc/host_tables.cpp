@@ -199,6 +199,17 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
             for (int tx = 0; tx < (L.w + kBlurTileW - 1) / kBlurTileW; ++tx)
                 g->blur_work.push_back((uint32_t)l << 24 | (uint32_t)ty << 12 | (uint32_t)tx);
     }
+    // small-cell levels first: k_fast<38> handles those, k_fast<64> the (rare, coarse) rest
+    {
+        std::vector<uint32_t> small, large;
+        for (uint32_t wk : g->fast_work) {
+            const LevelGeom &L = g->lv[wk >> 24];
+            (L.w_cell <= 38 && L.h_cell <= 38 ? small : large).push_back(wk);
+        }
+        g->n_fast_small = (int)small.size();
+        g->fast_work = small;
+        g->fast_work.insert(g->fast_work.end(), large.begin(), large.end());
+    }
     g->pyr_frame_bytes = img_off;
     g->cand_frame_elems = cand_off;
     g->kp_frame_cap = kp_off;

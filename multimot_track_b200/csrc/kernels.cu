@@ -142,193 +142,246 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 }
 
 // --------------------------------------------------------------------- FAST
-// One warp per 30-pixel cell (the reference calls cv::FAST once per cell, :809-815).
-// The cell (+3 ring) is staged in shared memory; a compass pre-test (any 9-arc holds
-// two adjacent compass points of one polarity) rejects most pixels, survivors are
-// ballot-compacted and scored densely (score = OpenCV cornerScore<16>: the largest
-// threshold at which the pixel is still a corner), then non-max suppressed inside the
-// cell's own rectangle.  An empty cell is redone with minThFAST (:812-816).
+// One 128-thread CTA per 30-pixel cell (the reference calls cv::FAST once per cell,
+// :809-815).  The cell and its 3-pixel ring are staged in shared memory as 16-bit
+// lanes, two horizontally adjacent pixels per 32-bit word, so every step works on a
+// pixel PAIR with the packed-halfword integer pipe (VIADD.16x2 / VIMNMX3.S16x2):
+//   A. compass pre-test (any 9-arc holds two adjacent compass points of one
+//      polarity) over all pairs; pairs that can hold a bright / dark corner are
+//      ballot-compacted into two lists;
+//   B. exact score of the listed pairs, one polarity per list:
+//         bright = max_k min(e_k..e_k+8) - 1,  dark = -min_k max(e_k..e_k+8) - 1,
+//      e_k = ring_k - centre  (OpenCV cornerScore<16>: the largest threshold at which
+//      the pixel is still a corner; corner at t <=> score >= t);
+//   C. non-max suppression inside the cell's own rectangle (outside counts as 0,
+//      like cv::FAST on the cell sub-image) and emission.
+// A cell with no survivor at iniThFAST is redone at minThFAST (:812-816).
 
-__device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
-__device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
-
-template <int TP>
-__device__ __forceinline__ int fast_score(const uint8_t *p)
-{
-    // ring in OpenCV order (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-    constexpr int off[16] = {3 * TP, 3 * TP + 1, 2 * TP + 2, TP + 3, 3, -TP + 3, -2 * TP + 2, -3 * TP + 1,
-                             -3 * TP, -3 * TP - 1, -2 * TP - 2, -TP - 3, -3, TP - 3, 2 * TP - 2, 3 * TP - 1};
-    const int c = p[0];
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = c - (int)p[off[k]];
-    int lo3[16], hi3[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        lo3[k] = min3i(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        hi3[k] = max3i(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    }
-    int a = -256, b = 256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        a = max(a, min3i(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]));
-        b = min(b, max3i(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]));
-    }
-    return max(a, -b) - 1;
-}
-
-template <int CELL>       // CELL = largest detection-area side this instantiation handles
+template <int CELL>       // largest detection-area side this instantiation handles
 struct FastCfg {
-    static constexpr int TW = CELL + 6 + 4;                 // tile width incl. word-alignment slack
-    static constexpr int TP = (TW + 3) & ~3;                // tile pitch (bytes)
+    static constexpr int NPMAX = (CELL + 1) / 2;            // pixel pairs per row
+    static constexpr int TPW = NPMAX + 5;                   // tile pitch in words: pairs -2 .. NPMAX+2
     static constexpr int TH = CELL + 6;
-    static constexpr int SP = (CELL + 2 + 3) & ~3;          // score-map pitch
+    static constexpr int SP = (CELL + 2 + 3) & ~3;          // score-map pitch (bytes)
     static constexpr int SH = CELL + 2;
-    static constexpr int L1N = CELL <= 34 ? 256 : 512;      // compass survivors per flush
-    static constexpr int L2N = CELL <= 34 ? 512 : 1536;     // corners per cell before falling back to a dense NMS scan
-    static constexpr int WARPS = CELL <= 34 ? 8 : 4;
-    static constexpr int WARP_BYTES = TH * TP + SH * SP + 2 * L1N + 2 * L2N;
+    static constexpr int LN = NPMAX * CELL;                 // worst-case pairs per polarity list
+    static constexpr int CN = CELL * CELL;                  // worst-case corners
+    static constexpr int SMEM = TH * TPW * 4 + SH * SP + 2 * LN * 2 + CN * 2;
+    static constexpr int THREADS = 128;
 };
 
+__device__ __forceinline__ unsigned add16x2(unsigned a, unsigned b) { return __vadd2(a, b); }
+
+// ring pair at column offset ox (pixels) relative to the pair's first pixel; row pointer given
+template <int OX>
+__device__ __forceinline__ unsigned ring_pair(const uint32_t *row, int j)
+{
+    if (OX % 2 == 0) return row[j + OX / 2];
+    const int a = j + (OX - 1) / 2;                 // floor division for odd OX of either sign
+    return __funnelshift_r(row[a], row[a + 1], 16);
+}
+
 template <int CELL>
-__global__ void __launch_bounds__(FastCfg<CELL>::WARPS * 32) k_fast(const DevParams *__restrict__ P, Src0 s0)
+__global__ void __launch_bounds__(FastCfg<CELL>::THREADS) k_fast(const DevParams *__restrict__ P, Src0 s0, int work_off)
 {
     using C = FastCfg<CELL>;
     extern __shared__ __align__(16) uint8_t fast_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int widx = blockIdx.x * C::WARPS + warp, frame = blockIdx.y;
-    if (widx >= P->n_fast_work) return;                      // warp-uniform; the kernel has no block barrier
+    __shared__ int s_nb, s_nd, s_nc, s_emitted;
+    uint32_t *tile = reinterpret_cast<uint32_t *>(fast_smem);                   // [TH][TPW] pixel pairs as 16x2
+    uint8_t *smap = fast_smem + C::TH * C::TPW * 4;                             // [SH][SP] corner scores
+    uint16_t *listB = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP);       // pairs to score, bright polarity
+    uint16_t *listD = listB + C::LN;
+    uint16_t *corners = listD + C::LN;
 
-    uint8_t *tile = fast_smem + (size_t)warp * C::WARP_BYTES;
-    uint8_t *smap = tile + C::TH * C::TP;
-    uint16_t *list1 = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP);
-    uint16_t *list2 = list1 + C::L1N;
-
-    const uint32_t wk = P->fast_work[widx];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.y;
+    const uint32_t wk = P->fast_work[work_off + blockIdx.x];
     const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
     const LevelGeom &G = P->lv[level];
     const int x0 = kEdge + cj * G.w_cell, x1 = min(x0 + G.w_cell, G.x_end);
     const int y0 = kEdge + ci * G.h_cell, y1 = min(y0 + G.h_cell, G.y_end);
-    const int dw = x1 - x0, dh = y1 - y0;
+    const int dw = x1 - x0, dh = y1 - y0, np = (dw + 1) >> 1;
 
-    int sp;
-    const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-    // stage rows [y0-3, y1+3) x cols [x0-3, x1+3) with aligned 32-bit loads
-    const int xb = (x0 - 3) & ~3, ox = (x0 - 3) - xb;
-    const int nwords = ((x1 + 3) - xb + 3) >> 2, nrows = dh + 6;
-    for (int i = lane; i < nrows * nwords; i += 32) {
-        const int r = i / nwords, c = i - r * nwords;
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)(y0 - 3 + r) * sp + xb) + c);
-        *reinterpret_cast<uint32_t *>(tile + r * C::TP + 4 * c) = v;
+    // ---- stage rows [y0-3, y1+3) x pixels [x0-4, x0-4+2*TPW) as 16-bit lanes (tile pixel u = x - x0 + 4)
+    {
+        int sp;
+        const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
+        const int xb = (x0 - 4) & ~3;
+        const int xlast = min(x0 - 4 + 2 * (np + 5), G.w);                      // exclusive; stays inside the row
+        const int nwords = (xlast - xb + 3) >> 2, nrows = dh + 6;
+        uint16_t *t16 = reinterpret_cast<uint16_t *>(tile);
+        for (int i = tid; i < nrows * nwords; i += C::THREADS) {
+            const int r = i / nwords, c = i - r * nwords;
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)(y0 - 3 + r) * sp + xb) + c);
+            const int u = xb + 4 * c - (x0 - 4);
+            uint16_t *d = t16 + r * (2 * C::TPW) + u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((unsigned)(u + k) < (unsigned)(2 * C::TPW)) d[k] = (uint16_t)((v >> (8 * k)) & 0xff);
+        }
+        for (int i = tid; i < (C::SH * C::SP) / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
+        if (tid == 0) { s_nb = 0; s_nd = 0; s_nc = 0; s_emitted = 0; }
     }
-    for (int i = lane; i < (C::SH * C::SP) / 4; i += 32) reinterpret_cast<uint32_t *>(smap)[i] = 0;
-    __syncwarp();
+    __syncthreads();
 
     uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
     uint32_t *cnt = P->cand_count + frame * P->nlevels + level;
-    const int npix = dw * dh;
-    const float inv_dw = 1.0f / (float)dw;
+    const int npairs = np * dh;
+    const float inv_np = 1.0f / (float)np;
     const unsigned lt = lanemask_lt();
 
     int th = P->ini_th;
     for (int pass = 0; pass < 2; ++pass) {
-        int n1 = 0, n2 = 0, emitted = 0;
-        bool overflow2 = false;
-        for (int base = 0; base < npix || n1 > 0; base += 32) {
-            // ---- compass pre-test over the next 32 pixels
-            if (base < npix) {
-                const int i = base + lane;
-                bool ok = false;
-                int dy = 0, dx = 0;
-                if (i < npix) {
-                    dy = (int)(((float)i + 0.5f) * inv_dw);
-                    dx = i - dy * dw;
-                    const uint8_t *p = tile + (dy + 3) * C::TP + dx + 3 + ox;
-                    const int c = p[0], hi = c + th, lo = c - th;
-                    const int n = p[-3 * C::TP], s = p[3 * C::TP], e = p[3], w = p[-3];
-                    const bool bn = n > hi, bs = s > hi, be = e > hi, bw = w > hi;
-                    const bool dn = n < lo, ds = s < lo, de = e < lo, dwk = w < lo;
-                    ok = (bn & be) | (be & bs) | (bs & bw) | (bw & bn) | (dn & de) | (de & ds) | (ds & dwk) | (dwk & dn);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) list1[n1 + __popc(m & lt)] = (uint16_t)(dy << 8 | dx);
-                n1 += __popc(m);
+        // ---- A: compass pre-test on every pair
+        const unsigned tb = 0x00010001u * (unsigned)(th + 1), td = 0x00010001u * (unsigned)th;
+        for (int base = warp * 32; base < npairs; base += C::THREADS) {
+            const int i = base + lane;
+            bool wb = false, wd = false;
+            int dy = 0, p = 0;
+            if (i < npairs) {
+                dy = (int)(((float)i + 0.5f) * inv_np);
+                p = i - dy * np;
+                const uint32_t *row = tile + (dy + 3) * C::TPW;
+                const int j = p + 2;
+                const unsigned c = row[j];
+                const unsigned negc = __vneg2(c);
+                const unsigned nb = __vsub2(negc, tb);                      // -(c + t + 1)
+                const unsigned nd = add16x2(negc, td);                      // -(c - t)
+                const unsigned n = row[j - 3 * C::TPW], s = row[j + 3 * C::TPW];
+                const unsigned e = ring_pair<3>(row, j), w = ring_pair<-3>(row, j);
+                // sign bit clear in ring+nb  <=> ring > c+t ; sign bit set in ring+nd <=> ring < c-t
+                const unsigned bn = add16x2(n, nb), bs = add16x2(s, nb), be = add16x2(e, nb), bw = add16x2(w, nb);
+                const unsigned dn = add16x2(n, nd), ds = add16x2(s, nd), de = add16x2(e, nd), dwk = add16x2(w, nd);
+                const unsigned bright = ~((bn & bs) | (be & bw)) & 0x80008000u;
+                const unsigned dark = (dn | ds) & (de | dwk) & 0x80008000u;
+                wb = bright != 0; wd = dark != 0;
             }
-            // ---- flush: score the compacted survivors densely
-            if (n1 > C::L1N - 32 || base + 32 >= npix) {
-                __syncwarp();
-                for (int b = 0; b < n1; b += 32) {
-                    bool corner = false;
-                    int e = 0;
-                    if (b + lane < n1) {
-                        e = list1[b + lane];
-                        const int dy = e >> 8, dx = e & 0xff;
-                        const int sc = fast_score<C::TP>(tile + (dy + 3) * C::TP + dx + 3 + ox);
-                        if (sc >= th) { corner = true; smap[(dy + 1) * C::SP + dx + 1] = (uint8_t)sc; }
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, corner);
-                    const int k = __popc(m);
-                    if (n2 + k <= C::L2N) { if (corner) list2[n2 + __popc(m & lt)] = (uint16_t)e; n2 += k; }
-                    else overflow2 = true;
+            const unsigned mb = __ballot_sync(0xffffffffu, wb), md = __ballot_sync(0xffffffffu, wd);
+            int ob = 0, od = 0;
+            if (lane == 0) { if (mb) ob = atomicAdd(&s_nb, __popc(mb)); if (md) od = atomicAdd(&s_nd, __popc(md)); }
+            ob = __shfl_sync(0xffffffffu, ob, 0); od = __shfl_sync(0xffffffffu, od, 0);
+            if (wb) listB[ob + __popc(mb & lt)] = (uint16_t)(dy << 8 | p);
+            if (wd) listD[od + __popc(md & lt)] = (uint16_t)(dy << 8 | p);
+        }
+        __syncthreads();
+        // ---- B: exact one-sided scores of the listed pairs
+        const int nb_ = s_nb, nd_ = s_nd;
+        for (int base = warp * 32; base < nb_ + nd_; base += C::THREADS) {
+            const int i = base + lane;
+            bool k0 = false, k1 = false;
+            int dy = 0, p = 0, s0v = 0, s1v = 0;
+            if (i < nb_ + nd_) {
+                const bool is_b = i < nb_;
+                const int ent = is_b ? listB[i] : listD[i - nb_];
+                dy = ent >> 8; p = ent & 0xff;
+                const uint32_t *row = tile + (dy + 3) * C::TPW;
+                const int j = p + 2;
+                const unsigned negc = __vneg2(row[j]);
+                unsigned e[16];
+                {
+                    const uint32_t *r3 = row + 3 * C::TPW, *r2 = row + 2 * C::TPW, *r1 = row + C::TPW;
+                    const uint32_t *m1 = row - C::TPW, *m2 = row - 2 * C::TPW, *m3 = row - 3 * C::TPW;
+                    e[0] = r3[j];               e[1] = ring_pair<1>(r3, j);   e[15] = ring_pair<-1>(r3, j);
+                    e[2] = r2[j + 1];           e[14] = r2[j - 1];
+                    e[3] = ring_pair<3>(r1, j); e[13] = ring_pair<-3>(r1, j);
+                    e[4] = ring_pair<3>(row, j); e[12] = ring_pair<-3>(row, j);
+                    e[5] = ring_pair<3>(m1, j); e[11] = ring_pair<-3>(m1, j);
+                    e[6] = m2[j + 1];           e[10] = m2[j - 1];
+                    e[8] = m3[j];               e[7] = ring_pair<1>(m3, j);   e[9] = ring_pair<-1>(m3, j);
                 }
-                n1 = 0;
-                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) e[k] = add16x2(e[k], negc);
+                unsigned res;
+                if (is_b) {                                        // max over arcs of min9
+                    unsigned t3[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) t3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+                    unsigned a[6];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) e[k] = __vimin3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) a[k] = __vimax3_s16x2(e[3 * k], e[3 * k + 1], e[3 * k + 2]);
+                    a[5] = e[15];
+                    res = __vimax3_s16x2(__vimax3_s16x2(a[0], a[1], a[2]), __vimax3_s16x2(a[3], a[4], a[5]), a[5]);
+                } else {                                           // -(min over arcs of max9)
+                    unsigned t3[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) t3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+                    unsigned a[6];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) e[k] = __vimax3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) a[k] = __vimin3_s16x2(e[3 * k], e[3 * k + 1], e[3 * k + 2]);
+                    a[5] = e[15];
+                    res = __vneg2(__vimin3_s16x2(__vimin3_s16x2(a[0], a[1], a[2]), __vimin3_s16x2(a[3], a[4], a[5]), a[5]));
+                }
+                s0v = (int)(short)(res & 0xffff) - 1;
+                s1v = (int)(short)(res >> 16) - 1;
+                k0 = s0v >= th;
+                k1 = s1v >= th && 2 * p + 1 < dw;
+                if (k0) smap[(dy + 1) * C::SP + 2 * p + 1] = (uint8_t)s0v;
+                if (k1) smap[(dy + 1) * C::SP + 2 * p + 2] = (uint8_t)s1v;
+            }
+            const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+            if (m0 | m1) {
+                int o = 0;
+                if (lane == 0) o = atomicAdd(&s_nc, __popc(m0) + __popc(m1));
+                o = __shfl_sync(0xffffffffu, o, 0);
+                if (k0) corners[o + __popc(m0 & lt)] = (uint16_t)(dy << 8 | (2 * p));
+                if (k1) corners[o + __popc(m0) + __popc(m1 & lt)] = (uint16_t)(dy << 8 | (2 * p + 1));
             }
         }
-        __syncwarp();
-        // ---- non-max suppression inside the cell rectangle (outside counts as 0) + emission
-        const int total = overflow2 ? npix : n2;
-        for (int b = 0; b < total; b += 32) {
+        __syncthreads();
+        // ---- C: non-max suppression + emission
+        const int nc = s_nc;
+        for (int base = warp * 32; base < nc; base += C::THREADS) {
+            const int i = base + lane;
             bool keep = false;
             int dy = 0, dx = 0, sc = 0;
-            if (b + lane < total) {
-                if (overflow2) { const int i = b + lane; dy = (int)(((float)i + 0.5f) * inv_dw); dx = i - dy * dw; }
-                else { const int e = list2[b + lane]; dy = e >> 8; dx = e & 0xff; }
+            if (i < nc) {
+                const int ent = corners[i];
+                dy = ent >> 8; dx = ent & 0xff;
                 const uint8_t *q = smap + (dy + 1) * C::SP + dx + 1;
                 sc = q[0];
-                keep = sc >= th && sc > 0 &&
-                       sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
+                keep = sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
                        sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1];
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (m) {
                 int slot = 0;
-                if (lane == 0) slot = (int)atomicAdd(cnt, (unsigned)__popc(m));
+                if (lane == 0) { slot = (int)atomicAdd(cnt, (unsigned)__popc(m)); s_emitted = 1; }
                 slot = __shfl_sync(0xffffffffu, slot, 0);
                 if (keep) {
                     const uint32_t xr = (uint32_t)(x0 + dx - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
                     const int at = slot + __popc(m & lt);
                     if (at < G.cand_cap) cand[at] = xr | yr << 12 | (uint32_t)sc << 24;
                 }
-                emitted += __popc(m);
             }
         }
-        if (emitted > 0 || pass == 1) break;
-        // nothing at iniThFAST: clear the score map and redo the cell at minThFAST
+        __syncthreads();
+        if (s_emitted || pass == 1 || P->min_th == th) break;
+        // nothing survived at iniThFAST: clear and redo the cell at minThFAST
+        __syncthreads();
         th = P->min_th;
-        __syncwarp();
-        for (int i = lane; i < (C::SH * C::SP) / 4; i += 32) reinterpret_cast<uint32_t *>(smap)[i] = 0;
-        __syncwarp();
+        for (int i = tid; i < (C::SH * C::SP) / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
+        if (tid == 0) { s_nb = 0; s_nd = 0; s_nc = 0; }
+        __syncthreads();
     }
 }
 
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, bool small_cells, cudaStream_t st, LaunchStats *ls)
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls)
 {
-    if (hP.n_fast_work == 0) return cudaSuccess;
-    if (small_cells) {
-        using C = FastCfg<34>;
-        const size_t smem = (size_t)C::WARPS * C::WARP_BYTES;
-        cudaFuncSetAttribute(k_fast<34>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid((hP.n_fast_work + C::WARPS - 1) / C::WARPS, nframes);
-        k_fast<34><<<grid, C::WARPS * 32, smem, st>>>(dP, s0);
-    } else {
-        using C = FastCfg<64>;
-        const size_t smem = (size_t)C::WARPS * C::WARP_BYTES;
-        cudaFuncSetAttribute(k_fast<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid((hP.n_fast_work + C::WARPS - 1) / C::WARPS, nframes);
-        k_fast<64><<<grid, C::WARPS * 32, smem, st>>>(dP, s0);
+    if (n_small > 0) {
+        using C = FastCfg<38>;
+        cudaFuncSetAttribute(k_fast<38>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast<38><<<dim3(n_small, nframes), C::THREADS, C::SMEM, st>>>(dP, s0, 0);
+        ls->launches++;
     }
-    ls->launches++;
+    if (hP.n_fast_work > n_small) {
+        using C = FastCfg<64>;
+        cudaFuncSetAttribute(k_fast<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast<64><<<dim3(hP.n_fast_work - n_small, nframes), C::THREADS, C::SMEM, st>>>(dP, s0, n_small);
+        ls->launches++;
+    }
     return cudaGetLastError();
 }
 

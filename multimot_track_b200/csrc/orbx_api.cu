@@ -22,7 +22,6 @@ struct orbx_handle {
     Tables tab;
     Geometry geo;
     bool geo_valid = false;
-    bool small_cells = false;
     int device = 0;
     cudaStream_t stream = nullptr;
     int batch_cap = 0;                  // frames the per-batch buffers hold
@@ -160,11 +159,7 @@ int ensure_geometry(orbx_handle *h, int width, int height, int nframes)
     std::memset(&P, 0, sizeof(P));
     P.nlevels = g.nlevels; P.ini_th = h->tab.ini_th; P.min_th = h->tab.min_th;
     P.kp_frame_cap = g.kp_frame_cap; P.pyr_frame_bytes = g.pyr_frame_bytes; P.cand_frame_elems = g.cand_frame_elems;
-    h->small_cells = true;
-    for (int l = 0; l < g.nlevels; ++l) {
-        P.lv[l] = g.lv[l]; P.xtab_off[l] = g.xtab_off[l]; P.ytab_off[l] = g.ytab_off[l];
-        if (g.lv[l].w_cell > 34 || g.lv[l].h_cell > 34) h->small_cells = false;
-    }
+    for (int l = 0; l < g.nlevels; ++l) { P.lv[l] = g.lv[l]; P.xtab_off[l] = g.xtab_off[l]; P.ytab_off[l] = g.ytab_off[l]; }
     for (int i = 0; i < 16; ++i) P.umax[i] = h->tab.umax[i];
     P.n_fast_work = (int)g.fast_work.size(); P.n_blur_work = (int)g.blur_work.size();
     h->geo_valid = true;
@@ -186,7 +181,7 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     MARK(2);
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
     MARK(3);
-    CU(launch_fast(h->d_params, P, s0, nframes, h->small_cells, st, &h->stats));
+    CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_fast_small, st, &h->stats));
     MARK(4);
     CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
     MARK(5);

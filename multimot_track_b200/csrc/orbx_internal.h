@@ -58,7 +58,8 @@ struct Geometry {
     long long cand_frame_elems = 0;  // candidate slots per frame
     int kp_frame_cap = 0;            // keypoint staging slots per frame == output capacity per frame
     int max_node_cap = 0, max_feat = 0, max_cand_cap = 0;
-    std::vector<uint32_t> fast_work; // (level<<24 | cell_row<<12 | cell_col), visited cells only
+    std::vector<uint32_t> fast_work; // (level<<24 | cell_row<<12 | cell_col), visited cells only; cells <= 38 px first
+    int n_fast_small = 0;            // entries of fast_work whose level has w_cell, h_cell <= 38
     std::vector<ResizeTab> xtab, ytab;   // concatenated per level (level 0 unused)
     int xtab_off[kMaxLevels], ytab_off[kMaxLevels];
     std::vector<uint32_t> blur_work; // (level<<24 | tile_y<<12 | tile_x)
