@@ -50,9 +50,131 @@ __device__ __forceinline__ unsigned lanemask_lt()
 // ------------------------------------------------------------------ pyramid
 // cv::resize INTER_LINEAR, 8UC1: H = S[s0]*a0 + S[s1]*a1 (11-bit weights), then
 // out = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.  The weight tables are
-// built on the host with OpenCV's float arithmetic (host_tables.cpp).
+// built on the host with OpenCV's float arithmetic (host_tables.cpp).  A CTA produces a
+// 128x16 destination tile; the source footprint (<= 2x down-scaling) is staged in shared
+// memory with aligned 32-bit loads, so global traffic is coalesced and each source byte
+// is fetched once per tile.
+
+constexpr int kRzTW = 128, kRzTH = 16, kRzSrcWords = 68, kRzSrcRows = 36;
+
+// One destination tile [x0, x0+128) x [y0, y_end) (y_end - y0 <= 16) of `level` from level-1.
+// Block-wide (256 threads as 32x8); contains two barriers, so call it uniformly.
+__device__ __forceinline__ void resize_tile(const DevParams *__restrict__ P, const uint8_t *S, int sp, uint8_t *dst, int level,
+                                            int x0, int y0, int y_end, uint32_t (*ssrc)[kRzSrcWords])
+{
+    const LevelGeom &D = P->lv[level];
+    const ResizeTab *xt = P->xtab + P->xtab_off[level], *yt = P->ytab + P->ytab_off[level];
+    const int xl = min(x0 + kRzTW, D.w) - 1, yl = y_end - 1;
+    const int sx_lo = xt[x0].s0 & ~3, sx_hi = xt[xl].s1, sy_lo = yt[y0].s0, sy_hi = yt[yl].s1;
+    const int nwords = ((sx_hi - sx_lo) >> 2) + 1, nrows = sy_hi - sy_lo + 1;
+    __syncthreads();                                               // the previous tile is done with ssrc
+    for (int i = threadIdx.x + threadIdx.y * 32; i < nrows * nwords; i += 256) {
+        const int r = i / nwords, c = i - r * nwords;
+        // plain (coherent) load: in the fused kernel the source level was written by this CTA moments ago
+        ssrc[r][c] = *(reinterpret_cast<const uint32_t *>(S + (long long)(sy_lo + r) * sp + sx_lo) + c);
+    }
+    __syncthreads();
+    const int x4 = x0 + threadIdx.x * 4;
+    if (x4 >= D.w) return;
+    ResizeTab tx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tx[k] = xt[x4 + k];                // tables are padded to a multiple of 4 entries
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(&ssrc[0][0]);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int y = y0 + threadIdx.y + 8 * rr;
+        if (y >= y_end) break;
+        const ResizeTab ty = yt[y];
+        const uint8_t *S0 = sb + (ty.s0 - sy_lo) * (kRzSrcWords * 4) - sx_lo, *S1 = sb + (ty.s1 - sy_lo) * (kRzSrcWords * 4) - sx_lo;
+        const int b0 = ty.c0, b1 = ty.c1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h0 = S0[tx[k].s0] * tx[k].c0 + S0[tx[k].s1] * tx[k].c1;
+            const int h1 = S1[tx[k].s0] * tx[k].c0 + S1[tx[k].s1] * tx[k].c1;
+            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (uint32_t)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;   // pitch % 64 == 0: padding absorbs the tail
+    }
+}
+
+// All levels in ONE launch.  The level chain (level l is resized from level l-1, :1124) is
+// kept inside a CTA: CTA (band, frame) owns a horizontal band of every level and also
+// computes the few extra rows of level l that its band of level l+1 reads, so it only
+// ever consumes rows it produced itself (made visible by the block barrier).  Halo rows
+// are computed redundantly by neighbouring bands with identical results.
+__global__ void __launch_bounds__(256) k_pyramid_fused(const DevParams *__restrict__ P, Src0 s0, int nbands)
+{
+    __shared__ uint32_t ssrc[kRzSrcRows][kRzSrcWords];
+    __shared__ int c_lo[kMaxLevels], c_hi[kMaxLevels];
+    const int band = blockIdx.x, frame = blockIdx.y, L = P->nlevels;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        for (int l = L - 1; l >= 1; --l) {
+            const int h = P->lv[l].h;
+            int lo = (int)((long long)h * band / nbands), hi = (int)((long long)h * (band + 1) / nbands);
+            if (l < L - 1 && c_hi[l + 1] > c_lo[l + 1]) {
+                const ResizeTab *yt = P->ytab + P->ytab_off[l + 1];
+                lo = min(lo, (int)yt[c_lo[l + 1]].s0);
+                hi = max(hi, (int)yt[c_hi[l + 1] - 1].s1 + 1);
+            }
+            c_lo[l] = lo; c_hi[l] = hi;
+        }
+    }
+    __syncthreads();
+    for (int l = 1; l < L; ++l) {
+        const LevelGeom &D = P->lv[l];
+        int sp;
+        const uint8_t *S = level_ptr(P, s0, frame, l - 1, &sp);
+        uint8_t *dst = P->pyr + (long long)frame * P->pyr_frame_bytes + D.img_off;
+        const int lo = c_lo[l], hi = c_hi[l];
+        const int ntx = (D.w + kRzTW - 1) / kRzTW, nty = (hi - lo + kRzTH - 1) / kRzTH;
+        for (int t = 0; t < ntx * nty; ++t) {
+            const int ty = t / ntx, tx = t - ty * ntx;
+            const int y0 = lo + ty * kRzTH;
+            resize_tile(P, S, sp, dst, l, tx * kRzTW, y0, min(y0 + kRzTH, hi), ssrc);
+        }
+        __threadfence_block();
+        __syncthreads();                                           // level l of this band is visible before level l+1 reads it
+    }
+}
 
 __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P, Src0 s0, int level)
+{
+    __shared__ uint32_t ssrc[kRzSrcRows][kRzSrcWords];
+    const LevelGeom &D = P->lv[level];
+    int sp;
+    const uint8_t *S = level_ptr(P, s0, blockIdx.z, level - 1, &sp);
+    uint8_t *dst = P->pyr + (long long)blockIdx.z * P->pyr_frame_bytes + D.img_off;
+    const int y0 = blockIdx.y * kRzTH;
+    resize_tile(P, S, sp, dst, level, blockIdx.x * kRzTW, y0, min(y0 + kRzTH, D.h), ssrc);
+}
+
+// Copies frames of arbitrary row stride / alignment into the 64-byte-pitched level-0 slots.
+__global__ void k_repack(const uint8_t *__restrict__ src, long long src_frame_stride, int src_pitch, uint8_t *__restrict__ dst,
+                         long long dst_frame_stride, int dst_pitch, int w, int h)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= w) return;
+    const uint8_t *s = src + f * src_frame_stride + (long long)y * src_pitch + x4;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (x4 + k < w) v |= (uint32_t)s[k] << (8 * k);
+    *reinterpret_cast<uint32_t *>(dst + f * dst_frame_stride + (long long)y * dst_pitch + x4) = v;
+}
+
+cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
+                          int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls)
+{
+    dim3 block(128), grid((w + 511) / 512, h, nframes);
+    k_repack<<<grid, block, 0, st>>>(src, src_frame_stride, src_pitch, dst, dst_frame_stride, dst_pitch, w, h);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
+// Fallback for scale factors above 2 (source footprint larger than the shared tile): direct global reads.
+__global__ void __launch_bounds__(256) k_resize_direct(const DevParams *__restrict__ P, Src0 s0, int level)
 {
     const LevelGeom &D = P->lv[level];
     const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -64,7 +186,7 @@ __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P,
     uint8_t *dst = P->pyr + (long long)frame * P->pyr_frame_bytes + D.img_off;
     const ResizeTab ty = P->ytab[P->ytab_off[level] + y];
     const uint8_t *S0 = S + (long long)ty.s0 * sp, *S1 = S + (long long)ty.s1 * sp;
-    const ResizeTab *tx = P->xtab + P->xtab_off[level] + x4;       // padded to a multiple of 4 entries
+    const ResizeTab *tx = P->xtab + P->xtab_off[level] + x4;
     const int b0 = ty.c0, b1 = ty.c1;
     uint32_t out = 0;
 #pragma unroll
@@ -76,15 +198,32 @@ __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P,
         v = min(max(v, 0), 255);
         out |= (uint32_t)v << (8 * k);
     }
-    *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;   // pitch % 64 == 0: padding absorbs the tail
+    *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;
 }
 
 cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls)
 {
+    if (hP.nlevels < 2) return cudaSuccess;
+    bool all_staged = true;
+    for (int l = 1; l < hP.nlevels; ++l) {
+        const LevelGeom &D = hP.lv[l], &Sg = hP.lv[l - 1];
+        // staged path needs the source footprint of a 128x16 tile to fit 68 words x 36 rows
+        const bool staged = (long long)Sg.w * (kRzTW + 2) <= (long long)D.w * (kRzSrcWords * 4 - 12) &&
+                            (long long)Sg.h * (kRzTH + 2) <= (long long)D.h * (kRzSrcRows - 3);
+        all_staged = all_staged && staged;
+    }
+    if (all_staged) {
+        // enough (band, frame) CTAs for two per SM, but bands no thinner than ~8 rows of the last level
+        int nbands = (2 * 148 + nframes - 1) / nframes;
+        nbands = max(1, min(nbands, max(1, hP.lv[hP.nlevels - 1].h / 8)));
+        k_pyramid_fused<<<dim3(nbands, nframes), dim3(32, 8), 0, st>>>(dP, s0, nbands);
+        ls->launches++;
+        return cudaGetLastError();
+    }
     for (int l = 1; l < hP.nlevels; ++l) {
         const LevelGeom &D = hP.lv[l];
         dim3 block(32, 8), grid((D.w + 127) / 128, (D.h + 7) / 8, nframes);
-        k_resize<<<grid, block, 0, st>>>(dP, s0, l);
+        k_resize_direct<<<grid, block, 0, st>>>(dP, s0, l);
         ls->launches++;
     }
     return cudaGetLastError();
@@ -93,44 +232,76 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
 // --------------------------------------------------------------------- blur
 // cv::GaussianBlur 7x7 sigma 2 on 8-bit: 8.8 fixed-point kernel [18,34,48,56,48,34,18],
 // horizontal pass to u16, vertical pass to u32, one rounding (+32768)>>16; reflect-101.
+// A 128x64 output tile per CTA.  The horizontal pass runs on pixel PAIRS packed as
+// 16x2 in one register (18..56 * 255 summed stays below 65536, so a plain 32-bit
+// multiply-add never carries between the two lanes); the vertical pass slides down
+// 8 rows per thread on the 16-bit row sums kept in shared memory.
 
 __global__ void __launch_bounds__(256) k_blur(const DevParams *__restrict__ P, Src0 s0)
 {
-    __shared__ uint8_t sin_[kBlurTileH + 6][kBlurTileW + 8];
-    __shared__ uint16_t sh[kBlurTileH + 6][kBlurTileW];
+    constexpr int TW = kBlurTileW, TH = kBlurTileH, RW = TW / 4 + 2;       // raw words per row: x from tx0-4 to tx0+TW+4
+    __shared__ uint32_t sraw[TH + 6][RW + 2];
+    __shared__ uint2 shv[TH + 6][TW / 4];
     const uint32_t wk = P->blur_work[blockIdx.x];
-    const int level = wk >> 24, ty0 = ((wk >> 12) & 0xfff) * kBlurTileH, tx0 = (wk & 0xfff) * kBlurTileW;
+    const int level = wk >> 24, ty0 = ((wk >> 12) & 0xfff) * TH, tx0 = (wk & 0xfff) * TW;
     const int frame = blockIdx.y;
     const LevelGeom &G = P->lv[level];
     int sp;
     const uint8_t *S = level_ptr(P, s0, frame, level, &sp);
     const int tid = threadIdx.x;
-    for (int i = tid; i < (kBlurTileH + 6) * (kBlurTileW + 6); i += 256) {
-        const int r = i / (kBlurTileW + 6), c = i - r * (kBlurTileW + 6);
-        const int gy = reflect101(ty0 + r - 3, G.h), gx = reflect101(tx0 + c - 3, G.w);
-        sin_[r][c] = S[(long long)gy * sp + gx];
+    // ---- raw rows ty0-3 .. ty0+TH+2 (reflected), columns tx0-4 .. tx0+TW+3
+    for (int i = tid; i < (TH + 6) * RW; i += 256) {
+        const int r = i / RW, c = i - r * RW;
+        const int gy = reflect101(ty0 + r - 3, G.h), gx = tx0 - 4 + 4 * c;
+        const uint8_t *row = S + (long long)gy * sp;
+        uint32_t v;
+        if (gx >= 0 && gx + 3 < G.w) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+        else v = (uint32_t)row[reflect101(gx, G.w)] | (uint32_t)row[reflect101(gx + 1, G.w)] << 8 |
+                 (uint32_t)row[reflect101(gx + 2, G.w)] << 16 | (uint32_t)row[reflect101(gx + 3, G.w)] << 24;
+        sraw[r][c] = v;
     }
     __syncthreads();
-    for (int i = tid; i < (kBlurTileH + 6) * kBlurTileW; i += 256) {
-        const int r = i / kBlurTileW, c = i - r * kBlurTileW;
-        const uint8_t *p = &sin_[r][c];
-        sh[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    // ---- horizontal pass, 4 pixels (two 16x2 pairs) per item
+    for (int i = tid; i < (TH + 6) * (TW / 4); i += 256) {
+        const int r = i / (TW / 4), q = i - r * (TW / 4);
+        const uint32_t w0 = sraw[r][q], w1 = sraw[r][q + 1], w2 = sraw[r][q + 2];     // pixels x-4..x-1 | x..x+3 | x+4..x+7
+        const uint32_t p0 = __byte_perm(w0, 0, 0x4140), p1 = __byte_perm(w0, 0, 0x4342), p2 = __byte_perm(w1, 0, 0x4140);
+        const uint32_t p3 = __byte_perm(w1, 0, 0x4342), p4 = __byte_perm(w2, 0, 0x4140), p5 = __byte_perm(w2, 0, 0x4342);
+        const uint32_t a0 = __funnelshift_r(p0, p1, 16), a1 = p1, a2 = __funnelshift_r(p1, p2, 16), a3 = p2;
+        const uint32_t a4 = __funnelshift_r(p2, p3, 16), a5 = p3, a6 = __funnelshift_r(p3, p4, 16), a7 = p4;
+        const uint32_t a8 = __funnelshift_r(p4, p5, 16);                   // a_k = pixels (x-3+k, x-2+k)
+        const uint32_t o01 = 18u * (a0 + a6) + 34u * (a1 + a5) + 48u * (a2 + a4) + 56u * a3;
+        const uint32_t o23 = 18u * (a2 + a8) + 34u * (a3 + a7) + 48u * (a4 + a6) + 56u * a5;
+        shv[r][q] = make_uint2(o01, o23);
     }
     __syncthreads();
-    const int r = tid >> 4, c4 = (tid & 15) * 4;
-    const int gy = ty0 + r, gx = tx0 + c4;
-    if (gy < G.h && gx < G.w) {
-        uint32_t out = 0;
+    // ---- vertical pass: thread = (pixel quad, 8-row segment)
+    const int q = tid & 31, seg = tid >> 5;
+    const int gx = tx0 + 4 * q, gy0 = ty0 + seg * 8;
+    if (gx >= G.w || gy0 >= G.h) return;
+    uint32_t out[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c4 + k;
-            const uint32_t acc = 18u * (sh[r][c] + sh[r + 6][c]) + 34u * (sh[r + 1][c] + sh[r + 5][c]) +
-                                 48u * (sh[r + 2][c] + sh[r + 4][c]) + 56u * sh[r + 3][c];
-            out |= ((acc + 32768u) >> 16) << (8 * k);
+    for (int r = 0; r < 8; ++r) out[r] = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t lo[14], hi[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) {
+            const uint2 t = shv[seg * 8 + j][q];
+            const uint32_t w = half ? t.y : t.x;
+            lo[j] = w & 0xffffu; hi[j] = w >> 16;
         }
-        uint8_t *dst = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off;
-        *reinterpret_cast<uint32_t *>(dst + (long long)gy * G.pitch + gx) = out;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t v0 = 18u * (lo[r] + lo[r + 6]) + 34u * (lo[r + 1] + lo[r + 5]) + 48u * (lo[r + 2] + lo[r + 4]) + 56u * lo[r + 3];
+            const uint32_t v1 = 18u * (hi[r] + hi[r + 6]) + 34u * (hi[r + 1] + hi[r + 5]) + 48u * (hi[r + 2] + hi[r + 4]) + 56u * hi[r + 3];
+            out[r] |= (((v0 + 32768u) >> 16) | ((v1 + 32768u) >> 16) << 8) << (16 * half);
+        }
     }
+    uint8_t *dst = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off + gx;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (gy0 + r < G.h) *reinterpret_cast<uint32_t *>(dst + (long long)(gy0 + r) * G.pitch) = out[r];
 }
 
 cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls)
@@ -159,15 +330,15 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 
 template <int CELL>       // largest detection-area side this instantiation handles
 struct FastCfg {
-    static constexpr int NPMAX = (CELL + 1) / 2;            // pixel pairs per row
+    static constexpr int NPMAX = (CELL + 2) / 2;            // pixel pairs per row (pairs start at an even image column)
     static constexpr int TPW = NPMAX + 5;                   // tile pitch in words: pairs -2 .. NPMAX+2
     static constexpr int TH = CELL + 6;
-    static constexpr int SP = (CELL + 2 + 3) & ~3;          // score-map pitch (bytes)
+    static constexpr int SP = (CELL + 3 + 3) & ~3;          // score-map pitch (bytes)
     static constexpr int SH = CELL + 2;
-    static constexpr int LN = NPMAX * CELL;                 // worst-case pairs per polarity list
-    static constexpr int CN = CELL * CELL;                  // worst-case corners
-    static constexpr int SMEM = TH * TPW * 4 + SH * SP + 2 * LN * 2 + CN * 2;
-    static constexpr int THREADS = 128;
+    static constexpr int THREADS = 128, WARPS = THREADS / 32;
+    static constexpr int WL = 2 * 32 * ((NPMAX * CELL + THREADS - 1) / THREADS);   // list entries per warp (worst case, incl. two-polarity pairs)
+    static constexpr int SMEM = TH * TPW * 4 + SH * SP + WARPS * WL * 2;
+    static constexpr int ROW_SLOTS = CELL <= 38 ? 16 : 32;  // staging: global words per tile row, rounded to a power of two
 };
 
 __device__ __forceinline__ unsigned add16x2(unsigned a, unsigned b) { return __vadd2(a, b); }
@@ -186,40 +357,42 @@ __global__ void __launch_bounds__(FastCfg<CELL>::THREADS) k_fast(const DevParams
 {
     using C = FastCfg<CELL>;
     extern __shared__ __align__(16) uint8_t fast_smem[];
-    __shared__ int s_nb, s_nd, s_nc, s_emitted;
+    __shared__ int s_emitted;
     uint32_t *tile = reinterpret_cast<uint32_t *>(fast_smem);                   // [TH][TPW] pixel pairs as 16x2
     uint8_t *smap = fast_smem + C::TH * C::TPW * 4;                             // [SH][SP] corner scores
-    uint16_t *listB = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP);       // pairs to score, bright polarity
-    uint16_t *listD = listB + C::LN;
-    uint16_t *corners = listD + C::LN;
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.y;
+    uint16_t *wlist = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP) + warp * C::WL;   // this warp's pairs to score
+
     const uint32_t wk = P->fast_work[work_off + blockIdx.x];
     const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
     const LevelGeom &G = P->lv[level];
     const int x0 = kEdge + cj * G.w_cell, x1 = min(x0 + G.w_cell, G.x_end);
     const int y0 = kEdge + ci * G.h_cell, y1 = min(y0 + G.h_cell, G.y_end);
-    const int dw = x1 - x0, dh = y1 - y0, np = (dw + 1) >> 1;
+    // pairs start at an even image column xs <= x0 so global words map onto whole tile words;
+    // dx' = x - xs runs over [0, dwp), of which [par, dwp) is the cell's detection area
+    const int par = x0 & 1, xs = x0 - par;
+    const int dwp = x1 - xs, dh = y1 - y0, np = (dwp + 1) >> 1;
 
-    // ---- stage rows [y0-3, y1+3) x pixels [x0-4, x0-4+2*TPW) as 16-bit lanes (tile pixel u = x - x0 + 4)
+    // ---- stage rows [y0-3, y1+3) x pixels [xs-4, xs-4+2*TPW) as 16-bit lanes (tile pixel u = x - xs + 4)
     {
         int sp;
         const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-        const int xb = (x0 - 4) & ~3;
-        const int xlast = min(x0 - 4 + 2 * (np + 5), G.w);                      // exclusive; stays inside the row
+        const int xb = (xs - 4) & ~3;
+        const int xlast = min(xs - 4 + 2 * C::TPW, G.w);                        // exclusive; stays inside the row
         const int nwords = (xlast - xb + 3) >> 2, nrows = dh + 6;
-        uint16_t *t16 = reinterpret_cast<uint16_t *>(tile);
-        for (int i = tid; i < nrows * nwords; i += C::THREADS) {
-            const int r = i / nwords, c = i - r * nwords;
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)(y0 - 3 + r) * sp + xb) + c);
-            const int u = xb + 4 * c - (x0 - 4);
-            uint16_t *d = t16 + r * (2 * C::TPW) + u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((unsigned)(u + k) < (unsigned)(2 * C::TPW)) d[k] = (uint16_t)((v >> (8 * k)) & 0xff);
+        const int w0 = (xb - (xs - 4)) >> 1;                                    // tile word of the first global word: 0 or -1
+        for (int i = tid; i < nrows * C::ROW_SLOTS; i += C::THREADS) {
+            const int r = i / C::ROW_SLOTS, c = i % C::ROW_SLOTS;
+            if (c < nwords) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)(y0 - 3 + r) * sp + xb) + c);
+                const int wi = w0 + 2 * c;
+                uint32_t *d = tile + r * C::TPW + wi;
+                if ((unsigned)wi < (unsigned)C::TPW) d[0] = __byte_perm(v, 0, 0x4140);          // pixels 0,1 -> 16x2
+                if ((unsigned)(wi + 1) < (unsigned)C::TPW) d[1] = __byte_perm(v, 0, 0x4342);    // pixels 2,3
+            }
         }
-        for (int i = tid; i < (C::SH * C::SP) / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
-        if (tid == 0) { s_nb = 0; s_nd = 0; s_nc = 0; s_emitted = 0; }
+        for (int i = tid; i < (dh + 2) * (C::SP / 4); i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
+        if (tid == 0) s_emitted = 0;
     }
     __syncthreads();
 
@@ -231,139 +404,126 @@ __global__ void __launch_bounds__(FastCfg<CELL>::THREADS) k_fast(const DevParams
 
     int th = P->ini_th;
     for (int pass = 0; pass < 2; ++pass) {
-        // ---- A: compass pre-test on every pair
-        const unsigned tb = 0x00010001u * (unsigned)(th + 1), td = 0x00010001u * (unsigned)th;
+        // ---- A: compass pre-test on every pair; survivors go to this warp's private list with a
+        //         polarity per pixel (1 = may be a bright corner, 2 = dark; 0 = cannot be a corner)
+        const unsigned kb = 0x00010001u * (unsigned)((-th) & 0xffff);       // ~c + kb = -(c + th + 1)
+        const unsigned kd = 0x00010001u * (unsigned)(th + 1);               // ~c + kd = -(c - th)
+        int nl = 0;
         for (int base = warp * 32; base < npairs; base += C::THREADS) {
             const int i = base + lane;
-            bool wb = false, wd = false;
+            unsigned bright = 0, dark = 0;
             int dy = 0, p = 0;
             if (i < npairs) {
                 dy = (int)(((float)i + 0.5f) * inv_np);
                 p = i - dy * np;
                 const uint32_t *row = tile + (dy + 3) * C::TPW;
                 const int j = p + 2;
-                const unsigned c = row[j];
-                const unsigned negc = __vneg2(c);
-                const unsigned nb = __vsub2(negc, tb);                      // -(c + t + 1)
-                const unsigned nd = add16x2(negc, td);                      // -(c - t)
+                const unsigned nc = ~row[j];
+                const unsigned nb = add16x2(nc, kb), nd = add16x2(nc, kd);
                 const unsigned n = row[j - 3 * C::TPW], s = row[j + 3 * C::TPW];
                 const unsigned e = ring_pair<3>(row, j), w = ring_pair<-3>(row, j);
                 // sign bit clear in ring+nb  <=> ring > c+t ; sign bit set in ring+nd <=> ring < c-t
                 const unsigned bn = add16x2(n, nb), bs = add16x2(s, nb), be = add16x2(e, nb), bw = add16x2(w, nb);
                 const unsigned dn = add16x2(n, nd), ds = add16x2(s, nd), de = add16x2(e, nd), dwk = add16x2(w, nd);
-                const unsigned bright = ~((bn & bs) | (be & bw)) & 0x80008000u;
-                const unsigned dark = (dn | ds) & (de | dwk) & 0x80008000u;
-                wb = bright != 0; wd = dark != 0;
+                const unsigned inside = (2 * p >= par ? 0x8000u : 0u) | (2 * p + 1 < dwp ? 0x80000000u : 0u);
+                bright = ~((bn & bs) | (be & bw)) & inside;
+                dark = (dn | ds) & (de | dwk) & inside;
             }
-            const unsigned mb = __ballot_sync(0xffffffffu, wb), md = __ballot_sync(0xffffffffu, wd);
-            int ob = 0, od = 0;
-            if (lane == 0) { if (mb) ob = atomicAdd(&s_nb, __popc(mb)); if (md) od = atomicAdd(&s_nd, __popc(md)); }
-            ob = __shfl_sync(0xffffffffu, ob, 0); od = __shfl_sync(0xffffffffu, od, 0);
-            if (wb) listB[ob + __popc(mb & lt)] = (uint16_t)(dy << 8 | p);
-            if (wd) listD[od + __popc(md & lt)] = (uint16_t)(dy << 8 | p);
+            const unsigned any = bright | dark, both = bright & dark;
+            const unsigned m = __ballot_sync(0xffffffffu, any != 0);
+            if (any) {
+                // primary entry: dark where flagged dark, else bright where flagged bright
+                const unsigned m0 = (dark & 0x8000u) ? 2u : ((bright & 0x8000u) ? 1u : 0u);
+                const unsigned m1 = (dark & 0x80000000u) ? 2u : ((bright & 0x80000000u) ? 1u : 0u);
+                wlist[nl + __popc(m & lt)] = (uint16_t)(p | dy << 6 | m0 << 12 | m1 << 14);
+            }
+            nl += __popc(m);
+            const unsigned m2 = __ballot_sync(0xffffffffu, both != 0);
+            if (m2) {                                                       // rare: a pixel passed the pre-test in both polarities
+                if (both) wlist[nl + __popc(m2 & lt)] = (uint16_t)(p | dy << 6 | ((both & 0x8000u) ? 1u : 0u) << 12 | ((both & 0x80000000u) ? 1u : 0u) << 14);
+                nl += __popc(m2);
+            }
         }
-        __syncthreads();
-        // ---- B: exact one-sided scores of the listed pairs
-        const int nb_ = s_nb, nd_ = s_nd;
-        for (int base = warp * 32; base < nb_ + nd_; base += C::THREADS) {
+        __syncwarp();
+        // ---- B: exact scores of this warp's listed pairs.  Dark-polarity pixels are scored on inverted
+        //         intensities (255-v), which turns "max over arcs of min(ring - c)" into the dark score.
+        for (int base = 0; base < nl; base += 32) {
             const int i = base + lane;
-            bool k0 = false, k1 = false;
-            int dy = 0, p = 0, s0v = 0, s1v = 0;
-            if (i < nb_ + nd_) {
-                const bool is_b = i < nb_;
-                const int ent = is_b ? listB[i] : listD[i - nb_];
-                dy = ent >> 8; p = ent & 0xff;
+            if (i < nl) {
+                const unsigned ent = wlist[i];
+                const int p = ent & 63, dy = (ent >> 6) & 63;
+                const unsigned m0 = (ent >> 12) & 3u, m1 = ent >> 14;
+                const unsigned xm = (m0 == 2u ? 0x000000ffu : 0u) | (m1 == 2u ? 0x00ff0000u : 0u);
                 const uint32_t *row = tile + (dy + 3) * C::TPW;
                 const int j = p + 2;
-                const unsigned negc = __vneg2(row[j]);
+                const unsigned negc = add16x2(~(row[j] ^ xm), 0x00010001u);
                 unsigned e[16];
                 {
                     const uint32_t *r3 = row + 3 * C::TPW, *r2 = row + 2 * C::TPW, *r1 = row + C::TPW;
-                    const uint32_t *m1 = row - C::TPW, *m2 = row - 2 * C::TPW, *m3 = row - 3 * C::TPW;
+                    const uint32_t *q1 = row - C::TPW, *q2 = row - 2 * C::TPW, *q3 = row - 3 * C::TPW;
                     e[0] = r3[j];               e[1] = ring_pair<1>(r3, j);   e[15] = ring_pair<-1>(r3, j);
                     e[2] = r2[j + 1];           e[14] = r2[j - 1];
                     e[3] = ring_pair<3>(r1, j); e[13] = ring_pair<-3>(r1, j);
                     e[4] = ring_pair<3>(row, j); e[12] = ring_pair<-3>(row, j);
-                    e[5] = ring_pair<3>(m1, j); e[11] = ring_pair<-3>(m1, j);
-                    e[6] = m2[j + 1];           e[10] = m2[j - 1];
-                    e[8] = m3[j];               e[7] = ring_pair<1>(m3, j);   e[9] = ring_pair<-1>(m3, j);
+                    e[5] = ring_pair<3>(q1, j); e[11] = ring_pair<-3>(q1, j);
+                    e[6] = q2[j + 1];           e[10] = q2[j - 1];
+                    e[8] = q3[j];               e[7] = ring_pair<1>(q3, j);   e[9] = ring_pair<-1>(q3, j);
                 }
 #pragma unroll
-                for (int k = 0; k < 16; ++k) e[k] = add16x2(e[k], negc);
-                unsigned res;
-                if (is_b) {                                        // max over arcs of min9
-                    unsigned t3[16];
+                for (int k = 0; k < 16; ++k) e[k] = add16x2(e[k] ^ xm, negc);
+                unsigned t3[16];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) t3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-                    unsigned a[6];
+                for (int k = 0; k < 16; ++k) t3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) e[k] = __vimin3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
+                for (int k = 0; k < 16; ++k) e[k] = __vimin3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
+                unsigned a[5];
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) a[k] = __vimax3_s16x2(e[3 * k], e[3 * k + 1], e[3 * k + 2]);
-                    a[5] = e[15];
-                    res = __vimax3_s16x2(__vimax3_s16x2(a[0], a[1], a[2]), __vimax3_s16x2(a[3], a[4], a[5]), a[5]);
-                } else {                                           // -(min over arcs of max9)
-                    unsigned t3[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) t3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-                    unsigned a[6];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) e[k] = __vimax3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) a[k] = __vimin3_s16x2(e[3 * k], e[3 * k + 1], e[3 * k + 2]);
-                    a[5] = e[15];
-                    res = __vneg2(__vimin3_s16x2(__vimin3_s16x2(a[0], a[1], a[2]), __vimin3_s16x2(a[3], a[4], a[5]), a[5]));
-                }
-                s0v = (int)(short)(res & 0xffff) - 1;
-                s1v = (int)(short)(res >> 16) - 1;
-                k0 = s0v >= th;
-                k1 = s1v >= th && 2 * p + 1 < dw;
-                if (k0) smap[(dy + 1) * C::SP + 2 * p + 1] = (uint8_t)s0v;
-                if (k1) smap[(dy + 1) * C::SP + 2 * p + 2] = (uint8_t)s1v;
-            }
-            const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
-            if (m0 | m1) {
-                int o = 0;
-                if (lane == 0) o = atomicAdd(&s_nc, __popc(m0) + __popc(m1));
-                o = __shfl_sync(0xffffffffu, o, 0);
-                if (k0) corners[o + __popc(m0 & lt)] = (uint16_t)(dy << 8 | (2 * p));
-                if (k1) corners[o + __popc(m0) + __popc(m1 & lt)] = (uint16_t)(dy << 8 | (2 * p + 1));
+                for (int k = 0; k < 5; ++k) a[k] = __vimax3_s16x2(e[3 * k], e[3 * k + 1], e[3 * k + 2]);
+                const unsigned res = __vimax3_s16x2(__vimax3_s16x2(a[0], a[1], a[2]), __vimax3_s16x2(a[3], a[4], e[15]), e[15]);
+                const int s0v = (int)(short)(res & 0xffff) - 1, s1v = (int)(short)(res >> 16) - 1;
+                uint8_t *q = smap + (dy + 1) * C::SP + 2 * p + 1;
+                if (m0 && s0v >= th) q[0] = (uint8_t)s0v;
+                if (m1 && s1v >= th) q[1] = (uint8_t)s1v;
             }
         }
         __syncthreads();
-        // ---- C: non-max suppression + emission
-        const int nc = s_nc;
-        for (int base = warp * 32; base < nc; base += C::THREADS) {
+        // ---- C: non-max suppression inside the cell rectangle (dense scan of the score map) + emission
+        for (int base = warp * 32; base < dh * (C::SP / 4); base += C::THREADS) {
             const int i = base + lane;
-            bool keep = false;
-            int dy = 0, dx = 0, sc = 0;
-            if (i < nc) {
-                const int ent = corners[i];
-                dy = ent >> 8; dx = ent & 0xff;
-                const uint8_t *q = smap + (dy + 1) * C::SP + dx + 1;
-                sc = q[0];
-                keep = sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
-                       sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1];
+            uint32_t wv = 0;
+            int dy = 0, c4 = 0;
+            if (i < dh * (C::SP / 4)) {
+                dy = i / (C::SP / 4); c4 = (i - dy * (C::SP / 4)) * 4;
+                wv = *reinterpret_cast<const uint32_t *>(smap + (dy + 1) * C::SP + c4);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-                int slot = 0;
-                if (lane == 0) { slot = (int)atomicAdd(cnt, (unsigned)__popc(m)); s_emitted = 1; }
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (keep) {
-                    const uint32_t xr = (uint32_t)(x0 + dx - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
-                    const int at = slot + __popc(m & lt);
-                    if (at < G.cand_cap) cand[at] = xr | yr << 12 | (uint32_t)sc << 24;
+            if (__ballot_sync(0xffffffffu, wv != 0) == 0) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int sc = (wv >> (8 * k)) & 0xff;
+                bool keep = false;
+                if (sc) {
+                    const uint8_t *q = smap + (dy + 1) * C::SP + c4 + k;
+                    keep = sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
+                           sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1];
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    int slot = 0;
+                    if (lane == 0) { slot = (int)atomicAdd(cnt, (unsigned)__popc(m)); s_emitted = 1; }
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (keep) {
+                        const uint32_t xr = (uint32_t)(xs + c4 + k - 1 - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
+                        const int at = slot + __popc(m & lt);
+                        if (at < G.cand_cap) cand[at] = xr | yr << 12 | (uint32_t)sc << 24;
+                    }
                 }
             }
         }
         __syncthreads();
         if (s_emitted || pass == 1 || P->min_th == th) break;
         // nothing survived at iniThFAST: clear and redo the cell at minThFAST
-        __syncthreads();
         th = P->min_th;
-        for (int i = tid; i < (C::SH * C::SP) / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
-        if (tid == 0) { s_nb = 0; s_nd = 0; s_nc = 0; }
+        for (int i = tid; i < (dh + 2) * (C::SP / 4); i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
         __syncthreads();
     }
 }
@@ -403,10 +563,9 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 // The winner of a node is the key with the greatest response, first in the reference's
 // candidate order (cell row, cell column, y, x) (:747-757).
 
-constexpr int kOctThreads = 1024;
-constexpr int kOctIPT = 8;                 // node records per thread in the block-wide passes
 typedef unsigned long long u64;
 
+template <int THREADS>
 __device__ __forceinline__ int block_scan_incl(int v, int *warp_sums, int *total)
 {
     // inclusive scan over threadIdx.x order; *total = block sum
@@ -418,7 +577,7 @@ __device__ __forceinline__ int block_scan_incl(int v, int *warp_sums, int *total
     if (lane == 31) warp_sums[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        int s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        int s = lane < THREADS / 32 ? warp_sums[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
         warp_sums[lane] = s;
@@ -428,54 +587,86 @@ __device__ __forceinline__ int block_scan_incl(int v, int *warp_sums, int *total
     return x + (warp > 0 ? warp_sums[warp - 1] : 0);
 }
 
-__device__ __forceinline__ void bitonic_sort(u64 *v, int n_pow2, bool descending)
+template <int THREADS>
+__device__ __forceinline__ void bitonic_sort_desc(u64 *v, int n_pow2)
 {
     for (int k = 2; k <= n_pow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += THREADS) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));       // lower index of the pair
                 const int p = i | j;
                 const u64 a = v[i], b = v[p];
-                const bool up = ((i & k) == 0) != descending;
-                if ((a > b) == up) { v[i] = b; v[p] = a; }
+                const bool down = (i & k) == 0;                             // descending run
+                if ((a < b) == down) { v[i] = b; v[p] = a; }
             }
             __syncthreads();
         }
     }
 }
 
-__device__ __forceinline__ int lower_child(const u64 *keys, int lo, int hi, int shift, unsigned c)
+// path code of one packed candidate: initial node, then the DivideNode child index per split
+__device__ __forceinline__ uint32_t path_code(uint32_t c, const LevelGeom &G)
 {
-    // first index in [lo,hi) whose 2-bit child field at `shift` (of the high word) is >= c
+    const int x = c & 0xfff, y = (c >> 12) & 0xfff;
+    int r = (int)__fdiv_rn((float)x, G.h_x);                               // vpIniNodes[kp.pt.x/hX], :569
+    r = min(r, G.n_ini - 1);
+    int ulx = G.root_ul[r], brx = G.root_br[r], uly = 0, bry = G.region_h;
+    uint32_t code = (uint32_t)r;
+    for (int d = 0; d < G.depth; ++d) {
+        const int midx = ulx + ((brx - ulx + 1) >> 1), midy = uly + ((bry - uly + 1) >> 1);   // ceil(w/2), :483-484
+        const bool right = x >= midx, down = y >= midy;
+        if (right) ulx = midx; else brx = midx;
+        if (down) uly = midy; else bry = midy;
+        code = code << 2 | (uint32_t)down << 1 | (uint32_t)right;
+    }
+    return code;
+}
+
+__device__ __forceinline__ int lower_child(const uint32_t *codes, int lo, int hi, int shift, unsigned c)
+{
+    // first index in [lo,hi) whose 2-bit child field at `shift` is >= c
     while (lo < hi) {
         const int m = (lo + hi) >> 1;
-        if ((((unsigned)(keys[m] >> 32) >> shift) & 3u) >= c) hi = m; else lo = m + 1;
+        if (((codes[m] >> shift) & 3u) >= c) hi = m; else lo = m + 1;
     }
     return lo;
 }
 
-size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
+struct OctreeSmem { size_t bytes; int key_cap, skey_cap; };
+
+static OctreeSmem octree_smem(int threads, int node_cap, int max_feat, size_t budget)
 {
-    int sp2 = 1;
-    while (sp2 < max_feat + 3) sp2 <<= 1;
-    const size_t node_bytes = (size_t)max_node_cap * 12 + (size_t)max_node_cap * 4 /*eidx*/ + (size_t)sp2 * 8 /*skey*/ + 256;
-    const size_t budget = 200 * 1024;
-    int kc = 1024;
-    while ((size_t)(kc * 2) * 8 + node_bytes <= budget) kc *= 2;
-    if (key_cap) *key_cap = kc;
-    return node_bytes + (size_t)kc * 8;
+    OctreeSmem o;
+    o.skey_cap = 1;
+    while (o.skey_cap < max_feat + 3) o.skey_cap <<= 1;
+    const size_t fixed = (size_t)o.skey_cap * 8 + (size_t)node_cap * 16 + (size_t)(threads / 32) * 256 * 4;
+    long long kc = ((long long)budget - (long long)fixed) / 8;
+    kc = kc < 256 ? 256 : kc;
+    o.key_cap = (int)(kc & ~31LL);
+    o.bytes = fixed + (size_t)o.key_cap * 8;
+    return o;
 }
 
-__global__ void __launch_bounds__(kOctThreads, 1)
+size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
+{
+    const int threads = max_node_cap <= 1024 ? 256 : (max_node_cap <= 4096 ? 512 : 1024);
+    const OctreeSmem o = octree_smem(threads, max_node_cap, max_feat, threads == 256 ? 100 * 1024 : 200 * 1024);
+    if (key_cap) *key_cap = o.key_cap;
+    return o.bytes;
+}
+
+template <int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS)
 k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap)
 {
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t oct_smem[];
     __shared__ int warp_sums[32];
     __shared__ int s_m, s_added;
 
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom &G = P->lv[level];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)min(P->cand_count[frame * P->nlevels + level], (unsigned)G.cand_cap);
     const int N = G.n_feat, D = G.depth;
 
@@ -484,51 +675,87 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     int *nhi = nlo + node_cap;
     int *ndep = nhi + node_cap;
     int *eidx = ndep + node_cap;
-    u64 *keys = reinterpret_cast<u64 *>(eidx + node_cap);            // 4 int arrays = 16*node_cap bytes: stays 8-aligned
-
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    if (n2 > key_cap)                                               // level too dense for shared memory: L2-resident scratch
-        keys = P->sort_scratch + ((long long)frame * P->cand_frame_elems + G.cand_off) * 2;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(eidx + node_cap);  // [WARPS][256]
+    uint32_t *bufA = hist + WARPS * 256, *bufB = bufA + key_cap;
+    if (n > key_cap) {                                              // level too dense for shared memory: L2-resident scratch
+        bufA = reinterpret_cast<uint32_t *>(P->sort_scratch + ((long long)frame * P->cand_frame_elems + G.cand_off) * 2);
+        bufB = bufA + G.cand_cap;
+    }
     const uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
     uint32_t *stage = P->kp_stage + (long long)frame * P->kp_frame_cap + G.kp_off;
     uint32_t *kp_count = P->kp_count + frame * P->nlevels + level;
 
     if (n == 0) { if (tid == 0) *kp_count = 0; return; }
 
-    // ---- path codes (:566-570 root assignment, :481-534 child tests)
-    for (int i = tid; i < n2; i += kOctThreads) {
-        u64 kv = ~0ull;
-        if (i < n) {
-            const uint32_t c = cand[i];
-            const int x = c & 0xfff, y = (c >> 12) & 0xfff;
-            int r = (int)__fdiv_rn((float)x, G.h_x);
-            r = min(r, G.n_ini - 1);
-            int ulx = G.root_ul[r], brx = G.root_br[r], uly = 0, bry = G.region_h;
-            uint32_t code = (uint32_t)r;
-            for (int d = 0; d < D; ++d) {
-                const int midx = ulx + ((brx - ulx + 1) >> 1), midy = uly + ((bry - uly + 1) >> 1);
-                const bool right = x >= midx, down = y >= midy;
-                if (right) ulx = midx; else brx = midx;
-                if (down) uly = midy; else bry = midy;
-                code = code << 2 | (uint32_t)down << 1 | (uint32_t)right;
+    // ---- LSD radix sort of the packed candidates by path code, 8 bits per pass (stable)
+    for (int i = tid; i < n; i += THREADS) bufA[i] = cand[i];
+    int code_bits = 2 * D;
+    for (int t = G.n_ini - 1; t > 0; t >>= 1) ++code_bits;
+    const int chunk = (((n + WARPS - 1) / WARPS) + 31) & ~31;
+    const int c_lo = min(warp * chunk, n), c_hi = min(c_lo + chunk, n);
+    const unsigned lt = lanemask_lt();
+    for (int shift = 0; shift < code_bits; shift += 8) {
+        for (int i = tid; i < WARPS * 256; i += THREADS) hist[i] = 0;
+        __syncthreads();
+        uint32_t *wh = hist + warp * 256;
+        for (int base = c_lo; base < c_hi; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < c_hi;
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned d = (path_code(bufA[i], G) >> shift) & 255u;
+                const unsigned peers = __match_any_sync(vm, d);
+                if ((peers & lt) == 0) wh[d] += __popc(peers);      // one leader per distinct digit
             }
-            kv = (u64)code << 32 | c;
+            __syncwarp();
         }
-        keys[i] = kv;
+        __syncthreads();
+        {   // exclusive scan over (digit major, warp minor)
+            constexpr int HPT = 256 * WARPS / THREADS;               // == 8
+            uint32_t v[HPT];
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) { const int e = tid * HPT + k; v[k] = hist[(e % WARPS) * 256 + e / WARPS]; sum += (int)v[k]; }
+            int tot;
+            int run = block_scan_incl<THREADS>(sum, warp_sums, &tot) - sum;
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) { const int e = tid * HPT + k; hist[(e % WARPS) * 256 + e / WARPS] = (uint32_t)run; run += (int)v[k]; }
+        }
+        __syncthreads();
+        for (int base = c_lo; base < c_hi; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < c_hi;
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            uint32_t key = 0; unsigned d = 0, peers = 0; uint32_t off = 0;
+            if (valid) {
+                key = bufA[i];
+                d = (path_code(key, G) >> shift) & 255u;
+                peers = __match_any_sync(vm, d);
+                off = wh[d];
+            }
+            __syncwarp();
+            if (valid) {
+                if ((peers & lt) == 0) wh[d] = off + __popc(peers);
+                bufB[off + __popc(peers & lt)] = key;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t *t = bufA; bufA = bufB; bufB = t;
     }
+    uint32_t *keys = bufA, *codes = bufB;                           // sorted candidates and their path codes
+    for (int i = tid; i < n; i += THREADS) codes[i] = path_code(keys[i], G);
     __syncthreads();
-    bitonic_sort(keys, n2, false);
 
     // ---- roots, reverse list order (:553-585)
     if (tid == 0) {
         int na = 0;
         for (int r = G.n_ini - 1; r >= 0; --r) {
             int lo = 0, hi = n;
-            while (lo < hi) { const int m = (lo + hi) >> 1; if (((unsigned)(keys[m] >> 32) >> (2 * D)) >= (unsigned)r) hi = m; else lo = m + 1; }
+            while (lo < hi) { const int m = (lo + hi) >> 1; if ((codes[m] >> (2 * D)) >= (unsigned)r) hi = m; else lo = m + 1; }
             const int a = lo;
-            lo = a; hi = n;
-            while (lo < hi) { const int m = (lo + hi) >> 1; if (((unsigned)(keys[m] >> 32) >> (2 * D)) >= (unsigned)(r + 1)) hi = m; else lo = m + 1; }
+            hi = n;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if ((codes[m] >> (2 * D)) >= (unsigned)(r + 1)) hi = m; else lo = m + 1; }
             if (lo > a) { nlo[na] = a; nhi[na] = lo; ndep[na] = 0; ++na; }
         }
         int ne = 0;
@@ -543,43 +770,43 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     for (;;) {
         const int prev_size = size;
         // ---- visit order
-        int sp2 = 1;
         if (careful) {
+            int sp2 = 1;
             while (sp2 < nE) sp2 <<= 1;
-            for (int i = tid; i < sp2; i += kOctThreads)
+            for (int i = tid; i < sp2; i += THREADS)
                 skey[i] = i < nE ? ((u64)(unsigned)(nhi[eidx[i]] - nlo[eidx[i]]) << 32 | (unsigned)eidx[i]) : 0ull;
             __syncthreads();
-            bitonic_sort(skey, sp2, true);
+            bitonic_sort_desc<THREADS>(skey, sp2);
         }
         // ---- pass 1: children of the parents this thread owns (visit ranks tid*IPT ..)
-        int pb[kOctIPT][3];
-        int pc[kOctIPT];
+        int pb[IPT][3];
+        int pc[IPT];
         int csum = 0;
 #pragma unroll
-        for (int k = 0; k < kOctIPT; ++k) {
-            const int r = tid * kOctIPT + k;
+        for (int k = 0; k < IPT; ++k) {
+            const int r = tid * IPT + k;
             pc[k] = 0;
             if (r < nE) {
                 const int p = careful ? (int)(skey[r] & 0xffffffffu) : eidx[nE - 1 - r];
                 const int lo = nlo[p], hi = nhi[p], shift = 2 * (D - 1 - ndep[p]);
-                const int b1 = lower_child(keys, lo, hi, shift, 1);
-                const int b2 = lower_child(keys, b1, hi, shift, 2);
-                const int b3 = lower_child(keys, b2, hi, shift, 3);
+                const int b1 = lower_child(codes, lo, hi, shift, 1);
+                const int b2 = lower_child(codes, b1, hi, shift, 2);
+                const int b3 = lower_child(codes, b2, hi, shift, 3);
                 pb[k][0] = b1; pb[k][1] = b2; pb[k][2] = b3;
                 pc[k] = (b1 > lo) + (b2 > b1) + (b3 > b2) + (hi > b3);
                 csum += pc[k];
             }
         }
         int total_c;
-        const int incl = block_scan_incl(csum, warp_sums, &total_c);
+        const int incl = block_scan_incl<THREADS>(csum, warp_sums, &total_c);
         // ---- cutoff m (careful phase: smallest m with size + sum_{i<m}(c_i - 1) >= N)
         if (tid == 0) { s_m = nE; s_added = total_c; }
         __syncthreads();
         if (careful) {
             int run = incl - csum;                                  // children of all earlier ranks
 #pragma unroll
-            for (int k = 0; k < kOctIPT; ++k) {
-                const int r = tid * kOctIPT + k;
+            for (int k = 0; k < IPT; ++k) {
+                const int r = tid * IPT + k;
                 if (r < nE) {
                     const int before = size + run - r;              // size + sum_{i<r}(c_i-1)
                     run += pc[k];
@@ -594,8 +821,8 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         {
             int off = incl - csum;
 #pragma unroll
-            for (int k = 0; k < kOctIPT; ++k) {
-                const int r = tid * kOctIPT + k;
+            for (int k = 0; k < IPT; ++k) {
+                const int r = tid * IPT + k;
                 if (r < nE && r < m) {
                     const int p = careful ? (int)(skey[r] & 0xffffffffu) : eidx[nE - 1 - r];
                     const int lo = nlo[p], hi = nhi[p], dep = ndep[p] + 1;
@@ -614,11 +841,11 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         size = size - m + added;
         // ---- stable compaction of the array + new expandable list
         {
-            int rl[kOctIPT], rh[kOctIPT], rd[kOctIPT];
+            int rl[IPT], rh[IPT], rd[IPT];
             int alive = 0, multi = 0;
 #pragma unroll
-            for (int k = 0; k < kOctIPT; ++k) {
-                const int i = tid * kOctIPT + k;
+            for (int k = 0; k < IPT; ++k) {
+                const int i = tid * IPT + k;
                 rd[k] = -1;
                 if (i < n_pre) {
                     rl[k] = nlo[i]; rh[k] = nhi[i]; rd[k] = ndep[i];
@@ -626,10 +853,10 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
                 }
             }
             int tot;
-            const int inc2 = block_scan_incl(alive | multi << 16, warp_sums, &tot);
+            const int inc2 = block_scan_incl<THREADS>(alive | multi << 16, warp_sums, &tot);
             int wa = (inc2 & 0xffff) - alive, we = (inc2 >> 16) - multi;
 #pragma unroll
-            for (int k = 0; k < kOctIPT; ++k) {
+            for (int k = 0; k < IPT; ++k) {
                 if (rd[k] >= 0) {
                     nlo[wa] = rl[k]; nhi[wa] = rh[k]; ndep[wa] = rd[k];
                     if (rh[k] - rl[k] > 1) eidx[we++] = wa;
@@ -646,11 +873,11 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
 
     // ---- winners, list order front->back == reverse array order (:740-760)
     const int n_cols = G.n_cols, w_cell = G.w_cell, h_cell = G.h_cell;
-    for (int j = tid >> 5; j < size; j += kOctThreads >> 5) {
+    for (int j = tid >> 5; j < size; j += WARPS) {
         const int nd = size - 1 - j;
         u64 best = 0;
         for (int i = nlo[nd] + lane; i < nhi[nd]; i += 32) {
-            const uint32_t c = (uint32_t)keys[i];
+            const uint32_t c = keys[i];
             const u64 x = c & 0xfff, y = (c >> 12) & 0xfff, s = c >> 24;
             const u64 order = ((u64)(((int)y - 3) / h_cell * n_cols + ((int)x - 3) / w_cell) << 24) | y << 12 | x;
             const u64 v = s << 40 | (~order & 0xffffffffffull);
@@ -666,18 +893,23 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     if (tid == 0) *kp_count = (uint32_t)size;
 }
 
+template <int THREADS, int IPT>
+static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int nframes, int node_cap, int max_feat, size_t budget, cudaStream_t st)
+{
+    const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget);
+    cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o.bytes);
+    if (e != cudaSuccess) return e;
+    k_octree<THREADS, IPT><<<dim3(hP.nlevels, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls)
 {
-    int key_cap = 0;
-    const size_t smem = octree_smem_bytes(max_node_cap, max_feat, &key_cap);
-    int sp2 = 1;
-    while (sp2 < max_feat + 3) sp2 <<= 1;
-    cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(hP.nlevels, nframes);
-    k_octree<<<grid, kOctThreads, smem, st>>>(dP, max_node_cap, sp2, key_cap);
     ls->launches++;
-    return cudaGetLastError();
+    // CTA size by node-array capacity (THREADS*IPT records); small CTAs leave room for 2+ per SM
+    if (max_node_cap <= 1024) return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, 100 * 1024, st);
+    if (max_node_cap <= 4096) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
+    return launch_octree_t<1024, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
 }
 
 // ------------------------------------------------- orientation + descriptor

@@ -39,6 +39,7 @@ struct orbx_handle {
     uint8_t *d_out_desc = nullptr;
     int *d_out_n = nullptr;
     uint8_t *d_pad = nullptr; size_t pad_bytes = 0;
+    uint8_t *d_in = nullptr; size_t in_bytes = 0;       // H2D landing area for host frames before the repack kernel
     // pinned host staging of the results
     orbx_keypoint *p_kps = nullptr;
     uint8_t *p_desc = nullptr;
@@ -251,7 +252,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_batch_buffers(h);
     free_geo_tables(h);
-    dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad);
+    dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad); dfree(h->d_in);
     dfree(h->m_A); dfree(h->m_B); dfree(h->m_out); dfree(h->m_acc); dfree(h->m_nacc); dfree(h->m_partial);
     for (int i = 0; i <= ORBX_NUM_STAGES; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -331,10 +332,8 @@ extern "C" int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int n
         s0.ptr = d_frames; s0.pitch = stride_bytes; s0.frame_stride = (long long)frame_stride_bytes;   // used in place
     } else {
         const LevelGeom &L0 = h->geo.lv[0];
-        for (int f = 0; f < nframes; ++f)
-            CU(cudaMemcpy2DAsync(h->d_pyr + (size_t)f * h->geo.pyr_frame_bytes + L0.img_off, L0.pitch,
-                                 d_frames + (size_t)f * frame_stride_bytes, stride_bytes, width, height,
-                                 cudaMemcpyDeviceToDevice, h->stream));
+        CU(launch_repack(d_frames, (long long)frame_stride_bytes, stride_bytes, h->d_pyr + L0.img_off, h->geo.pyr_frame_bytes, L0.pitch,
+                         width, height, nframes, h->stream, &h->stats));
         s0.ptr = h->d_pyr + L0.img_off; s0.pitch = L0.pitch; s0.frame_stride = h->geo.pyr_frame_bytes;
     }
     return enqueue_pipeline(h, s0, nframes);
@@ -353,9 +352,25 @@ extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, in
     if (rc != ORBX_OK) return rc;
     if (h->profiling) CU(cudaEventRecord(h->ev[0], h->stream));
     const LevelGeom &L0 = h->geo.lv[0];
-    for (int f = 0; f < nframes; ++f)
-        CU(cudaMemcpy2DAsync(h->d_pyr + (size_t)f * h->geo.pyr_frame_bytes + L0.img_off, L0.pitch, frames[f], stride_bytes,
-                             width, height, cudaMemcpyHostToDevice, h->stream));
+    // H2D as plain 1-D copies (one per frame, or one for the whole batch when the frames are
+    // contiguous in host memory), then a device kernel re-pitches rows into the aligned level-0 slots
+    const size_t frame_bytes = (size_t)stride_bytes * (size_t)(height - 1) + (size_t)width;
+    const size_t slot = (size_t)stride_bytes * (size_t)height;
+    if (slot * (size_t)nframes > h->in_bytes) {
+        CU(cudaStreamSynchronize(h->stream));
+        dfree(h->d_in);
+        CU(cudaMalloc(&h->d_in, slot * (size_t)nframes));
+        h->in_bytes = slot * (size_t)nframes;
+    }
+    bool contiguous = true;
+    for (int f = 1; f < nframes; ++f) contiguous = contiguous && frames[f] == frames[0] + (size_t)f * slot;
+    if (contiguous)
+        CU(cudaMemcpyAsync(h->d_in, frames[0], slot * (size_t)(nframes - 1) + frame_bytes, cudaMemcpyHostToDevice, h->stream));
+    else
+        for (int f = 0; f < nframes; ++f)
+            CU(cudaMemcpyAsync(h->d_in + (size_t)f * slot, frames[f], frame_bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_repack(h->d_in, (long long)slot, stride_bytes, h->d_pyr + L0.img_off, h->geo.pyr_frame_bytes, L0.pitch, width, height,
+                     nframes, h->stream, &h->stats));
     Src0 s0;
     s0.ptr = h->d_pyr + L0.img_off; s0.pitch = L0.pitch; s0.frame_stride = h->geo.pyr_frame_bytes;
     return enqueue_pipeline(h, s0, nframes);

@@ -78,7 +78,7 @@ void build_tables(int nfeatures, float scale_factor, int nlevels, int ini_th, in
 // returns ORBX_OK / ORBX_ERR_UNSUPPORTED (+ message)
 int build_geometry(const Tables &t, int width, int height, Geometry *g, std::string *err);
 
-constexpr int kBlurTileW = 64, kBlurTileH = 16;
+constexpr int kBlurTileW = 128, kBlurTileH = 64;
 
 } // namespace orbx
 
