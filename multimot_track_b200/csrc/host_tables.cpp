@@ -101,7 +101,7 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
         *err = msg; return ORBX_ERR_UNSUPPORTED;
     }
     g->width = width; g->height = height; g->nlevels = t.nlevels;
-    g->fast_work.clear(); g->blur_work.clear(); g->xtab.clear(); g->ytab.clear();
+    g->fast_work.clear(); g->blur_work.clear(); g->fscore_work.clear(); g->oct_lut.clear(); g->xtab.clear(); g->ytab.clear();
     long long img_off = 0, cand_off = 0;
     int kp_off = 0;
     g->max_node_cap = g->max_feat = g->max_cand_cap = 0;
@@ -162,6 +162,22 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
         L.cand_off = cand_off;
         cand_off += (cap + 63) & ~63LL;
 
+        // ---- score tiles: 128 pixels x (a multiple of 7 rows, <= 42) over the detection region [19,x_end) x [19,y_end)
+        {
+            const int rh = L.y_end - kEdge, rw = L.x_end - (kEdge - 1);
+            if (rh > 0 && rw > 0) {
+                int nty = (rh + 34) / 35;
+                int rows = ((rh + nty - 1) / nty + 6) / 7 * 7;
+                if (rows > 42) rows = 42;
+                L.fs_tile_rows = rows;
+                nty = (rh + rows - 1) / rows;
+                const int ntx = (rw + 127) / 128;
+                for (int ty = 0; ty < nty; ++ty)
+                    for (int tx = 0; tx < ntx; ++tx)
+                        g->fscore_work.push_back((uint32_t)l << 24 | (uint32_t)ty << 12 | (uint32_t)tx);
+            } else L.fs_tile_rows = 7;
+        }
+
         // ---- octree roots (:543-560)
         const int ow = maxBX - minBX, oh = maxBY - minBY;
         L.n_feat = t.nfeat[l];
@@ -181,6 +197,38 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
         L.region_h = oh;
         L.depth = 0;
         while ((1 << L.depth) < maxdim) ++L.depth;
+        // Path-code tables.  DivideNode (:481-537) halves x and y independently (ceil(w/2) to the left/upper
+        // child), so the 2-bit child index at every depth splits into an x bit and a y bit that depend only on
+        // x (and the initial node, :569) or only on y: code(x, y) = lut_x[x] | lut_y[y].
+        L.region_w = ow;
+        L.lut_off = (int)g->oct_lut.size();
+        for (int x = 0; x < ow; ++x) {
+            int r = (int)((float)x / L.h_x);
+            if (r > L.n_ini - 1) r = L.n_ini - 1;
+            int ul = L.root_ul[r], br = L.root_br[r];
+            uint32_t code = (uint32_t)r << (2 * L.depth);
+            for (int d = 0; d < L.depth; ++d) {
+                const int mid = ul + ((br - ul + 1) >> 1);
+                const bool right = x >= mid;
+                if (right) ul = mid; else br = mid;
+                code |= (uint32_t)right << (2 * (L.depth - 1 - d));
+            }
+            g->oct_lut.push_back(code);
+        }
+        for (int y = 0; y < oh; ++y) {
+            int ul = 0, br = oh;
+            uint32_t code = 0;
+            for (int d = 0; d < L.depth; ++d) {
+                const int mid = ul + ((br - ul + 1) >> 1);
+                const bool down = y >= mid;
+                if (down) ul = mid; else br = mid;
+                code |= (uint32_t)down << (2 * (L.depth - 1 - d) + 1);
+            }
+            g->oct_lut.push_back(code);
+        }
+        // candidate order of the reference = (cell row, cell column, y, x) (:789-829): cell indices per coordinate
+        for (int x = 0; x < ow; ++x) g->oct_lut.push_back(x >= 3 ? (uint32_t)((x - 3) / L.w_cell) : 0u);
+        for (int y = 0; y < oh; ++y) g->oct_lut.push_back(y >= 3 ? (uint32_t)((y - 3) / L.h_cell * L.n_cols) : 0u);
         const int nmax = std::max(L.n_feat, 4 * L.n_ini);
         L.kp_cap = nmax + 3;
         L.kp_off = kp_off;
@@ -199,12 +247,12 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
             for (int tx = 0; tx < (L.w + kBlurTileW - 1) / kBlurTileW; ++tx)
                 g->blur_work.push_back((uint32_t)l << 24 | (uint32_t)ty << 12 | (uint32_t)tx);
     }
-    // small-cell levels first: k_fast<38> handles those, k_fast<64> the (rare, coarse) rest
+    // small-cell levels first: k_fast_cells<44> handles those, k_fast_cells<64> the (rare, coarse) rest
     {
         std::vector<uint32_t> small, large;
         for (uint32_t wk : g->fast_work) {
             const LevelGeom &L = g->lv[wk >> 24];
-            (L.w_cell <= 38 && L.h_cell <= 38 ? small : large).push_back(wk);
+            (L.w_cell <= 44 && L.h_cell <= 44 ? small : large).push_back(wk);
         }
         g->n_fast_small = (int)small.size();
         g->fast_work = small;

@@ -213,11 +213,13 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
         all_staged = all_staged && staged;
     }
     if (all_staged) {
-        // enough (band, frame) CTAs for two per SM, but bands no thinner than ~8 rows of the last level
-        int nbands = (2 * 148 + nframes - 1) / nframes;
-        nbands = max(1, min(nbands, max(1, hP.lv[hP.nlevels - 1].h / 8)));
-        k_pyramid_fused<<<dim3(nbands, nframes), dim3(32, 8), 0, st>>>(dP, s0, nbands);
-        ls->launches++;
+        // one launch per level: thousands of independent tiles hide the load latency better than the
+        // single-launch k_pyramid_fused (few long-running CTAs), which measured 1.6x slower at batch 32
+        for (int l = 1; l < hP.nlevels; ++l) {
+            const LevelGeom &D = hP.lv[l];
+            k_resize<<<dim3((D.w + kRzTW - 1) / kRzTW, (D.h + kRzTH - 1) / kRzTH, nframes), dim3(32, 8), 0, st>>>(dP, s0, l);
+            ls->launches++;
+        }
         return cudaGetLastError();
     }
     for (int l = 1; l < hP.nlevels; ++l) {
@@ -313,233 +315,259 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 }
 
 // --------------------------------------------------------------------- FAST
-// One 128-thread CTA per 30-pixel cell (the reference calls cv::FAST once per cell,
-// :809-815).  The cell and its 3-pixel ring are staged in shared memory as 16-bit
-// lanes, two horizontally adjacent pixels per 32-bit word, so every step works on a
-// pixel PAIR with the packed-halfword integer pipe (VIADD.16x2 / VIMNMX3.S16x2):
-//   A. compass pre-test (any 9-arc holds two adjacent compass points of one
-//      polarity) over all pairs; pairs that can hold a bright / dark corner are
-//      ballot-compacted into two lists;
-//   B. exact score of the listed pairs, one polarity per list:
-//         bright = max_k min(e_k..e_k+8) - 1,  dark = -min_k max(e_k..e_k+8) - 1,
-//      e_k = ring_k - centre  (OpenCV cornerScore<16>: the largest threshold at which
-//      the pixel is still a corner; corner at t <=> score >= t);
-//   C. non-max suppression inside the cell's own rectangle (outside counts as 0,
-//      like cv::FAST on the cell sub-image) and emission.
-// A cell with no survivor at iniThFAST is redone at minThFAST (:812-816).
+// The reference calls cv::FAST once per ~30-pixel cell with iniThFAST and again with
+// minThFAST when the cell stayed empty (:789-829).  The corner score (OpenCV
+// cornerScore<16>: the largest threshold at which the pixel is still a FAST-9 corner)
+// does not depend on the threshold or on the cell, and "corner at t" <=> score >= t, so
+// the work splits into
+//   k_fast_score  dense, cell-agnostic: score map S = (score >= minThFAST ? score : 0)
+//                 for the whole detection region of every level;
+//   k_fast_cells  per cell: non-max suppression restricted to the cell's own rectangle
+//                 (outside counts as 0, like cv::FAST on the cell sub-image), survivors
+//                 with S >= iniThFAST, or with S >= minThFAST if there were none.
+// k_fast_score works on pixel PAIRS held as 16x2 lanes so the packed-halfword integer
+// pipe does two pixels per instruction (VIADD.16x2, VIMNMX3.S16x2):
+//   bright = max_k min(e_k..e_k+8), dark = -min_k max(e_k..e_k+8), e_k = ring_k - centre,
+//   score = max(bright, dark) - 1.
+// Each lane owns one pair column and walks down the tile rows keeping the 7-row ring
+// neighbourhood in registers (5 shared-memory loads + 4 funnel shifts per new row).
 
-template <int CELL>       // largest detection-area side this instantiation handles
-struct FastCfg {
-    static constexpr int NPMAX = (CELL + 2) / 2;            // pixel pairs per row (pairs start at an even image column)
-    static constexpr int TPW = NPMAX + 5;                   // tile pitch in words: pairs -2 .. NPMAX+2
-    static constexpr int TH = CELL + 6;
-    static constexpr int SP = (CELL + 3 + 3) & ~3;          // score-map pitch (bytes)
-    static constexpr int SH = CELL + 2;
-    static constexpr int THREADS = 128, WARPS = THREADS / 32;
-    static constexpr int WL = 2 * 32 * ((NPMAX * CELL + THREADS - 1) / THREADS);   // list entries per warp (worst case, incl. two-polarity pairs)
-    static constexpr int SMEM = TH * TPW * 4 + SH * SP + WARPS * WL * 2;
-    static constexpr int ROW_SLOTS = CELL <= 38 ? 16 : 32;  // staging: global words per tile row, rounded to a power of two
-};
+constexpr int kFsLanes = 64;                       // pair columns per CTA -> 128 pixels
+constexpr int kFsMaxRows = 42;                     // tile rows (a multiple of 7, chosen per level on the host)
+constexpr int kFsPitch = kFsLanes + 4 + 1;         // tile pitch in words: pairs -2 .. 65 (+1: odd pitch)
 
-__device__ __forceinline__ unsigned add16x2(unsigned a, unsigned b) { return __vadd2(a, b); }
-
-// ring pair at column offset ox (pixels) relative to the pair's first pixel; row pointer given
-template <int OX>
-__device__ __forceinline__ unsigned ring_pair(const uint32_t *row, int j)
+__global__ void __launch_bounds__(kFsLanes) k_fast_score(const DevParams *__restrict__ P, Src0 s0)
 {
-    if (OX % 2 == 0) return row[j + OX / 2];
-    const int a = j + (OX - 1) / 2;                 // floor division for odd OX of either sign
-    return __funnelshift_r(row[a], row[a + 1], 16);
+    __shared__ uint32_t tile[(kFsMaxRows + 6) * kFsPitch];
+    const uint32_t wk = P->fscore_work[blockIdx.x];
+    const int level = wk >> 24, tyi = (wk >> 12) & 0xfff, txi = wk & 0xfff, frame = blockIdx.y;
+    const LevelGeom &G = P->lv[level];
+    const int trows = G.fs_tile_rows;
+    const int xs = (kEdge - 1) + txi * (2 * kFsLanes);            // even image column of pair 0 (the region starts at 19)
+    const int y0 = kEdge + tyi * trows;
+    const int nrows = min(trows, G.y_end - y0);                    // centre rows of this tile
+    const int tid = threadIdx.x;
+    int sp;
+    const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
+    // ---- stage rows y0-3 .. y0+nrows+2, pixels xs-4 .. xs+131 as 16-bit lanes (tile pixel u = x - xs + 4)
+    {
+        const int xb = (xs - 4) & ~3;                              // == xs - 6: the region starts at an odd column
+        const int w0 = (xb - (xs - 4)) >> 1;                       // tile word of the first global word: -1
+        constexpr int NW = (2 * (kFsLanes + 4) + 2 + 3) / 4;       // global words per row
+        const int xmaxw = (sp >> 2) - 1;                           // last whole word inside the row pitch
+        const int srows = nrows + 6;
+        for (int i = tid; i < srows * NW; i += kFsLanes) {
+            const int r = i / NW, c = i - r * NW;
+            const int gy = min(y0 - 3 + r, G.h - 1);
+            const int gw = min((xb >> 2) + c, xmaxw);
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)gy * sp) + gw);
+            const int wi = w0 + 2 * c;
+            uint32_t *d = tile + r * kFsPitch + wi;
+            if ((unsigned)wi < (unsigned)(kFsLanes + 4)) d[0] = __byte_perm(v, 0, 0x4140);
+            if ((unsigned)(wi + 1) < (unsigned)(kFsLanes + 4)) d[1] = __byte_perm(v, 0, 0x4342);
+        }
+    }
+    __syncthreads();
+    const int x = xs + 2 * tid;                                    // first pixel of this lane's pair
+    if (x >= G.x_end) return;
+    const bool in0 = x >= kEdge, in1 = x + 1 < G.x_end;            // pixel inside the detection region?
+    const int th = min(P->min_th, P->ini_th);                      // scores below both thresholds are never needed
+    uint8_t *out = P->smap + (long long)frame * P->pyr_frame_bytes + G.img_off + x;
+
+    // window slot r%7 holds tile row r: a[.][0..2] = pairs at dx -2,0,+2 ; o[.][0..3] = pairs at dx -3,-1,+1,+3
+    unsigned a[7][3], o[7][4];
+    const uint32_t *col = tile + tid + 2;                          // word of this lane's own pair in row 0
+#define FS_LOAD(slot, r)                                                                        \
+    {                                                                                           \
+        const uint32_t *q = col + (r) * kFsPitch;                                               \
+        const unsigned w0_ = q[-2], w1_ = q[-1], w2_ = q[0], w3_ = q[1], w4_ = q[2];            \
+        a[slot][0] = w1_; a[slot][1] = w2_; a[slot][2] = w3_;                                   \
+        o[slot][0] = __funnelshift_r(w0_, w1_, 16); o[slot][1] = __funnelshift_r(w1_, w2_, 16); \
+        o[slot][2] = __funnelshift_r(w2_, w3_, 16); o[slot][3] = __funnelshift_r(w3_, w4_, 16); \
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) FS_LOAD(r, r)
+    for (int g = 0; g < nrows; g += 7) {
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int y = g + u;                                   // centre row (tile row y+3); slot of tile row r is r % 7
+            if (y < nrows) {
+                FS_LOAD((u + 6) % 7, y + 6)
+                constexpr int dummy = 0; (void)dummy;
+                const int sc = (u + 3) % 7, sp3 = (u + 6) % 7, sp2 = (u + 5) % 7, sp1 = (u + 4) % 7;
+                const int sm1 = (u + 2) % 7, sm2 = (u + 1) % 7, sm3 = u % 7;
+                // min/max commute with subtracting the centre: min_arc(ring - c) = min_arc(ring) - c
+                const unsigned cc = a[sc][1];
+                unsigned e[16];
+                e[0] = a[sp3][1]; e[1] = o[sp3][2]; e[15] = o[sp3][1];
+                e[2] = a[sp2][2]; e[14] = a[sp2][0];
+                e[3] = o[sp1][3]; e[13] = o[sp1][0];
+                e[4] = o[sc][3];  e[12] = o[sc][0];
+                e[5] = o[sm1][3]; e[11] = o[sm1][0];
+                e[6] = a[sm2][2]; e[10] = a[sm2][0];
+                e[7] = o[sm3][2]; e[8] = a[sm3][1]; e[9] = o[sm3][1];
+                unsigned lo3[16], hi3[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    lo3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+                    hi3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+                }
+                unsigned lo9[16], hi9[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    lo9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+                    hi9[k] = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+                }
+                unsigned bm[5], dm[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    bm[k] = __vimax3_s16x2(lo9[3 * k], lo9[3 * k + 1], lo9[3 * k + 2]);
+                    dm[k] = __vimin3_s16x2(hi9[3 * k], hi9[3 * k + 1], hi9[3 * k + 2]);
+                }
+                const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bm[0], bm[1], bm[2]), __vimax3_s16x2(bm[3], bm[4], lo9[15]), lo9[15]);
+                const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dm[0], dm[1], dm[2]), __vimin3_s16x2(dm[3], dm[4], hi9[15]), hi9[15]);
+                // bright = maxmin - c, dark = c - minmax; a +256 bias per lane keeps both halves positive, so plain
+                // 32-bit adds never borrow across the two lanes
+                const unsigned best = __vmaxs2(maxmin + 0x01000100u - cc, cc + 0x01000100u - minmax);
+                const int s0v = (int)(best & 0xffff) - 257, s1v = (int)(best >> 16) - 257;
+                const unsigned b0 = (in0 && s0v >= th) ? (unsigned)s0v : 0u, b1 = (in1 && s1v >= th) ? (unsigned)s1v : 0u;
+                *reinterpret_cast<uint16_t *>(out + (long long)(y0 + y) * G.pitch) = (uint16_t)(b0 | b1 << 8);
+            }
+        }
+    }
+#undef FS_LOAD
 }
 
+// Per cell: non-max suppression inside the cell rectangle + threshold choice + emission.
+// One warp per cell.  The cell's part of the score map is copied with aligned word loads
+// (bytes of neighbouring cells masked to 0) into a private shared-memory map with a zero
+// border; non-zero scores are ballot-compacted into a list and only those are tested.
 template <int CELL>
-__global__ void __launch_bounds__(FastCfg<CELL>::THREADS) k_fast(const DevParams *__restrict__ P, Src0 s0, int work_off)
-{
-    using C = FastCfg<CELL>;
-    extern __shared__ __align__(16) uint8_t fast_smem[];
-    __shared__ int s_emitted;
-    uint32_t *tile = reinterpret_cast<uint32_t *>(fast_smem);                   // [TH][TPW] pixel pairs as 16x2
-    uint8_t *smap = fast_smem + C::TH * C::TPW * 4;                             // [SH][SP] corner scores
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.y;
-    uint16_t *wlist = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP) + warp * C::WL;   // this warp's pairs to score
+struct FcCfg {
+    static constexpr int WARPS = CELL <= 44 ? 8 : 4;
+    static constexpr int SP = 4 * ((CELL + 3 + 3) / 4 + 2);       // a zero word left of the span, the cell (+ word misalignment), a zero word right
+    static constexpr int SH = CELL + 2;
+    static constexpr int LIST = CELL * CELL;
+    static constexpr int WARP_BYTES = SH * SP + LIST * 2;
+    static constexpr int SMEM = WARPS * WARP_BYTES;
+};
 
-    const uint32_t wk = P->fast_work[work_off + blockIdx.x];
+template <int CELL>
+__global__ void __launch_bounds__(FcCfg<CELL>::WARPS * 32) k_fast_cells(const DevParams *__restrict__ P, int work_off, int work_end)
+{
+    using C = FcCfg<CELL>;
+    extern __shared__ __align__(16) uint8_t fc_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.y;
+    const int widx = work_off + blockIdx.x * C::WARPS + warp;
+    if (widx >= work_end) return;                                 // warp-uniform; no block barrier in this kernel
+    uint8_t *smap = fc_smem + (size_t)warp * C::WARP_BYTES;
+    uint16_t *list = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP);
+    const uint32_t wk = P->fast_work[widx];
     const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
     const LevelGeom &G = P->lv[level];
     const int x0 = kEdge + cj * G.w_cell, x1 = min(x0 + G.w_cell, G.x_end);
     const int y0 = kEdge + ci * G.h_cell, y1 = min(y0 + G.h_cell, G.y_end);
-    // pairs start at an even image column xs <= x0 so global words map onto whole tile words;
-    // dx' = x - xs runs over [0, dwp), of which [par, dwp) is the cell's detection area
-    const int par = x0 & 1, xs = x0 - par;
-    const int dwp = x1 - xs, dh = y1 - y0, np = (dwp + 1) >> 1;
-
-    // ---- stage rows [y0-3, y1+3) x pixels [xs-4, xs-4+2*TPW) as 16-bit lanes (tile pixel u = x - xs + 4)
-    {
-        int sp;
-        const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-        const int xb = (xs - 4) & ~3;
-        const int xlast = min(xs - 4 + 2 * C::TPW, G.w);                        // exclusive; stays inside the row
-        const int nwords = (xlast - xb + 3) >> 2, nrows = dh + 6;
-        const int w0 = (xb - (xs - 4)) >> 1;                                    // tile word of the first global word: 0 or -1
-        for (int i = tid; i < nrows * C::ROW_SLOTS; i += C::THREADS) {
-            const int r = i / C::ROW_SLOTS, c = i % C::ROW_SLOTS;
-            if (c < nwords) {
-                const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)(y0 - 3 + r) * sp + xb) + c);
-                const int wi = w0 + 2 * c;
-                uint32_t *d = tile + r * C::TPW + wi;
-                if ((unsigned)wi < (unsigned)C::TPW) d[0] = __byte_perm(v, 0, 0x4140);          // pixels 0,1 -> 16x2
-                if ((unsigned)(wi + 1) < (unsigned)C::TPW) d[1] = __byte_perm(v, 0, 0x4342);    // pixels 2,3
-            }
+    const int dh = y1 - y0;
+    const int xb = x0 & ~3, mis = x0 & 3, nw = (x1 - xb + 3) >> 2;   // words per cell row
+    const uint8_t *S = P->smap + (long long)frame * P->pyr_frame_bytes + G.img_off;
+    const unsigned lt = lanemask_lt();
+    uint32_t *smw = reinterpret_cast<uint32_t *>(smap);
+    constexpr int SPW = C::SP / 4;
+    // zero rows 0 and dh+1, and the words left / right of the loaded span in the rows between
+    for (int i = lane; i < 2 * SPW; i += 32) smw[(i < SPW ? 0 : (dh + 1) * SPW - SPW) + i] = 0;
+    for (int i = lane; i < 2 * dh; i += 32) { const int r = (i >> 1) + 1; smw[r * SPW + ((i & 1) ? nw + 1 : 0)] = 0; }
+    __syncwarp();
+    const int ini = P->ini_th;
+    int nl = 0;
+    const int nitems = dh * nw;
+    const float inv_nw = 1.0f / (float)nw;
+    for (int base = 0; base < nitems; base += 32) {
+        const int i = base + lane;
+        uint32_t v = 0;
+        int dy = 0, k = 0;
+        if (i < nitems) {
+            dy = (int)(((float)i + 0.5f) * inv_nw);
+            k = i - dy * nw;
+            v = __ldg(reinterpret_cast<const uint32_t *>(S + (long long)(y0 + dy) * G.pitch + xb) + k);
+            if (k == 0) v &= 0xffffffffu << (8 * mis);                          // bytes left of the cell
+            const int nvalid = x1 - (xb + 4 * k);                               // bytes of this word that belong to the cell
+            if (nvalid < 4) v &= (1u << (8 * nvalid)) - 1u;
+            smw[(dy + 1) * SPW + 1 + k] = v;                                    // cell pixel dx sits at byte column 4 + mis + dx
         }
-        for (int i = tid; i < (dh + 2) * (C::SP / 4); i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
-        if (tid == 0) s_emitted = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {                                           // list the corners at iniThFAST
+            const int sc = (v >> (8 * b)) & 0xff;
+            const unsigned m = __ballot_sync(0xffffffffu, sc >= ini);
+            if (sc >= ini) list[nl + __popc(m & lt)] = (uint16_t)(dy << 8 | (4 * k + b + 4));   // byte column inside the local map
+            nl += __popc(m);
+        }
     }
-    __syncthreads();
-
+    __syncwarp();
     uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
     uint32_t *cnt = P->cand_count + frame * P->nlevels + level;
-    const int npairs = np * dh;
-    const float inv_np = 1.0f / (float)np;
-    const unsigned lt = lanemask_lt();
-
-    int th = P->ini_th;
+    int th = ini;
     for (int pass = 0; pass < 2; ++pass) {
-        // ---- A: compass pre-test on every pair; survivors go to this warp's private list with a
-        //         polarity per pixel (1 = may be a bright corner, 2 = dark; 0 = cannot be a corner)
-        const unsigned kb = 0x00010001u * (unsigned)((-th) & 0xffff);       // ~c + kb = -(c + th + 1)
-        const unsigned kd = 0x00010001u * (unsigned)(th + 1);               // ~c + kd = -(c - th)
-        int nl = 0;
-        for (int base = warp * 32; base < npairs; base += C::THREADS) {
+        int emitted = 0;
+        for (int base = 0; base < nl; base += 32) {
+            bool keep = false;
+            int dy = 0, col = 0, sc = 0;
+            if (base + lane < nl) {
+                const int ent = list[base + lane];
+                dy = ent >> 8; col = ent & 0xff;
+                const uint8_t *q = smap + (dy + 1) * C::SP + col;
+                sc = q[0];
+                keep = sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
+                       sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                int slot = 0;
+                if (lane == 0) slot = (int)atomicAdd(cnt, (unsigned)__popc(m));
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (keep) {
+                    const uint32_t xr = (uint32_t)(xb + col - 4 - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
+                    const int at = slot + __popc(m & lt);
+                    if (at < G.cand_cap) cand[at] = xr | yr << 12 | (uint32_t)sc << 24;
+                }
+                emitted += __popc(m);
+            }
+        }
+        if (emitted > 0 || pass == 1 || P->min_th >= ini) break;
+        // nothing at iniThFAST: redo the cell at minThFAST (:812-816) -- list every stored score (all are >= minThFAST)
+        th = P->min_th;
+        nl = 0;
+        for (int base = 0; base < nitems; base += 32) {
             const int i = base + lane;
-            unsigned bright = 0, dark = 0;
-            int dy = 0, p = 0;
-            if (i < npairs) {
-                dy = (int)(((float)i + 0.5f) * inv_np);
-                p = i - dy * np;
-                const uint32_t *row = tile + (dy + 3) * C::TPW;
-                const int j = p + 2;
-                const unsigned nc = ~row[j];
-                const unsigned nb = add16x2(nc, kb), nd = add16x2(nc, kd);
-                const unsigned n = row[j - 3 * C::TPW], s = row[j + 3 * C::TPW];
-                const unsigned e = ring_pair<3>(row, j), w = ring_pair<-3>(row, j);
-                // sign bit clear in ring+nb  <=> ring > c+t ; sign bit set in ring+nd <=> ring < c-t
-                const unsigned bn = add16x2(n, nb), bs = add16x2(s, nb), be = add16x2(e, nb), bw = add16x2(w, nb);
-                const unsigned dn = add16x2(n, nd), ds = add16x2(s, nd), de = add16x2(e, nd), dwk = add16x2(w, nd);
-                const unsigned inside = (2 * p >= par ? 0x8000u : 0u) | (2 * p + 1 < dwp ? 0x80000000u : 0u);
-                bright = ~((bn & bs) | (be & bw)) & inside;
-                dark = (dn | ds) & (de | dwk) & inside;
-            }
-            const unsigned any = bright | dark, both = bright & dark;
-            const unsigned m = __ballot_sync(0xffffffffu, any != 0);
-            if (any) {
-                // primary entry: dark where flagged dark, else bright where flagged bright
-                const unsigned m0 = (dark & 0x8000u) ? 2u : ((bright & 0x8000u) ? 1u : 0u);
-                const unsigned m1 = (dark & 0x80000000u) ? 2u : ((bright & 0x80000000u) ? 1u : 0u);
-                wlist[nl + __popc(m & lt)] = (uint16_t)(p | dy << 6 | m0 << 12 | m1 << 14);
-            }
-            nl += __popc(m);
-            const unsigned m2 = __ballot_sync(0xffffffffu, both != 0);
-            if (m2) {                                                       // rare: a pixel passed the pre-test in both polarities
-                if (both) wlist[nl + __popc(m2 & lt)] = (uint16_t)(p | dy << 6 | ((both & 0x8000u) ? 1u : 0u) << 12 | ((both & 0x80000000u) ? 1u : 0u) << 14);
-                nl += __popc(m2);
+            uint32_t v = 0;
+            int dy = 0, k = 0;
+            if (i < nitems) { dy = (int)(((float)i + 0.5f) * inv_nw); k = i - dy * nw; v = smw[(dy + 1) * SPW + 1 + k]; }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int sc = (v >> (8 * b)) & 0xff;
+                const unsigned m = __ballot_sync(0xffffffffu, sc >= th);
+                if (sc >= th) list[nl + __popc(m & lt)] = (uint16_t)(dy << 8 | (4 * k + b + 4));
+                nl += __popc(m);
             }
         }
         __syncwarp();
-        // ---- B: exact scores of this warp's listed pairs.  Dark-polarity pixels are scored on inverted
-        //         intensities (255-v), which turns "max over arcs of min(ring - c)" into the dark score.
-        for (int base = 0; base < nl; base += 32) {
-            const int i = base + lane;
-            if (i < nl) {
-                const unsigned ent = wlist[i];
-                const int p = ent & 63, dy = (ent >> 6) & 63;
-                const unsigned m0 = (ent >> 12) & 3u, m1 = ent >> 14;
-                const unsigned xm = (m0 == 2u ? 0x000000ffu : 0u) | (m1 == 2u ? 0x00ff0000u : 0u);
-                const uint32_t *row = tile + (dy + 3) * C::TPW;
-                const int j = p + 2;
-                const unsigned negc = add16x2(~(row[j] ^ xm), 0x00010001u);
-                unsigned e[16];
-                {
-                    const uint32_t *r3 = row + 3 * C::TPW, *r2 = row + 2 * C::TPW, *r1 = row + C::TPW;
-                    const uint32_t *q1 = row - C::TPW, *q2 = row - 2 * C::TPW, *q3 = row - 3 * C::TPW;
-                    e[0] = r3[j];               e[1] = ring_pair<1>(r3, j);   e[15] = ring_pair<-1>(r3, j);
-                    e[2] = r2[j + 1];           e[14] = r2[j - 1];
-                    e[3] = ring_pair<3>(r1, j); e[13] = ring_pair<-3>(r1, j);
-                    e[4] = ring_pair<3>(row, j); e[12] = ring_pair<-3>(row, j);
-                    e[5] = ring_pair<3>(q1, j); e[11] = ring_pair<-3>(q1, j);
-                    e[6] = q2[j + 1];           e[10] = q2[j - 1];
-                    e[8] = q3[j];               e[7] = ring_pair<1>(q3, j);   e[9] = ring_pair<-1>(q3, j);
-                }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) e[k] = add16x2(e[k] ^ xm, negc);
-                unsigned t3[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) t3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) e[k] = __vimin3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
-                unsigned a[5];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) a[k] = __vimax3_s16x2(e[3 * k], e[3 * k + 1], e[3 * k + 2]);
-                const unsigned res = __vimax3_s16x2(__vimax3_s16x2(a[0], a[1], a[2]), __vimax3_s16x2(a[3], a[4], e[15]), e[15]);
-                const int s0v = (int)(short)(res & 0xffff) - 1, s1v = (int)(short)(res >> 16) - 1;
-                uint8_t *q = smap + (dy + 1) * C::SP + 2 * p + 1;
-                if (m0 && s0v >= th) q[0] = (uint8_t)s0v;
-                if (m1 && s1v >= th) q[1] = (uint8_t)s1v;
-            }
-        }
-        __syncthreads();
-        // ---- C: non-max suppression inside the cell rectangle (dense scan of the score map) + emission
-        for (int base = warp * 32; base < dh * (C::SP / 4); base += C::THREADS) {
-            const int i = base + lane;
-            uint32_t wv = 0;
-            int dy = 0, c4 = 0;
-            if (i < dh * (C::SP / 4)) {
-                dy = i / (C::SP / 4); c4 = (i - dy * (C::SP / 4)) * 4;
-                wv = *reinterpret_cast<const uint32_t *>(smap + (dy + 1) * C::SP + c4);
-            }
-            if (__ballot_sync(0xffffffffu, wv != 0) == 0) continue;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int sc = (wv >> (8 * k)) & 0xff;
-                bool keep = false;
-                if (sc) {
-                    const uint8_t *q = smap + (dy + 1) * C::SP + c4 + k;
-                    keep = sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
-                           sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1];
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (m) {
-                    int slot = 0;
-                    if (lane == 0) { slot = (int)atomicAdd(cnt, (unsigned)__popc(m)); s_emitted = 1; }
-                    slot = __shfl_sync(0xffffffffu, slot, 0);
-                    if (keep) {
-                        const uint32_t xr = (uint32_t)(xs + c4 + k - 1 - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
-                        const int at = slot + __popc(m & lt);
-                        if (at < G.cand_cap) cand[at] = xr | yr << 12 | (uint32_t)sc << 24;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (s_emitted || pass == 1 || P->min_th == th) break;
-        // nothing survived at iniThFAST: clear and redo the cell at minThFAST
-        th = P->min_th;
-        for (int i = tid; i < (dh + 2) * (C::SP / 4); i += C::THREADS) reinterpret_cast<uint32_t *>(smap)[i] = 0;
-        __syncthreads();
     }
 }
 
 cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls)
 {
+    if (hP.n_fast_work == 0) return cudaSuccess;
+    k_fast_score<<<dim3(hP.n_fscore_work, nframes), kFsLanes, 0, st>>>(dP, s0);
+    ls->launches++;
     if (n_small > 0) {
-        using C = FastCfg<38>;
-        cudaFuncSetAttribute(k_fast<38>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        k_fast<38><<<dim3(n_small, nframes), C::THREADS, C::SMEM, st>>>(dP, s0, 0);
+        using C = FcCfg<44>;
+        cudaFuncSetAttribute(k_fast_cells<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast_cells<44><<<dim3((n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, 0, n_small);
         ls->launches++;
     }
     if (hP.n_fast_work > n_small) {
-        using C = FastCfg<64>;
-        cudaFuncSetAttribute(k_fast<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        k_fast<64><<<dim3(hP.n_fast_work - n_small, nframes), C::THREADS, C::SMEM, st>>>(dP, s0, n_small);
+        using C = FcCfg<64>;
+        cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast_cells<64><<<dim3((hP.n_fast_work - n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, n_small, hP.n_fast_work);
         ls->launches++;
     }
     return cudaGetLastError();
@@ -604,22 +632,11 @@ __device__ __forceinline__ void bitonic_sort_desc(u64 *v, int n_pow2)
     }
 }
 
-// path code of one packed candidate: initial node, then the DivideNode child index per split
-__device__ __forceinline__ uint32_t path_code(uint32_t c, const LevelGeom &G)
+// path code of one packed candidate: initial node, then the DivideNode child index per split.
+// x and y halve independently, so the code is the OR of two host-built tables (host_tables.cpp).
+__device__ __forceinline__ uint32_t path_code(uint32_t c, const uint32_t *__restrict__ lut_x, const uint32_t *__restrict__ lut_y)
 {
-    const int x = c & 0xfff, y = (c >> 12) & 0xfff;
-    int r = (int)__fdiv_rn((float)x, G.h_x);                               // vpIniNodes[kp.pt.x/hX], :569
-    r = min(r, G.n_ini - 1);
-    int ulx = G.root_ul[r], brx = G.root_br[r], uly = 0, bry = G.region_h;
-    uint32_t code = (uint32_t)r;
-    for (int d = 0; d < G.depth; ++d) {
-        const int midx = ulx + ((brx - ulx + 1) >> 1), midy = uly + ((bry - uly + 1) >> 1);   // ceil(w/2), :483-484
-        const bool right = x >= midx, down = y >= midy;
-        if (right) ulx = midx; else brx = midx;
-        if (down) uly = midy; else bry = midy;
-        code = code << 2 | (uint32_t)down << 1 | (uint32_t)right;
-    }
-    return code;
+    return __ldg(lut_x + (c & 0xfff)) | __ldg(lut_y + ((c >> 12) & 0xfff));
 }
 
 __device__ __forceinline__ int lower_child(const uint32_t *codes, int lo, int hi, int shift, unsigned c)
@@ -669,6 +686,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)min(P->cand_count[frame * P->nlevels + level], (unsigned)G.cand_cap);
     const int N = G.n_feat, D = G.depth;
+    const uint32_t *lut_x = P->oct_lut + G.lut_off, *lut_y = lut_x + G.region_w;
 
     u64 *skey = reinterpret_cast<u64 *>(oct_smem);                 // careful-phase sort buffer
     int *nlo = reinterpret_cast<int *>(skey + skey_cap);
@@ -703,7 +721,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             const bool valid = i < c_hi;
             const unsigned vm = __ballot_sync(0xffffffffu, valid);
             if (valid) {
-                const unsigned d = (path_code(bufA[i], G) >> shift) & 255u;
+                const unsigned d = (path_code(bufA[i], lut_x, lut_y) >> shift) & 255u;
                 const unsigned peers = __match_any_sync(vm, d);
                 if ((peers & lt) == 0) wh[d] += __popc(peers);      // one leader per distinct digit
             }
@@ -729,7 +747,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             uint32_t key = 0; unsigned d = 0, peers = 0; uint32_t off = 0;
             if (valid) {
                 key = bufA[i];
-                d = (path_code(key, G) >> shift) & 255u;
+                d = (path_code(key, lut_x, lut_y) >> shift) & 255u;
                 peers = __match_any_sync(vm, d);
                 off = wh[d];
             }
@@ -744,7 +762,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         uint32_t *t = bufA; bufA = bufB; bufB = t;
     }
     uint32_t *keys = bufA, *codes = bufB;                           // sorted candidates and their path codes
-    for (int i = tid; i < n; i += THREADS) codes[i] = path_code(keys[i], G);
+    for (int i = tid; i < n; i += THREADS) codes[i] = path_code(keys[i], lut_x, lut_y);
     __syncthreads();
 
     // ---- roots, reverse list order (:553-585)
@@ -871,24 +889,21 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         if (!careful && size + 3 * nE > N) careful = true;
     }
 
-    // ---- winners, list order front->back == reverse array order (:740-760)
-    const int n_cols = G.n_cols, w_cell = G.w_cell, h_cell = G.h_cell;
-    for (int j = tid >> 5; j < size; j += WARPS) {
+    // ---- winners, list order front->back == reverse array order (:740-760): greatest response, first in the
+    //      reference's candidate order (cell row, cell column, y, x).  One thread per node.
+    const uint32_t *lut_cx = lut_y + G.region_h, *lut_cy = lut_cx + G.region_w;
+    for (int j = tid; j < size; j += THREADS) {
         const int nd = size - 1 - j;
         u64 best = 0;
-        for (int i = nlo[nd] + lane; i < nhi[nd]; i += 32) {
+        for (int i = nlo[nd]; i < nhi[nd]; ++i) {
             const uint32_t c = keys[i];
-            const u64 x = c & 0xfff, y = (c >> 12) & 0xfff, s = c >> 24;
-            const u64 order = ((u64)(((int)y - 3) / h_cell * n_cols + ((int)x - 3) / w_cell) << 24) | y << 12 | x;
-            const u64 v = s << 40 | (~order & 0xffffffffffull);
+            const uint32_t x = c & 0xfff, y = (c >> 12) & 0xfff;
+            const u64 order = (u64)(__ldg(lut_cy + y) + __ldg(lut_cx + x)) << 24 | (c & 0xffffffu);
+            const u64 v = (u64)(c >> 24) << 40 | (~order & 0xffffffffffull);
             best = v > best ? v : best;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
-        if (lane == 0) {
-            const u64 order = ~best & 0xffffffffffull;
-            stage[j] = (uint32_t)(order & 0xffffff) | (uint32_t)(best >> 40) << 24;
-        }
+        const u64 order = ~best & 0xffffffffffull;
+        stage[j] = (uint32_t)(order & 0xffffff) | (uint32_t)(best >> 40) << 24;
     }
     if (tid == 0) *kp_count = (uint32_t)size;
 }

@@ -21,6 +21,7 @@ struct DevParams {
     // buffers (batch-major: frame f at base + f*stride)
     uint8_t *pyr;                 // [F][pyr_frame_bytes]   levels 0..L-1, un-padded, pitch = lv.pitch
     uint8_t *blur;                // [F][pyr_frame_bytes]   7x7 sigma=2 blurred levels
+    uint8_t *smap;                // [F][pyr_frame_bytes]   FAST score map (score >= minThFAST, else 0), detection region only
     uint32_t *cand;               // [F][cand_frame_elems]  packed x | y<<12 | score<<24 (relative to (16,16))
     uint32_t *cand_count;         // [F][nlevels]
     uint32_t *kp_stage;           // [F][kp_frame_cap]      octree winners, packed like cand, list order per level
@@ -30,9 +31,11 @@ struct DevParams {
     uint8_t *out_desc;            // [F][kp_frame_cap][32]
     int *out_n;                   // [F]
     const ResizeTab *xtab, *ytab;
-    const uint32_t *fast_work;  int n_fast_work;
+    const uint32_t *fast_work;  int n_fast_work;       // one entry per visited FAST cell
+    const uint32_t *fscore_work; int n_fscore_work;    // one entry per 128 x fs_tile_rows score tile
     const uint32_t *blur_work;  int n_blur_work;
     const int8_t *pattern;        // 512 x (x,y)
+    const uint32_t *oct_lut;      // octree path-code / cell-order tables, LevelGeom::lut_off
 };
 
 // Level-0 source of the current batch (either the caller's device frames used in
