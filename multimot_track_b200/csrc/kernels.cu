@@ -55,10 +55,12 @@ __device__ __forceinline__ unsigned lanemask_lt()
 // memory with aligned 32-bit loads, so global traffic is coalesced and each source byte
 // is fetched once per tile.
 
-constexpr int kRzTW = 128, kRzTH = 16, kRzSrcWords = 68, kRzSrcRows = 36;
+constexpr int kRzTW = 128, kRzTH = 32, kRzSrcWords = 68, kRzSrcRows = 68;
 
-// One destination tile [x0, x0+128) x [y0, y_end) (y_end - y0 <= 16) of `level` from level-1.
-// Block-wide (256 threads as 32x8); contains two barriers, so call it uniformly.
+// One destination tile [x0, x0+128) x [y0, y_end) (y_end - y0 <= 32) of `level` from level-1.
+// Block-wide (256 threads as 32x8, 4 pixels x 4 rows per thread); contains two barriers, so call it uniformly.
+// No clamp is needed on the result: the two weights of an axis sum to at most 2049, so
+// ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) <= 1020 and (x + 2) >> 2 <= 255.
 __device__ __forceinline__ void resize_tile(const DevParams *__restrict__ P, const uint8_t *S, int sp, uint8_t *dst, int level,
                                             int x0, int y0, int y_end, uint32_t (*ssrc)[kRzSrcWords])
 {
@@ -68,32 +70,34 @@ __device__ __forceinline__ void resize_tile(const DevParams *__restrict__ P, con
     const int sx_lo = xt[x0].s0 & ~3, sx_hi = xt[xl].s1, sy_lo = yt[y0].s0, sy_hi = yt[yl].s1;
     const int nwords = ((sx_hi - sx_lo) >> 2) + 1, nrows = sy_hi - sy_lo + 1;
     __syncthreads();                                               // the previous tile is done with ssrc
-    for (int i = threadIdx.x + threadIdx.y * 32; i < nrows * nwords; i += 256) {
-        const int r = i / nwords, c = i - r * nwords;
-        // plain (coherent) load: in the fused kernel the source level was written by this CTA moments ago
-        ssrc[r][c] = *(reinterpret_cast<const uint32_t *>(S + (long long)(sy_lo + r) * sp + sx_lo) + c);
+    for (int r = threadIdx.y; r < nrows; r += 8) {
+        // plain (coherent) loads: in the fused kernel the source level was written by this CTA moments ago
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(S + (long long)(sy_lo + r) * sp + sx_lo);
+        for (int c = threadIdx.x; c < nwords; c += 32) ssrc[r][c] = row[c];
     }
     __syncthreads();
     const int x4 = x0 + threadIdx.x * 4;
     if (x4 >= D.w) return;
-    ResizeTab tx[4];
+    int o0[4], o1[4], c0[4], c1[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tx[k] = xt[x4 + k];                // tables are padded to a multiple of 4 entries
+    for (int k = 0; k < 4; ++k) {                                  // tables are padded to a multiple of 4 entries
+        const ResizeTab t = xt[x4 + k];
+        o0[k] = t.s0 - sx_lo; o1[k] = t.s1 - sx_lo; c0[k] = t.c0; c1[k] = t.c1;
+    }
     const uint8_t *sb = reinterpret_cast<const uint8_t *>(&ssrc[0][0]);
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
+    for (int rr = 0; rr < 4; ++rr) {
         const int y = y0 + threadIdx.y + 8 * rr;
         if (y >= y_end) break;
         const ResizeTab ty = yt[y];
-        const uint8_t *S0 = sb + (ty.s0 - sy_lo) * (kRzSrcWords * 4) - sx_lo, *S1 = sb + (ty.s1 - sy_lo) * (kRzSrcWords * 4) - sx_lo;
+        const uint8_t *S0 = sb + (ty.s0 - sy_lo) * (kRzSrcWords * 4), *S1 = sb + (ty.s1 - sy_lo) * (kRzSrcWords * 4);
         const int b0 = ty.c0, b1 = ty.c1;
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int h0 = S0[tx[k].s0] * tx[k].c0 + S0[tx[k].s1] * tx[k].c1;
-            const int h1 = S1[tx[k].s0] * tx[k].c0 + S1[tx[k].s1] * tx[k].c1;
-            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
+            const int h0 = S0[o0[k]] * c0[k] + S0[o1[k]] * c1[k];
+            const int h1 = S1[o0[k]] * c0[k] + S1[o1[k]] * c1[k];
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
             out |= (uint32_t)v << (8 * k);
         }
         *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;   // pitch % 64 == 0: padding absorbs the tail
@@ -207,7 +211,7 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
     bool all_staged = true;
     for (int l = 1; l < hP.nlevels; ++l) {
         const LevelGeom &D = hP.lv[l], &Sg = hP.lv[l - 1];
-        // staged path needs the source footprint of a 128x16 tile to fit 68 words x 36 rows
+        // staged path needs the source footprint of a 128x32 tile to fit 68 words x 68 rows
         const bool staged = (long long)Sg.w * (kRzTW + 2) <= (long long)D.w * (kRzSrcWords * 4 - 12) &&
                             (long long)Sg.h * (kRzTH + 2) <= (long long)D.h * (kRzSrcRows - 3);
         all_staged = all_staged && staged;
@@ -954,93 +958,122 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 constexpr int kOdWarps = 8;
+constexpr int kOdPitchW = 10;                     // patch pitch in words (37 + up to 3 bytes of misalignment)
 
 __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(const DevParams *__restrict__ P, Src0 s0)
 {
     __shared__ int8_t spat[1024];
-    for (int i = threadIdx.x; i < 1024; i += kOdWarps * 32) spat[i] = P->pattern[i];
-    __syncthreads();
+    __shared__ int s_prefix[kMaxLevels + 1], s_count[kMaxLevels];
+    __shared__ uint32_t spatch[kOdWarps][37 * kOdPitchW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kOdWarps + warp, frame = blockIdx.y;
-    const int L = P->nlevels;
-    // level of this staging slot and its row in the frame's output
-    int level = -1, out_idx = 0, total = 0;
-    const uint32_t *counts = P->kp_count + frame * L;
-    for (int l = 0; l < L; ++l) {
-        const int c = min((int)counts[l], P->lv[l].kp_cap);
-        const int rel = slot - P->lv[l].kp_off;
-        if (rel >= 0 && rel < c) { level = l; out_idx = total + rel; }
-        total += c;
+    const int frame = blockIdx.y, L = P->nlevels;
+    for (int i = threadIdx.x; i < 256; i += kOdWarps * 32) reinterpret_cast<uint32_t *>(spat)[i] = __ldg(reinterpret_cast<const uint32_t *>(P->pattern) + i);
+    if (threadIdx.x < 32) {                       // keypoints per level of this frame and their running offsets
+        int c = lane < L ? min((int)P->kp_count[frame * L + lane], P->lv[lane].kp_cap) : 0;
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < L) { s_count[lane] = c; s_prefix[lane] = x - c; }
+        if (lane == L - 1) s_prefix[L] = x;
     }
-    if (slot == 0 && lane == 0) P->out_n[frame] = total;
-    if (level < 0) return;
+    __syncthreads();
+    const int slot = blockIdx.x * kOdWarps + warp;
+    if (slot == 0 && lane == 0) P->out_n[frame] = s_prefix[L];
+    // level of this staging slot (slots are level-major with a fixed capacity per level)
+    int level = 0;
+    while (level + 1 < L && slot >= P->lv[level + 1].kp_off) ++level;
+    const int rel = slot - P->lv[level].kp_off;
+    if (rel >= s_count[level]) return;
+    const int out_idx = s_prefix[level] + rel;
 
     const LevelGeom &G = P->lv[level];
     const uint32_t c = P->kp_stage[(long long)frame * P->kp_frame_cap + slot];
     const int cx = (int)(c & 0xfff) + kMinBorder, cy = (int)((c >> 12) & 0xfff) + kMinBorder;
-    int sp;
-    const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-    // ---- IC_Angle
-    const int u = lane - 15;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const uint8_t *ctr = img + (long long)cy * sp + cx + u;
-        const int au = abs(u);
-        for (int v = -15; v <= 15; ++v) {
-            if (au <= P->umax[abs(v)]) {
-                const int val = ctr[(long long)v * sp];
-                m10 += u * val;
-                m01 += v * val;
-            }
-        }
-    }
-    m10 = warp_sum(m10);
-    m01 = warp_sum(m01);
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- steered rBRIEF on the blurred level
-    const uint8_t *bl = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off;
-    const int bp = G.pitch;
-    constexpr float kFactorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    const float ang = __fmul_rn(angle, kFactorPI);
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t *ctr = bl + (long long)cy * bp + cx;
-    const int8_t *pp = spat + lane * 32;
-    unsigned byte = 0;
+    uint32_t *patch = spatch[warp];
+    const uint8_t *pb = reinterpret_cast<const uint8_t *>(patch);
+    // ---- IC_Angle: stage the 31x31 neighbourhood with aligned word loads, then one column per lane
+    {
+        int sp;
+        const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
+        const int xa = (cx - 15) & ~3, nw = ((cx + 15 - xa) >> 2) + 1;          // <= 9 words
+        const uint8_t *src = img + (long long)(cy - 15) * sp + xa;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1], x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = ctr[r0 * bp + c0], t1 = ctr[r1 * bp + c1];
-        byte |= (unsigned)(t0 < t1) << k;
-    }
-    // gather 32 bytes -> 8 words -> two uint4 stores
-    const int q = lane & 7;
-    unsigned w = __shfl_sync(0xffffffffu, byte, 4 * q) | __shfl_sync(0xffffffffu, byte, 4 * q + 1) << 8 |
-                 __shfl_sync(0xffffffffu, byte, 4 * q + 2) << 16 | __shfl_sync(0xffffffffu, byte, 4 * q + 3) << 24;
-    const int h4 = (lane & 1) * 4;
-    uint4 v;
-    v.x = __shfl_sync(0xffffffffu, w, h4); v.y = __shfl_sync(0xffffffffu, w, h4 + 1);
-    v.z = __shfl_sync(0xffffffffu, w, h4 + 2); v.w = __shfl_sync(0xffffffffu, w, h4 + 3);
-    const long long row = (long long)frame * P->kp_frame_cap + out_idx;
-    if (lane < 2) reinterpret_cast<uint4 *>(P->out_desc + row * 32)[lane] = v;
-
-    // ---- cv::KeyPoint record (:837-847, :1098-1104)
-    if (lane < 7) {
-        float f;
-        switch (lane) {
-        case 0: f = __fmul_rn((float)cx, G.scale); break;
-        case 1: f = __fmul_rn((float)cy, G.scale); break;
-        case 2: f = G.kp_size; break;
-        case 3: f = angle; break;
-        case 4: f = (float)(c >> 24); break;
-        case 5: f = __int_as_float(level); break;
-        default: f = __int_as_float(-1); break;
+        for (int it = 0; it < 10; ++it) {
+            const int i = it * 32 + lane, r = i / kOdPitchW, k = i - r * kOdPitchW;
+            if (r < 31 && k < nw) patch[i] = __ldg(reinterpret_cast<const uint32_t *>(src + (long long)r * sp) + k);
         }
-        reinterpret_cast<float *>(P->out_kps + row)[lane] = f;
+        __syncwarp();
+        const int off = cx - 15 - xa;
+        const int u = lane - 15, au = abs(u);
+        // rows of this column inside the circular patch: |v| <= umax[|u|] (the patch is symmetric, :453-469)
+        const int vm = lane < 31 ? P->umax[au] : -1;
+        const uint8_t *col = pb + 15 * (kOdPitchW * 4) + off + lane;
+        int sum = 0, m01 = 0;
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) {
+            const int val = (v < 0 ? -v : v) <= vm ? (int)col[v * (kOdPitchW * 4)] : 0;
+            sum += val;
+            m01 += v * val;
+        }
+        int m10 = u * sum;
+        m10 = warp_sum(m10);
+        m01 = warp_sum(m01);
+        __syncwarp();
+        // ---- angle
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- steered rBRIEF: stage the 37x37 neighbourhood of the blurred level the same way
+        const uint8_t *bl = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off;
+        const int bp = G.pitch;
+        const int xb = (cx - 18) & ~3, nwb = ((cx + 18 - xb) >> 2) + 1;         // <= 10 words
+        const uint8_t *bsrc = bl + (long long)(cy - 18) * bp + xb;
+#pragma unroll
+        for (int it = 0; it < 12; ++it) {
+            const int i = it * 32 + lane, r = i / kOdPitchW, k = i - r * kOdPitchW;
+            if (r < 37 && k < nwb) patch[i] = __ldg(reinterpret_cast<const uint32_t *>(bsrc + (long long)r * bp) + k);
+        }
+        __syncwarp();
+        constexpr float kFactorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+        const float ang = __fmul_rn(angle, kFactorPI);
+        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        const uint8_t *ctr = pb + 18 * (kOdPitchW * 4) + (cx - 18 - xb) + 18;
+        const int8_t *pp = spat + lane * 32;
+        unsigned byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1], x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = ctr[r0 * (kOdPitchW * 4) + c0], t1 = ctr[r1 * (kOdPitchW * 4) + c1];
+            byte |= (unsigned)(t0 < t1) << k;
+        }
+        // gather 32 bytes -> 8 words -> two uint4 stores
+        const int q = lane & 7;
+        unsigned w = __shfl_sync(0xffffffffu, byte, 4 * q) | __shfl_sync(0xffffffffu, byte, 4 * q + 1) << 8 |
+                     __shfl_sync(0xffffffffu, byte, 4 * q + 2) << 16 | __shfl_sync(0xffffffffu, byte, 4 * q + 3) << 24;
+        const int h4 = (lane & 1) * 4;
+        uint4 v;
+        v.x = __shfl_sync(0xffffffffu, w, h4); v.y = __shfl_sync(0xffffffffu, w, h4 + 1);
+        v.z = __shfl_sync(0xffffffffu, w, h4 + 2); v.w = __shfl_sync(0xffffffffu, w, h4 + 3);
+        const long long row = (long long)frame * P->kp_frame_cap + out_idx;
+        if (lane < 2) reinterpret_cast<uint4 *>(P->out_desc + row * 32)[lane] = v;
+
+        // ---- cv::KeyPoint record (:837-847, :1098-1104)
+        if (lane < 7) {
+            float f;
+            switch (lane) {
+            case 0: f = __fmul_rn((float)cx, G.scale); break;
+            case 1: f = __fmul_rn((float)cy, G.scale); break;
+            case 2: f = G.kp_size; break;
+            case 3: f = angle; break;
+            case 4: f = (float)(c >> 24); break;
+            case 5: f = __int_as_float(level); break;
+            default: f = __int_as_float(-1); break;
+            }
+            reinterpret_cast<float *>(P->out_kps + row)[lane] = f;
+        }
     }
 }
 

@@ -108,9 +108,9 @@ int ensure_batch(orbx_handle *h, int nframes)
     free_batch_buffers(h);
     const Geometry &g = h->geo;
     const size_t F = (size_t)nframes, L = (size_t)g.nlevels;
-    CU(cudaMalloc(&h->d_pyr, F * g.pyr_frame_bytes));
-    CU(cudaMalloc(&h->d_blur, F * g.pyr_frame_bytes));
-    CU(cudaMalloc(&h->d_smap, F * g.pyr_frame_bytes));
+    CU(cudaMalloc(&h->d_pyr, F * g.pyr_frame_bytes + 256));       // +256: word-granular tile staging may read a few bytes past the last row
+    CU(cudaMalloc(&h->d_blur, F * g.pyr_frame_bytes + 256));
+    CU(cudaMalloc(&h->d_smap, F * g.pyr_frame_bytes + 256));
     CU(cudaMalloc(&h->d_cand, F * g.cand_frame_elems * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_sort, F * g.cand_frame_elems * 2 * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_cand_count, F * L * sizeof(uint32_t)));

@@ -51,7 +51,7 @@ struct LevelGeom {
     float kp_size;                   // (float)(int)(PATCH_SIZE*scale), :837
 };
 
-struct ResizeTab {                   // cv::resize INTER_LINEAR coefficients, one per dst column / row
+struct alignas(8) ResizeTab {        // cv::resize INTER_LINEAR coefficients, one per dst column / row (one 64-bit load)
     uint16_t s0, s1;                 // source indices (s1 clamped)
     int16_t c0, c1;                  // 11-bit fixed point weights
 };
