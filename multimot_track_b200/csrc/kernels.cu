@@ -557,11 +557,13 @@ __global__ void __launch_bounds__(FcCfg<CELL>::WARPS * 32) k_fast_cells(const De
     }
 }
 
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls)
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls,
+                        cudaEvent_t between)
 {
-    if (hP.n_fast_work == 0) return cudaSuccess;
+    if (hP.n_fast_work == 0) { if (between) cudaEventRecord(between, st); return cudaSuccess; }
     k_fast_score<<<dim3(hP.n_fscore_work, nframes), kFsLanes, 0, st>>>(dP, s0);
     ls->launches++;
+    if (between) cudaEventRecord(between, st);
     if (n_small > 0) {
         using C = FcCfg<44>;
         cudaFuncSetAttribute(k_fast_cells<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);

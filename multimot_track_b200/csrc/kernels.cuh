@@ -52,7 +52,8 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
 cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
                           int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_cells, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_cells, cudaStream_t st, LaunchStats *ls,
+                        cudaEvent_t between = nullptr);
 cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_pad_level(const uint8_t *src, int w, int h, int pitch, uint8_t *dst, int dst_pitch, cudaStream_t st, LaunchStats *ls);

@@ -187,17 +187,18 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     MARK(2);
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
     MARK(3);
-    CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_fast_small, st, &h->stats));
-    MARK(4);
-    CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
+    cudaEvent_t mid = prof ? h->ev[4] : nullptr;                   // between k_fast_score and k_fast_cells
+    CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_fast_small, st, &h->stats, mid));
     MARK(5);
-    CU(launch_orient_desc(h->d_params, P, s0, nframes, st, &h->stats));
+    CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
     MARK(6);
+    CU(launch_orient_desc(h->d_params, P, s0, nframes, st, &h->stats));
+    MARK(7);
     const size_t cap = (size_t)P.kp_frame_cap;
     CU(cudaMemcpyAsync(h->p_n, h->d_out_n, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_desc, h->d_out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, st));
-    MARK(7);
+    MARK(8);
 #undef MARK
     h->ev_valid = prof;
     h->pending = true; h->have_batch = true; h->last_nframes = nframes; h->last_src0 = s0;
@@ -585,7 +586,7 @@ extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const ui
 
 // ---------------------------------------------------------------- profiling
 
-static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h"};
+static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast_score", "fast_cells", "octree", "orient_desc", "d2h"};
 
 extern "C" const char *orbx_stage_name(int stage) { return stage >= 0 && stage < ORBX_NUM_STAGES ? kStageNames[stage] : ""; }
 

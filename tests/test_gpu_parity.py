@@ -221,3 +221,32 @@ def test_full_size_properties(orb, oracle_mod):
         m = orb.ORBmatcher(0.9, extractor=ext)
         idx, d1, _, _ = m.match(desc, desc, 100, 0.9)
         assert (d1 == 0).all() and (idx <= np.arange(len(desc))).all()
+
+
+def test_cpp_adapter_drop_in(orb, oracle_mod, tmp_path):
+    """The C++ adapter with the reference's class surface (multimot_track_b200/adapter), driven like
+    Frame::ExtractORB (src/Frame.cc:621), gives the oracle's keypoints, descriptors and mvImagePyramid."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "multimot_track_b200", "adapter", "adapter_demo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    img = synth(3, 375, 1242)
+    raw, out = tmp_path / "gray.raw", tmp_path / "out.bin"
+    raw.write_bytes(img.tobytes())
+    params = (2000, 1.2, 8, 20, 7)
+    subprocess.check_call([exe, str(raw), "1242", "375"] + [str(p) for p in params] + [str(out)])
+    blob = out.read_bytes()
+    n = int(np.frombuffer(blob, np.int32, 1)[0])
+    kps = np.frombuffer(blob, orb.KEYPOINT_DTYPE, n, 4)
+    desc = np.frombuffer(blob, np.uint8, n * 32, 4 + 28 * n).reshape(n, 32)
+    o = oracle_mod.Oracle(*params)
+    okps, odesc = o(img)
+    assert kps_equal_exact(kps, okps) and np.array_equal(kps["angle"], okps["angle"])
+    assert np.array_equal(desc, odesc)
+    off = 4 + 60 * n
+    for l in range(8):
+        w, h = (int(v) for v in np.frombuffer(blob, np.int32, 2, off)); off += 8
+        padded = np.frombuffer(blob, np.uint8, (w + 38) * (h + 38), off).reshape(h + 38, w + 38); off += (w + 38) * (h + 38)
+        assert np.array_equal(padded, o.level_padded(l)), l
