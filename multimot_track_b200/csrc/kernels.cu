@@ -445,14 +445,16 @@ __global__ void __launch_bounds__(kFsLanes) k_fast_score(const DevParams *__rest
 // Per cell: non-max suppression inside the cell rectangle + threshold choice + emission.
 // One warp per cell.  The cell's part of the score map is copied with aligned word loads
 // (bytes of neighbouring cells masked to 0) into a private shared-memory map with a zero
-// border; non-zero scores are ballot-compacted into a list and only those are tested.
+// border.  Each lane then scans its own words: a SWAR test finds the bytes that can reach
+// the threshold, only those get the 8-neighbour test.  Survivors collect in a per-warp
+// list that is flushed with one global atomic per cell.
 template <int CELL>
 struct FcCfg {
     static constexpr int WARPS = CELL <= 44 ? 8 : 4;
     static constexpr int SP = 4 * ((CELL + 3 + 3) / 4 + 2);       // a zero word left of the span, the cell (+ word misalignment), a zero word right
     static constexpr int SH = CELL + 2;
-    static constexpr int LIST = CELL * CELL;
-    static constexpr int WARP_BYTES = SH * SP + LIST * 2;
+    static constexpr int LIST = ((CELL + 1) / 2) * ((CELL + 1) / 2);   // NMS survivors of a CELL x CELL rectangle
+    static constexpr int WARP_BYTES = SH * SP + LIST * 4;
     static constexpr int SMEM = WARPS * WARP_BYTES;
 };
 
@@ -461,11 +463,12 @@ __global__ void __launch_bounds__(FcCfg<CELL>::WARPS * 32) k_fast_cells(const De
 {
     using C = FcCfg<CELL>;
     extern __shared__ __align__(16) uint8_t fc_smem[];
+    __shared__ int s_cnt[C::WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.y;
     const int widx = work_off + blockIdx.x * C::WARPS + warp;
     if (widx >= work_end) return;                                 // warp-uniform; no block barrier in this kernel
     uint8_t *smap = fc_smem + (size_t)warp * C::WARP_BYTES;
-    uint16_t *list = reinterpret_cast<uint16_t *>(smap + C::SH * C::SP);
+    uint32_t *list = reinterpret_cast<uint32_t *>(smap + C::SH * C::SP);
     const uint32_t wk = P->fast_work[widx];
     const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
     const LevelGeom &G = P->lv[level];
@@ -474,86 +477,68 @@ __global__ void __launch_bounds__(FcCfg<CELL>::WARPS * 32) k_fast_cells(const De
     const int dh = y1 - y0;
     const int xb = x0 & ~3, mis = x0 & 3, nw = (x1 - xb + 3) >> 2;   // words per cell row
     const uint8_t *S = P->smap + (long long)frame * P->pyr_frame_bytes + G.img_off;
-    const unsigned lt = lanemask_lt();
     uint32_t *smw = reinterpret_cast<uint32_t *>(smap);
     constexpr int SPW = C::SP / 4;
     // zero rows 0 and dh+1, and the words left / right of the loaded span in the rows between
     for (int i = lane; i < 2 * SPW; i += 32) smw[(i < SPW ? 0 : (dh + 1) * SPW - SPW) + i] = 0;
     for (int i = lane; i < 2 * dh; i += 32) { const int r = (i >> 1) + 1; smw[r * SPW + ((i & 1) ? nw + 1 : 0)] = 0; }
-    __syncwarp();
+    if (lane == 0) s_cnt[warp] = 0;
     const int ini = P->ini_th;
-    int nl = 0;
     const int nitems = dh * nw;
     const float inv_nw = 1.0f / (float)nw;
+    unsigned has_ini = 0;
     for (int base = 0; base < nitems; base += 32) {
         const int i = base + lane;
-        uint32_t v = 0;
-        int dy = 0, k = 0;
         if (i < nitems) {
-            dy = (int)(((float)i + 0.5f) * inv_nw);
-            k = i - dy * nw;
-            v = __ldg(reinterpret_cast<const uint32_t *>(S + (long long)(y0 + dy) * G.pitch + xb) + k);
+            const int dy = (int)(((float)i + 0.5f) * inv_nw), k = i - dy * nw;
+            uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(S + (long long)(y0 + dy) * G.pitch + xb) + k);
             if (k == 0) v &= 0xffffffffu << (8 * mis);                          // bytes left of the cell
             const int nvalid = x1 - (xb + 4 * k);                               // bytes of this word that belong to the cell
             if (nvalid < 4) v &= (1u << (8 * nvalid)) - 1u;
             smw[(dy + 1) * SPW + 1 + k] = v;                                    // cell pixel dx sits at byte column 4 + mis + dx
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {                                           // list the corners at iniThFAST
-            const int sc = (v >> (8 * b)) & 0xff;
-            const unsigned m = __ballot_sync(0xffffffffu, sc >= ini);
-            if (sc >= ini) list[nl + __popc(m & lt)] = (uint16_t)(dy << 8 | (4 * k + b + 4));   // byte column inside the local map
-            nl += __popc(m);
+            // any byte >= ini?  per-byte (b | ((b & 0x7f) + 0x80 - ini)) has bit 7 set iff b >= ini (1 <= ini <= 128)
+            has_ini |= (v | ((v & 0x7f7f7f7fu) + 0x01010101u * (unsigned)(128 - min(ini, 128)))) & 0x80808080u;
         }
     }
+    const bool any_ini = __any_sync(0xffffffffu, has_ini != 0);
     __syncwarp();
-    uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
-    uint32_t *cnt = P->cand_count + frame * P->nlevels + level;
-    int th = ini;
+    int th = (any_ini || P->min_th >= ini) ? ini : P->min_th;     // no score reaches iniThFAST: only minThFAST can emit
     for (int pass = 0; pass < 2; ++pass) {
-        int emitted = 0;
-        for (int base = 0; base < nl; base += 32) {
-            bool keep = false;
-            int dy = 0, col = 0, sc = 0;
-            if (base + lane < nl) {
-                const int ent = list[base + lane];
-                dy = ent >> 8; col = ent & 0xff;
-                const uint8_t *q = smap + (dy + 1) * C::SP + col;
-                sc = q[0];
-                keep = sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
-                       sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1];
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-                int slot = 0;
-                if (lane == 0) slot = (int)atomicAdd(cnt, (unsigned)__popc(m));
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (keep) {
-                    const uint32_t xr = (uint32_t)(xb + col - 4 - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
-                    const int at = slot + __popc(m & lt);
-                    if (at < G.cand_cap) cand[at] = xr | yr << 12 | (uint32_t)sc << 24;
-                }
-                emitted += __popc(m);
-            }
-        }
-        if (emitted > 0 || pass == 1 || P->min_th >= ini) break;
-        // nothing at iniThFAST: redo the cell at minThFAST (:812-816) -- list every stored score (all are >= minThFAST)
-        th = P->min_th;
-        nl = 0;
+        const unsigned kadd = 0x01010101u * (unsigned)(128 - min(th, 128));
         for (int base = 0; base < nitems; base += 32) {
             const int i = base + lane;
-            uint32_t v = 0;
-            int dy = 0, k = 0;
-            if (i < nitems) { dy = (int)(((float)i + 0.5f) * inv_nw); k = i - dy * nw; v = smw[(dy + 1) * SPW + 1 + k]; }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int sc = (v >> (8 * b)) & 0xff;
-                const unsigned m = __ballot_sync(0xffffffffu, sc >= th);
-                if (sc >= th) list[nl + __popc(m & lt)] = (uint16_t)(dy << 8 | (4 * k + b + 4));
-                nl += __popc(m);
+            if (i < nitems) {
+                const int dy = (int)(((float)i + 0.5f) * inv_nw), k = i - dy * nw;
+                const uint32_t v = smw[(dy + 1) * SPW + 1 + k];
+                unsigned hot = (v | ((v & 0x7f7f7f7fu) + kadd)) & 0x80808080u;      // bytes >= th
+                while (hot) {
+                    const int b = (__ffs(hot) - 1) >> 3;
+                    hot &= hot - 1;
+                    const int col = 4 * k + b + 4;
+                    const uint8_t *q = smap + (dy + 1) * C::SP + col;
+                    const int sc = q[0];
+                    if (sc >= th && sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
+                        sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1]) {       // (sc >= th: the SWAR test is exact only up to 128)
+                        const int at = atomicAdd(&s_cnt[warp], 1);
+                        const uint32_t xr = (uint32_t)(xb + col - 4 - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
+                        if (at < C::LIST) list[at] = xr | yr << 12 | (uint32_t)sc << 24;
+                    }
+                }
             }
         }
         __syncwarp();
+        const int n = min(s_cnt[warp], C::LIST);
+        if (n > 0 || pass == 1 || th != ini || P->min_th >= ini) {
+            if (n > 0) {                                          // one global atomic per cell, coalesced copy-out
+                uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
+                int slot = 0;
+                if (lane == 0) slot = (int)atomicAdd(P->cand_count + frame * P->nlevels + level, (unsigned)n);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                for (int i = lane; i < n; i += 32) if (slot + i < G.cand_cap) cand[slot + i] = list[i];
+            }
+            break;
+        }
+        th = P->min_th;                                            // nothing survived at iniThFAST: redo the cell at minThFAST (:812-816)
     }
 }
 
@@ -964,27 +949,27 @@ constexpr int kOdPitchW = 10;                     // patch pitch in words (37 + 
 
 __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(const DevParams *__restrict__ P, Src0 s0)
 {
-    __shared__ int8_t spat[1024];
-    __shared__ int s_prefix[kMaxLevels + 1], s_count[kMaxLevels];
+    __shared__ int8_t spat[1024];                 // pattern, transposed: component e (0..31) of byte-lane l at [e*32 + l]
+    __shared__ int s_prefix[kMaxLevels + 1], s_count[kMaxLevels], s_kpoff[kMaxLevels + 1];
     __shared__ uint32_t spatch[kOdWarps][37 * kOdPitchW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int frame = blockIdx.y, L = P->nlevels;
-    for (int i = threadIdx.x; i < 256; i += kOdWarps * 32) reinterpret_cast<uint32_t *>(spat)[i] = __ldg(reinterpret_cast<const uint32_t *>(P->pattern) + i);
+    for (int i = threadIdx.x; i < 1024; i += kOdWarps * 32) spat[(i & 31) * 32 + (i >> 5)] = P->pattern[i];
     if (threadIdx.x < 32) {                       // keypoints per level of this frame and their running offsets
         int c = lane < L ? min((int)P->kp_count[frame * L + lane], P->lv[lane].kp_cap) : 0;
         int x = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane < L) { s_count[lane] = c; s_prefix[lane] = x - c; }
-        if (lane == L - 1) s_prefix[L] = x;
+        if (lane < L) { s_count[lane] = c; s_prefix[lane] = x - c; s_kpoff[lane] = P->lv[lane].kp_off; }
+        if (lane == L - 1) { s_prefix[L] = x; s_kpoff[L] = 0x7fffffff; }
     }
     __syncthreads();
     const int slot = blockIdx.x * kOdWarps + warp;
     if (slot == 0 && lane == 0) P->out_n[frame] = s_prefix[L];
     // level of this staging slot (slots are level-major with a fixed capacity per level)
     int level = 0;
-    while (level + 1 < L && slot >= P->lv[level + 1].kp_off) ++level;
-    const int rel = slot - P->lv[level].kp_off;
+    while (slot >= s_kpoff[level + 1]) ++level;
+    const int rel = slot - s_kpoff[level];
     if (rel >= s_count[level]) return;
     const int out_idx = s_prefix[level] + rel;
 
@@ -998,11 +983,13 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(const DevParams *
         int sp;
         const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
         const int xa = (cx - 15) & ~3, nw = ((cx + 15 - xa) >> 2) + 1;          // <= 9 words
-        const uint8_t *src = img + (long long)(cy - 15) * sp + xa;
+        const int lr = lane / kOdPitchW, lk = lane - lr * kOdPitchW;           // lanes 0..29: 3 rows x 10 words per step
+        {
+            const uint8_t *src = img + (long long)(cy - 15 + lr) * sp + xa + 4 * lk;
+            const bool on = lane < 30 && lk < nw;
 #pragma unroll
-        for (int it = 0; it < 10; ++it) {
-            const int i = it * 32 + lane, r = i / kOdPitchW, k = i - r * kOdPitchW;
-            if (r < 31 && k < nw) patch[i] = __ldg(reinterpret_cast<const uint32_t *>(src + (long long)r * sp) + k);
+            for (int it = 0; it < 11; ++it, src += 3 * (long long)sp)
+                if (on && 3 * it + lr < 31) patch[it * 30 + lane] = __ldg(reinterpret_cast<const uint32_t *>(src));
         }
         __syncwarp();
         const int off = cx - 15 - xa;
@@ -1028,22 +1015,23 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(const DevParams *
         const uint8_t *bl = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off;
         const int bp = G.pitch;
         const int xb = (cx - 18) & ~3, nwb = ((cx + 18 - xb) >> 2) + 1;         // <= 10 words
-        const uint8_t *bsrc = bl + (long long)(cy - 18) * bp + xb;
+        {
+            const uint8_t *bsrc = bl + (long long)(cy - 18 + lr) * bp + xb + 4 * lk;
+            const bool on = lane < 30 && lk < nwb;
 #pragma unroll
-        for (int it = 0; it < 12; ++it) {
-            const int i = it * 32 + lane, r = i / kOdPitchW, k = i - r * kOdPitchW;
-            if (r < 37 && k < nwb) patch[i] = __ldg(reinterpret_cast<const uint32_t *>(bsrc + (long long)r * bp) + k);
+            for (int it = 0; it < 13; ++it, bsrc += 3 * (long long)bp)
+                if (on && 3 * it + lr < 37) patch[it * 30 + lane] = __ldg(reinterpret_cast<const uint32_t *>(bsrc));
         }
         __syncwarp();
         constexpr float kFactorPI = (float)(3.1415926535897932384626433832795 / 180.f);
         const float ang = __fmul_rn(angle, kFactorPI);
         const float a = (float)cos((double)ang), b = (float)sin((double)ang);
         const uint8_t *ctr = pb + 18 * (kOdPitchW * 4) + (cx - 18 - xb) + 18;
-        const int8_t *pp = spat + lane * 32;
+        const int8_t *pp = spat + lane;
         unsigned byte = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1], x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
+            const float x0 = (float)pp[(4 * k) * 32], y0 = (float)pp[(4 * k + 1) * 32], x1 = (float)pp[(4 * k + 2) * 32], y1 = (float)pp[(4 * k + 3) * 32];
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
