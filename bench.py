@@ -97,7 +97,7 @@ def algorithmic_bytes(level_sizes, C, K):
     """per-frame algorithmic bytes by stage (P = sum of level pixels, C candidates, K keypoints)."""
     px = [w * h for w, h in level_sizes]
     P, P0, Plast = sum(px), px[0], px[-1]
-    st = {"pyramid": P0 + (P - Plast) + P, "fast_score": P, "fast_cells": 8 * C, "octree": 8 * C + 12 * K,
+    st = {"pyramid": P0 + (P - Plast) + P, "fast": P + 8 * C, "octree": 8 * C + 12 * K,
           "orient_desc": min(749 * K, P) + 4 * K + min(512 * K, P) + 80 * K, "blur": 2 * P}
     st["total"] = sum(st.values())
     return st
@@ -274,7 +274,7 @@ def main():
     dom_bytes = alg[dom] * batch
     achieved = dom_bytes / (kernel_stages[dom] * 1e-3) / 1e9
     step_ms_single = sum(acc.values())
-    kname = {"pyramid": "k_resize (x%d levels)" % (nlev - 1), "fast_score": "k_fast_score", "fast_cells": "k_fast_cells",
+    kname = {"pyramid": "k_resize (x%d levels)" % (nlev - 1), "fast": "k_fast_fused",
              "octree": "k_octree", "orient_desc": "k_orient_desc", "blur": "k_blur"}[dom]
     traffic = None                      # dram__bytes_read+write per launch from the committed `ncu --set full` capture
     tf = os.path.join(ROOT, "profiles", "r1_traffic.json")

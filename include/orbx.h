@@ -205,9 +205,9 @@ int orbx_match_device(orbx_handle *h, const uint8_t *d_descA, int nA, const uint
 /* With profiling on, every submit brackets its stages with CUDA events on the
  * handle's stream; after the matching collect, orbx_get_stage_ms returns the device
  * time of each stage of that batch in milliseconds (stage i named orbx_stage_name(i):
- * "input", "pyramid", "blur", "fast_score", "fast_cells", "octree", "orient_desc", "d2h").  Returns the
+ * "input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h").  Returns the
  * number of stages.  Off by default (the events cost a few microseconds per batch). */
-#define ORBX_NUM_STAGES 8
+#define ORBX_NUM_STAGES 7
 int orbx_set_profiling(orbx_handle *h, int on);
 int orbx_get_stage_ms(orbx_handle *h, float *ms, int cap);
 const char *orbx_stage_name(int stage);

@@ -101,7 +101,7 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
         *err = msg; return ORBX_ERR_UNSUPPORTED;
     }
     g->width = width; g->height = height; g->nlevels = t.nlevels;
-    g->fast_work.clear(); g->blur_work.clear(); g->fscore_work.clear(); g->oct_lut.clear(); g->xtab.clear(); g->ytab.clear();
+    g->blur_work.clear(); g->ffast_work.clear(); g->oct_lut.clear(); g->xtab.clear(); g->ytab.clear();
     long long img_off = 0, cand_off = 0;
     int kp_off = 0;
     g->max_node_cap = g->max_feat = g->max_cand_cap = 0;
@@ -148,35 +148,18 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
         if (L.w_cell > 64 || L.h_cell > 64) {          // cannot happen for levels >= 62 px (cell < 60)
             *err = "internal: FAST cell larger than 64"; return ORBX_ERR_UNSUPPORTED;
         }
-        L.cell_work_off = (int)g->fast_work.size();
-        long long cap = 0;
+        L.cell_work_off = 0;
+        long long cap = 0;                           // worst case survivors of the cell-local NMS: ceil(w/2)*ceil(h/2) per cell
         for (int i = 0; i < L.rows_vis; ++i)
             for (int j = 0; j < L.cols_vis; ++j) {
                 const int x0 = kEdge + j * L.w_cell, x1 = std::min(x0 + L.w_cell, L.x_end);
                 const int y0 = kEdge + i * L.h_cell, y1 = std::min(y0 + L.h_cell, L.y_end);
                 if (x1 <= x0 || y1 <= y0) continue;
                 cap += (long long)((x1 - x0 + 1) / 2) * ((y1 - y0 + 1) / 2);
-                g->fast_work.push_back((uint32_t)l << 24 | (uint32_t)i << 12 | (uint32_t)j);
             }
         L.cand_cap = (int)cap;
         L.cand_off = cand_off;
         cand_off += (cap + 63) & ~63LL;
-
-        // ---- score tiles: 128 pixels x (a multiple of 7 rows, <= 42) over the detection region [19,x_end) x [19,y_end)
-        {
-            const int rh = L.y_end - kEdge, rw = L.x_end - (kEdge - 1);
-            if (rh > 0 && rw > 0) {
-                int nty = (rh + 34) / 35;
-                int rows = ((rh + nty - 1) / nty + 6) / 7 * 7;
-                if (rows > 42) rows = 42;
-                L.fs_tile_rows = rows;
-                nty = (rh + rows - 1) / rows;
-                const int ntx = (rw + 127) / 128;
-                for (int ty = 0; ty < nty; ++ty)
-                    for (int tx = 0; tx < ntx; ++tx)
-                        g->fscore_work.push_back((uint32_t)l << 24 | (uint32_t)ty << 12 | (uint32_t)tx);
-            } else L.fs_tile_rows = 7;
-        }
 
         // ---- octree roots (:543-560)
         const int ow = maxBX - minBX, oh = maxBY - minBY;
@@ -247,16 +230,22 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
             for (int tx = 0; tx < (L.w + kBlurTileW - 1) / kBlurTileW; ++tx)
                 g->blur_work.push_back((uint32_t)l << 24 | (uint32_t)ty << 12 | (uint32_t)tx);
     }
-    // small-cell levels first: k_fast_cells<44> handles those, k_fast_cells<64> the (rare, coarse) rest
+    // FAST jobs: one warp per cell row x (64 / w_cell) adjacent cells; levels with cells <= 44 px first (k_fast_fused<44>)
     {
         std::vector<uint32_t> small, large;
-        for (uint32_t wk : g->fast_work) {
-            const LevelGeom &L = g->lv[wk >> 24];
-            (L.w_cell <= 44 && L.h_cell <= 44 ? small : large).push_back(wk);
+        for (int l = 0; l < t.nlevels; ++l) {
+            const LevelGeom &L = g->lv[l];
+            const int cpw = std::max(1, 64 / L.w_cell);
+            for (int i = 0; i < L.rows_vis; ++i) {
+                const int y0 = kEdge + i * L.h_cell;
+                if (std::min(y0 + L.h_cell, L.y_end) <= y0) continue;
+                for (int j = 0; j < L.cols_vis; j += cpw)
+                    (L.w_cell <= 44 && L.h_cell <= 44 ? small : large).push_back((uint32_t)l << 24 | (uint32_t)i << 12 | (uint32_t)j);
+            }
         }
-        g->n_fast_small = (int)small.size();
-        g->fast_work = small;
-        g->fast_work.insert(g->fast_work.end(), large.begin(), large.end());
+        g->n_ffast_small = (int)small.size();
+        g->ffast_work = small;
+        g->ffast_work.insert(g->ffast_work.end(), large.begin(), large.end());
     }
     g->pyr_frame_bytes = img_off;
     g->cand_frame_elems = cand_off;

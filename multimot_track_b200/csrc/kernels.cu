@@ -322,85 +322,118 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 // The reference calls cv::FAST once per ~30-pixel cell with iniThFAST and again with
 // minThFAST when the cell stayed empty (:789-829).  The corner score (OpenCV
 // cornerScore<16>: the largest threshold at which the pixel is still a FAST-9 corner)
-// does not depend on the threshold or on the cell, and "corner at t" <=> score >= t, so
-// the work splits into
-//   k_fast_score  dense, cell-agnostic: score map S = (score >= minThFAST ? score : 0)
-//                 for the whole detection region of every level;
-//   k_fast_cells  per cell: non-max suppression restricted to the cell's own rectangle
-//                 (outside counts as 0, like cv::FAST on the cell sub-image), survivors
-//                 with S >= iniThFAST, or with S >= minThFAST if there were none.
-// k_fast_score works on pixel PAIRS held as 16x2 lanes so the packed-halfword integer
-// pipe does two pixels per instruction (VIADD.16x2, VIMNMX3.S16x2):
-//   bright = max_k min(e_k..e_k+8), dark = -min_k max(e_k..e_k+8), e_k = ring_k - centre,
-//   score = max(bright, dark) - 1.
-// Each lane owns one pair column and walks down the tile rows keeping the 7-row ring
-// neighbourhood in registers (5 shared-memory loads + 4 funnel shifts per new row).
+// does not depend on the threshold, and "corner at t" <=> score >= t, so one dense
+// scoring pass serves both thresholds.  Scores are computed on pixel PAIRS held as 16x2
+// lanes so the packed-halfword integer pipe does two pixels per instruction
+// (VIMNMX3.S16x2):  bright = max_k min(r_k..r_k+8) - c,  dark = c - min_k max(r_k..r_k+8)
+// over the 16 ring pixels r_k (min/max commute with subtracting the centre c),
+// score = max(bright, dark) - 1.  Each lane owns one pair column and walks down the rows
+// keeping the 7-row ring neighbourhood in registers (5 shared-memory loads + 4 funnel
+// shifts per new row).
 
-constexpr int kFsLanes = 64;                       // pair columns per CTA -> 128 pixels
-constexpr int kFsMaxRows = 42;                     // tile rows (a multiple of 7, chosen per level on the host)
-constexpr int kFsPitch = kFsLanes + 4 + 1;         // tile pitch in words: pairs -2 .. 65 (+1: odd pitch)
+// ---- score + per-cell NMS + threshold choice + emission in one kernel ---------------------------------------
+// One WARP per job = one cell row x up to two horizontally adjacent cells (<= 64 pixels = 32 pixel pairs, the
+// pairs start at the cell boundary).  The warp walks down the cell's rows; the
+// scores of the previous rows stay in registers, left / right neighbours come from the adjacent lanes by
+// shuffle, and neighbours that belong to another cell are masked to 0 (cv::FAST runs on the cell sub-image,
+// so pixels outside it do not take part in the non-max suppression).  Survivors with score >= min(ini,min)
+// go to a per-warp list; when the job's rows are done the cell decides iniThFAST vs minThFAST (:812-816).
+template <int CELL>
+struct FfCfg {
+    static constexpr int WARPS = 4;
+    static constexpr int PITCH = 37;                                   // tile words per row: pairs -2 .. 33, +1
+    static constexpr int ROWS = CELL + 6;
+    static constexpr int LIST = 2 * ((CELL + 1) / 2) * ((CELL + 1) / 2);   // NMS survivors of two CELL x CELL rectangles
+    static constexpr int WARP_WORDS = ROWS * PITCH + LIST;
+    static constexpr int SMEM = WARPS * WARP_WORDS * 4;
+};
 
-__global__ void __launch_bounds__(kFsLanes) k_fast_score(const DevParams *__restrict__ P, Src0 s0)
+template <int CELL>
+__global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const DevParams *__restrict__ P, Src0 s0, int work_off, int work_end)
 {
-    __shared__ uint32_t tile[(kFsMaxRows + 6) * kFsPitch];
-    const uint32_t wk = P->fscore_work[blockIdx.x];
-    const int level = wk >> 24, tyi = (wk >> 12) & 0xfff, txi = wk & 0xfff, frame = blockIdx.y;
+    using C = FfCfg<CELL>;
+    extern __shared__ __align__(16) uint32_t ff_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.y;
+    const int widx = work_off + blockIdx.x * C::WARPS + warp;
+    if (widx >= work_end) return;                                      // warp-uniform; the kernel has no block barrier
+    uint32_t *tile = ff_smem + (size_t)warp * C::WARP_WORDS;
+    uint32_t *list = tile + C::ROWS * C::PITCH;
+    const uint32_t wk = P->ffast_work[widx];
+    const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
     const LevelGeom &G = P->lv[level];
-    const int trows = G.fs_tile_rows;
-    const int xs = (kEdge - 1) + txi * (2 * kFsLanes);            // even image column of pair 0 (the region starts at 19)
-    const int y0 = kEdge + tyi * trows;
-    const int nrows = min(trows, G.y_end - y0);                    // centre rows of this tile
-    const int tid = threadIdx.x;
+    const int wc = G.w_cell;
+    const int ncell = min(max(1, 64 / wc), G.cols_vis - cj);
+    const int x0 = kEdge + cj * wc, x1 = min(x0 + ncell * wc, G.x_end);
+    const int y0 = kEdge + ci * G.h_cell, y1 = min(y0 + G.h_cell, G.y_end);
+    const int span = x1 - x0, nrows = y1 - y0;
     int sp;
     const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-    // ---- stage rows y0-3 .. y0+nrows+2, pixels xs-4 .. xs+131 as 16-bit lanes (tile pixel u = x - xs + 4)
+    // ---- stage rows y0-3 .. y1+2, pixels x0-4 .. x0+67 as 16-bit lanes (tile pixel u = x - x0 + 4)
     {
-        const int xb = (xs - 4) & ~3;                              // == xs - 6: the region starts at an odd column
-        const int w0 = (xb - (xs - 4)) >> 1;                       // tile word of the first global word: -1
-        constexpr int NW = (2 * (kFsLanes + 4) + 2 + 3) / 4;       // global words per row
-        const int xmaxw = (sp >> 2) - 1;                           // last whole word inside the row pitch
-        const int srows = nrows + 6;
-        for (int i = tid; i < srows * NW; i += kFsLanes) {
+        const int xb = (x0 - 4) & ~3, ush = xb - (x0 - 4);            // tile pixel of the first byte of global word 0: -3..0
+        const int xmaxw = (sp >> 2) - 1, srows = nrows + 6;
+        uint16_t *t16 = reinterpret_cast<uint16_t *>(tile);
+        constexpr int NW = 19;                                         // 72 pixels + 3 of misalignment
+        for (int i = lane; i < srows * NW; i += 32) {
             const int r = i / NW, c = i - r * NW;
-            const int gy = min(y0 - 3 + r, G.h - 1);
-            const int gw = min((xb >> 2) + c, xmaxw);
+            const int gy = min(y0 - 3 + r, G.h - 1), gw = min((xb >> 2) + c, xmaxw);
             const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)gy * sp) + gw);
-            const int wi = w0 + 2 * c;
-            uint32_t *d = tile + r * kFsPitch + wi;
-            if ((unsigned)wi < (unsigned)(kFsLanes + 4)) d[0] = __byte_perm(v, 0, 0x4140);
-            if ((unsigned)(wi + 1) < (unsigned)(kFsLanes + 4)) d[1] = __byte_perm(v, 0, 0x4342);
+            const int u = ush + 4 * c;
+            uint16_t *d = t16 + r * (2 * C::PITCH) + u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((unsigned)(u + k) < 72u) d[k] = (uint16_t)((v >> (8 * k)) & 0xff);
         }
     }
-    __syncthreads();
-    const int x = xs + 2 * tid;                                    // first pixel of this lane's pair
-    if (x >= G.x_end) return;
-    const bool in0 = x >= kEdge, in1 = x + 1 < G.x_end;            // pixel inside the detection region?
-    const int th = min(P->min_th, P->ini_th);                      // scores below both thresholds are never needed
-    uint8_t *out = P->smap + (long long)frame * P->pyr_frame_bytes + G.img_off + x;
+    __syncwarp();
+    // ---- per-lane constants: which of my two pixels are inside the job, and which neighbours share their cell
+    const int dx0 = 2 * lane, dx1 = dx0 + 1;
+    const bool in0 = dx0 < span, in1 = dx1 < span;
+    const int c0 = dx0 >= wc, c1 = dx1 >= wc;                          // cell (0/1) of my pixels
+    const unsigned in_mask = (in0 ? 0xffffu : 0u) | (in1 ? 0xffff0000u : 0u);
+    // Lv = (left neighbour of px0, px0 as left neighbour of px1); Rv = (px1 as right neighbour of px0, right neighbour of px1)
+    const unsigned mL = ((dx0 > 0 && (dx0 - 1 >= wc) == c0) ? 0xffffu : 0u) | ((c0 == c1) ? 0xffff0000u : 0u);
+    const unsigned mR = ((in1 && c0 == c1) ? 0xffffu : 0u) | ((dx1 + 1 < span && (dx1 + 1 >= wc) == c1) ? 0xffff0000u : 0u);
+    const int th_store = min(P->min_th, P->ini_th);
+    const unsigned thv = 0x00010001u * (unsigned)(th_store + 257);     // biased compare: best >= th + 257  <=>  score >= th
+    const unsigned lt = lanemask_lt();
+    int nl = 0;
+    unsigned T2 = 0, T1 = 0, U1 = 0, C1 = 0;                           // T/U/centre of rows y-2 and y-1 (0 outside the cell)
 
-    // window slot r%7 holds tile row r: a[.][0..2] = pairs at dx -2,0,+2 ; o[.][0..3] = pairs at dx -3,-1,+1,+3
     unsigned a[7][3], o[7][4];
-    const uint32_t *col = tile + tid + 2;                          // word of this lane's own pair in row 0
-#define FS_LOAD(slot, r)                                                                        \
+    const uint32_t *col = tile + lane + 2;
+#define FF_LOAD(slot, r)                                                                        \
     {                                                                                           \
-        const uint32_t *q = col + (r) * kFsPitch;                                               \
+        const uint32_t *q = col + (r) * C::PITCH;                                               \
         const unsigned w0_ = q[-2], w1_ = q[-1], w2_ = q[0], w3_ = q[1], w4_ = q[2];            \
         a[slot][0] = w1_; a[slot][1] = w2_; a[slot][2] = w3_;                                   \
         o[slot][0] = __funnelshift_r(w0_, w1_, 16); o[slot][1] = __funnelshift_r(w1_, w2_, 16); \
         o[slot][2] = __funnelshift_r(w2_, w3_, 16); o[slot][3] = __funnelshift_r(w3_, w4_, 16); \
     }
+    // finalize the non-max suppression of row `yy` whose centre is Cc, with max-of-3 of the rows above / below
+#define FF_NMS(yy, Tabove, Umid, Cc, Tbelow)                                                                     \
+    {                                                                                                            \
+        const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
+        const unsigned df = m8 + 0x01000100u - (Cc);              /* lane < 256 <=> centre > all 8 neighbours */ \
+        const bool k0 = !(df & 0x100u) && ((Cc) & 0xffffu), k1 = !(df & 0x01000000u) && ((Cc) >> 16);           \
+        const unsigned b0_ = __ballot_sync(0xffffffffu, k0), b1_ = __ballot_sync(0xffffffffu, k1);               \
+        if (b0_ | b1_) {                                                                                         \
+            const uint32_t yr = (uint32_t)(y0 + (yy) - kMinBorder) << 12;                                       \
+            if (k0) list[nl + __popc(b0_ & lt)] = (uint32_t)(x0 + dx0 - kMinBorder) | yr | ((Cc) & 0xffu) << 24; \
+            if (k1) list[nl + __popc(b0_) + __popc(b1_ & lt)] = (uint32_t)(x0 + dx1 - kMinBorder) | yr | (((Cc) >> 16) & 0xffu) << 24; \
+            nl += __popc(b0_) + __popc(b1_);                                                                     \
+        }                                                                                                        \
+    }
 #pragma unroll
-    for (int r = 0; r < 6; ++r) FS_LOAD(r, r)
+    for (int r = 0; r < 6; ++r) FF_LOAD(r, r)
     for (int g = 0; g < nrows; g += 7) {
 #pragma unroll
         for (int u = 0; u < 7; ++u) {
-            const int y = g + u;                                   // centre row (tile row y+3); slot of tile row r is r % 7
+            const int y = g + u;
             if (y < nrows) {
-                FS_LOAD((u + 6) % 7, y + 6)
-                constexpr int dummy = 0; (void)dummy;
+                FF_LOAD((u + 6) % 7, y + 6)
                 const int sc = (u + 3) % 7, sp3 = (u + 6) % 7, sp2 = (u + 5) % 7, sp1 = (u + 4) % 7;
                 const int sm1 = (u + 2) % 7, sm2 = (u + 1) % 7, sm3 = u % 7;
-                // min/max commute with subtracting the centre: min_arc(ring - c) = min_arc(ring) - c
                 const unsigned cc = a[sc][1];
                 unsigned e[16];
                 e[0] = a[sp3][1]; e[1] = o[sp3][2]; e[15] = o[sp3][1];
@@ -430,135 +463,73 @@ __global__ void __launch_bounds__(kFsLanes) k_fast_score(const DevParams *__rest
                 }
                 const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bm[0], bm[1], bm[2]), __vimax3_s16x2(bm[3], bm[4], lo9[15]), lo9[15]);
                 const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dm[0], dm[1], dm[2]), __vimin3_s16x2(dm[3], dm[4], hi9[15]), hi9[15]);
-                // bright = maxmin - c, dark = c - minmax; a +256 bias per lane keeps both halves positive, so plain
-                // 32-bit adds never borrow across the two lanes
-                const unsigned best = __vmaxs2(maxmin + 0x01000100u - cc, cc + 0x01000100u - minmax);
-                const int s0v = (int)(best & 0xffff) - 257, s1v = (int)(best >> 16) - 257;
-                const unsigned b0 = (in0 && s0v >= th) ? (unsigned)s0v : 0u, b1 = (in1 && s1v >= th) ? (unsigned)s1v : 0u;
-                *reinterpret_cast<uint16_t *>(out + (long long)(y0 + y) * G.pitch) = (uint16_t)(b0 | b1 << 8);
+                const unsigned best = __vmaxs2(maxmin + 0x01000100u - cc, cc + 0x01000100u - minmax);   // score + 257 per lane
+                // S = score where score >= th_store and the pixel is inside the job, else 0 (per 16-bit lane)
+                const unsigned ge = __vcmpges2(best, thv);                                                // 0xffff per lane that passes
+                const unsigned Cv = (best - 0x00010001u) & ge & in_mask & 0x00ff00ffu;                    // (score + 256) & 0xff == score; best >= 1: no borrow
+                // neighbours in the same row, masked to the pixels' own cells
+                const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
+                const unsigned Lv = __funnelshift_r(Pl, Cv, 16) & mL, Rv = __funnelshift_r(Cv, Pr, 16) & mR;
+                const unsigned T0 = __vimax3_s16x2(Lv, Cv, Rv), U0 = __vmaxs2(Lv, Rv);
+                if (y > 0) FF_NMS(y - 1, T2, U1, C1, T0)
+                T2 = T1; T1 = T0; U1 = U0; C1 = Cv;
             }
         }
     }
-#undef FS_LOAD
-}
-
-// Per cell: non-max suppression inside the cell rectangle + threshold choice + emission.
-// One warp per cell.  The cell's part of the score map is copied with aligned word loads
-// (bytes of neighbouring cells masked to 0) into a private shared-memory map with a zero
-// border.  Each lane then scans its own words: a SWAR test finds the bytes that can reach
-// the threshold, only those get the 8-neighbour test.  Survivors collect in a per-warp
-// list that is flushed with one global atomic per cell.
-template <int CELL>
-struct FcCfg {
-    static constexpr int WARPS = CELL <= 44 ? 8 : 4;
-    static constexpr int SP = 4 * ((CELL + 3 + 3) / 4 + 2);       // a zero word left of the span, the cell (+ word misalignment), a zero word right
-    static constexpr int SH = CELL + 2;
-    static constexpr int LIST = ((CELL + 1) / 2) * ((CELL + 1) / 2);   // NMS survivors of a CELL x CELL rectangle
-    static constexpr int WARP_BYTES = SH * SP + LIST * 4;
-    static constexpr int SMEM = WARPS * WARP_BYTES;
-};
-
-template <int CELL>
-__global__ void __launch_bounds__(FcCfg<CELL>::WARPS * 32) k_fast_cells(const DevParams *__restrict__ P, int work_off, int work_end)
-{
-    using C = FcCfg<CELL>;
-    extern __shared__ __align__(16) uint8_t fc_smem[];
-    __shared__ int s_cnt[C::WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.y;
-    const int widx = work_off + blockIdx.x * C::WARPS + warp;
-    if (widx >= work_end) return;                                 // warp-uniform; no block barrier in this kernel
-    uint8_t *smap = fc_smem + (size_t)warp * C::WARP_BYTES;
-    uint32_t *list = reinterpret_cast<uint32_t *>(smap + C::SH * C::SP);
-    const uint32_t wk = P->fast_work[widx];
-    const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
-    const LevelGeom &G = P->lv[level];
-    const int x0 = kEdge + cj * G.w_cell, x1 = min(x0 + G.w_cell, G.x_end);
-    const int y0 = kEdge + ci * G.h_cell, y1 = min(y0 + G.h_cell, G.y_end);
-    const int dh = y1 - y0;
-    const int xb = x0 & ~3, mis = x0 & 3, nw = (x1 - xb + 3) >> 2;   // words per cell row
-    const uint8_t *S = P->smap + (long long)frame * P->pyr_frame_bytes + G.img_off;
-    uint32_t *smw = reinterpret_cast<uint32_t *>(smap);
-    constexpr int SPW = C::SP / 4;
-    // zero rows 0 and dh+1, and the words left / right of the loaded span in the rows between
-    for (int i = lane; i < 2 * SPW; i += 32) smw[(i < SPW ? 0 : (dh + 1) * SPW - SPW) + i] = 0;
-    for (int i = lane; i < 2 * dh; i += 32) { const int r = (i >> 1) + 1; smw[r * SPW + ((i & 1) ? nw + 1 : 0)] = 0; }
-    if (lane == 0) s_cnt[warp] = 0;
-    const int ini = P->ini_th;
-    const int nitems = dh * nw;
-    const float inv_nw = 1.0f / (float)nw;
-    unsigned has_ini = 0;
-    for (int base = 0; base < nitems; base += 32) {
-        const int i = base + lane;
-        if (i < nitems) {
-            const int dy = (int)(((float)i + 0.5f) * inv_nw), k = i - dy * nw;
-            uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(S + (long long)(y0 + dy) * G.pitch + xb) + k);
-            if (k == 0) v &= 0xffffffffu << (8 * mis);                          // bytes left of the cell
-            const int nvalid = x1 - (xb + 4 * k);                               // bytes of this word that belong to the cell
-            if (nvalid < 4) v &= (1u << (8 * nvalid)) - 1u;
-            smw[(dy + 1) * SPW + 1 + k] = v;                                    // cell pixel dx sits at byte column 4 + mis + dx
-            // any byte >= ini?  per-byte (b | ((b & 0x7f) + 0x80 - ini)) has bit 7 set iff b >= ini (1 <= ini <= 128)
-            has_ini |= (v | ((v & 0x7f7f7f7fu) + 0x01010101u * (unsigned)(128 - min(ini, 128)))) & 0x80808080u;
-        }
-    }
-    const bool any_ini = __any_sync(0xffffffffu, has_ini != 0);
+    FF_NMS(nrows - 1, T2, U1, C1, 0u)
+#undef FF_LOAD
+#undef FF_NMS
     __syncwarp();
-    int th = (any_ini || P->min_th >= ini) ? ini : P->min_th;     // no score reaches iniThFAST: only minThFAST can emit
-    for (int pass = 0; pass < 2; ++pass) {
-        const unsigned kadd = 0x01010101u * (unsigned)(128 - min(th, 128));
-        for (int base = 0; base < nitems; base += 32) {
-            const int i = base + lane;
-            if (i < nitems) {
-                const int dy = (int)(((float)i + 0.5f) * inv_nw), k = i - dy * nw;
-                const uint32_t v = smw[(dy + 1) * SPW + 1 + k];
-                unsigned hot = (v | ((v & 0x7f7f7f7fu) + kadd)) & 0x80808080u;      // bytes >= th
-                while (hot) {
-                    const int b = (__ffs(hot) - 1) >> 3;
-                    hot &= hot - 1;
-                    const int col = 4 * k + b + 4;
-                    const uint8_t *q = smap + (dy + 1) * C::SP + col;
-                    const int sc = q[0];
-                    if (sc >= th && sc > q[-1] && sc > q[1] && sc > q[-C::SP - 1] && sc > q[-C::SP] && sc > q[-C::SP + 1] &&
-                        sc > q[C::SP - 1] && sc > q[C::SP] && sc > q[C::SP + 1]) {       // (sc >= th: the SWAR test is exact only up to 128)
-                        const int at = atomicAdd(&s_cnt[warp], 1);
-                        const uint32_t xr = (uint32_t)(xb + col - 4 - kMinBorder), yr = (uint32_t)(y0 + dy - kMinBorder);
-                        if (at < C::LIST) list[at] = xr | yr << 12 | (uint32_t)sc << 24;
-                    }
-                }
-            }
+    // ---- threshold choice per cell and emission
+    const int ini = P->ini_th, mn = P->min_th;
+    bool has0 = false, has1 = false;
+    for (int base = 0; base < nl; base += 32) {
+        const int i = base + lane;
+        bool a0 = false, a1 = false;
+        if (i < nl) {
+            const uint32_t c = list[i];
+            const bool second = (int)(c & 0xfff) + kMinBorder - x0 >= wc;
+            const bool strong = (int)(c >> 24) >= ini;
+            a0 = strong && !second; a1 = strong && second;
         }
-        __syncwarp();
-        const int n = min(s_cnt[warp], C::LIST);
-        if (n > 0 || pass == 1 || th != ini || P->min_th >= ini) {
-            if (n > 0) {                                          // one global atomic per cell, coalesced copy-out
-                uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
-                int slot = 0;
-                if (lane == 0) slot = (int)atomicAdd(P->cand_count + frame * P->nlevels + level, (unsigned)n);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                for (int i = lane; i < n; i += 32) if (slot + i < G.cand_cap) cand[slot + i] = list[i];
-            }
-            break;
+        has0 |= __any_sync(0xffffffffu, a0); has1 |= __any_sync(0xffffffffu, a1);
+    }
+    const int t0c = has0 ? ini : (mn < ini ? mn : 256), t1c = has1 ? ini : (mn < ini ? mn : 256);
+    uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
+    uint32_t *cnt = P->cand_count + frame * P->nlevels + level;
+    for (int base = 0; base < nl; base += 32) {
+        const int i = base + lane;
+        bool emit = false;
+        uint32_t c = 0;
+        if (i < nl) {
+            c = list[i];
+            const bool second = (int)(c & 0xfff) + kMinBorder - x0 >= wc;
+            emit = (int)(c >> 24) >= (second ? t1c : t0c);
         }
-        th = P->min_th;                                            // nothing survived at iniThFAST: redo the cell at minThFAST (:812-816)
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (m) {
+            int slot = 0;
+            if (lane == 0) slot = (int)atomicAdd(cnt, (unsigned)__popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            const int at = slot + __popc(m & lt);
+            if (emit && at < G.cand_cap) cand[at] = c;
+        }
     }
 }
 
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls,
-                        cudaEvent_t between)
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls)
 {
-    if (hP.n_fast_work == 0) { if (between) cudaEventRecord(between, st); return cudaSuccess; }
-    k_fast_score<<<dim3(hP.n_fscore_work, nframes), kFsLanes, 0, st>>>(dP, s0);
-    ls->launches++;
-    if (between) cudaEventRecord(between, st);
+    if (hP.n_ffast_work == 0) return cudaSuccess;
     if (n_small > 0) {
-        using C = FcCfg<44>;
-        cudaFuncSetAttribute(k_fast_cells<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        k_fast_cells<44><<<dim3((n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, 0, n_small);
+        using C = FfCfg<44>;
+        cudaFuncSetAttribute(k_fast_fused<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast_fused<44><<<dim3((n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small);
         ls->launches++;
     }
-    if (hP.n_fast_work > n_small) {
-        using C = FcCfg<64>;
-        cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        k_fast_cells<64><<<dim3((hP.n_fast_work - n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, n_small, hP.n_fast_work);
+    if (hP.n_ffast_work > n_small) {
+        using C = FfCfg<64>;
+        cudaFuncSetAttribute(k_fast_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast_fused<64><<<dim3((hP.n_ffast_work - n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, s0, n_small, hP.n_ffast_work);
         ls->launches++;
     }
     return cudaGetLastError();

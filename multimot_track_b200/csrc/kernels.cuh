@@ -21,7 +21,6 @@ struct DevParams {
     // buffers (batch-major: frame f at base + f*stride)
     uint8_t *pyr;                 // [F][pyr_frame_bytes]   levels 0..L-1, un-padded, pitch = lv.pitch
     uint8_t *blur;                // [F][pyr_frame_bytes]   7x7 sigma=2 blurred levels
-    uint8_t *smap;                // [F][pyr_frame_bytes]   FAST score map (score >= minThFAST, else 0), detection region only
     uint32_t *cand;               // [F][cand_frame_elems]  packed x | y<<12 | score<<24 (relative to (16,16))
     uint32_t *cand_count;         // [F][nlevels]
     uint32_t *kp_stage;           // [F][kp_frame_cap]      octree winners, packed like cand, list order per level
@@ -31,8 +30,7 @@ struct DevParams {
     uint8_t *out_desc;            // [F][kp_frame_cap][32]
     int *out_n;                   // [F]
     const ResizeTab *xtab, *ytab;
-    const uint32_t *fast_work;  int n_fast_work;       // one entry per visited FAST cell
-    const uint32_t *fscore_work; int n_fscore_work;    // one entry per 128 x fs_tile_rows score tile
+    const uint32_t *ffast_work; int n_ffast_work;      // k_fast_fused jobs: (level<<24 | cell_row<<12 | first cell col), 1-2 cells each
     const uint32_t *blur_work;  int n_blur_work;
     const int8_t *pattern;        // 512 x (x,y)
     const uint32_t *oct_lut;      // octree path-code / cell-order tables, LevelGeom::lut_off
@@ -52,8 +50,7 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
 cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
                           int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_cells, cudaStream_t st, LaunchStats *ls,
-                        cudaEvent_t between = nullptr);
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_jobs, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_pad_level(const uint8_t *src, int w, int h, int pitch, uint8_t *dst, int dst_pitch, cudaStream_t st, LaunchStats *ls);

@@ -29,10 +29,10 @@ struct orbx_handle {
     DevParams *d_params = nullptr;
     // geometry-sized device tables
     ResizeTab *d_xtab = nullptr, *d_ytab = nullptr;
-    uint32_t *d_fast_work = nullptr, *d_blur_work = nullptr, *d_fscore_work = nullptr, *d_oct_lut = nullptr;
+    uint32_t *d_blur_work = nullptr, *d_ffast_work = nullptr, *d_oct_lut = nullptr;
     int8_t *d_pattern = nullptr;
     // batch-sized device buffers
-    uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_smap = nullptr;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
     uint32_t *d_cand = nullptr, *d_cand_count = nullptr, *d_kp_stage = nullptr, *d_kp_count = nullptr;
     unsigned long long *d_sort = nullptr;
     orbx_keypoint *d_out_kps = nullptr;
@@ -80,21 +80,21 @@ template <typename T> void hfree(T *&p) { if (p) cudaFreeHost(p); p = nullptr; }
 
 void free_batch_buffers(orbx_handle *h)
 {
-    dfree(h->d_pyr); dfree(h->d_blur); dfree(h->d_smap); dfree(h->d_cand); dfree(h->d_cand_count); dfree(h->d_kp_stage);
+    dfree(h->d_pyr); dfree(h->d_blur); dfree(h->d_cand); dfree(h->d_cand_count); dfree(h->d_kp_stage);
     dfree(h->d_kp_count); dfree(h->d_sort); dfree(h->d_out_kps); dfree(h->d_out_desc); dfree(h->d_out_n);
     hfree(h->p_kps); hfree(h->p_desc); hfree(h->p_n);
     h->batch_cap = 0;
 }
 
-void free_geo_tables(orbx_handle *h) { dfree(h->d_xtab); dfree(h->d_ytab); dfree(h->d_fast_work); dfree(h->d_blur_work); dfree(h->d_fscore_work); dfree(h->d_oct_lut); }
+void free_geo_tables(orbx_handle *h) { dfree(h->d_xtab); dfree(h->d_ytab); dfree(h->d_blur_work); dfree(h->d_ffast_work); dfree(h->d_oct_lut); }
 
 int upload_params(orbx_handle *h)
 {
     DevParams &P = h->hp;
-    P.pyr = h->d_pyr; P.blur = h->d_blur; P.smap = h->d_smap; P.cand = h->d_cand; P.cand_count = h->d_cand_count;
+    P.pyr = h->d_pyr; P.blur = h->d_blur; P.cand = h->d_cand; P.cand_count = h->d_cand_count;
     P.kp_stage = h->d_kp_stage; P.kp_count = h->d_kp_count; P.sort_scratch = h->d_sort;
     P.out_kps = h->d_out_kps; P.out_desc = h->d_out_desc; P.out_n = h->d_out_n;
-    P.xtab = h->d_xtab; P.ytab = h->d_ytab; P.fast_work = h->d_fast_work; P.blur_work = h->d_blur_work; P.fscore_work = h->d_fscore_work; P.oct_lut = h->d_oct_lut;
+    P.xtab = h->d_xtab; P.ytab = h->d_ytab; P.blur_work = h->d_blur_work; P.ffast_work = h->d_ffast_work; P.oct_lut = h->d_oct_lut;
     P.pattern = h->d_pattern;
     CU(cudaMemcpyAsync(h->d_params, &P, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));      // hp is reused; keep it simple: params change rarely
@@ -110,7 +110,6 @@ int ensure_batch(orbx_handle *h, int nframes)
     const size_t F = (size_t)nframes, L = (size_t)g.nlevels;
     CU(cudaMalloc(&h->d_pyr, F * g.pyr_frame_bytes + 256));       // +256: word-granular tile staging may read a few bytes past the last row
     CU(cudaMalloc(&h->d_blur, F * g.pyr_frame_bytes + 256));
-    CU(cudaMalloc(&h->d_smap, F * g.pyr_frame_bytes + 256));
     CU(cudaMalloc(&h->d_cand, F * g.cand_frame_elems * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_sort, F * g.cand_frame_elems * 2 * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_cand_count, F * L * sizeof(uint32_t)));
@@ -150,15 +149,13 @@ int ensure_geometry(orbx_handle *h, int width, int height, int nframes)
     h->geo = g;
     CU(cudaMalloc(&h->d_xtab, std::max<size_t>(g.xtab.size(), 4) * sizeof(ResizeTab)));
     CU(cudaMalloc(&h->d_ytab, std::max<size_t>(g.ytab.size(), 4) * sizeof(ResizeTab)));
-    CU(cudaMalloc(&h->d_fast_work, std::max<size_t>(g.fast_work.size(), 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_blur_work, std::max<size_t>(g.blur_work.size(), 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&h->d_fscore_work, std::max<size_t>(g.fscore_work.size(), 1) * sizeof(uint32_t)));
     if (!g.xtab.empty()) CU(cudaMemcpy(h->d_xtab, g.xtab.data(), g.xtab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!g.ytab.empty()) CU(cudaMemcpy(h->d_ytab, g.ytab.data(), g.ytab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
-    if (!g.fast_work.empty()) CU(cudaMemcpy(h->d_fast_work, g.fast_work.data(), g.fast_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->d_ffast_work, std::max<size_t>(g.ffast_work.size(), 1) * sizeof(uint32_t)));
+    if (!g.ffast_work.empty()) CU(cudaMemcpy(h->d_ffast_work, g.ffast_work.data(), g.ffast_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&h->d_oct_lut, std::max<size_t>(g.oct_lut.size(), 1) * sizeof(uint32_t)));
     if (!g.oct_lut.empty()) CU(cudaMemcpy(h->d_oct_lut, g.oct_lut.data(), g.oct_lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (!g.fscore_work.empty()) CU(cudaMemcpy(h->d_fscore_work, g.fscore_work.data(), g.fscore_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!g.blur_work.empty()) CU(cudaMemcpy(h->d_blur_work, g.blur_work.data(), g.blur_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
     DevParams &P = h->hp;
@@ -167,7 +164,7 @@ int ensure_geometry(orbx_handle *h, int width, int height, int nframes)
     P.kp_frame_cap = g.kp_frame_cap; P.pyr_frame_bytes = g.pyr_frame_bytes; P.cand_frame_elems = g.cand_frame_elems;
     for (int l = 0; l < g.nlevels; ++l) { P.lv[l] = g.lv[l]; P.xtab_off[l] = g.xtab_off[l]; P.ytab_off[l] = g.ytab_off[l]; }
     for (int i = 0; i < 16; ++i) P.umax[i] = h->tab.umax[i];
-    P.n_fast_work = (int)g.fast_work.size(); P.n_blur_work = (int)g.blur_work.size(); P.n_fscore_work = (int)g.fscore_work.size();
+    P.n_blur_work = (int)g.blur_work.size(); P.n_ffast_work = (int)g.ffast_work.size();
     h->geo_valid = true;
     return ensure_batch(h, std::max(nframes, keep_cap));
 }
@@ -187,18 +184,17 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     MARK(2);
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
     MARK(3);
-    cudaEvent_t mid = prof ? h->ev[4] : nullptr;                   // between k_fast_score and k_fast_cells
-    CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_fast_small, st, &h->stats, mid));
-    MARK(5);
+    CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_ffast_small, st, &h->stats));
+    MARK(4);
     CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
-    MARK(6);
+    MARK(5);
     CU(launch_orient_desc(h->d_params, P, s0, nframes, st, &h->stats));
-    MARK(7);
+    MARK(6);
     const size_t cap = (size_t)P.kp_frame_cap;
     CU(cudaMemcpyAsync(h->p_n, h->d_out_n, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_desc, h->d_out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, st));
-    MARK(8);
+    MARK(7);
 #undef MARK
     h->ev_valid = prof;
     h->pending = true; h->have_batch = true; h->last_nframes = nframes; h->last_src0 = s0;
@@ -586,7 +582,7 @@ extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const ui
 
 // ---------------------------------------------------------------- profiling
 
-static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast_score", "fast_cells", "octree", "orient_desc", "d2h"};
+static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h"};
 
 extern "C" const char *orbx_stage_name(int stage) { return stage >= 0 && stage < ORBX_NUM_STAGES ? kStageNames[stage] : ""; }
 

@@ -29,7 +29,6 @@ struct LevelGeom {
     int cols_vis, rows_vis;          // cells actually visited (after the two `continue`s)
     int x_end, y_end;                // exclusive end of the detection area in level coordinates
     int cell_work_off;               // first entry of this level in the FAST work list
-    int fs_tile_rows;                // rows per k_fast_score tile (multiple of 7)
     // DistributeOctTree, :539-763
     int n_feat;                      // mnFeaturesPerLevel[level]
     int n_ini;                       // initial nodes
@@ -63,13 +62,12 @@ struct Geometry {
     long long cand_frame_elems = 0;  // candidate slots per frame
     int kp_frame_cap = 0;            // keypoint staging slots per frame == output capacity per frame
     int max_node_cap = 0, max_feat = 0, max_cand_cap = 0;
-    std::vector<uint32_t> fast_work; // (level<<24 | cell_row<<12 | cell_col), visited cells only; cells <= 44 px first
-    int n_fast_small = 0;            // entries of fast_work whose level has w_cell, h_cell <= 44
     std::vector<ResizeTab> xtab, ytab;   // concatenated per level (level 0 unused)
     int xtab_off[kMaxLevels], ytab_off[kMaxLevels];
     std::vector<uint32_t> blur_work; // (level<<24 | tile_y<<12 | tile_x)
+    std::vector<uint32_t> ffast_work; // k_fast_fused jobs (level<<24 | cell_row<<12 | first cell col); small-cell levels first
+    int n_ffast_small = 0;
     std::vector<uint32_t> oct_lut;   // per-level octree lookup tables (see LevelGeom::lut_off)
-    std::vector<uint32_t> fscore_work; // (level<<24 | tile_y<<12 | tile_x) of k_fast_score
 };
 
 struct Tables {                      // ORBextractor constructor, :410-470
