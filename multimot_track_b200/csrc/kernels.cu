@@ -368,21 +368,30 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const De
     const int span = x1 - x0, nrows = y1 - y0;
     int sp;
     const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-    // ---- stage rows y0-3 .. y1+2, pixels x0-4 .. x0+67 as 16-bit lanes (tile pixel u = x - x0 + 4)
+    // ---- stage rows y0-3 .. y1+2, pixels x0-4 .. x0+67 as 16-bit lanes (tile pixel u = x - x0 + 4).
+    //      A lane takes one aligned global word (4 pixels) and writes two whole tile words; when the cell starts
+    //      at an odd column the pairs straddle global words and the missing byte comes from the previous lane.
     {
         const int xb = (x0 - 4) & ~3, ush = xb - (x0 - 4);            // tile pixel of the first byte of global word 0: -3..0
         const int xmaxw = (sp >> 2) - 1, srows = nrows + 6;
-        uint16_t *t16 = reinterpret_cast<uint16_t *>(tile);
-        constexpr int NW = 19;                                         // 72 pixels + 3 of misalignment
-        for (int i = lane; i < srows * NW; i += 32) {
-            const int r = i / NW, c = i - r * NW;
-            const int gy = min(y0 - 3 + r, G.h - 1), gw = min((xb >> 2) + c, xmaxw);
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)gy * sp) + gw);
-            const int u = ush + 4 * c;
-            uint16_t *d = t16 + r * (2 * C::PITCH) + u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((unsigned)(u + k) < 72u) d[k] = (uint16_t)((v >> (8 * k)) & 0xff);
+        constexpr int NW = 20;                                         // 72 pixels + 3 of misalignment (+1 spare)
+        const bool odd = ush & 1;
+        const int c = lane;                                            // lanes 0..19: the words of one row
+        const int u = ush + 4 * c - (odd ? 1 : 0);                     // tile pixel of my first output pair (even)
+        const int gw = min((xb >> 2) + c, xmaxw);
+        uint32_t *d = tile + (u >> 1);
+        const bool st0 = lane < NW && (unsigned)u < 72u, st1 = lane < NW && (unsigned)(u + 2) < 72u;
+#pragma unroll 4
+        for (int r = 0; r < srows; ++r) {
+            const int gy = min(y0 - 3 + r, G.h - 1);
+            uint32_t v = 0;
+            if (lane < NW) v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)gy * sp) + gw);
+            const uint32_t pv = __shfl_up_sync(0xffffffffu, v, 1);
+            // even shift: pairs (b0,b1),(b2,b3); odd shift: pairs (prev.b3,b0),(b1,b2)
+            const uint32_t w_lo = odd ? (__byte_perm(pv, v, 0x0403) & 0x00ff00ffu) : __byte_perm(v, 0, 0x4140);
+            const uint32_t w_hi = odd ? __byte_perm(v, 0, 0x4241) : __byte_perm(v, 0, 0x4342);
+            if (st0) d[r * C::PITCH] = w_lo;
+            if (st1) d[r * C::PITCH + 1] = w_hi;
         }
     }
     __syncwarp();
