@@ -237,7 +237,12 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, kp, sum(h.launch_count for h in handles) - l0, (t0, t1)
+        nl = sum(h.launch_count for h in handles) - l0
+        if world > 1:                                  # our kernels launched by all ranks inside the timed region
+            c = torch.tensor([nl], dtype=torch.int64, device="cuda")
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            nl = int(c.item())
+        return ms, kp, nl, (t0, t1)
 
     # ---- value: device-resident inputs
     sampler = ClockSampler(local)
