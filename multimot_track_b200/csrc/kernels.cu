@@ -57,10 +57,44 @@ __device__ __forceinline__ unsigned lanemask_lt()
 
 constexpr int kRzTW = 128, kRzTH = 32, kRzSrcWords = 68, kRzSrcRows = 68;
 
-// One destination tile [x0, x0+128) x [y0, y_end) (y_end - y0 <= 32) of `level` from level-1.
-// Block-wide (256 threads as 32x8, 4 pixels x 4 rows per thread); contains two barriers, so call it uniformly.
+// Rows [y0, y_end) x columns [x0, x0+128) of `level` from a staged source window: sb points at source pixel
+// (sx_lo, sy_lo), row pitch `spitch` bytes.  256 threads as 32x8, 4 pixels x 4 rows per thread.
 // No clamp is needed on the result: the two weights of an axis sum to at most 2049, so
 // ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) <= 1020 and (x + 2) >> 2 <= 255.
+__device__ __forceinline__ void resize_rows(const DevParams *__restrict__ P, int level, const uint8_t *sb, int spitch, int sx_lo, int sy_lo,
+                                            int x0, int y0, int y_end, uint8_t *dst)
+{
+    const LevelGeom &D = P->lv[level];
+    const ResizeTab *xt = P->xtab + P->xtab_off[level], *yt = P->ytab + P->ytab_off[level];
+    const int x4 = x0 + threadIdx.x * 4;
+    if (x4 >= D.w) return;
+    int o0[4], o1[4], c0[4], c1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                  // tables are padded to a multiple of 4 entries
+        const ResizeTab t = xt[x4 + k];
+        o0[k] = t.s0 - sx_lo; o1[k] = t.s1 - sx_lo; c0[k] = t.c0; c1[k] = t.c1;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int y = y0 + threadIdx.y + 8 * rr;
+        if (y >= y_end) break;
+        const ResizeTab ty = yt[y];
+        const uint8_t *S0 = sb + (ty.s0 - sy_lo) * spitch, *S1 = sb + (ty.s1 - sy_lo) * spitch;
+        const int b0 = ty.c0, b1 = ty.c1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h0 = S0[o0[k]] * c0[k] + S0[o1[k]] * c1[k];
+            const int h1 = S1[o0[k]] * c0[k] + S1[o1[k]] * c1[k];
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;   // pitch % 64 == 0: padding absorbs the tail
+    }
+}
+
+// One destination tile [x0, x0+128) x [y0, y_end) (y_end - y0 <= 32) of `level` from level-1.
+// Block-wide (256 threads as 32x8); contains two barriers, so call it uniformly.
 __device__ __forceinline__ void resize_tile(const DevParams *__restrict__ P, const uint8_t *S, int sp, uint8_t *dst, int level,
                                             int x0, int y0, int y_end, uint32_t (*ssrc)[kRzSrcWords])
 {
@@ -76,32 +110,7 @@ __device__ __forceinline__ void resize_tile(const DevParams *__restrict__ P, con
         for (int c = threadIdx.x; c < nwords; c += 32) ssrc[r][c] = row[c];
     }
     __syncthreads();
-    const int x4 = x0 + threadIdx.x * 4;
-    if (x4 >= D.w) return;
-    int o0[4], o1[4], c0[4], c1[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {                                  // tables are padded to a multiple of 4 entries
-        const ResizeTab t = xt[x4 + k];
-        o0[k] = t.s0 - sx_lo; o1[k] = t.s1 - sx_lo; c0[k] = t.c0; c1[k] = t.c1;
-    }
-    const uint8_t *sb = reinterpret_cast<const uint8_t *>(&ssrc[0][0]);
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-        const int y = y0 + threadIdx.y + 8 * rr;
-        if (y >= y_end) break;
-        const ResizeTab ty = yt[y];
-        const uint8_t *S0 = sb + (ty.s0 - sy_lo) * (kRzSrcWords * 4), *S1 = sb + (ty.s1 - sy_lo) * (kRzSrcWords * 4);
-        const int b0 = ty.c0, b1 = ty.c1;
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int h0 = S0[o0[k]] * c0[k] + S0[o1[k]] * c1[k];
-            const int h1 = S1[o0[k]] * c0[k] + S1[o1[k]] * c1[k];
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)v << (8 * k);
-        }
-        *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;   // pitch % 64 == 0: padding absorbs the tail
-    }
+    resize_rows(P, level, reinterpret_cast<const uint8_t *>(&ssrc[0][0]), kRzSrcWords * 4, sx_lo, sy_lo, x0, y0, y_end, dst);
 }
 
 // All levels in ONE launch.  The level chain (level l is resized from level l-1, :1124) is
@@ -155,6 +164,82 @@ __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P,
     resize_tile(P, S, sp, dst, level, blockIdx.x * kRzTW, y0, min(y0 + kRzTH, D.h), ssrc);
 }
 
+// ---- TMA-staged variant: the source window of a tile is one cp.async.bulk.tensor box ------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
+{
+    const unsigned a = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();                                                      // a lost TMA completion must fail loudly, never hang the GPU
+}
+
+__global__ void __launch_bounds__(256)
+k_resize_tma(const DevParams *__restrict__ P, const __grid_constant__ CUtensorMap tmap, int level, int box_w, int box_h)
+{
+    extern __shared__ __align__(128) uint8_t sbox[];               // [box_h][box_w] source bytes, dense
+    __shared__ __align__(8) uint64_t mbar;
+    const LevelGeom &D = P->lv[level];
+    const int x0 = blockIdx.x * kRzTW, y0 = blockIdx.y * kRzTH, frame = blockIdx.z;
+    const int y_end = min(y0 + kRzTH, D.h);
+    const ResizeTab *xt = P->xtab + P->xtab_off[level], *yt = P->ytab + P->ytab_off[level];
+    const int sx_lo = xt[x0].s0 & ~15, sy_lo = yt[y0].s0;         // 16-byte aligned box origin
+    const int tid = threadIdx.x + threadIdx.y * 32;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(box_w * box_h) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     :: "r"(smem_u32(sbox)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar)),
+                        "r"(sx_lo), "r"(sy_lo), "r"(frame) : "memory");
+    }
+    mbar_wait_parity(&mbar, 0);
+    uint8_t *dst = P->pyr + (long long)frame * P->pyr_frame_bytes + D.img_off;
+    resize_rows(P, level, sbox, box_w, sx_lo, sy_lo, x0, y0, y_end, dst);
+}
+
+void resize_box(const LevelGeom &src, const LevelGeom &dst, int *box_w, int *box_h)
+{
+    // footprint of a 128x32 destination tile: ceil(128*ratio)+2 source columns, +15 for the 16-byte aligned origin
+    const int fw = (int)(((long long)kRzTW * src.w + dst.w - 1) / dst.w) + 2 + 15 + 1;
+    const int fh = (int)(((long long)kRzTH * src.h + dst.h - 1) / dst.h) + 3;
+    const int bw = (fw + 15) & ~15;
+    if (bw > 256 || fh > 256) { *box_w = 0; *box_h = 0; return; }
+    *box_w = bw; *box_h = fh;
+}
+
+bool encode_image_map(CUtensorMap *out, const void *base, int pitch, int rows, long long frame_stride, int nframes, int box_w, int box_h)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_fn>(p);
+    }
+    if (!fn || box_w <= 0 || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (frame_stride & 15)) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)nframes};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Copies frames of arbitrary row stride / alignment into the 64-byte-pitched level-0 slots.
 __global__ void k_repack(const uint8_t *__restrict__ src, long long src_frame_stride, int src_pitch, uint8_t *__restrict__ dst,
                          long long dst_frame_stride, int dst_pitch, int w, int h)
@@ -205,7 +290,7 @@ __global__ void __launch_bounds__(256) k_resize_direct(const DevParams *__restri
     *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = out;
 }
 
-cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls)
+cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls, const TmaMaps *tma)
 {
     if (hP.nlevels < 2) return cudaSuccess;
     bool all_staged = true;
@@ -221,7 +306,11 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
         // single-launch k_pyramid_fused (few long-running CTAs), which measured 1.6x slower at batch 32
         for (int l = 1; l < hP.nlevels; ++l) {
             const LevelGeom &D = hP.lv[l];
-            k_resize<<<dim3((D.w + kRzTW - 1) / kRzTW, (D.h + kRzTH - 1) / kRzTH, nframes), dim3(32, 8), 0, st>>>(dP, s0, l);
+            const dim3 grid((D.w + kRzTW - 1) / kRzTW, (D.h + kRzTH - 1) / kRzTH, nframes);
+            if (tma && tma->ok[l])                                 // source window by TMA (cp.async.bulk.tensor)
+                k_resize_tma<<<grid, dim3(32, 8), (size_t)tma->box_w[l] * tma->box_h[l], st>>>(dP, tma->src[l], l, tma->box_w[l], tma->box_h[l]);
+            else
+                k_resize<<<grid, dim3(32, 8), 0, st>>>(dP, s0, l);
             ls->launches++;
         }
         return cudaGetLastError();

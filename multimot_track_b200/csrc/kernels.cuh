@@ -2,6 +2,7 @@
 #ifndef ORBX_KERNELS_CUH
 #define ORBX_KERNELS_CUH
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,7 +47,20 @@ struct Src0 {
 
 struct LaunchStats { long long launches = 0; };
 
-cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
+// TMA descriptors for the pyramid: src[l] describes the level l-1 images (bytes; x, y, frame) that level l is
+// resized from, with a box large enough for the source footprint of one 128x32 destination tile.
+struct TmaMaps {
+    CUtensorMap src[kMaxLevels];
+    int box_w[kMaxLevels], box_h[kMaxLevels];
+    bool ok[kMaxLevels];
+};
+// Encodes one 3-D (x bytes, y rows, frame) uint8 tensor map; false when the driver entry point is missing or the
+// shape breaks a TMA constraint (then the caller keeps the plain shared-memory staging path).
+bool encode_image_map(CUtensorMap *out, const void *base, int pitch, int rows, long long frame_stride, int nframes, int box_w, int box_h);
+void resize_box(const LevelGeom &src, const LevelGeom &dst, int *box_w, int *box_h);   // box for dst tiles of 128x32; box_w = 0 if it cannot fit
+
+cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls,
+                           const TmaMaps *tma = nullptr);
 cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
                           int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);

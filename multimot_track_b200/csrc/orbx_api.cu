@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -52,6 +53,9 @@ struct orbx_handle {
     uint32_t *m_A = nullptr, *m_B = nullptr; size_t m_capA = 0, m_capB = 0;
     int32_t *m_out = nullptr; uint8_t *m_acc = nullptr; int *m_nacc = nullptr; size_t m_cap_out = 0;
     int4 *m_partial = nullptr; size_t m_cap_partial = 0;
+    TmaMaps tma;                        // pyramid source descriptors (levels >= 2 from our buffer, level 1 from the batch's level 0)
+    const void *tma_l0_base = nullptr; long long tma_l0_fs = 0; int tma_l0_pitch = 0, tma_l0_frames = 0;
+    bool use_tma = true;
     LaunchStats stats;
     bool profiling = false;
     cudaEvent_t ev[ORBX_NUM_STAGES + 1] = {};
@@ -126,6 +130,15 @@ int ensure_batch(orbx_handle *h, int nframes)
     CU(cudaMemsetAsync(h->d_pyr, 0, F * g.pyr_frame_bytes, h->stream));
     CU(cudaMemsetAsync(h->d_blur, 0, F * g.pyr_frame_bytes, h->stream));
     h->batch_cap = nframes;
+    // TMA descriptors of the pyramid levels that live in our own buffer (source of level l is level l-1 >= 1)
+    h->use_tma = std::getenv("ORBX_NO_TMA") == nullptr;
+    for (int l = 0; l < kMaxLevels; ++l) h->tma.ok[l] = false;
+    h->tma_l0_base = nullptr;
+    for (int l = 2; l < g.nlevels && h->use_tma; ++l) {
+        resize_box(g.lv[l - 1], g.lv[l], &h->tma.box_w[l], &h->tma.box_h[l]);
+        h->tma.ok[l] = encode_image_map(&h->tma.src[l], h->d_pyr + g.lv[l - 1].img_off, g.lv[l - 1].pitch, g.lv[l - 1].h,
+                                        g.pyr_frame_bytes, nframes, h->tma.box_w[l], h->tma.box_h[l]);
+    }
     return upload_params(h);
 }
 
@@ -180,7 +193,14 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
 #define MARK(i) do { if (prof) CU(cudaEventRecord(h->ev[i], st)); } while (0)
     MARK(1);                                     // ev[0] was recorded by the caller before the input copies
     CU(cudaMemsetAsync(h->d_cand_count, 0, (size_t)nframes * P.nlevels * sizeof(uint32_t), st));
-    CU(launch_pyramid(h->d_params, P, s0, nframes, st, &h->stats));
+    if (h->use_tma && P.nlevels > 1 &&
+        (h->tma_l0_base != s0.ptr || h->tma_l0_fs != s0.frame_stride || h->tma_l0_pitch != s0.pitch || h->tma_l0_frames < nframes)) {
+        // level 1 reads the batch's level-0 images: the caller's frames in place, or our level-0 slots
+        resize_box(h->geo.lv[0], h->geo.lv[1], &h->tma.box_w[1], &h->tma.box_h[1]);
+        h->tma.ok[1] = encode_image_map(&h->tma.src[1], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, h->tma.box_w[1], h->tma.box_h[1]);
+        h->tma_l0_base = s0.ptr; h->tma_l0_fs = s0.frame_stride; h->tma_l0_pitch = s0.pitch; h->tma_l0_frames = nframes;
+    }
+    CU(launch_pyramid(h->d_params, P, s0, nframes, st, &h->stats, h->use_tma ? &h->tma : nullptr));
     MARK(2);
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
     MARK(3);

@@ -250,3 +250,22 @@ def test_cpp_adapter_drop_in(orb, oracle_mod, tmp_path):
         w, h = (int(v) for v in np.frombuffer(blob, np.int32, 2, off)); off += 8
         padded = np.frombuffer(blob, np.uint8, (w + 38) * (h + 38), off).reshape(h + 38, w + 38); off += (w + 38) * (h + 38)
         assert np.array_equal(padded, o.level_padded(l)), l
+
+
+def test_tma_and_plain_staging_agree(orb, oracle_mod):
+    """The pyramid's TMA-staged kernel (cp.async.bulk.tensor) and its plain shared-memory staging fallback
+    (forced with ORBX_NO_TMA) both reproduce the oracle bit for bit."""
+    import os
+    img = synth(11, 375, 1242)
+    o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
+    o(img)
+    for no_tma in (False, True):
+        if no_tma:
+            os.environ["ORBX_NO_TMA"] = "1"
+        try:
+            ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+            ext(img)
+            for l in range(8):
+                assert np.array_equal(ext.pyramid_level(l), o.level_image(l)), (no_tma, l)
+        finally:
+            os.environ.pop("ORBX_NO_TMA", None)
