@@ -47,6 +47,21 @@ __device__ __forceinline__ unsigned lanemask_lt()
     return m;
 }
 
+// ---- TMA / mbarrier helpers (cp.async.bulk.tensor lands a 2-D box of image bytes in shared memory) ----------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
+{
+    const unsigned a = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();                                                      // a lost TMA completion must fail loudly, never hang the GPU
+}
+
 // ------------------------------------------------------------------ pyramid
 // cv::resize INTER_LINEAR, 8UC1: H = S[s0]*a0 + S[s1]*a1 (11-bit weights), then
 // out = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.  The weight tables are
@@ -165,20 +180,6 @@ __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P,
 }
 
 // ---- TMA-staged variant: the source window of a tile is one cp.async.bulk.tensor box ------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
-{
-    const unsigned a = smem_u32(bar);
-    for (int spin = 0; spin < (1 << 24); ++spin) {
-        unsigned ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();                                                      // a lost TMA completion must fail loudly, never hang the GPU
-}
-
 __global__ void __launch_bounds__(256)
 k_resize_tma(const DevParams *__restrict__ P, const __grid_constant__ CUtensorMap tmap, int level, int box_w, int box_h)
 {
@@ -332,77 +333,161 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
 // multiply-add never carries between the two lanes); the vertical pass slides down
 // 8 rows per thread on the 16-bit row sums kept in shared memory.
 
-__global__ void __launch_bounds__(256) k_blur(const DevParams *__restrict__ P, Src0 s0)
+// Persistent CTAs walk the (tile, frame) work list.  The raw tile (rows ty0-3 .. ty0+66, columns tx0-16 .. tx0+143,
+// 160-byte pitch: TMA needs a 16-byte aligned box origin) arrives as ONE cp.async.bulk.tensor box, double buffered so
+// the box of the next tile is in flight while this one is filtered.  Pixels outside the image come back as zeros (or
+// row padding); only the <= 3 the 7-tap kernel can reach on each side are overwritten with their reflect-101 sources.
+constexpr int kBlurRawWords = kBlurBoxW / 4;
+
+struct BlurItem { int level, tx0, ty0, frame; };
+
+__device__ __forceinline__ BlurItem blur_item(const DevParams *__restrict__ P, int item)
 {
-    constexpr int TW = kBlurTileW, TH = kBlurTileH, RW = TW / 4 + 2;       // raw words per row: x from tx0-4 to tx0+TW+4
-    __shared__ uint32_t sraw[TH + 6][RW + 2];
-    __shared__ uint2 shv[TH + 6][TW / 4];
-    const uint32_t wk = P->blur_work[blockIdx.x];
-    const int level = wk >> 24, ty0 = ((wk >> 12) & 0xfff) * TH, tx0 = (wk & 0xfff) * TW;
-    const int frame = blockIdx.y;
-    const LevelGeom &G = P->lv[level];
-    int sp;
-    const uint8_t *S = level_ptr(P, s0, frame, level, &sp);
-    const int tid = threadIdx.x;
-    // ---- raw rows ty0-3 .. ty0+TH+2 (reflected), columns tx0-4 .. tx0+TW+3
-    for (int i = tid; i < (TH + 6) * RW; i += 256) {
-        const int r = i / RW, c = i - r * RW;
-        const int gy = reflect101(ty0 + r - 3, G.h), gx = tx0 - 4 + 4 * c;
-        const uint8_t *row = S + (long long)gy * sp;
-        uint32_t v;
-        if (gx >= 0 && gx + 3 < G.w) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
-        else v = (uint32_t)row[reflect101(gx, G.w)] | (uint32_t)row[reflect101(gx + 1, G.w)] << 8 |
-                 (uint32_t)row[reflect101(gx + 2, G.w)] << 16 | (uint32_t)row[reflect101(gx + 3, G.w)] << 24;
-        sraw[r][c] = v;
-    }
-    __syncthreads();
-    // ---- horizontal pass, 4 pixels (two 16x2 pairs) per item
-    for (int i = tid; i < (TH + 6) * (TW / 4); i += 256) {
-        const int r = i / (TW / 4), q = i - r * (TW / 4);
-        const uint32_t w0 = sraw[r][q], w1 = sraw[r][q + 1], w2 = sraw[r][q + 2];     // pixels x-4..x-1 | x..x+3 | x+4..x+7
-        const uint32_t p0 = __byte_perm(w0, 0, 0x4140), p1 = __byte_perm(w0, 0, 0x4342), p2 = __byte_perm(w1, 0, 0x4140);
-        const uint32_t p3 = __byte_perm(w1, 0, 0x4342), p4 = __byte_perm(w2, 0, 0x4140), p5 = __byte_perm(w2, 0, 0x4342);
-        const uint32_t a0 = __funnelshift_r(p0, p1, 16), a1 = p1, a2 = __funnelshift_r(p1, p2, 16), a3 = p2;
-        const uint32_t a4 = __funnelshift_r(p2, p3, 16), a5 = p3, a6 = __funnelshift_r(p3, p4, 16), a7 = p4;
-        const uint32_t a8 = __funnelshift_r(p4, p5, 16);                   // a_k = pixels (x-3+k, x-2+k)
-        const uint32_t o01 = 18u * (a0 + a6) + 34u * (a1 + a5) + 48u * (a2 + a4) + 56u * a3;
-        const uint32_t o23 = 18u * (a2 + a8) + 34u * (a3 + a7) + 48u * (a4 + a6) + 56u * a5;
-        shv[r][q] = make_uint2(o01, o23);
-    }
-    __syncthreads();
-    // ---- vertical pass: thread = (pixel quad, 8-row segment)
-    const int q = tid & 31, seg = tid >> 5;
-    const int gx = tx0 + 4 * q, gy0 = ty0 + seg * 8;
-    if (gx >= G.w || gy0 >= G.h) return;
-    uint32_t out[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) out[r] = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t lo[14], hi[14];
-#pragma unroll
-        for (int j = 0; j < 14; ++j) {
-            const uint2 t = shv[seg * 8 + j][q];
-            const uint32_t w = half ? t.y : t.x;
-            lo[j] = w & 0xffffu; hi[j] = w >> 16;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint32_t v0 = 18u * (lo[r] + lo[r + 6]) + 34u * (lo[r + 1] + lo[r + 5]) + 48u * (lo[r + 2] + lo[r + 4]) + 56u * lo[r + 3];
-            const uint32_t v1 = 18u * (hi[r] + hi[r + 6]) + 34u * (hi[r + 1] + hi[r + 5]) + 48u * (hi[r + 2] + hi[r + 4]) + 56u * hi[r + 3];
-            out[r] |= (((v0 + 32768u) >> 16) | ((v1 + 32768u) >> 16) << 8) << (16 * half);
-        }
-    }
-    uint8_t *dst = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off + gx;
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-        if (gy0 + r < G.h) *reinterpret_cast<uint32_t *>(dst + (long long)(gy0 + r) * G.pitch) = out[r];
+    const int nw = P->n_blur_work, frame = item / nw;
+    const uint32_t wk = P->blur_work[item - frame * nw];
+    BlurItem it;
+    it.level = wk >> 24; it.ty0 = ((wk >> 12) & 0xfff) * kBlurTileH; it.tx0 = (wk & 0xfff) * kBlurTileW; it.frame = frame;
+    return it;
 }
 
-cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls)
+__global__ void __launch_bounds__(256)
+k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMaps maps, unsigned tma_levels, int total_items)
 {
-    dim3 grid(hP.n_blur_work, nframes);
-    k_blur<<<grid, 256, 0, st>>>(dP, s0);
+    constexpr int TW = kBlurTileW, TH = kBlurTileH, RWD = kBlurRawWords, PB = kBlurBoxW;
+    struct __align__(128) RawBuf { uint32_t w[TH + 6][RWD]; };        // TMA destinations must be 128-byte aligned
+    __shared__ RawBuf sraw[2];
+    __shared__ uint2 shv[TH + 6][TW / 4];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // thread 0: start the box of `item` into buffer b (no-op for a level without a tensor map)
+    auto issue = [&](int item, int b) {
+        const BlurItem it = blur_item(P, item);
+        if (!((tma_levels >> it.level) & 1u)) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads/writes of this buffer come first
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar[b])), "r"((TH + 6) * PB) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     :: "r"(smem_u32(&sraw[b].w[0][0])), "l"(reinterpret_cast<unsigned long long>(&maps.m[it.level])), "r"(smem_u32(&mbar[b])),
+                        "r"(it.tx0 - 16), "r"(it.ty0 - 3), "r"(it.frame) : "memory");
+    };
+    int item = blockIdx.x;
+    if (tid == 0 && item < total_items) issue(item, 0);
+    unsigned phase = 0;                                              // bit b = parity the next wait on buffer b uses
+    for (int n = 0; item < total_items; item += gridDim.x, ++n) {
+        const int b = n & 1;
+        if (tid == 0 && item + (int)gridDim.x < total_items) issue(item + gridDim.x, b ^ 1);
+        const BlurItem it = blur_item(P, item);
+        const int level = it.level, tx0 = it.tx0, ty0 = it.ty0, frame = it.frame;
+        const LevelGeom &G = P->lv[level];
+        uint32_t (*raw)[RWD] = sraw[b].w;
+        if ((tma_levels >> level) & 1u) {
+            mbar_wait_parity(&mbar[b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+            uint8_t *sb = reinterpret_cast<uint8_t *>(&raw[0][0]);
+            // rows above / below the image: whole-row copies from their reflect-101 source rows (inside the tile)
+            const int rb = G.h - ty0 + 3;                            // tile row of image row h
+            if (ty0 == 0 || rb < TH + 6) {
+                if (tid < 6 * RWD) {
+                    const int k = tid / RWD, c = tid - k * RWD;
+                    const int r = k < 3 ? k : rb + k - 3;
+                    const int gy = ty0 - 3 + r;
+                    if (r < TH + 6 && (unsigned)gy >= (unsigned)G.h && gy < G.h + 3)
+                        raw[r][c] = raw[reflect101(gy, G.h) - (ty0 - 3)][c];
+                }
+                __syncthreads();
+            }
+            // columns left / right of the image
+            const bool left = tx0 == 0, right = tx0 + TW + 3 > G.w;
+            if (left || right) {
+                if (tid < 2 * (TH + 6)) {
+                    const int side = tid >= TH + 6, r = tid - side * (TH + 6);
+                    uint8_t *row = sb + r * PB;
+                    if (side == 0 && left) {
+#pragma unroll
+                        for (int k = 1; k <= 3; ++k) row[16 - k] = row[16 + k];
+                    }
+                    if (side == 1 && right) {
+                        const int cl = G.w - 1 - (tx0 - 16);
+#pragma unroll
+                        for (int k = 1; k <= 3; ++k) if (cl + k < PB) row[cl + k] = row[cl - k];
+                    }
+                }
+            }
+        } else {
+            int sp;
+            const uint8_t *S = level_ptr(P, s0, frame, level, &sp);
+            // ---- raw rows ty0-3 .. ty0+TH+2 (reflected), columns tx0-4 .. tx0+TW+3 (tile words 3 .. 36)
+            for (int i = tid; i < (TH + 6) * (TW / 4 + 2); i += 256) {
+                const int r = i / (TW / 4 + 2), c = i - r * (TW / 4 + 2);
+                const int gy = reflect101(ty0 + r - 3, G.h), gx = tx0 - 4 + 4 * c;
+                const uint8_t *row = S + (long long)gy * sp;
+                uint32_t v;
+                if (gx >= 0 && gx + 3 < G.w) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+                else v = (uint32_t)row[reflect101(gx, G.w)] | (uint32_t)row[reflect101(gx + 1, G.w)] << 8 |
+                         (uint32_t)row[reflect101(gx + 2, G.w)] << 16 | (uint32_t)row[reflect101(gx + 3, G.w)] << 24;
+                raw[r][c + 3] = v;
+            }
+        }
+        __syncthreads();
+        // ---- horizontal pass, 4 pixels (two 16x2 pairs) per item
+        for (int i = tid; i < (TH + 6) * (TW / 4); i += 256) {
+            const int r = i / (TW / 4), q = i - r * (TW / 4);
+            const uint32_t w0 = raw[r][q + 3], w1 = raw[r][q + 4], w2 = raw[r][q + 5];   // pixels x-4..x-1 | x..x+3 | x+4..x+7
+            const uint32_t p0 = __byte_perm(w0, 0, 0x4140), p1 = __byte_perm(w0, 0, 0x4342), p2 = __byte_perm(w1, 0, 0x4140);
+            const uint32_t p3 = __byte_perm(w1, 0, 0x4342), p4 = __byte_perm(w2, 0, 0x4140), p5 = __byte_perm(w2, 0, 0x4342);
+            const uint32_t a0 = __funnelshift_r(p0, p1, 16), a1 = p1, a2 = __funnelshift_r(p1, p2, 16), a3 = p2;
+            const uint32_t a4 = __funnelshift_r(p2, p3, 16), a5 = p3, a6 = __funnelshift_r(p3, p4, 16), a7 = p4;
+            const uint32_t a8 = __funnelshift_r(p4, p5, 16);                   // a_k = pixels (x-3+k, x-2+k)
+            const uint32_t o01 = 18u * (a0 + a6) + 34u * (a1 + a5) + 48u * (a2 + a4) + 56u * a3;
+            const uint32_t o23 = 18u * (a2 + a8) + 34u * (a3 + a7) + 48u * (a4 + a6) + 56u * a5;
+            shv[r][q] = make_uint2(o01, o23);
+        }
+        __syncthreads();
+        // ---- vertical pass: thread = (pixel quad, 8-row segment)
+        const int q = tid & 31, seg = tid >> 5;
+        const int gx = tx0 + 4 * q, gy0 = ty0 + seg * 8;
+        if (gx < G.w && gy0 < G.h) {
+            uint32_t out[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) out[r] = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t lo[14], hi[14];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    const uint2 t = shv[seg * 8 + j][q];
+                    const uint32_t w = half ? t.y : t.x;
+                    lo[j] = w & 0xffffu; hi[j] = w >> 16;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t v0 = 18u * (lo[r] + lo[r + 6]) + 34u * (lo[r + 1] + lo[r + 5]) + 48u * (lo[r + 2] + lo[r + 4]) + 56u * lo[r + 3];
+                    const uint32_t v1 = 18u * (hi[r] + hi[r + 6]) + 34u * (hi[r + 1] + hi[r + 5]) + 48u * (hi[r + 2] + hi[r + 4]) + 56u * hi[r + 3];
+                    out[r] |= (((v0 + 32768u) >> 16) | ((v1 + 32768u) >> 16) << 8) << (16 * half);
+                }
+            }
+            uint8_t *dst = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off + gx;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (gy0 + r < G.h) *reinterpret_cast<uint32_t *>(dst + (long long)(gy0 + r) * G.pitch) = out[r];
+        }
+        __syncthreads();                                               // shv and raw[b] are free again
+    }
+}
+
+cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls,
+                        const BlurMaps *maps, unsigned tma_levels)
+{
+    static const BlurMaps zero_maps = {};
+    const int total = hP.n_blur_work * nframes;
+    if (total <= 0) return cudaSuccess;
+    const int grid = total < 148 * 4 ? total : 148 * 4;               // 4 resident CTAs per SM (64 registers x 256 threads)
+    k_blur<<<grid, 256, 0, st>>>(dP, s0, maps ? *maps : zero_maps, maps ? tma_levels : 0u, total);
     ls->launches++;
     return cudaGetLastError();
 }

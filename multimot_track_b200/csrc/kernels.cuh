@@ -63,7 +63,12 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
                            const TmaMaps *tma = nullptr);
 cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
                           int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls);
-cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
+// maps->m[l]: the level-l images of this batch (level 0 = the caller's frames or our level-0 slots); bit l of tma_levels
+// set = level l's blur tiles are staged by TMA (box kBlurBoxW x kBlurBoxH bytes).  Passed by value as a __grid_constant__.
+struct BlurMaps { CUtensorMap m[kMaxLevels]; };
+cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls,
+                        const BlurMaps *maps = nullptr, unsigned tma_levels = 0);
+constexpr int kBlurBoxW = kBlurTileW + 32, kBlurBoxH = kBlurTileH + 6;   // 16 bytes of halo each side keep the box origin 16-byte aligned
 cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_jobs, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);

@@ -56,6 +56,7 @@ struct orbx_handle {
     TmaMaps tma;                        // pyramid source descriptors (levels >= 2 from our buffer, level 1 from the batch's level 0)
     const void *tma_l0_base = nullptr; long long tma_l0_fs = 0; int tma_l0_pitch = 0, tma_l0_frames = 0;
     bool use_tma = true;
+    BlurMaps blur_maps; unsigned blur_tma_levels = 0;       // blur source boxes: bit l set = maps.m[l] valid (level 0 per batch source)
     LaunchStats stats;
     bool profiling = false;
     cudaEvent_t ev[ORBX_NUM_STAGES + 1] = {};
@@ -139,6 +140,12 @@ int ensure_batch(orbx_handle *h, int nframes)
         h->tma.ok[l] = encode_image_map(&h->tma.src[l], h->d_pyr + g.lv[l - 1].img_off, g.lv[l - 1].pitch, g.lv[l - 1].h,
                                         g.pyr_frame_bytes, nframes, h->tma.box_w[l], h->tma.box_h[l]);
     }
+    // blur source boxes: one descriptor per level of our pyramid buffer (level 0 follows the batch's source, enqueue_pipeline)
+    h->blur_tma_levels = 0;
+    std::memset(&h->blur_maps, 0, sizeof(h->blur_maps));
+    for (int l = 1; l < g.nlevels && h->use_tma; ++l)
+        if (encode_image_map(&h->blur_maps.m[l], h->d_pyr + g.lv[l].img_off, g.lv[l].pitch, g.lv[l].h, g.pyr_frame_bytes, nframes, kBlurBoxW, kBlurBoxH))
+            h->blur_tma_levels |= 1u << l;
     return upload_params(h);
 }
 
@@ -193,16 +200,18 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
 #define MARK(i) do { if (prof) CU(cudaEventRecord(h->ev[i], st)); } while (0)
     MARK(1);                                     // ev[0] was recorded by the caller before the input copies
     CU(cudaMemsetAsync(h->d_cand_count, 0, (size_t)nframes * P.nlevels * sizeof(uint32_t), st));
-    if (h->use_tma && P.nlevels > 1 &&
+    if (h->use_tma &&
         (h->tma_l0_base != s0.ptr || h->tma_l0_fs != s0.frame_stride || h->tma_l0_pitch != s0.pitch || h->tma_l0_frames < nframes)) {
         // level 1 reads the batch's level-0 images: the caller's frames in place, or our level-0 slots
-        resize_box(h->geo.lv[0], h->geo.lv[1], &h->tma.box_w[1], &h->tma.box_h[1]);
-        h->tma.ok[1] = encode_image_map(&h->tma.src[1], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, h->tma.box_w[1], h->tma.box_h[1]);
+        if (P.nlevels > 1) resize_box(h->geo.lv[0], h->geo.lv[1], &h->tma.box_w[1], &h->tma.box_h[1]);
+        if (P.nlevels > 1) h->tma.ok[1] = encode_image_map(&h->tma.src[1], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, h->tma.box_w[1], h->tma.box_h[1]);
+        if (encode_image_map(&h->blur_maps.m[0], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, kBlurBoxW, kBlurBoxH)) h->blur_tma_levels |= 1u;
+        else h->blur_tma_levels &= ~1u;
         h->tma_l0_base = s0.ptr; h->tma_l0_fs = s0.frame_stride; h->tma_l0_pitch = s0.pitch; h->tma_l0_frames = nframes;
     }
     CU(launch_pyramid(h->d_params, P, s0, nframes, st, &h->stats, h->use_tma ? &h->tma : nullptr));
     MARK(2);
-    CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats));
+    CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats, h->use_tma ? &h->blur_maps : nullptr, h->blur_tma_levels));
     MARK(3);
     CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_ffast_small, st, &h->stats));
     MARK(4);
