@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace orbx {
 
@@ -1098,6 +1099,43 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+
+// cos / sin of a float angle in [0, 2*pi], each correctly rounded to float in all but ~1e-8 of the cases (the same
+// as rounding CUDA's double cos()/sin()): one Cody-Waite reduction by pi/2 and two Taylor polynomials in fp64,
+// shared between the two results.  The reference calls cosf/sinf of glibc, which round the same way (:112-113).
+__device__ __forceinline__ void sincos_f32_via_f64(float ang, float *sn, float *cs)
+{
+    const double x = (double)ang;
+    const int q = __double2int_rn(x * 0.63661977236758134308);
+    const double qd = (double)q;
+    double r = fma(qd, -1.57079632679489655800e+00, x);
+    r = fma(qd, -6.12323399573676603587e-17, r);
+    const double r2 = r * r;
+    double ps = -1.0 / 355687428096000.0;                          // sin: r - r^3/3! + ... - r^19-free tail below 1e-19
+    ps = fma(ps, r2, 1.0 / 1307674368000.0);
+    ps = fma(ps, r2, -1.0 / 6227020800.0);
+    ps = fma(ps, r2, 1.0 / 39916800.0);
+    ps = fma(ps, r2, -1.0 / 362880.0);
+    ps = fma(ps, r2, 1.0 / 5040.0);
+    ps = fma(ps, r2, -1.0 / 120.0);
+    ps = fma(ps, r2, 1.0 / 6.0);
+    const double sr = fma(-ps * r2, r, r);
+    double pc = 1.0 / 20922789888000.0;                            // cos: 1 - r^2/2! + ... + r^16/16!
+    pc = fma(pc, r2, -1.0 / 87178291200.0);
+    pc = fma(pc, r2, 1.0 / 479001600.0);
+    pc = fma(pc, r2, -1.0 / 3628800.0);
+    pc = fma(pc, r2, 1.0 / 40320.0);
+    pc = fma(pc, r2, -1.0 / 720.0);
+    pc = fma(pc, r2, 1.0 / 24.0);
+    pc = fma(pc, r2, -0.5);
+    const double cr = fma(pc, r2, 1.0);
+    const bool swap = q & 1;
+    double s_ = swap ? cr : sr, c_ = swap ? sr : cr;
+    if (q & 2) s_ = -s_;
+    if ((q + 1) & 2) c_ = -c_;
+    *sn = (float)s_; *cs = (float)c_;
+}
+
 constexpr int kOdWarps = 8;
 constexpr int kOdPitchW = 10;                     // patch pitch in words (37 + up to 3 bytes of misalignment)
 
@@ -1221,11 +1259,239 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(const DevParams *
     }
 }
 
-cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls)
+// ---- TMA variant: persistent warps, one keypoint at a time per warp.  The 31x31 source neighbourhood and the
+// 37x37 blurred neighbourhood of a keypoint arrive as two cp.async.bulk.tensor boxes (16-byte aligned origin, so
+// 48 and 64 bytes wide) and are double buffered: the boxes of the warp's next keypoint are in flight while the
+// current one is processed.  Moments: lane = patch row, four pixels per IDP.4A against constant weights, the
+// circular mask (umax, :453-469) as byte masks.  rBRIEF: the 256 sample pairs as a float4 table in shared memory.
+constexpr int kOdIcW = 48, kOdIcH = 31, kOdBlW = 64, kOdBlH = 37;
+constexpr int kOdIcBytes = 1536, kOdBlBytes = 2432;                  // each rounded up to a multiple of 128 (TMA destination alignment)
+constexpr int kOdBufBytes = kOdIcBytes + kOdBlBytes;
+constexpr int kOdSmemBytes = 4096 + 1024 + kOdWarps * 2 * kOdBufBytes;
+
+__device__ __forceinline__ unsigned lds_u8(unsigned addr)
 {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevParams *__restrict__ P, const __grid_constant__ OdMaps maps, Src0 s0)
+{
+    extern __shared__ __align__(128) uint8_t od_smem[];
+    __shared__ int s_prefix[kMaxLevels + 1], s_kpoff[kMaxLevels];
+    __shared__ __align__(8) uint64_t s_bar[kOdWarps][2];
+    float4 *spatf = reinterpret_cast<float4 *>(od_smem);               // [k][lane]: (x0, y0, x1, y1) of bit k of byte `lane`
+    uint32_t *smask = reinterpret_cast<uint32_t *>(od_smem + 4096);    // [word k][row]: bytes of the row inside the circular patch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int frame = blockIdx.y, L = P->nlevels;
+    uint8_t *wbuf = od_smem + 4096 + 1024 + warp * 2 * kOdBufBytes;
+    for (int i = threadIdx.x; i < 256; i += kOdWarps * 32) {
+        const int l = i >> 3, k = i & 7;
+        const int8_t *pt = P->pattern + 32 * l + 4 * k;
+        spatf[k * 32 + l] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], (float)pt[3]);
+    }
+    {
+        const int k = threadIdx.x >> 5, r = threadIdx.x & 31;          // 8 warps x 32 lanes == the 8 x 32 mask table
+        uint32_t m = 0;
+        if (r < 31) {
+            const int d = P->umax[abs(r - 15)];
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) if (abs(4 * k + bb - 15) <= d) m |= 0xffu << (8 * bb);
+        }
+        smask[k * 32 + r] = m;
+    }
+    if (threadIdx.x < 32) {                       // keypoints per level of this frame and their running offsets
+        int c = lane < L ? min((int)P->kp_count[frame * L + lane], P->lv[lane].kp_cap) : 0;
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < L) { s_prefix[lane] = x - c; s_kpoff[lane] = P->lv[lane].kp_off; }
+        if (lane == L - 1) s_prefix[L] = x;
+    }
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[warp][0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[warp][1])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n = s_prefix[L];
+    if (blockIdx.x == 0 && threadIdx.x == 0) P->out_n[frame] = n;
+    const int step = gridDim.x * kOdWarps;
+    int j = blockIdx.x * kOdWarps + warp;
+    if (j >= n) return;
+    const int my_pre = lane < L ? s_prefix[lane + 1] : 0x7fffffff;     // first output index of level lane+1
+    const uint32_t *stage = P->kp_stage + (long long)frame * P->kp_frame_cap;
+    // level and packed candidate of output index jj
+    auto fetch = [&](int jj, int *level) -> uint32_t {
+        const int lv = __popc(__ballot_sync(0xffffffffu, my_pre <= jj));
+        *level = lv;
+        return __ldg(stage + s_kpoff[lv] + jj - s_prefix[lv]);
+    };
+    // chunk q of a patch = 16 bytes at (row q / chunks_per_row, column chunk q % chunks_per_row): lane-constant
+    int ic_row[3], ic_col[3], bl_row[5], bl_col[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int q = lane + 32 * i; ic_row[i] = q / 3; ic_col[i] = (q - ic_row[i] * 3) * 16; }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { const int q = lane + 32 * i; bl_row[i] = q >> 2; bl_col[i] = (q & 3) * 16; }
+    auto issue = [&](uint32_t c, int level, int b) {                   // both neighbourhoods of one keypoint into buffer b
+        const int cx = (int)(c & 0xfff) + kMinBorder, cy = (int)((c >> 12) & 0xfff) + kMinBorder;
+        if (TMA) {
+            if (lane != 0) return;
+            const unsigned bar = smem_u32(&s_bar[warp][b]), dst = smem_u32(wbuf + b * kOdBufBytes);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(kOdIcW * kOdIcH + kOdBlW * kOdBlH) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(&maps.img[level])), "r"(bar),
+                            "r"((cx - 15) & ~15), "r"(cy - 15), "r"(frame) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         :: "r"(dst + kOdIcBytes), "l"(reinterpret_cast<unsigned long long>(&maps.blr[level])), "r"(bar),
+                            "r"((cx - 18) & ~15), "r"(cy - 18), "r"(frame) : "memory");
+        } else {
+            // LDGSTS: 93 + 148 sixteen-byte chunks, eight cp.async per lane; rows stay inside the level (keypoints are
+            // >= 19 pixels from every edge) and the pitch is a multiple of 16, so every chunk is in bounds and aligned
+            int sp;
+            const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
+            const int bp = P->lv[level].pitch;
+            const uint8_t *ics = img + (long long)(cy - 15) * sp + ((cx - 15) & ~15);
+            const uint8_t *bls = P->blur + (long long)frame * P->pyr_frame_bytes + P->lv[level].img_off + (long long)(cy - 18) * bp + ((cx - 18) & ~15);
+            const unsigned dst = smem_u32(wbuf + b * kOdBufBytes) + lane * 16;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (i < 2 || lane < 93 - 64)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + 512 * i), "l"(ics + ic_row[i] * sp + ic_col[i]) : "memory");
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+                if (i < 4 || lane < 148 - 128)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + kOdIcBytes + 512 * i), "l"(bls + bl_row[i] * bp + bl_col[i]) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+    int lv0, lv1 = 0, lv2 = 0;
+    uint32_t c0 = fetch(j, &lv0), c1 = 0, c2 = 0;
+    issue(c0, lv0, 0);
+    bool v1 = j + step < n, v2 = false;
+    if (v1) c1 = fetch(j + step, &lv1);
+    unsigned phase = 0;
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
+        __syncwarp();                                                  // every lane is done reading buffer b^1
+        if (v1) issue(c1, lv1, b ^ 1);
+        v2 = j + 2 * step < n;
+        if (v2) c2 = fetch(j + 2 * step, &lv2);
+        if (TMA) {
+            mbar_wait_parity(&s_bar[warp][b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+        } else {
+            if (v1) asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the group just committed
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
+
+        const uint32_t c = c0;
+        const int level = lv0;
+        const LevelGeom &G = P->lv[level];
+        const int cx = (int)(c & 0xfff) + kMinBorder, cy = (int)((c >> 12) & 0xfff) + kMinBorder;
+        const uint8_t *icp = wbuf + b * kOdBufBytes, *blp = icp + kOdIcBytes;
+        // ---- IC_Angle (:77-104): lane = patch row v = lane-15; the 32 pixels u = -15..16 of the row as 8 aligned words
+        int m10, m01;
+        {
+            const int xoff = cx - 15 - ((cx - 15) & ~15);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(icp + (lane < 31 ? lane : 0) * kOdIcW + (xoff & ~3));
+            const int sh = (xoff & 3) * 8;
+            uint32_t w[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w[k] = row[k];
+            int rowsum = 0, mu = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t v = __funnelshift_r(w[k], w[k + 1], sh) & smask[k * 32 + lane];
+                constexpr int kOnes = 0x01010101;
+                const int u0 = 4 * k - 15;
+                const int wu = (u0 & 0xff) | ((u0 + 1) & 0xff) << 8 | ((u0 + 2) & 0xff) << 16 | ((u0 + 3) & 0xff) << 24;
+                rowsum = dp4a_us(v, kOnes, rowsum);
+                mu = dp4a_us(v, wu, mu);
+            }
+            m10 = warp_sum(mu);
+            m01 = warp_sum((lane - 15) * rowsum);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // ---- steered rBRIEF (:108-147)
+        constexpr float kFactorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+        const float ang = __fmul_rn(angle, kFactorPI);
+        float a, bs;
+        sincos_f32_via_f64(ang, &bs, &a);
+        // cvRound(s) for |s| < 2^22 is the low mantissa of fl(s + 1.5*2^23) (round-half-even, like cvRound); the bias
+        // of the two integers is folded into the patch pointer, so no F2I is issued
+        constexpr float kMagic = 12582912.f;
+        constexpr int kMagicBits = 0x4B400000;
+        const unsigned ctr = smem_u32(blp) + 18 * kOdBlW + (cx - 18 - ((cx - 18) & ~15)) + 18 - (unsigned)kMagicBits * (kOdBlW + 1);
+        unsigned byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 pt = spatf[k * 32 + lane];
+            const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, bs), __fmul_rn(pt.y, a)), kMagic));
+            const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, bs)), kMagic));
+            const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, bs), __fmul_rn(pt.w, a)), kMagic));
+            const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, bs)), kMagic));
+            const unsigned t0 = lds_u8(ctr + (unsigned)r0 * kOdBlW + (unsigned)q0), t1 = lds_u8(ctr + (unsigned)r1 * kOdBlW + (unsigned)q1);
+            byte |= (unsigned)(t0 < t1) << k;
+        }
+        // gather 32 bytes -> 8 words (lanes 0, 4, .., 28) -> two uint4 stores (lanes 0 and 16)
+        unsigned wd = byte | __shfl_down_sync(0xffffffffu, byte, 1) << 8;
+        wd = (wd & 0xffffu) | __shfl_down_sync(0xffffffffu, wd, 2) << 16;
+        uint4 v;
+        v.x = wd; v.y = __shfl_down_sync(0xffffffffu, wd, 4);
+        v.z = __shfl_down_sync(0xffffffffu, wd, 8); v.w = __shfl_down_sync(0xffffffffu, wd, 12);
+        const long long orow = (long long)frame * P->kp_frame_cap + j;
+        if ((lane & 15) == 0) reinterpret_cast<uint4 *>(P->out_desc + orow * 32)[lane >> 4] = v;
+        // ---- cv::KeyPoint record (:837-847, :1098-1104): lanes 0..6 = x, y, size, angle, response, octave, class_id
+        {
+            const float fx = __fmul_rn((float)cx, G.scale), fy = __fmul_rn((float)cy, G.scale);
+            float f = lane == 0 ? fx : fy;
+            f = lane == 2 ? G.kp_size : f;
+            f = lane == 3 ? angle : f;
+            f = lane == 4 ? (float)(c >> 24) : f;
+            f = lane == 5 ? __int_as_float(level) : f;
+            f = lane == 6 ? __int_as_float(-1) : f;
+            if (lane < 7) reinterpret_cast<float *>(P->out_kps + orow)[lane] = f;
+        }
+        if (!v1) break;
+        c0 = c1; lv0 = lv1; c1 = c2; lv1 = lv2; v1 = v2; j += step;
+    }
+}
+
+cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls, const OdMaps *maps)
+{
+    ls->launches++;
+    if (maps) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_orient_desc_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOdSmemBytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orient_desc_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOdSmemBytes);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        // 3 CTAs of 8 warps per SM resident; every warp walks several keypoints of its frame
+        int per_frame = 148 * 3 / nframes;                             // one wave: never more CTAs than resident slots
+        const int max_useful = (hP.kp_frame_cap + kOdWarps - 1) / kOdWarps;
+        if (per_frame > max_useful) per_frame = max_useful;
+        if (per_frame < 1) per_frame = 1;
+        static const int mode = std::getenv("ORBX_OD_MODE") ? std::atoi(std::getenv("ORBX_OD_MODE")) : 1;   // 0 = LDGSTS chunks (measured slower), 1 = TMA boxes
+        if (mode == 1) k_orient_desc_tma<true><<<dim3(per_frame, nframes), kOdWarps * 32, kOdSmemBytes, st>>>(dP, *maps, s0);
+        else k_orient_desc_tma<false><<<dim3(per_frame, nframes), kOdWarps * 32, kOdSmemBytes, st>>>(dP, *maps, s0);
+        return cudaGetLastError();
+    }
     dim3 grid((hP.kp_frame_cap + kOdWarps - 1) / kOdWarps, nframes);
     k_orient_desc<<<grid, kOdWarps * 32, 0, st>>>(dP, s0);
-    ls->launches++;
     return cudaGetLastError();
 }
 

@@ -71,7 +71,11 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 constexpr int kBlurBoxW = kBlurTileW + 32, kBlurBoxH = kBlurTileH + 6;   // 16 bytes of halo each side keep the box origin 16-byte aligned
 cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_jobs, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls);
-cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls);
+// img[l] / blr[l]: level-l images of the batch and their blurred copies, boxes kOdIcBoxW x kOdIcBoxH and kOdBlBoxW x kOdBlBoxH
+struct OdMaps { CUtensorMap img[kMaxLevels], blr[kMaxLevels]; };
+constexpr int kOdIcBoxW = 48, kOdIcBoxH = 31, kOdBlBoxW = 64, kOdBlBoxH = 37;
+cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls,
+                               const OdMaps *maps = nullptr);     // maps == nullptr: plain shared-memory staging
 cudaError_t launch_pad_level(const uint8_t *src, int w, int h, int pitch, uint8_t *dst, int dst_pitch, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB, int th, float ratio,
                          int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept, int *d_naccept,

@@ -20,7 +20,8 @@ agg = collections.OrderedDict()
 for r in b["rows"]:
     key = (int(r[iline]), r[isrc].strip())
     a = agg.setdefault(key, [0, 0, 0, 0])
-    a[0] += int(r[iinst] or 0); a[1] += int(r[isamp] or 0); a[2] += int(r[ithr] or 0); a[3] += 1
+    num = lambda v: int(v) if v.strip().lstrip("-").isdigit() else 0
+    a[0] += num(r[iinst]); a[1] += num(r[isamp]); a[2] += num(r[ithr]); a[3] += 1
 tot_i = sum(a[0] for a in agg.values()); tot_s = sum(a[1] for a in agg.values())
 print("kernel block 0: total warp instructions %d, samples %d, sass lines %d" % (tot_i, tot_s, len(b["rows"])))
 for (ln, src), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
