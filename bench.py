@@ -11,7 +11,7 @@ frame-parallel, the data path has no collective, so scaling is "weak" (fixed wor
 
   value     frames/s of the whole job, inputs resident in HBM when the clock starts,
             results (keypoints + descriptors) copied back to pinned host memory inside
-            the timed region; three handles (streams) keep consecutive batches in flight
+            the timed region; six handles (streams) keep consecutive batches in flight
   e2e       the same through the host-buffer entry point: H2D of every frame from pinned
             host memory + D2H of the results inside the timed region
   roofline  the dominant kernel: algorithmic bytes per launch / its mean
@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="k1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--handles", type=int, default=3)
+    ap.add_argument("--handles", type=int, default=6)
     args = ap.parse_args()
     H, W, nfeat, nlev, batch, desc = WORKLOADS[args.workload]
 

@@ -340,6 +340,19 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
 // row padding); only the <= 3 the 7-tap kernel can reach on each side are overwritten with their reflect-101 sources.
 constexpr int kBlurRawWords = kBlurBoxW / 4;
 
+// 18*(p0+p6) + 34*(p1+p5) + 48*(p2+p4) + 56*p3 + acc as a chain of IMADs (kept from being re-associated into adds)
+__device__ __forceinline__ uint32_t mad7(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t p5, uint32_t p6, uint32_t acc)
+{
+    asm("mad.lo.u32 %0, %1, 56, %0;" : "+r"(acc) : "r"(p3));
+    asm("mad.lo.u32 %0, %1, 48, %0;" : "+r"(acc) : "r"(p2));
+    asm("mad.lo.u32 %0, %1, 48, %0;" : "+r"(acc) : "r"(p4));
+    asm("mad.lo.u32 %0, %1, 34, %0;" : "+r"(acc) : "r"(p1));
+    asm("mad.lo.u32 %0, %1, 34, %0;" : "+r"(acc) : "r"(p5));
+    asm("mad.lo.u32 %0, %1, 18, %0;" : "+r"(acc) : "r"(p0));
+    asm("mad.lo.u32 %0, %1, 18, %0;" : "+r"(acc) : "r"(p6));
+    return acc;
+}
+
 struct BlurItem { int level, tx0, ty0, frame; };
 
 __device__ __forceinline__ BlurItem blur_item(const DevParams *__restrict__ P, int item)
@@ -444,8 +457,8 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
             const uint32_t a0 = __funnelshift_r(p0, p1, 16), a1 = p1, a2 = __funnelshift_r(p1, p2, 16), a3 = p2;
             const uint32_t a4 = __funnelshift_r(p2, p3, 16), a5 = p3, a6 = __funnelshift_r(p3, p4, 16), a7 = p4;
             const uint32_t a8 = __funnelshift_r(p4, p5, 16);                   // a_k = pixels (x-3+k, x-2+k)
-            const uint32_t o01 = 18u * (a0 + a6) + 34u * (a1 + a5) + 48u * (a2 + a4) + 56u * a3;
-            const uint32_t o23 = 18u * (a2 + a8) + 34u * (a3 + a7) + 48u * (a4 + a6) + 56u * a5;
+            // seven multiply-adds each (IMAD runs on the FMA pipe, which has twice the integer-ALU throughput)
+            const uint32_t o01 = mad7(a0, a1, a2, a3, a4, a5, a6, 0u), o23 = mad7(a2, a3, a4, a5, a6, a7, a8, 0u);
             shv[r][q] = make_uint2(o01, o23);
         }
         __syncthreads();
@@ -467,9 +480,9 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
                 }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const uint32_t v0 = 18u * (lo[r] + lo[r + 6]) + 34u * (lo[r + 1] + lo[r + 5]) + 48u * (lo[r + 2] + lo[r + 4]) + 56u * lo[r + 3];
-                    const uint32_t v1 = 18u * (hi[r] + hi[r + 6]) + 34u * (hi[r + 1] + hi[r + 5]) + 48u * (hi[r + 2] + hi[r + 4]) + 56u * hi[r + 3];
-                    out[r] |= (((v0 + 32768u) >> 16) | ((v1 + 32768u) >> 16) << 8) << (16 * half);
+                    const uint32_t v0 = mad7(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5], lo[r + 6], 32768u);
+                    const uint32_t v1 = mad7(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5], hi[r + 6], 32768u);
+                    out[r] |= ((v0 >> 16) | (v1 >> 16) << 8) << (16 * half);
                 }
             }
             uint8_t *dst = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off + gx;
@@ -518,58 +531,39 @@ struct FfCfg {
     static constexpr int WARPS = 4;
     static constexpr int PITCH = 37;                                   // tile words per row: pairs -2 .. 33, +1
     static constexpr int ROWS = CELL + 6;
-    static constexpr int LIST = 2 * ((CELL + 1) / 2) * ((CELL + 1) / 2);   // NMS survivors of two CELL x CELL rectangles
+    static constexpr int LIST_LANES = 32 * ((CELL + 1) / 2);           // per-lane survivor slots: a column pair keeps <= one pixel every 2nd row
+    static constexpr int LIST = LIST_LANES + (CELL + 1) / 2;           // + the second column of the lane that straddles two cells
     static constexpr int WARP_WORDS = ROWS * PITCH + LIST;
     static constexpr int SMEM = WARPS * WARP_WORDS * 4;
 };
 
+// A job = one cell row x up to two adjacent cells of one level of one frame.
+struct FfJob { int level, x0, y0, nrows, span, wc, frame; };
+
+__device__ __forceinline__ FfJob ff_job(const DevParams *__restrict__ P, int widx, int frame)
+{
+    const uint32_t wk = P->ffast_work[widx];
+    FfJob j;
+    j.level = wk >> 24;
+    const int ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
+    const LevelGeom &G = P->lv[j.level];
+    j.wc = G.w_cell;
+    const int ncell = min(max(1, 64 / j.wc), G.cols_vis - cj);
+    j.x0 = kEdge + cj * j.wc;
+    const int x1 = min(j.x0 + ncell * j.wc, G.x_end);
+    j.y0 = kEdge + ci * G.h_cell;
+    const int y1 = min(j.y0 + G.h_cell, G.y_end);
+    j.span = x1 - j.x0; j.nrows = y1 - j.y0; j.frame = frame;
+    return j;
+}
+
+// Scores, cell-local non-max suppression, threshold choice and emission of one job whose 16-bit tile is staged.
 template <int CELL>
-__global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const DevParams *__restrict__ P, Src0 s0, int work_off, int work_end)
+__device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, const FfJob &J, uint32_t *tile, uint32_t *list, int lane)
 {
     using C = FfCfg<CELL>;
-    extern __shared__ __align__(16) uint32_t ff_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.y;
-    const int widx = work_off + blockIdx.x * C::WARPS + warp;
-    if (widx >= work_end) return;                                      // warp-uniform; the kernel has no block barrier
-    uint32_t *tile = ff_smem + (size_t)warp * C::WARP_WORDS;
-    uint32_t *list = tile + C::ROWS * C::PITCH;
-    const uint32_t wk = P->ffast_work[widx];
-    const int level = wk >> 24, ci = (wk >> 12) & 0xfff, cj = wk & 0xfff;
+    const int level = J.level, x0 = J.x0, y0 = J.y0, nrows = J.nrows, span = J.span, wc = J.wc, frame = J.frame;
     const LevelGeom &G = P->lv[level];
-    const int wc = G.w_cell;
-    const int ncell = min(max(1, 64 / wc), G.cols_vis - cj);
-    const int x0 = kEdge + cj * wc, x1 = min(x0 + ncell * wc, G.x_end);
-    const int y0 = kEdge + ci * G.h_cell, y1 = min(y0 + G.h_cell, G.y_end);
-    const int span = x1 - x0, nrows = y1 - y0;
-    int sp;
-    const uint8_t *img = level_ptr(P, s0, frame, level, &sp);
-    // ---- stage rows y0-3 .. y1+2, pixels x0-4 .. x0+67 as 16-bit lanes (tile pixel u = x - x0 + 4).
-    //      A lane takes one aligned global word (4 pixels) and writes two whole tile words; when the cell starts
-    //      at an odd column the pairs straddle global words and the missing byte comes from the previous lane.
-    {
-        const int xb = (x0 - 4) & ~3, ush = xb - (x0 - 4);            // tile pixel of the first byte of global word 0: -3..0
-        const int xmaxw = (sp >> 2) - 1, srows = nrows + 6;
-        constexpr int NW = 20;                                         // 72 pixels + 3 of misalignment (+1 spare)
-        const bool odd = ush & 1;
-        const int c = lane;                                            // lanes 0..19: the words of one row
-        const int u = ush + 4 * c - (odd ? 1 : 0);                     // tile pixel of my first output pair (even)
-        const int gw = min((xb >> 2) + c, xmaxw);
-        uint32_t *d = tile + (u >> 1);
-        const bool st0 = lane < NW && (unsigned)u < 72u, st1 = lane < NW && (unsigned)(u + 2) < 72u;
-#pragma unroll 4
-        for (int r = 0; r < srows; ++r) {
-            const int gy = min(y0 - 3 + r, G.h - 1);
-            uint32_t v = 0;
-            if (lane < NW) v = __ldg(reinterpret_cast<const uint32_t *>(img + (long long)gy * sp) + gw);
-            const uint32_t pv = __shfl_up_sync(0xffffffffu, v, 1);
-            // even shift: pairs (b0,b1),(b2,b3); odd shift: pairs (prev.b3,b0),(b1,b2)
-            const uint32_t w_lo = odd ? (__byte_perm(pv, v, 0x0403) & 0x00ff00ffu) : __byte_perm(v, 0, 0x4140);
-            const uint32_t w_hi = odd ? __byte_perm(v, 0, 0x4241) : __byte_perm(v, 0, 0x4342);
-            if (st0) d[r * C::PITCH] = w_lo;
-            if (st1) d[r * C::PITCH + 1] = w_hi;
-        }
-    }
-    __syncwarp();
     // ---- per-lane constants: which of my two pixels are inside the job, and which neighbours share their cell
     const int dx0 = 2 * lane, dx1 = dx0 + 1;
     const bool in0 = dx0 < span, in1 = dx1 < span;
@@ -578,11 +572,14 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const De
     // Lv = (left neighbour of px0, px0 as left neighbour of px1); Rv = (px1 as right neighbour of px0, right neighbour of px1)
     const unsigned mL = ((dx0 > 0 && (dx0 - 1 >= wc) == c0) ? 0xffffu : 0u) | ((c0 == c1) ? 0xffff0000u : 0u);
     const unsigned mR = ((in1 && c0 == c1) ? 0xffffu : 0u) | ((dx1 + 1 < span && (dx1 + 1 >= wc) == c1) ? 0xffff0000u : 0u);
+    const bool straddle = in1 && c0 != c1;                             // my two pixels belong to different cells: independent columns
     const int th_store = min(P->min_th, P->ini_th);
-    const unsigned thv = 0x00010001u * (unsigned)(th_store + 257);     // biased compare: best >= th + 257  <=>  score >= th
-    const unsigned lt = lanemask_lt();
-    int nl = 0;
+    // S' = score - th_store + 1 where the pixel is a corner at th_store (>= 1), else 0.  VIADD.16x2 / VIADDMNMX.S16x2 are
+    // the native packed forms; there is no packed subtract, so differences are written as x + ~y (= x - y - 1).
+    const unsigned k1mth = 0x00010001u * (unsigned)((1 - th_store) & 0xffff);
+    int nl = 0, nl2 = 0;
     unsigned T2 = 0, T1 = 0, U1 = 0, C1 = 0;                           // T/U/centre of rows y-2 and y-1 (0 outside the cell)
+    uint32_t *ovf = list + C::LIST_LANES;                              // second-pixel survivors of the one lane that straddles two cells
 
     unsigned a[7][3], o[7][4];
     const uint32_t *col = tile + lane + 2;
@@ -594,18 +591,20 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const De
         o[slot][0] = __funnelshift_r(w0_, w1_, 16); o[slot][1] = __funnelshift_r(w1_, w2_, 16); \
         o[slot][2] = __funnelshift_r(w2_, w3_, 16); o[slot][3] = __funnelshift_r(w3_, w4_, 16); \
     }
-    // finalize the non-max suppression of row `yy` whose centre is Cc, with max-of-3 of the rows above / below
+    // finalize the non-max suppression of row `yy` whose centre is Cc, with max-of-3 of the rows above / below.
+    // Cc + ~m8 = Cc - m8 - 1 >= 0  <=>  centre strictly greater than all 8 neighbours (and then Cc >= 1).  Survivors go
+    // to a private list per lane (slot-major, so no ballot / prefix is needed): S' | pixel << 9 | row << 10.
 #define FF_NMS(yy, Tabove, Umid, Cc, Tbelow)                                                                     \
     {                                                                                                            \
         const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
-        const unsigned df = m8 + 0x01000100u - (Cc);              /* lane < 256 <=> centre > all 8 neighbours */ \
-        const bool k0 = !(df & 0x100u) && ((Cc) & 0xffffu), k1 = !(df & 0x01000000u) && ((Cc) >> 16);           \
-        const unsigned b0_ = __ballot_sync(0xffffffffu, k0), b1_ = __ballot_sync(0xffffffffu, k1);               \
-        if (b0_ | b1_) {                                                                                         \
-            const uint32_t yr = (uint32_t)(y0 + (yy) - kMinBorder) << 12;                                       \
-            if (k0) list[nl + __popc(b0_ & lt)] = (uint32_t)(x0 + dx0 - kMinBorder) | yr | ((Cc) & 0xffu) << 24; \
-            if (k1) list[nl + __popc(b0_) + __popc(b1_ & lt)] = (uint32_t)(x0 + dx1 - kMinBorder) | yr | (((Cc) >> 16) & 0xffu) << 24; \
-            nl += __popc(b0_) + __popc(b1_);                                                                     \
+        const unsigned kb = ~__vadd2(~m8, (Cc)) & 0x80008000u;                                                   \
+        if (kb) {                                                                                                \
+            const unsigned yb = (unsigned)(yy) << 10;                                                            \
+            if (kb & 0x8000u) { list[nl * 32 + lane] = ((Cc) & 0xffffu) | yb; ++nl; }                            \
+            if (kb & 0x80000000u) {                                                                              \
+                const unsigned e1 = ((Cc) >> 16) | 0x200u | yb;                                                  \
+                if (straddle) { ovf[nl2] = e1; ++nl2; } else { list[nl * 32 + lane] = e1; ++nl; }                \
+            }                                                                                                    \
         }                                                                                                        \
     }
 #pragma unroll
@@ -647,10 +646,9 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const De
                 }
                 const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bm[0], bm[1], bm[2]), __vimax3_s16x2(bm[3], bm[4], lo9[15]), lo9[15]);
                 const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dm[0], dm[1], dm[2]), __vimin3_s16x2(dm[3], dm[4], hi9[15]), hi9[15]);
-                const unsigned best = __vmaxs2(maxmin + 0x01000100u - cc, cc + 0x01000100u - minmax);   // score + 257 per lane
-                // S = score where score >= th_store and the pixel is inside the job, else 0 (per 16-bit lane)
-                const unsigned ge = __vcmpges2(best, thv);                                                // 0xffff per lane that passes
-                const unsigned Cv = (best - 0x00010001u) & ge & in_mask & 0x00ff00ffu;                    // (score + 256) & 0xff == score; best >= 1: no borrow
+                // bright: maxmin - c - th = maxmin + (~c + 1 - th); dark: c - minmax - th = (c + 1 - th) + ~minmax
+                const unsigned tb = __viaddmax_s16x2_relu(maxmin, __vadd2(~cc, k1mth), 0u);
+                const unsigned Cv = __viaddmax_s16x2(__vadd2(cc, k1mth), ~minmax, tb) & in_mask;
                 // neighbours in the same row, masked to the pixels' own cells
                 const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
                 const unsigned Lv = __funnelshift_r(Pl, Cv, 16) & mL, Rv = __funnelshift_r(Cv, Pr, 16) & mR;
@@ -664,50 +662,202 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32) k_fast_fused(const De
 #undef FF_LOAD
 #undef FF_NMS
     __syncwarp();
-    // ---- threshold choice per cell and emission
+    // ---- threshold choice per cell (:812-816) and emission
     const int ini = P->ini_th, mn = P->min_th;
-    bool has0 = false, has1 = false;
-    for (int base = 0; base < nl; base += 32) {
-        const int i = base + lane;
-        bool a0 = false, a1 = false;
-        if (i < nl) {
-            const uint32_t c = list[i];
-            const bool second = (int)(c & 0xfff) + kMinBorder - x0 >= wc;
-            const bool strong = (int)(c >> 24) >= ini;
-            a0 = strong && !second; a1 = strong && second;
+    const int ntot = nl + nl2, nmax = __reduce_max_sync(0xffffffffu, ntot);
+    const int s_ini = ini - th_store + 1;                              // S' >= s_ini  <=>  score >= iniThFAST
+    int strong0 = 0, strong1 = 0, weak0 = 0, weak1 = 0;
+    for (int i = 0; i < nmax; ++i) {
+        if (i < ntot) {
+            const uint32_t en = i < nl ? list[i * 32 + lane] : ovf[i - nl];
+            const bool cell1 = dx0 + (int)((en >> 9) & 1u) >= wc, st = (int)(en & 0x1ffu) >= s_ini;
+            strong0 += st && !cell1; strong1 += st && cell1; weak0 += !st && !cell1; weak1 += !st && cell1;
         }
-        has0 |= __any_sync(0xffffffffu, a0); has1 |= __any_sync(0xffffffffu, a1);
     }
-    const int t0c = has0 ? ini : (mn < ini ? mn : 256), t1c = has1 ? ini : (mn < ini ? mn : 256);
+    const bool has0 = __any_sync(0xffffffffu, strong0 > 0), has1 = __any_sync(0xffffffffu, strong1 > 0);
+    // a cell with a corner at iniThFAST keeps only those; an empty one falls back to minThFAST (when that is lower)
+    const int s0c = has0 ? s_ini : (mn < ini ? 1 : 0x7fffffff), s1c = has1 ? s_ini : (mn < ini ? 1 : 0x7fffffff);
+    const int mine = strong0 + strong1 + (has0 || mn >= ini ? 0 : weak0) + (has1 || mn >= ini ? 0 : weak1);
+    int incl = mine;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, ofs); if (lane >= ofs) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
     uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
-    uint32_t *cnt = P->cand_count + frame * P->nlevels + level;
-    for (int base = 0; base < nl; base += 32) {
-        const int i = base + lane;
-        bool emit = false;
-        uint32_t c = 0;
-        if (i < nl) {
-            c = list[i];
-            const bool second = (int)(c & 0xfff) + kMinBorder - x0 >= wc;
-            emit = (int)(c >> 24) >= (second ? t1c : t0c);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, emit);
-        if (m) {
-            int slot = 0;
-            if (lane == 0) slot = (int)atomicAdd(cnt, (unsigned)__popc(m));
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            const int at = slot + __popc(m & lt);
-            if (emit && at < G.cand_cap) cand[at] = c;
+    int base = 0;
+    if (lane == 0) base = (int)atomicAdd(P->cand_count + frame * P->nlevels + level, (unsigned)total);
+    int at = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
+    const uint32_t yx0 = (uint32_t)(x0 + dx0 - kMinBorder) | (uint32_t)(y0 - kMinBorder) << 12;
+    for (int i = 0; i < ntot; ++i) {
+        const uint32_t en = i < nl ? list[i * 32 + lane] : ovf[i - nl];
+        const int px = (en >> 9) & 1u, sv = en & 0x1ffu;
+        if (sv >= (dx0 + px >= wc ? s1c : s0c)) {
+            if (at < G.cand_cap) cand[at] = yx0 + (uint32_t)px + ((en >> 10) << 12) + ((uint32_t)(sv + th_store - 1) << 24);
+            ++at;
         }
     }
 }
 
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls)
+// Rows of the job's tile from `src` (row pitch sp bytes, word index base wbase): a lane takes one aligned source word
+// (4 pixels) and writes two whole tile words; when the cell starts at an odd column the pairs straddle source words
+// and the missing byte comes from the previous lane.  SMEM_SRC: the source is the TMA-staged raw box in shared memory.
+template <int CELL, bool SMEM_SRC, int UNR = 4>
+__device__ __forceinline__ void ff_stage(const uint8_t *src, int sp, int x_org, int row_org, int row_max, int xmaxw,
+                                         const FfJob &J, uint32_t *tile, int lane)
+{
+    using C = FfCfg<CELL>;
+    const int xb = (J.x0 - 4) & ~3, ush = xb - (J.x0 - 4);          // tile pixel of the first byte of source word 0: -3..0
+    const int srows = J.nrows + 6;
+    constexpr int NW = 20;                                           // 72 pixels + 3 of misalignment (+1 spare)
+    const bool odd = ush & 1;
+    const int c = lane;                                              // lanes 0..19: the words of one row
+    const int u = ush + 4 * c - (odd ? 1 : 0);                       // tile pixel of my first output pair (even)
+    const int gw = min(((xb - x_org) >> 2) + c, xmaxw);
+    uint32_t *d = tile + (u >> 1);
+    const bool st0 = lane < NW && (unsigned)u < 72u, st1 = lane < NW && (unsigned)(u + 2) < 72u;
+#pragma unroll UNR
+    for (int r = 0; r < srows; ++r) {
+        const int gy = min(J.y0 - 3 + r, row_max) - row_org;
+        uint32_t v = 0;
+        if (lane < NW) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(src + (long long)gy * sp) + gw;
+            v = SMEM_SRC ? *q : __ldg(q);
+        }
+        const uint32_t pv = __shfl_up_sync(0xffffffffu, v, 1);
+        // even shift: pairs (b0,b1),(b2,b3); odd shift: pairs (prev.b3,b0),(b1,b2)
+        const uint32_t w_lo = odd ? (__byte_perm(pv, v, 0x0403) & 0x00ff00ffu) : __byte_perm(v, 0, 0x4140);
+        const uint32_t w_hi = odd ? __byte_perm(v, 0, 0x4241) : __byte_perm(v, 0, 0x4342);
+        if (st0) d[r * C::PITCH] = w_lo;
+        if (st1) d[r * C::PITCH + 1] = w_hi;
+    }
+}
+
+template <int CELL, int MINB = 4, int UNR = 4>
+__global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, MINB) k_fast_fused(const DevParams *__restrict__ P, Src0 s0, int work_off, int work_end)
+{
+    using C = FfCfg<CELL>;
+    extern __shared__ __align__(16) uint32_t ff_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.y;
+    const int widx = work_off + blockIdx.x * C::WARPS + warp;
+    if (widx >= work_end) return;                                      // warp-uniform; the kernel has no block barrier
+    uint32_t *tile = ff_smem + (size_t)warp * C::WARP_WORDS;
+    uint32_t *list = tile + C::ROWS * C::PITCH;
+    const FfJob J = ff_job(P, widx, frame);
+    int sp;
+    const uint8_t *img = level_ptr(P, s0, frame, J.level, &sp);
+    ff_stage<CELL, false, UNR>(img, sp, 0, 0, P->lv[J.level].h - 1, (sp >> 2) - 1, J, tile, lane);
+    __syncwarp();
+    ff_process<CELL>(P, J, tile, list, lane);
+}
+
+// ---- persistent TMA variant: every warp walks (job, frame) items; the raw pixel box of the NEXT item (96 bytes x
+// h_cell+6 rows, 16-byte aligned origin) is fetched by cp.async.bulk.tensor while the current item is scored.
+template <int CELL>
+struct FfTmaCfg {
+    using C = FfCfg<CELL>;
+    static constexpr int RAW_BYTES = (kFfBoxW * C::ROWS + 127) / 128 * 128;
+    static constexpr int WARP_BYTES = (RAW_BYTES + C::WARP_WORDS * 4 + 127) / 128 * 128;
+    static constexpr int SMEM = C::WARPS * WARP_BYTES;
+};
+
+template <int CELL>
+__global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32)
+k_fast_fused_tma(const DevParams *__restrict__ P, const __grid_constant__ FastMaps maps, int work_off, int work_end, int nframes)
+{
+    using C = FfCfg<CELL>;
+    using T = FfTmaCfg<CELL>;
+    extern __shared__ __align__(128) uint8_t fft_smem[];
+    __shared__ __align__(8) uint64_t s_bar[C::WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *raw = fft_smem + (size_t)warp * T::WARP_BYTES;
+    uint32_t *tile = reinterpret_cast<uint32_t *>(raw + T::RAW_BYTES);
+    uint32_t *list = tile + C::ROWS * C::PITCH;
+    const int njobs = work_end - work_off, total = njobs * nframes;
+    const int stride = gridDim.x * C::WARPS;
+    int item = blockIdx.x * C::WARPS + warp;
+    if (item >= total) return;                                         // warp-uniform; the kernel has no block barrier
+    const unsigned bar = smem_u32(&s_bar[warp]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](const FfJob &J) {                                 // lane 0
+        const int rows = P->lv[J.level].h_cell + 6;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(kFfBoxW * rows) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     :: "r"(smem_u32(raw)), "l"(reinterpret_cast<unsigned long long>(&maps.m[J.level])), "r"(bar),
+                        "r"((J.x0 - 4) & ~15), "r"(J.y0 - 3), "r"(J.frame) : "memory");
+    };
+    FfJob J = ff_job(P, work_off + item % njobs, item / njobs);
+    if (lane == 0) issue(J);
+    unsigned phase = 0;
+    for (;;) {
+        mbar_wait_parity(&s_bar[warp], phase);
+        phase ^= 1u;
+        // rows past the image come back as zeros; they only feed pixels outside the detection area
+        ff_stage<CELL, true>(raw, kFfBoxW, (J.x0 - 4) & ~15, J.y0 - 3, 0x7fffffff, kFfBoxW / 4 - 1, J, tile, lane);
+        __syncwarp();                                                  // raw is consumed, the tile is complete
+        const int next = item + stride;
+        FfJob Jn = J;
+        if (next < total) {
+            Jn = ff_job(P, work_off + next % njobs, next / njobs);
+            if (lane == 0) issue(Jn);
+        }
+        ff_process<CELL>(P, J, tile, list, lane);
+        if (next >= total) break;
+        __syncwarp();
+        item = next; J = Jn;
+    }
+}
+
+template <int CELL>
+static cudaError_t launch_fast_tma(const DevParams *dP, const FastMaps &maps, int work_off, int work_end, int nframes, cudaStream_t st)
+{
+    using C = FfCfg<CELL>;
+    using T = FfTmaCfg<CELL>;
+    cudaError_t e = cudaFuncSetAttribute(k_fast_fused_tma<CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
+    if (e != cudaSuccess) return e;
+    const int per_sm = (227 * 1024) / (T::SMEM + 1024);
+    const int total = (work_end - work_off) * nframes;
+    int grid = 148 * (per_sm < 1 ? 1 : per_sm);
+    if (grid > (total + C::WARPS - 1) / C::WARPS) grid = (total + C::WARPS - 1) / C::WARPS;
+    k_fast_fused_tma<CELL><<<grid, C::WARPS * 32, T::SMEM, st>>>(dP, maps, work_off, work_end, nframes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small, cudaStream_t st, LaunchStats *ls,
+                        const FastMaps *maps)
 {
     if (hP.n_ffast_work == 0) return cudaSuccess;
+    if (maps) {
+        if (n_small > 0) {
+            cudaError_t e = launch_fast_tma<44>(dP, *maps, 0, n_small, nframes, st);
+            if (e != cudaSuccess) return e;
+            ls->launches++;
+        }
+        if (hP.n_ffast_work > n_small) {
+            cudaError_t e = launch_fast_tma<64>(dP, *maps, n_small, hP.n_ffast_work, nframes, st);
+            if (e != cudaSuccess) return e;
+            ls->launches++;
+        }
+        return cudaSuccess;
+    }
     if (n_small > 0) {
         using C = FfCfg<44>;
-        cudaFuncSetAttribute(k_fast_fused<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        k_fast_fused<44><<<dim3((n_small + C::WARPS - 1) / C::WARPS, nframes), C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small);
+        static const int variant = std::getenv("ORBX_FF_VARIANT") ? std::atoi(std::getenv("ORBX_FF_VARIANT")) : 0;
+        const dim3 grid((n_small + C::WARPS - 1) / C::WARPS, nframes);
+#define FF_GO(...) do { cudaFuncSetAttribute(k_fast_fused<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); \
+                        k_fast_fused<__VA_ARGS__><<<grid, C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small); } while (0)
+        switch (variant) {
+        case 1: FF_GO(44, 5, 4); break;
+        case 2: FF_GO(44, 4, 12); break;
+        case 3: FF_GO(44, 5, 12); break;
+        case 4: FF_GO(44, 4, 4); break;
+        default: FF_GO(44, 4, 12); break;
+        }
+#undef FF_GO
         ls->launches++;
     }
     if (hP.n_ffast_work > n_small) {
@@ -810,10 +960,17 @@ static OctreeSmem octree_smem(int threads, int node_cap, int max_feat, size_t bu
     return o;
 }
 
+// shared-memory budget of the 256-thread octree CTA (experiment knob ORBX_OCT_BUDGET_KB)
+static size_t oct_small_budget()
+{
+    static const size_t b = std::getenv("ORBX_OCT_BUDGET_KB") ? (size_t)std::atoi(std::getenv("ORBX_OCT_BUDGET_KB")) * 1024 : 100 * 1024;
+    return b;
+}
+
 size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
 {
     const int threads = max_node_cap <= 1024 ? 256 : (max_node_cap <= 4096 ? 512 : 1024);
-    const OctreeSmem o = octree_smem(threads, max_node_cap, max_feat, threads == 256 ? 100 * 1024 : 200 * 1024);
+    const OctreeSmem o = octree_smem(threads, max_node_cap, max_feat, threads == 256 ? oct_small_budget() : 200 * 1024);
     if (key_cap) *key_cap = o.key_cap;
     return o.bytes;
 }
@@ -1068,7 +1225,7 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
 {
     ls->launches++;
     // CTA size by node-array capacity (THREADS*IPT records); small CTAs leave room for 2+ per SM
-    if (max_node_cap <= 1024) return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, 100 * 1024, st);
+    if (max_node_cap <= 1024) return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget(), st);
     if (max_node_cap <= 4096) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
     return launch_octree_t<1024, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
 }

@@ -69,7 +69,11 @@ struct BlurMaps { CUtensorMap m[kMaxLevels]; };
 cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls,
                         const BlurMaps *maps = nullptr, unsigned tma_levels = 0);
 constexpr int kBlurBoxW = kBlurTileW + 32, kBlurBoxH = kBlurTileH + 6;   // 16 bytes of halo each side keep the box origin 16-byte aligned
-cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_jobs, cudaStream_t st, LaunchStats *ls);
+// maps->m[l]: level-l images of the batch, box kFfBoxW bytes x (h_cell + 6) rows; nullptr = plain global staging
+struct FastMaps { CUtensorMap m[kMaxLevels]; };
+constexpr int kFfBoxW = 96;
+cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, int n_small_jobs, cudaStream_t st, LaunchStats *ls,
+                        const FastMaps *maps = nullptr);
 cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes, int max_node_cap, int max_feat, cudaStream_t st, LaunchStats *ls);
 // img[l] / blr[l]: level-l images of the batch and their blurred copies, boxes kOdIcBoxW x kOdIcBoxH and kOdBlBoxW x kOdBlBoxH
 struct OdMaps { CUtensorMap img[kMaxLevels], blr[kMaxLevels]; };

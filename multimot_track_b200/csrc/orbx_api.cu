@@ -56,6 +56,7 @@ struct orbx_handle {
     TmaMaps tma;                        // pyramid source descriptors (levels >= 2 from our buffer, level 1 from the batch's level 0)
     const void *tma_l0_base = nullptr; long long tma_l0_fs = 0; int tma_l0_pitch = 0, tma_l0_frames = 0;
     bool use_tma = true;
+    FastMaps fast_maps; unsigned fast_ok = 0;               // FAST raw boxes (bit l = level l encoded)
     OdMaps od_maps; unsigned od_img_ok = 0, od_blr_ok = 0;  // orientation / descriptor patch boxes (bit l = level l encoded)
     BlurMaps blur_maps; unsigned blur_tma_levels = 0;       // blur source boxes: bit l set = maps.m[l] valid (level 0 per batch source)
     LaunchStats stats;
@@ -142,7 +143,11 @@ int ensure_batch(orbx_handle *h, int nframes)
                                         g.pyr_frame_bytes, nframes, h->tma.box_w[l], h->tma.box_h[l]);
     }
     // blur source boxes: one descriptor per level of our pyramid buffer (level 0 follows the batch's source, enqueue_pipeline)
-    h->blur_tma_levels = 0; h->od_img_ok = 0; h->od_blr_ok = 0;
+    h->blur_tma_levels = 0; h->od_img_ok = 0; h->od_blr_ok = 0; h->fast_ok = 0;
+    std::memset(&h->fast_maps, 0, sizeof(h->fast_maps));
+    for (int l = 1; l < g.nlevels && h->use_tma; ++l)
+        if (encode_image_map(&h->fast_maps.m[l], h->d_pyr + g.lv[l].img_off, g.lv[l].pitch, g.lv[l].h, g.pyr_frame_bytes, nframes, kFfBoxW, g.lv[l].h_cell + 6))
+            h->fast_ok |= 1u << l;
     std::memset(&h->blur_maps, 0, sizeof(h->blur_maps));
     std::memset(&h->od_maps, 0, sizeof(h->od_maps));
     for (int l = 0; l < g.nlevels && h->use_tma; ++l) {
@@ -215,6 +220,8 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
         if (P.nlevels > 1) h->tma.ok[1] = encode_image_map(&h->tma.src[1], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, h->tma.box_w[1], h->tma.box_h[1]);
         if (encode_image_map(&h->blur_maps.m[0], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, kBlurBoxW, kBlurBoxH)) h->blur_tma_levels |= 1u;
         else h->blur_tma_levels &= ~1u;
+        if (encode_image_map(&h->fast_maps.m[0], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, kFfBoxW, h->geo.lv[0].h_cell + 6)) h->fast_ok |= 1u;
+        else h->fast_ok &= ~1u;
         if (encode_image_map(&h->od_maps.img[0], s0.ptr, s0.pitch, h->geo.lv[0].h, s0.frame_stride, nframes, kOdIcBoxW, kOdIcBoxH)) h->od_img_ok |= 1u;
         else h->od_img_ok &= ~1u;
         h->tma_l0_base = s0.ptr; h->tma_l0_fs = s0.frame_stride; h->tma_l0_pitch = s0.pitch; h->tma_l0_frames = nframes;
@@ -223,7 +230,11 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     MARK(2);
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats, h->use_tma ? &h->blur_maps : nullptr, h->blur_tma_levels));
     MARK(3);
-    CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_ffast_small, st, &h->stats));
+    {
+        const unsigned all = P.nlevels >= 32 ? 0xffffffffu : (1u << P.nlevels) - 1u;
+        const bool fast_tma = h->use_tma && (h->fast_ok & all) == all && std::getenv("ORBX_FAST_TMA");   // opt-in: measured slower (12 warps / SM)
+        CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_ffast_small, st, &h->stats, fast_tma ? &h->fast_maps : nullptr));
+    }
     MARK(4);
     CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
     MARK(5);
