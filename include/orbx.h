@@ -200,6 +200,18 @@ int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const uint8_t *desc
 int orbx_match_device(orbx_handle *h, const uint8_t *d_descA, int nA, const uint8_t *d_descB, int nB,
                       int th, float ratio, int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept);
 
+/* Rotation-consistency check of the matchers (mbCheckOrientation): src/ORBmatcher.cc:545 and 610-620 (histogram of
+ * angleA[i] - angleB[idx[i]] over the accepted matches, 30 bins, bin = round(rot * (1.0f / HISTO_LENGTH)) as the
+ * reference writes it), ComputeThreeMaxima :2233-2274, pruning :641-660.  accept[nA] is updated in place (host
+ * pointers; angleB has nB entries); hist[30] and top3[3] (ind1..ind3, -1 = none) may be NULL.
+ * Returns the number of matches kept (>= 0) or a negative status. */
+int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, uint8_t *accept, const float *angleA,
+                         const float *angleB, int nB, int32_t *hist, int32_t *top3);
+
+/* Same on device arrays, asynchronous on the handle's stream; d_kept (may be NULL) receives the count. */
+int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA,
+                                const float *d_angleB, int32_t *d_hist, int32_t *d_top3, int32_t *d_kept);
+
 /* ---- per-stage device timing ---------------------------------------------- */
 
 /* With profiling on, every submit brackets its stages with CUDA events on the

@@ -1737,6 +1737,66 @@ __global__ void k_match_merge(const int4 *__restrict__ partial, int nA, int nchu
     }
 }
 
+// mbCheckOrientation (src/ORBmatcher.cc:545, 610-620, 641-660; ComputeThreeMaxima :2233-2274): 30-bin histogram of
+// the angle differences of the accepted matches, bin = round(rot * (1.0f / HISTO_LENGTH)) exactly as the reference
+// writes it (only bins 0..12 can fill; kept for parity), the three most populated bins survive (second / third only
+// when >= 0.1 * first, ties to the lower bin as the reference's strict > scan does).  One CTA; counts are
+// order-independent, so shared-memory atomics are exact.
+__device__ __forceinline__ int rotation_bin(float a, float b)
+{
+    float rot = __fsub_rn(a, b);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / ORBX_HISTO_LENGTH));
+    return bin == ORBX_HISTO_LENGTH ? 0 : bin;
+}
+
+__global__ void __launch_bounds__(1024)
+k_rotation_filter(int nA, const int32_t *__restrict__ idx, uint8_t *__restrict__ accept, const float *__restrict__ angleA,
+                  const float *__restrict__ angleB, int32_t *__restrict__ hist_out, int32_t *__restrict__ top3_out, int *__restrict__ kept_out)
+{
+    __shared__ int cnt[32], sel[3], kept;
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) kept = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nA; i += blockDim.x)
+        if (accept[i]) atomicAdd(&cnt[rotation_bin(angleA[i], angleB[idx[i]])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < ORBX_HISTO_LENGTH; ++i) {
+            const int s = cnt[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+            else if (s > max3) { max3 = s; i3 = i; }
+        }
+        const float lim = __fmul_rn(0.1f, (float)max1);
+        if ((float)max2 < lim) { i2 = -1; i3 = -1; }
+        else if ((float)max3 < lim) i3 = -1;
+        sel[0] = i1; sel[1] = i2; sel[2] = i3;
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < nA; i += blockDim.x)
+        if (accept[i]) {
+            const int b = rotation_bin(angleA[i], angleB[idx[i]]);
+            if (b == sel[0] || b == sel[1] || b == sel[2]) ++mine; else accept[i] = 0;
+        }
+    mine = warp_sum(mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&kept, mine);
+    __syncthreads();
+    if (threadIdx.x < ORBX_HISTO_LENGTH && hist_out) hist_out[threadIdx.x] = cnt[threadIdx.x];
+    if (threadIdx.x < 3 && top3_out) top3_out[threadIdx.x] = sel[threadIdx.x];
+    if (threadIdx.x == 0 && kept_out) *kept_out = kept;
+}
+
+cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA, const float *d_angleB,
+                                   int32_t *d_hist, int32_t *d_top3, int *d_kept, cudaStream_t st, LaunchStats *ls)
+{
+    k_rotation_filter<<<1, 1024, 0, st>>>(nA, d_idx, d_accept, d_angleA, d_angleB, d_hist, d_top3, d_kept);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 int match_chunks(int nA, int nB)
 {
     if (nB <= 0) return 1;

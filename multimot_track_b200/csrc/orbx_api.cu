@@ -634,6 +634,53 @@ extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const ui
     return nacc;
 }
 
+extern "C" int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA,
+                                           const float *d_angleB, int32_t *d_hist, int32_t *d_top3, int32_t *d_kept)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (nA < 0 || (nA > 0 && (!d_idx || !d_accept || !d_angleA || !d_angleB))) return fail(h, ORBX_ERR_BAD_ARG, "orbx_rotation_filter_device: bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(launch_rotation_filter(nA, d_idx, d_accept, d_angleA, d_angleB, d_hist, d_top3, d_kept, h->stream, &h->stats));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, uint8_t *accept, const float *angleA,
+                                    const float *angleB, int nB, int32_t *hist, int32_t *top3)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (nA < 0 || nB < 0 || (nA > 0 && (!idx || !accept || !angleA)) || (nB > 0 && !angleB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_rotation_filter: bad argument");
+    for (int i = 0; i < nA; ++i)
+        if (accept[i] && (idx[i] < 0 || idx[i] >= nB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_rotation_filter: accepted match with idx outside [0, nB)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    // one scratch block: idx | angleA | angleB | hist[30] top3[3] kept[1] | accept
+    const size_t words = (size_t)nA * 2 + (size_t)nB + 34;
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, words * 4 + (size_t)nA + 16));
+    int32_t *d_idx = (int32_t *)d; float *d_a = (float *)(d + nA), *d_b = (float *)(d + 2 * (size_t)nA);
+    int32_t *d_hist = (int32_t *)(d + 2 * (size_t)nA + nB); uint8_t *d_acc = (uint8_t *)(d + words);
+    int32_t res[34];
+    auto body = [&]() -> int {
+        if (nA > 0) {
+            CU(cudaMemcpyAsync(d_idx, idx, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(d_a, angleA, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(d_acc, accept, (size_t)nA, cudaMemcpyHostToDevice, st));
+        }
+        if (nB > 0) CU(cudaMemcpyAsync(d_b, angleB, (size_t)nB * 4, cudaMemcpyHostToDevice, st));
+        CU(launch_rotation_filter(nA, d_idx, d_acc, d_a, d_b, d_hist, d_hist + 30, d_hist + 33, st, &h->stats));
+        if (nA > 0) CU(cudaMemcpyAsync(accept, d_acc, (size_t)nA, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(res, d_hist, sizeof(res), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return ORBX_OK;
+    };
+    const int rc = body();
+    cudaFree(d);
+    if (rc != ORBX_OK) return rc;
+    if (hist) std::memcpy(hist, res, 30 * sizeof(int32_t));
+    if (top3) std::memcpy(top3, res + 30, 3 * sizeof(int32_t));
+    return res[33];
+}
+
 // ---------------------------------------------------------------- profiling
 
 static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h"};

@@ -226,3 +226,17 @@ class ORBextractor:
                                   idx.ctypes.data, d1.ctypes.data, d2.ctypes.data, acc.ctypes.data)
         self._ck(rc)
         return idx, d1, d2, acc.astype(bool)
+
+    def rotation_filter(self, idx, accept, angleA, angleB):
+        """mbCheckOrientation (src/ORBmatcher.cc:610-620, 641-660, 2233-2274) on the GPU.
+        Returns (accept_after[nA] bool, hist[30], top3[3])."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        acc = np.ascontiguousarray(accept, np.uint8).copy()
+        a = np.ascontiguousarray(angleA, np.float32); b = np.ascontiguousarray(angleB, np.float32)
+        if len(acc) != len(idx) or len(a) != len(idx):
+            raise ValueError("idx, accept and angleA must have one entry per query")
+        hist = np.zeros(30, np.int32); top3 = np.zeros(3, np.int32)
+        rc = self._lib.orbx_rotation_filter(self._h, len(idx), idx.ctypes.data, acc.ctypes.data, a.ctypes.data, b.ctypes.data, len(b),
+                                            hist.ctypes.data, top3.ctypes.data)
+        self._ck(rc)
+        return acc.astype(bool), hist, top3

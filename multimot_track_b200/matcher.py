@@ -36,3 +36,13 @@ class ORBmatcher:
         th = self.TH_LOW if th is None else th
         ratio = self.mfNNratio if ratio is None else ratio
         return self._ext.match(descA, descB, th, ratio)
+
+    def match_oriented(self, descA, anglesA, descB, anglesB, th=None, ratio=None):
+        """match() followed, when mbCheckOrientation is set, by the rotation-consistency pruning every SearchBy*
+        applies to its accepted matches (src/ORBmatcher.cc:610-620, 641-660; ComputeThreeMaxima :2233-2274).
+        Returns idx, best, second, accept (after pruning), hist[30], top3[3]."""
+        idx, d1, d2, acc = self.match(descA, descB, th, ratio)
+        if not self.mbCheckOrientation:
+            return idx, d1, d2, acc, np.zeros(30, np.int32), np.full(3, -1, np.int32)
+        acc, hist, top3 = self._ext.rotation_filter(idx, acc, anglesA, anglesB)
+        return idx, d1, d2, acc, hist, top3

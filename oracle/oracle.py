@@ -59,6 +59,7 @@ class Oracle:
             L.orbo_hamming256.argtypes = [_VP, _VP]
             L.orbo_match.argtypes = [_VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP]
             L.orbo_match_mt.argtypes = [_VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP, _I]
+            L.orbo_rotation_filter.argtypes = [_I, _VP, _VP, _VP, _VP, _VP, _VP]
             L.orbo_extract_many.restype = ctypes.c_double
             L.orbo_extract_many.argtypes = [_I, _F, _I, _I, _I, _VP, _I, _I, _I, _I, _VP]
             cls._lib = L
@@ -149,6 +150,15 @@ class Oracle:
         return idx, d1, d2, acc.astype(bool)
 
     @classmethod
+    def rotation_filter(cls, idx, accept, angleA, angleB):
+        """mbCheckOrientation: returns (accept_after, hist[30], top3[3])."""
+        idx = np.ascontiguousarray(idx, np.int32); acc = np.ascontiguousarray(accept, np.uint8).copy()
+        a = np.ascontiguousarray(angleA, np.float32); b = np.ascontiguousarray(angleB, np.float32)
+        hist = np.zeros(30, np.int32); top3 = np.zeros(3, np.int32)
+        cls.lib().orbo_rotation_filter(len(idx), idx.ctypes.data, acc.ctypes.data, a.ctypes.data, b.ctypes.data, hist.ctypes.data, top3.ctypes.data)
+        return acc.astype(bool), hist, top3
+
+    @classmethod
     def extract_many(cls, params, frames, threads):
         """CPU baseline: frames [F,H,W] uint8 contiguous; returns (seconds, total keypoints)."""
         f = np.ascontiguousarray(frames, np.uint8)
@@ -179,6 +189,8 @@ class RefExtractor:
             L.orbref_distribute.argtypes = [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _I]
             L.orbref_descriptor_distance.argtypes = [_VP, _VP]
             L.orbref_thresholds.argtypes = [_VP, _VP, _VP]
+            if hasattr(L, "orbref_rotation_filter"):
+                L.orbref_rotation_filter.argtypes = [_I, _VP, _VP, _VP, _VP, _VP, _VP]
             if hasattr(L, "orbref_extract_many"):
                 L.orbref_extract_many.restype = ctypes.c_double
                 L.orbref_extract_many.argtypes = [_I, _F, _I, _I, _I, _VP, _I, _I, _I, _I, _VP]
@@ -226,6 +238,15 @@ class RefExtractor:
     def descriptor_distance(cls, a, b, variant="canon"):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return cls.lib(variant).orbref_descriptor_distance(a.ctypes.data, b.ctypes.data)
+
+    @classmethod
+    def rotation_filter(cls, idx, accept, angleA, angleB, variant="canon"):
+        """The reference's own ComputeThreeMaxima around the call-site code of SearchByBoW (:610-620, 641-660)."""
+        idx = np.ascontiguousarray(idx, np.int32); acc = np.ascontiguousarray(accept, np.uint8).copy()
+        a = np.ascontiguousarray(angleA, np.float32); b = np.ascontiguousarray(angleB, np.float32)
+        hist = np.zeros(30, np.int32); top3 = np.zeros(3, np.int32)
+        cls.lib(variant).orbref_rotation_filter(len(idx), idx.ctypes.data, acc.ctypes.data, a.ctypes.data, b.ctypes.data, hist.ctypes.data, top3.ctypes.data)
+        return acc.astype(bool), hist, top3
 
     @classmethod
     def extract_many(cls, params, frames, threads, variant="asis"):

@@ -533,6 +533,50 @@ int orbo_match_mt(const uint8_t *A, int nA, const uint8_t *B, int nB, int th, fl
     return acc;
 }
 
+/* Rotation-consistency check of the matchers (mbCheckOrientation): histogram fill as in src/ORBmatcher.cc:610-620
+ * (factor = 1.0f/HISTO_LENGTH, :545), ComputeThreeMaxima :2233-2274, pruning :641-660. */
+static void three_maxima(const int *cnt, int L, int *ind1, int *ind2, int *ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+        else if (s > max3) { max3 = s; *ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+int orbo_rotation_bin(float angle_a, float angle_b)
+{
+    const float factor = 1.0f / 30;
+    float rot = angle_a - angle_b;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == 30) bin = 0;
+    return bin;
+}
+
+int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
+                         int32_t *hist, int32_t *top3)
+{
+    int cnt[30] = {0};
+    for (int i = 0; i < nA; ++i)
+        if (accept[i]) cnt[orbo_rotation_bin(angleA[i], angleB[idx[i]])]++;
+    int i1 = -1, i2 = -1, i3 = -1;
+    three_maxima(cnt, 30, &i1, &i2, &i3);
+    int kept = 0;
+    for (int i = 0; i < nA; ++i)
+        if (accept[i]) {
+            const int b = orbo_rotation_bin(angleA[i], angleB[idx[i]]);
+            if (b == i1 || b == i2 || b == i3) ++kept; else accept[i] = 0;
+        }
+    if (hist) for (int i = 0; i < 30; ++i) hist[i] = cnt[i];
+    if (top3) { top3[0] = i1; top3[1] = i2; top3[2] = i3; }
+    return kept;
+}
+
 /* ----------------------------------------------------------- CPU baseline */
 
 typedef struct {

@@ -72,6 +72,10 @@ int orbo_hamming256(const uint8_t *a, const uint8_t *b);           /* SWAR popco
 int orbo_match(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int th, float ratio,
                int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept);
 /* Same, query rows split over `threads` pthreads (CPU baseline). */
+/* mbCheckOrientation (src/ORBmatcher.cc:610-620, 641-660, 2233-2274): prunes accept[] in place, returns matches kept */
+int orbo_rotation_bin(float angle_a, float angle_b);
+int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
+                         int32_t *hist, int32_t *top3);
 int orbo_match_mt(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int th, float ratio,
                   int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept, int threads);
 

@@ -5,6 +5,7 @@
 // oracle/minicv) and ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2279-2295,
 // excerpted at build time by oracle/Makefile).  Built into oracle/_ref/*.so.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -19,6 +20,7 @@ public:
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
+    void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);   // :2233-2274, protected there
 };
 }
 
@@ -119,6 +121,35 @@ int orbref_descriptor_distance(const uint8_t *a, const uint8_t *b)
     std::memcpy(ta, a, 32); std::memcpy(tb, b, 32);
     cv::Mat ma(1, 32, CV_8UC1, ta), mb(1, 32, CV_8UC1, tb);
     return ORB_SLAM2::ORBmatcher::DescriptorDistance(ma, mb);
+}
+
+// mbCheckOrientation around the reference's own ComputeThreeMaxima.  The histogram fill and the pruning are call-site
+// code inside SearchByBoW (src/ORBmatcher.cc:545, 610-620, 641-660); they are restated here line for line.
+int orbref_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
+                           int32_t *hist, int32_t *top3)
+{
+    const int HISTO_LENGTH = ORB_SLAM2::ORBmatcher::HISTO_LENGTH;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < nA; ++i) {
+        if (!accept[i]) continue;
+        float rot = angleA[i] - angleB[idx[i]];
+        if (rot < 0.0) rot += 360.0f;
+        int bin = round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(i);
+    }
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    ORB_SLAM2::ORBmatcher m;
+    m.ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    int kept = 0;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        if (i == ind1 || i == ind2 || i == ind3) { kept += (int)rotHist[i].size(); continue; }
+        for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) accept[rotHist[i][j]] = 0;
+    }
+    if (hist) for (int i = 0; i < HISTO_LENGTH; ++i) hist[i] = (int32_t)rotHist[i].size();
+    if (top3) { top3[0] = ind1; top3[1] = ind2; top3[2] = ind3; }
+    return kept;
 }
 
 void orbref_thresholds(int *th_low, int *th_high, int *histo_length)

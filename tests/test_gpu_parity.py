@@ -198,6 +198,28 @@ def test_matcher_vs_oracle(orb, oracle_mod):
     assert (idx == -1).all() and (d1 == 256).all() and not acc.any()
 
 
+def test_rotation_filter_vs_oracle(orb, oracle_mod):
+    """mbCheckOrientation after the match (src/ORBmatcher.cc:610-620, 641-660, 2233-2274): bit-exact accept flags,
+    histogram and the three selected bins, on real extractor output and on constructed tie / wrap-around cases."""
+    from test_oracle_vs_ref import _rotation_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    (kA, dA), (kB, dB) = ext.extract_batch([synth(0, 375, 1242), synth(1, 375, 1242)])
+    m = orb.ORBmatcher(0.9, True, extractor=ext)
+    for A, angA, B, angB in ((dA, kA["angle"], dB, kB["angle"]), (dA, kA["angle"], dA, kA["angle"])):
+        for th in (orb.ORBmatcher.TH_LOW, orb.ORBmatcher.TH_HIGH):
+            idx, d1, d2, acc, hist, top3 = m.match_oriented(A, angA, B, angB, th, 0.9)
+            oi, o1, o2, oa = oracle_mod.Oracle.match(A, B, th, 0.9)
+            ka, oh, ot = oracle_mod.Oracle.rotation_filter(oi, oa, angA, angB)
+            assert np.array_equal(idx, oi) and np.array_equal(acc, ka) and np.array_equal(hist, oh) and np.array_equal(top3, ot)
+            assert acc.sum() == hist[top3[top3 >= 0]].sum()
+    for idx, acc0, a, b in _rotation_cases():
+        acc, hist, top3 = ext.rotation_filter(idx, acc0, a, b)
+        ka, oh, ot = oracle_mod.Oracle.rotation_filter(idx, acc0, a, b)
+        assert np.array_equal(acc, ka) and np.array_equal(hist, oh) and np.array_equal(top3, ot)
+    with pytest.raises(orb.OrbxError):            # an accepted match must point into B
+        ext.rotation_filter(np.array([5], np.int32), np.array([1], np.uint8), np.zeros(1, np.float32), np.zeros(3, np.float32))
+
+
 def test_full_size_properties(orb, oracle_mod):
     """BASELINE configs 3 and 5 at full size: one frame each against the oracle (seconds on the CPU),
     and size-independent properties on the batch: determinism, self-match, level-major ordering, bounds."""

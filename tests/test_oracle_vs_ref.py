@@ -106,3 +106,48 @@ def test_hamming_and_matcher_rule(oracle_mod):
     assert np.array_equal(i2, idx) and np.array_equal(a1, d1) and np.array_equal(a2, d2) and np.array_equal(ac2, acc)
     e_idx, e_d1, e_d2, e_acc = oracle_mod.Oracle.match(A, np.zeros((0, 32), np.uint8), 100, 0.9)
     assert (e_idx == -1).all() and (e_d1 == 256).all() and not e_acc.any()
+
+
+def _rotation_cases():
+    rng = np.random.default_rng(17)
+    cases = []
+    for n, nB, mode in ((400, 380, "spread"), (900, 900, "peaked"), (64, 50, "ties"), (7, 9, "tiny"), (0, 5, "empty")):
+        idx = rng.integers(0, max(nB, 1), n).astype(np.int32)
+        acc = rng.random(n) < 0.7
+        b = (rng.random(nB) * 360).astype(np.float32)
+        if mode == "peaked":                      # most matches rotate by ~12 degrees, a few outliers
+            a = (b[idx] + np.float32(12) + rng.normal(0, 3, n).astype(np.float32)) % np.float32(360)
+            out = rng.random(n) < 0.15
+            a[out] = (rng.random(int(out.sum())) * 360).astype(np.float32)
+        elif mode == "ties":                      # equal bin counts: the first bin must win
+            a = (b[idx] + np.float32(30) * (np.arange(n) % 4).astype(np.float32) + np.float32(1)) % np.float32(360)
+            acc[:] = True
+        else:
+            a = (rng.random(n) * 360).astype(np.float32)
+        a = a.astype(np.float32)
+        a[::11] = np.float32(0); b[::13] = np.float32(359.99997)      # wrap-around and exact-boundary angles
+        if n:
+            a[-1] = b[idx[-1]]                    # rot == 0
+        cases.append((idx, acc, a, b))
+    return cases
+
+
+def test_rotation_filter_port_vs_reference(oracle_mod):
+    """mbCheckOrientation: the port against a numpy restatement, and against the reference's own compiled
+    ComputeThreeMaxima (src/ORBmatcher.cc:2233-2274) when /root/reference is here."""
+    for idx, acc, a, b in _rotation_cases():
+        k_acc, hist, top3 = oracle_mod.Oracle.rotation_filter(idx, acc, a, b)
+        # numpy restatement of :610-620 (float32 arithmetic, round half away from zero)
+        rot = (a - b[idx] if len(idx) else np.zeros(0, np.float32)).astype(np.float32)
+        rot = np.where(rot < 0, (rot + np.float32(360)).astype(np.float32), rot)
+        t = (rot * np.float32(1.0 / 30)).astype(np.float32)
+        bins = np.floor(t.astype(np.float64) + 0.5).astype(np.int64)
+        bins[bins == 30] = 0
+        exp_hist = np.bincount(bins[acc], minlength=30)[:30] if len(idx) else np.zeros(30, np.int64)
+        assert np.array_equal(hist, exp_hist)
+        assert hist[13:].sum() == 0               # factor = 1/30: the reference only ever fills bins 0..12
+        keep = np.isin(bins, top3[top3 >= 0]) & acc if len(idx) else acc
+        assert np.array_equal(k_acc, keep)
+        if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_rotation_filter"):
+            r_acc, r_hist, r_top3 = oracle_mod.RefExtractor.rotation_filter(idx, acc, a, b)
+            assert np.array_equal(r_acc, k_acc) and np.array_equal(r_hist, hist) and np.array_equal(r_top3, top3)
