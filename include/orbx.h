@@ -212,6 +212,21 @@ int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, uint8_t *ac
 int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA,
                                 const float *d_angleB, int32_t *d_hist, int32_t *d_top3, int32_t *d_kept);
 
+/* ---- stereo association ------------------------------------- */
+
+/* Frame::ComputeStereoMatches (src/Frame.cc:849-1038) on the results of two extractors that are still resident on the
+ * device: frame `frame_left` of the last batch of `left` against frame `frame_right` of the last batch of `right`
+ * (keypoints, descriptors and pyramids; both handles on the same device, same constructor parameters and image size).
+ * Per left keypoint i (i < *n_left <= cap): u_right[i] = mvuRight (sub-pixel right column, -1 = no match),
+ * depth[i] = mvDepth = bf / disparity (-1 = none), desc_index[i] = vDescIndex (best right keypoint by Hamming distance,
+ * with the reference's quirk that index 0 is never recorded, :948).  Gates as in the reference of this fork:
+ * row band 1.2 * scale, octave +-1, disparity in [0, 200), Hamming < (TH_HIGH+TH_LOW)/2 for the 11x11 SAD refinement,
+ * final cut at 1.5 * 1.4 * median SAD.  Any output pointer may be NULL.
+ * Returns the number of matches kept (>= 0; 0 also when no match reached the median step, where the reference reads
+ * an empty vector) or a negative status. */
+int orbx_stereo_match(orbx_handle *left, orbx_handle *right, int frame_left, int frame_right, float bf,
+                      float *u_right, float *depth, int32_t *desc_index, int cap, int *n_left);
+
 /* ---- per-stage device timing ---------------------------------------------- */
 
 /* With profiling on, every submit brackets its stages with CUDA events on the

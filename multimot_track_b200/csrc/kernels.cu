@@ -977,14 +977,14 @@ size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
 
 template <int THREADS, int IPT>
 __global__ void __launch_bounds__(THREADS)
-k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap)
+k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap, int level_off)
 {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t oct_smem[];
     __shared__ int warp_sums[32];
     __shared__ int s_m, s_added;
 
-    const int level = blockIdx.x, frame = blockIdx.y;
+    const int level = blockIdx.x + level_off, frame = blockIdx.y;
     const LevelGeom &G = P->lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)min(P->cand_count[frame * P->nlevels + level], (unsigned)G.cand_cap);
@@ -1212,12 +1212,18 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
 }
 
 template <int THREADS, int IPT>
-static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int nframes, int node_cap, int max_feat, size_t budget, cudaStream_t st)
+static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int nframes, int node_cap, int max_feat, size_t budget, cudaStream_t st,
+                                   int level_off = 0, int level_cnt = -1)
 {
     const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget);
-    cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o.bytes);
-    if (e != cudaSuccess) return e;
-    k_octree<THREADS, IPT><<<dim3(hP.nlevels, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap);
+    static size_t attr = 0;                                          // the attribute is a maximum: raise it once per size
+    if (o.bytes > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o.bytes);
+        if (e != cudaSuccess) return e;
+        attr = o.bytes;
+    }
+    if (level_cnt < 0) level_cnt = hP.nlevels - level_off;
+    k_octree<THREADS, IPT><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off);
     return cudaGetLastError();
 }
 
@@ -1225,7 +1231,22 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
 {
     ls->launches++;
     // CTA size by node-array capacity (THREADS*IPT records); small CTAs leave room for 2+ per SM
-    if (max_node_cap <= 1024) return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget(), st);
+    if (max_node_cap <= 1024) {
+        // Batches: the small levels first with a small shared-memory footprint, then the big ones.  Either launch has
+        // about one CTA per SM, so the latency-bound octree leaves room for the other handles' kernels on every SM
+        // (one launch of all levels at 100 KB per CTA pins two CTAs = 200 KB on most SMs for ~100 us).
+        int split = 0;                                                // first level whose image has < 40 % of level 0's pixels
+        const long long p0 = (long long)hP.lv[0].w * hP.lv[0].h;
+        while (split < hP.nlevels && (long long)hP.lv[split].w * hP.lv[split].h * 5 >= p0 * 2) ++split;
+        static const bool no_split = std::getenv("ORBX_OCT_NOSPLIT") != nullptr;
+        if (nframes >= 8 && split > 0 && split < hP.nlevels && !no_split) {
+            ls->launches++;
+            cudaError_t e = launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget() / 2 + 4096, st, split, hP.nlevels - split);
+            if (e != cudaSuccess) return e;
+            return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget(), st, 0, split);
+        }
+        return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget(), st);
+    }
     if (max_node_cap <= 4096) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
     return launch_octree_t<1024, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
 }
@@ -1794,6 +1815,174 @@ cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_acce
 {
     k_rotation_filter<<<1, 1024, 0, st>>>(nA, d_idx, d_accept, d_angleA, d_angleB, d_hist, d_top3, d_kept);
     ls->launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------- stereo
+// Frame::ComputeStereoMatches (src/Frame.cc:849-1038) on the device-resident results of a left and a right extractor.
+// One warp per left keypoint: (1) scan of ALL right keypoints with the reference's row-band / octave / disparity gates
+// (the row table vRowIndices of :861-881 is a gate "row(int)vL in [floor(y-r), ceil(y+r)]", candidates in ascending iR,
+// strict < keeps the first minimum, :914-941), Hamming by __popc; (2) the 11-position SAD search on the 11x11 patches of
+// the two pyramids, patches normalised by their centre pixel (:949-985; integer-valued floats, so integer arithmetic is
+// exact), parabola fit and disparity in the reference's float operation order (:990-1019).  A second, single-CTA kernel
+// applies the median cut of :1022-1037 by rank selection (no sort needed: only the median VALUE enters thDist).
+struct StereoSide {
+    const DevParams *P; Src0 s0; int frame;
+};
+
+__global__ void __launch_bounds__(256)
+k_stereo_match(StereoSide L, StereoSide R, StereoScales sc, float bf, float *__restrict__ u_right, float *__restrict__ depth,
+               int32_t *__restrict__ desc_index, int32_t *__restrict__ sad_out)
+{
+    __shared__ int sIL[8][121 + 231];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 8 + warp;
+    const DevParams *PL = L.P, *PR = R.P;
+    const int nL = PL->out_n[L.frame], nR = PR->out_n[R.frame];
+    if (iL >= nL) return;
+    const orbx_keypoint *kL = PL->out_kps + (long long)L.frame * PL->kp_frame_cap;
+    const orbx_keypoint *kR = PR->out_kps + (long long)R.frame * PR->kp_frame_cap;
+    const uint4 *dLp = reinterpret_cast<const uint4 *>(PL->out_desc + ((long long)L.frame * PL->kp_frame_cap + iL) * 32);
+    const uint8_t *dRb = PR->out_desc + (long long)R.frame * PR->kp_frame_cap * 32;
+    float ur_o = -1.0f, dp_o = -1.0f; int di_o = -1, sad_o = -1;
+    const float uL = kL[iL].x, vL = kL[iL].y;
+    const int levelL = kL[iL].octave;
+    const int row = (int)vL;
+    const float minU = __fsub_rn(uL, 200.0f), maxU = uL;
+    bool live = !(maxU < 0);
+    unsigned key = 100u << 16;                                        // bestDist = TH_HIGH, bestIdxR = 0
+    bool any = false;
+    if (live) {
+        const uint4 a0 = dLp[0], a1 = dLp[1];
+        for (int iR = lane; iR < nR; iR += 32) {
+            const float y = kR[iR].y;
+            const int oc = kR[iR].octave;
+            const float r = __fmul_rn(1.2f, sc.scale[oc]);
+            const int maxr = (int)ceilf(__fadd_rn(y, r)), minr = (int)floorf(__fsub_rn(y, r));
+            if (row < minr || row > maxr) continue;
+            any = true;
+            if (oc < levelL - 1 || oc > levelL + 1) continue;
+            const float uR = kR[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const uint4 b0 = reinterpret_cast<const uint4 *>(dRb + (long long)iR * 32)[0], b1 = reinterpret_cast<const uint4 *>(dRb + (long long)iR * 32)[1];
+                const unsigned dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                      __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                const unsigned k2 = dist << 16 | (unsigned)iR;            // iR < 65536 (kp_frame_cap is far below)
+                if (dist < (key >> 16)) key = k2;                        // ascending iR per lane: strict < keeps the first
+            }
+        }
+        any = __any_sync(0xffffffffu, any);
+        key = __reduce_min_sync(0xffffffffu, key);                       // lowest distance, then lowest iR
+    }
+    if (live && any) {
+        const int bestDist = (int)(key >> 16), bestIdxR = (int)(key & 0xffffu);
+        if (bestIdxR != 0) di_o = bestIdxR;                              // :948 (index 0 is never recorded)
+        if (bestDist < (ORBX_TH_HIGH + ORBX_TH_LOW) / 2) {
+            const float uR0 = kR[bestIdxR].x;
+            const float sf = sc.inv_scale[levelL];
+            const float suL = roundf(__fmul_rn(uL, sf)), svL = roundf(__fmul_rn(vL, sf)), suR0 = roundf(__fmul_rn(uR0, sf));
+            const LevelGeom &G = PL->lv[levelL];
+            const float iniu = suR0, endu = __fadd_rn(suR0, 11.0f);      // scaleduR0 + L - w, scaleduR0 + L + w + 1 with L = w = 5
+            if (!(iniu < 0 || endu >= (float)G.w)) {
+                int spL, spR;
+                const uint8_t *imL = level_ptr(PL, L.s0, L.frame, levelL, &spL), *imR = level_ptr(PR, R.s0, R.frame, levelL, &spR);
+                const int y0 = (int)svL - 5, xl = (int)suL - 5, xr0 = (int)suR0 - 10;
+                int *pl = sIL[warp], *pr = pl + 121;
+                for (int i = lane; i < 121; i += 32) { const int yy = i / 11, xx = i - yy * 11; pl[i] = imL[(long long)(y0 + yy) * spL + xl + xx]; }
+                for (int i = lane; i < 231; i += 32) { const int yy = i / 21, xx = i - yy * 21; pr[i] = imR[(long long)(y0 + yy) * spR + xr0 + xx]; }
+                __syncwarp();
+                int acc = 0x7fffff;
+                if (lane < 11) {                                         // lane = incR + 5
+                    const int cl = pl[5 * 11 + 5], cr = pr[5 * 21 + 5 + lane];
+                    acc = 0;
+                    for (int yy = 0; yy < 11; ++yy)
+#pragma unroll
+                        for (int xx = 0; xx < 11; ++xx) acc += abs((pl[yy * 11 + xx] - cl) - (pr[yy * 21 + xx + lane] - cr));
+                }
+                const unsigned k3 = __reduce_min_sync(0xffffffffu, (unsigned)acc << 8 | (unsigned)lane);   // first minimum over incR
+                const int bestk = (int)(k3 & 0xffu), bestD = (int)(k3 >> 8);
+                const int d1i = __shfl_sync(0xffffffffu, acc, max(bestk - 1, 0)), d3i = __shfl_sync(0xffffffffu, acc, min(bestk + 1, 10));
+                if (bestk != 0 && bestk != 10) {
+                    const float dist1 = (float)d1i, dist2 = (float)bestD, dist3 = (float)d3i;
+                    const float num = __fsub_rn(dist1, dist3);
+                    const float den = __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2)));
+                    const float deltaR = __fdiv_rn(num, den);
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        const float t = __fadd_rn(__fadd_rn(suR0, (float)(bestk - 5)), deltaR);
+                        float bestuR = __fmul_rn(sc.scale[levelL], t);
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= 0 && disparity < 200.0f) {
+                            if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                            dp_o = __fdiv_rn(bf, disparity);
+                            ur_o = bestuR;
+                            sad_o = bestD;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { u_right[iL] = ur_o; depth[iL] = dp_o; desc_index[iL] = di_o; sad_out[iL] = sad_o; }
+}
+
+// Median cut (:1022-1037): thDist = 1.5f*1.4f*median of the SADs of the pushed matches (the element of rank n/2 of the
+// sorted list); every pushed match with SAD >= thDist is invalidated.  SAD <= 121*510 < 2^16: two 256-bin histograms.
+__global__ void __launch_bounds__(1024)
+k_stereo_median(const DevParams *__restrict__ PL, int frame, float *__restrict__ u_right, float *__restrict__ depth,
+                int32_t *__restrict__ desc_index, const int32_t *__restrict__ sad, int *__restrict__ kept_out)
+{
+    __shared__ int hist[256], s_bin, s_rank, s_total, s_kept;
+    __shared__ float s_th;
+    const int n = PL->out_n[frame];
+    for (int pass = 0; pass < 2; ++pass) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        if (threadIdx.x == 0 && pass == 0) s_kept = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int v = sad[i];
+            if (v < 0) continue;
+            if (pass == 0) atomicAdd(&hist[v >> 8], 1);
+            else if ((v >> 8) == s_bin) atomicAdd(&hist[v & 255], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (pass == 0) {
+                int tot = 0;
+                for (int b = 0; b < 256; ++b) tot += hist[b];
+                s_total = tot;
+                int rank = tot / 2, b = 0;
+                while (b < 255 && rank >= hist[b]) { rank -= hist[b]; ++b; }
+                s_bin = b; s_rank = rank;
+            } else {
+                int rank = s_rank, b = 0;
+                while (b < 255 && rank >= hist[b]) { rank -= hist[b]; ++b; }
+                const float median = (float)(s_bin << 8 | b);
+                s_th = __fmul_rn(__fmul_rn(1.5f, 1.4f), median);
+            }
+        }
+        __syncthreads();
+        if (s_total == 0) { if (threadIdx.x == 0 && kept_out) *kept_out = -1; return; }   // the reference reads an empty vector here
+    }
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int v = sad[i];
+        if (v < 0) continue;
+        if (!((float)v < s_th)) { u_right[i] = -1.0f; depth[i] = -1.0f; desc_index[i] = -1; }
+        else ++mine;
+    }
+    mine = warp_sum(mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_kept, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && kept_out) *kept_out = s_kept;
+}
+
+cudaError_t launch_stereo(const DevParams *dPL, Src0 s0L, int frameL, const DevParams *dPR, Src0 s0R, int frameR, const StereoScales &sc, float bf,
+                          int capL, float *d_u_right, float *d_depth, int32_t *d_desc_index, int32_t *d_sad, int *d_kept, cudaStream_t st, LaunchStats *ls)
+{
+    StereoSide L = {dPL, s0L, frameL}, R = {dPR, s0R, frameR};
+    k_stereo_match<<<(capL + 7) / 8, 256, 0, st>>>(L, R, sc, bf, d_u_right, d_depth, d_desc_index, d_sad);
+    k_stereo_median<<<1, 1024, 0, st>>>(dPL, frameL, d_u_right, d_depth, d_desc_index, d_sad, d_kept);
+    ls->launches += 2;
     return cudaGetLastError();
 }
 

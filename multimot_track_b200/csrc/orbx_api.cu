@@ -681,6 +681,56 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     return res[33];
 }
 
+// ------------------------------------------------------------------- stereo
+
+extern "C" int orbx_stereo_match(orbx_handle *L, orbx_handle *R, int frame_left, int frame_right, float bf,
+                                 float *u_right, float *depth, int32_t *desc_index, int cap, int *n_left)
+{
+    orbx_handle *h = L;
+    if (!L || !R) return ORBX_ERR_BAD_ARG;
+    int rc = stage_ready(L, frame_left, 0);
+    if (rc != ORBX_OK) return rc;
+    rc = stage_ready(R, frame_right, 0);
+    if (rc != ORBX_OK) return fail(L, rc, "right handle: " + R->err);
+    if (L->pending || R->pending) return fail(L, ORBX_ERR_STATE, "orbx_stereo_match: collect the pending batches first");
+    if (L->device != R->device) return fail(L, ORBX_ERR_BAD_ARG, "orbx_stereo_match: the two handles live on different devices");
+    if (L->geo.width != R->geo.width || L->geo.height != R->geo.height || L->tab.nlevels != R->tab.nlevels ||
+        L->tab.scale_factor_f != R->tab.scale_factor_f)
+        return fail(L, ORBX_ERR_BAD_ARG, "orbx_stereo_match: the two extractors differ in image size / levels / scale factor");
+    CU(cudaSetDevice(L->device));
+    const int capL = L->geo.kp_frame_cap;
+    // scratch: u_right | depth | desc_index | sad (capL each) | kept
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, ((size_t)capL * 4 + 4) * sizeof(uint32_t)));
+    float *d_ur = (float *)d, *d_dp = d_ur + capL;
+    int32_t *d_di = (int32_t *)(d_dp + capL), *d_sad = d_di + capL;
+    int *d_kept = (int *)(d_sad + capL);
+    StereoScales sc;
+    for (int l = 0; l < kMaxLevels; ++l) { sc.scale[l] = l < L->tab.nlevels ? L->tab.scale[l] : 1.f; sc.inv_scale[l] = l < L->tab.nlevels ? L->tab.inv_scale[l] : 1.f; }
+    int nL = 0, kept = 0;
+    auto body = [&]() -> int {
+        CU(cudaStreamSynchronize(R->stream));                          // the right extractor's results are complete
+        cudaStream_t st = L->stream;
+        CU(launch_stereo(L->d_params, L->last_src0, frame_left, R->d_params, R->last_src0, frame_right, sc, bf, capL,
+                         d_ur, d_dp, d_di, d_sad, d_kept, st, &L->stats));
+        CU(cudaMemcpyAsync(&nL, L->d_out_n + frame_left, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&kept, d_kept, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (nL > capL) nL = capL;
+        if (n_left) *n_left = nL;
+        if (nL > cap && (u_right || depth || desc_index)) return fail(h, ORBX_ERR_CAPACITY, "orbx_stereo_match: cap is smaller than the number of left keypoints");
+        if (u_right && nL) CU(cudaMemcpyAsync(u_right, d_ur, (size_t)nL * 4, cudaMemcpyDeviceToHost, st));
+        if (depth && nL) CU(cudaMemcpyAsync(depth, d_dp, (size_t)nL * 4, cudaMemcpyDeviceToHost, st));
+        if (desc_index && nL) CU(cudaMemcpyAsync(desc_index, d_di, (size_t)nL * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return ORBX_OK;
+    };
+    rc = body();
+    cudaFree(d);
+    if (rc != ORBX_OK) return rc;
+    return kept < 0 ? 0 : kept;
+}
+
 // ---------------------------------------------------------------- profiling
 
 static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h"};

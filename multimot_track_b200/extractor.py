@@ -240,3 +240,17 @@ class ORBextractor:
                                             hist.ctypes.data, top3.ctypes.data)
         self._ck(rc)
         return acc.astype(bool), hist, top3
+
+    def stereo_match(self, right, bf, frame_left=0, frame_right=0):
+        """Frame::ComputeStereoMatches (src/Frame.cc:849-1038): this extractor's last results are the left frame,
+        `right` (another ORBextractor on the same device) holds the right one.
+        Returns (mvuRight[n], mvDepth[n], vDescIndex[n], matches_kept)."""
+        n0 = ctypes.c_int(0)                         # first call: how many left keypoints are there
+        self._ck(self._lib.orbx_stereo_match(self._h, right._h, int(frame_left), int(frame_right), float(bf), None, None, None, 0, ctypes.byref(n0)))
+        cap = max(n0.value, 1)
+        ur = np.zeros(cap, np.float32); dp = np.zeros(cap, np.float32); di = np.zeros(cap, np.int32)
+        n = ctypes.c_int(0)
+        rc = self._lib.orbx_stereo_match(self._h, right._h, int(frame_left), int(frame_right), float(bf), ur.ctypes.data, dp.ctypes.data,
+                                         di.ctypes.data, cap, ctypes.byref(n))
+        self._ck(rc)
+        return ur[:n.value].copy(), dp[:n.value].copy(), di[:n.value].copy(), rc

@@ -6,7 +6,8 @@
 // under /root/reference, into oracle/_ref/ (see oracle/Makefile).  The real
 // OpenCV C++ library is not present in this image.  Image primitives forward to
 // oracle/cvprim.c (bit-exact to cv2 4.13.0, tests/test_oracle_cvprim.py).
-// Only CV_8UC1 matrices are supported, which is all the hot path touches.
+// CV_8UC1 matrices everywhere; CV_32F only for the 11x11 patch arithmetic of
+// Frame::ComputeStereoMatches (src/Frame.cc:949-985: convertTo, Mat - float*Mat::ones, cv::norm L1).
 #ifndef ORACLE_MINICV_HPP
 #define ORACLE_MINICV_HPP
 
@@ -23,6 +24,8 @@
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 
 typedef unsigned char uchar;
 
@@ -90,26 +93,27 @@ struct MatExpr { int rows, cols, type; };
 
 class Mat {
 public:
-    Mat() : rows(0), cols(0), data(nullptr), step(0), type_(CV_8UC1) {}
+    Mat() : rows(0), cols(0), data(nullptr), step(0), type_(CV_8UC1), esz_(1) {}
     Mat(const MatExpr &e) : Mat() { *this = e; }
     Mat &operator=(const MatExpr &e)
     {
         create(e.rows, e.cols, e.type);
-        for (int y = 0; y < rows; ++y) std::memset(data + (size_t)y * step, 0, (size_t)cols);
+        for (int y = 0; y < rows; ++y) std::memset(data + (size_t)y * step, 0, (size_t)cols * esz_);
         return *this;
     }
     Mat(int r, int c, int type) : Mat() { create(r, c, type); }
     Mat(Size sz, int type) : Mat() { create(sz.height, sz.width, type); }
     // external (non-owning) data, like cv::Mat(rows, cols, type, data, step)
     Mat(int r, int c, int type, void *ext, size_t _step = 0)
-        : rows(r), cols(c), data((uchar *)ext), step(_step ? _step : (size_t)c), type_(type) { assert(type == CV_8UC1); }
+        : rows(r), cols(c), data((uchar *)ext), step(_step ? _step : (size_t)c), type_(type), esz_(1) { assert(type == CV_8UC1); }
 
     void create(int r, int c, int type)
     {
-        assert(type == CV_8UC1);
-        if (data && r == rows && c == cols) return;   // cv::Mat::create keeps a matching buffer
-        rows = r; cols = c; step = (size_t)c; type_ = type;
-        buf_.reset(new uchar[(size_t)r * (size_t)c + 64], std::default_delete<uchar[]>());
+        assert(type == CV_8UC1 || type == CV_32F);
+        if (data && r == rows && c == cols && type == type_) return;   // cv::Mat::create keeps a matching buffer
+        esz_ = type == CV_32F ? 4 : 1;
+        rows = r; cols = c; step = (size_t)c * esz_; type_ = type;
+        buf_.reset(new uchar[(size_t)r * (size_t)c * esz_ + 64], std::default_delete<uchar[]>());
         data = buf_.get();
     }
     void create(Size sz, int type) { create(sz.height, sz.width, type); }
@@ -120,11 +124,28 @@ public:
     Mat clone() const
     {
         Mat m(rows, cols, type_);
-        for (int y = 0; y < rows; ++y) std::memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols);
+        for (int y = 0; y < rows; ++y) std::memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols * esz_);
         return m;
     }
-    Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
-    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
+    Mat rowRange(int a, int b) const { assert(0 <= a && a <= b && b <= rows); Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
+    Mat colRange(int a, int b) const { assert(0 <= a && a <= b && b <= cols); Mat m(*this); m.data = data + (size_t)a * esz_; m.cols = b - a; return m; }
+    // 8U -> 32F (or a copy); dst may alias *this, like cv::Mat::convertTo
+    void convertTo(Mat &dst, int type) const
+    {
+        assert(type == CV_32F);
+        Mat t(rows, cols, CV_32F);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x)
+                t.at<float>(y, x) = type_ == CV_32F ? at<float>(y, x) : (float)at<uchar>(y, x);
+        dst = t;
+    }
+    static Mat ones(int r, int c, int type)
+    {
+        assert(type == CV_32F);
+        Mat t(r, c, CV_32F);
+        for (int y = 0; y < r; ++y) for (int x = 0; x < c; ++x) t.at<float>(y, x) = 1.0f;
+        return t;
+    }
     Mat operator()(const Rect &r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
     Mat row(int y) const { return rowRange(y, y + 1); }
 
@@ -147,8 +168,34 @@ public:
 
 private:
     int type_;
+    size_t esz_;
     std::shared_ptr<uchar> buf_;
 };
+
+// CV_32F element-wise arithmetic used by Frame::ComputeStereoMatches (:951, :969, :971)
+enum { NORM_L1 = 2 };
+static inline Mat operator*(float s, const Mat &m)
+{
+    assert(m.type() == CV_32F);
+    Mat t(m.rows, m.cols, CV_32F);
+    for (int y = 0; y < m.rows; ++y) for (int x = 0; x < m.cols; ++x) t.at<float>(y, x) = s * m.at<float>(y, x);
+    return t;
+}
+static inline Mat operator-(const Mat &a, const Mat &b)
+{
+    assert(a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    Mat t(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; ++y) for (int x = 0; x < a.cols; ++x) t.at<float>(y, x) = a.at<float>(y, x) - b.at<float>(y, x);
+    return t;
+}
+static inline double norm(const Mat &a, const Mat &b, int normType)
+{
+    assert(normType == NORM_L1 && a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    (void)normType;
+    double s = 0;                                   // cv::norm accumulates |a-b| of CV_32F in double
+    for (int y = 0; y < a.rows; ++y) for (int x = 0; x < a.cols; ++x) s += std::fabs((double)a.at<float>(y, x) - (double)b.at<float>(y, x));
+    return s;
+}
 
 class _InputArray {
 public:

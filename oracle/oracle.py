@@ -150,6 +150,22 @@ class Oracle:
         return idx, d1, d2, acc.astype(bool)
 
     @classmethod
+    def stereo_matches(cls, kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR, bf):
+        """Frame::ComputeStereoMatches (src/Frame.cc:849-1038).  pyrL / pyrR: lists of un-padded level images.
+        Returns dict(u_right, depth, desc_index, best_dist, best_idx, sad, kept)."""
+        a = _stereo_args(kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR)
+        nL = a["nL"]
+        out = dict(u_right=np.zeros(nL, np.float32), depth=np.zeros(nL, np.float32), desc_index=np.zeros(nL, np.int32),
+                   best_dist=np.zeros(nL, np.int32), best_idx=np.zeros(nL, np.int32), sad=np.zeros(nL, np.int32))
+        L = cls.lib()
+        L.orbo_stereo_matches.argtypes = [_I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F] + [_VP] * 6
+        out["kept"] = L.orbo_stereo_matches(nL, a["kL"].ctypes.data, a["dL"].ctypes.data, a["nR"], a["kR"].ctypes.data, a["dR"].ctypes.data,
+                                            a["nlevels"], a["scale"].ctypes.data, a["inv"].ctypes.data, a["pL"], a["pR"],
+                                            a["pitch"].ctypes.data, a["lw"].ctypes.data, a["lh"].ctypes.data, float(bf),
+                                            *[out[k].ctypes.data for k in ("u_right", "depth", "desc_index", "best_dist", "best_idx", "sad")])
+        return out
+
+    @classmethod
     def rotation_filter(cls, idx, accept, angleA, angleB):
         """mbCheckOrientation: returns (accept_after, hist[30], top3[3])."""
         idx = np.ascontiguousarray(idx, np.int32); acc = np.ascontiguousarray(accept, np.uint8).copy()
@@ -166,6 +182,28 @@ class Oracle:
         s = cls.lib().orbo_extract_many(int(params[0]), float(params[1]), int(params[2]), int(params[3]), int(params[4]),
                                         f.ctypes.data, f.shape[0], f.shape[2], f.shape[1], int(threads), ctypes.byref(tot))
         return s, tot.value
+
+
+def _stereo_args(kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR):
+    kL = np.ascontiguousarray(kpsL, KEYPOINT_DTYPE); kR = np.ascontiguousarray(kpsR, KEYPOINT_DTYPE)
+    dL = np.ascontiguousarray(descL, np.uint8).reshape(-1, 32); dR = np.ascontiguousarray(descR, np.uint8).reshape(-1, 32)
+    nlevels = len(pyrL)
+    keep = [np.ascontiguousarray(p, np.uint8) for p in list(pyrL) + list(pyrR)]
+    for l in range(nlevels):
+        assert keep[l].shape == keep[nlevels + l].shape
+    ptr = ctypes.c_void_p * nlevels
+    return dict(kL=kL, kR=kR, dL=dL, dR=dR, nL=len(kL), nR=len(kR), nlevels=nlevels,
+                scale=np.ascontiguousarray(scale, np.float32), inv=np.ascontiguousarray(inv_scale, np.float32),
+                pL=ptr(*[p.ctypes.data for p in keep[:nlevels]]), pR=ptr(*[p.ctypes.data for p in keep[nlevels:]]),
+                pitch=np.array([p.strides[0] for p in keep[:nlevels]], np.int32), lw=np.array([p.shape[1] for p in keep[:nlevels]], np.int32),
+                lh=np.array([p.shape[0] for p in keep[:nlevels]], np.int32), _keep=keep)
+
+
+def _kps_to_rows(k):
+    r = np.zeros((len(k), 7), np.float32)
+    for i, name in enumerate(["x", "y", "size", "angle", "response", "octave", "class_id"]):
+        r[:, i] = k[name]
+    return r
 
 
 class RefExtractor:
@@ -238,6 +276,22 @@ class RefExtractor:
     def descriptor_distance(cls, a, b, variant="canon"):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return cls.lib(variant).orbref_descriptor_distance(a.ctypes.data, b.ctypes.data)
+
+    @classmethod
+    def stereo_matches(cls, kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR, bf, variant="canon"):
+        """The reference's own compiled Frame::ComputeStereoMatches (excerpt of src/Frame.cc:849-1038)."""
+        a = _stereo_args(kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR)
+        assert (a["pitch"] == [p.strides[0] for p in a["_keep"][a["nlevels"]:]]).all()
+        nL = a["nL"]
+        rL, rR = _kps_to_rows(a["kL"]), _kps_to_rows(a["kR"])
+        out = dict(u_right=np.zeros(nL, np.float32), depth=np.zeros(nL, np.float32), desc_index=np.zeros(nL, np.int32))
+        L = cls.lib(variant)
+        L.orbref_stereo_matches.argtypes = [_I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]
+        out["kept"] = L.orbref_stereo_matches(nL, rL.ctypes.data, a["dL"].ctypes.data, a["nR"], rR.ctypes.data, a["dR"].ctypes.data,
+                                              a["nlevels"], a["scale"].ctypes.data, a["inv"].ctypes.data, a["pL"], a["pR"],
+                                              a["pitch"].ctypes.data, a["lw"].ctypes.data, a["lh"].ctypes.data, float(bf),
+                                              out["u_right"].ctypes.data, out["depth"].ctypes.data, out["desc_index"].ctypes.data)
+        return out
 
     @classmethod
     def rotation_filter(cls, idx, accept, angleA, angleB, variant="canon"):

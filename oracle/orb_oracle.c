@@ -8,6 +8,7 @@
 #include "orb_oracle.h"
 #include "cvprim.h"
 
+#include <limits.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -574,6 +575,120 @@ int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const floa
         }
     if (hist) for (int i = 0; i < 30; ++i) hist[i] = cnt[i];
     if (top3) { top3[0] = i1; top3[1] = i2; top3[2] = i3; }
+    return kept;
+}
+
+/* ------------------------------------------------------------------ stereo
+ * Frame::ComputeStereoMatches, src/Frame.cc:849-1038 of the reference (this fork: minD = 0, maxD = 200, row band
+ * r = 1.2 * scale, patches normalised by their centre pixel, vDescIndex with its `bestIdxR != 0` quirk).
+ * Float operations are written one per statement in the reference's order; compile with -ffp-contract=off. */
+int orbo_stereo_matches(int nL, const orbo_keypoint *kL, const uint8_t *dL, int nR, const orbo_keypoint *kR, const uint8_t *dR,
+                        int nlevels, const float *scale, const float *inv_scale,
+                        const uint8_t *const *pyrL, const uint8_t *const *pyrR, const int *pitch, const int *lw, const int *lh,
+                        float bf, float *u_right, float *depth, int32_t *desc_index, int32_t *best_dist, int32_t *best_idx, int32_t *sad)
+{
+    (void)nlevels; (void)lh;
+    const int thOrbDist = (100 + 50) / 2;                                   /* :856 */
+    int *minr = (int *)malloc(sizeof(int) * (size_t)(nR > 0 ? nR : 1)), *maxr = (int *)malloc(sizeof(int) * (size_t)(nR > 0 ? nR : 1));
+    for (int iR = 0; iR < nR; ++iR) {                                       /* :870-881 */
+        const float kpY = kR[iR].y;
+        const float r = 1.2f * scale[kR[iR].octave];
+        maxr[iR] = (int)ceilf(kpY + r);
+        minr[iR] = (int)floorf(kpY - r);
+    }
+    const float minD = 0, maxD = 200;                                       /* :885-886 */
+    int *vd = (int *)malloc(sizeof(int) * (size_t)(nL > 0 ? nL : 1)), nv = 0;
+    for (int iL = 0; iL < nL; ++iL) {
+        u_right[iL] = -1.0f; depth[iL] = -1.0f; desc_index[iL] = -1;
+        if (best_dist) best_dist[iL] = 100;
+        if (best_idx) best_idx[iL] = 0;
+        if (sad) sad[iL] = -1;
+    }
+    for (int iL = 0; iL < nL; ++iL) {
+        const int levelL = kL[iL].octave;
+        const float vL = kL[iL].y, uL = kL[iL].x;
+        const int row = (int)vL;                                            /* vRowIndices[vL], :902 */
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = 100, bestIdxR = 0, any = 0;
+        for (int iR = 0; iR < nR; ++iR) {                                   /* candidates of the row, ascending iR */
+            if (row < minr[iR] || row > maxr[iR]) continue;
+            any = 1;
+            if (kR[iR].octave < levelL - 1 || kR[iR].octave > levelL + 1) continue;
+            const float uR = kR[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orbo_hamming256(dL + (size_t)iL * 32, dR + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (!any) continue;                                                 /* vCandidates.empty(), :904 */
+        if (best_dist) best_dist[iL] = bestDist;
+        if (best_idx) best_idx[iL] = bestIdxR;
+        if (bestIdxR != 0) desc_index[iL] = bestIdxR;                        /* :948 */
+        if (bestDist < thOrbDist) {                                         /* :954 */
+            const float uR0 = kR[bestIdxR].x;
+            const float scaleFactor = inv_scale[levelL];
+            const float scaleduL = roundf(kL[iL].x * scaleFactor);
+            const float scaledvL = roundf(kL[iL].y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5, L = 5;
+            const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= (float)lw[levelL]) continue;           /* :975 */
+            const uint8_t *IL = pyrL[levelL], *IR = pyrR[levelL];
+            const int p = pitch[levelL], y0 = (int)scaledvL - w, xl = (int)scaleduL - w;
+            const int cl = IL[(size_t)(y0 + w) * p + xl + w];
+            int bestD = INT_MAX, bestincR = 0;
+            float vDists[11];
+            for (int incR = -L; incR <= L; ++incR) {
+                const int xr = (int)scaleduR0 + incR - w;
+                const int cr = IR[(size_t)(y0 + w) * p + xr + w];
+                int acc = 0;                                                /* L1 norm of integer-valued floats: exact */
+                for (int yy = 0; yy < 11; ++yy)
+                    for (int xx = 0; xx < 11; ++xx)
+                        acc += abs((IL[(size_t)(y0 + yy) * p + xl + xx] - cl) - (IR[(size_t)(y0 + yy) * p + xr + xx] - cr));
+                const float dist = (float)acc;
+                if (dist < (float)bestD) { bestD = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+            const float num = dist1 - dist3;
+            const float den = 2.0f * (dist1 + dist3 - 2.0f * dist2);
+            const float deltaR = num / den;
+            if (deltaR < -1 || deltaR > 1) continue;
+            float t = scaleduR0 + (float)bestincR;
+            t = t + deltaR;
+            float bestuR = scale[levelL] * t;
+            float disparity = uL - bestuR;
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                depth[iL] = bf / disparity;
+                u_right[iL] = bestuR;
+                if (sad) sad[iL] = bestD;
+                vd[nv++] = bestD;
+            }
+        }
+    }
+    int kept = -1;
+    if (nv > 0) {                                                           /* :1023-1037; the reference has UB when nv == 0 */
+        int *sorted = (int *)malloc(sizeof(int) * (size_t)nv);
+        memcpy(sorted, vd, sizeof(int) * (size_t)nv);
+        for (int i = 1; i < nv; ++i) { const int v = sorted[i]; int j = i - 1; while (j >= 0 && sorted[j] > v) { sorted[j + 1] = sorted[j]; --j; } sorted[j + 1] = v; }
+        const float median = (float)sorted[nv / 2];
+        const float thDist = 1.5f * 1.4f * median;
+        free(sorted);
+        kept = 0;
+        /* the reference walks the sorted list from the back and stops at the first SAD < thDist: every pushed keypoint
+         * with SAD >= thDist is invalidated.  Pushed <=> depth was set (bf / disparity > 0), in ascending iL. */
+        int k = 0;
+        for (int iL = 0; iL < nL; ++iL) {
+            if (depth[iL] < 0) continue;
+            const int v = vd[k++];
+            if (!((float)v < thDist)) { u_right[iL] = -1; depth[iL] = -1; desc_index[iL] = -1; }
+            else ++kept;
+        }
+    }
+    free(minr); free(maxr); free(vd);
     return kept;
 }
 

@@ -76,6 +76,14 @@ int orbo_match(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int t
 int orbo_rotation_bin(float angle_a, float angle_b);
 int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
                          int32_t *hist, int32_t *top3);
+/* Frame::ComputeStereoMatches (src/Frame.cc:849-1038).  pyr*[l]: un-padded level images (pitch[l], lw[l] x lh[l]).
+ * Outputs per left keypoint: mvuRight, mvDepth, vDescIndex; optional debug: best Hamming distance / index, SAD of the
+ * pushed matches (-1 otherwise).  Returns the matches kept, or -1 when none was pushed (the reference then reads an
+ * empty vector, :1024). */
+int orbo_stereo_matches(int nL, const orbo_keypoint *kL, const uint8_t *dL, int nR, const orbo_keypoint *kR, const uint8_t *dR,
+                        int nlevels, const float *scale, const float *inv_scale,
+                        const uint8_t *const *pyrL, const uint8_t *const *pyrR, const int *pitch, const int *lw, const int *lh,
+                        float bf, float *u_right, float *depth, int32_t *desc_index, int32_t *best_dist, int32_t *best_idx, int32_t *sad);
 int orbo_match_mt(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int th, float ratio,
                   int32_t *idx, int32_t *d1, int32_t *d2, uint8_t *accept, int threads);
 

@@ -220,6 +220,29 @@ def test_rotation_filter_vs_oracle(orb, oracle_mod):
         ext.rotation_filter(np.array([5], np.int32), np.array([1], np.uint8), np.zeros(1, np.float32), np.zeros(3, np.float32))
 
 
+@pytest.mark.parametrize("seed,shape,params", [(3, (375, 1242), (2000, 1.2, 8, 20, 7)), (5, (240, 400), (600, 1.2, 4, 20, 7))])
+def test_stereo_matches_vs_oracle(orb, oracle_mod, seed, shape, params):
+    """Frame::ComputeStereoMatches (src/Frame.cc:849-1038) on the device-resident results of two extractors:
+    mvuRight, mvDepth bit-identical, vDescIndex identical to the oracle port (itself pinned to the reference's code)."""
+    from test_oracle_vs_ref import _stereo_inputs
+    L, R, kL, dL, kR, dR, t, pyrL, pyrR = _stereo_inputs(oracle_mod, seed, shape[0], shape[1], params)
+    eL, eR = orb.ORBextractor(*params), orb.ORBextractor(*params)
+    gkL, gdL = eL(L); gkR, gdR = eR(R)
+    assert np.array_equal(gdL, dL) and np.array_equal(gdR, dR) and kps_equal_exact(gkL, kL) and kps_equal_exact(gkR, kR)
+    exp = oracle_mod.Oracle.stereo_matches(kL, dL, kR, dR, t["scale"], t["inv_scale"], pyrL, pyrR, 386.1448)
+    ur, dp, di, kept = eL.stereo_match(eR, 386.1448)
+    assert kept == exp["kept"] and len(ur) == len(kL)
+    assert np.array_equal(ur.view(np.uint32), exp["u_right"].view(np.uint32))
+    assert np.array_equal(dp.view(np.uint32), exp["depth"].view(np.uint32))
+    assert np.array_equal(di, exp["desc_index"])
+    # frames of a batch: left = frame 1 of a two-frame batch, right = frame 0 of another
+    eL.extract_batch([R, L]); eR.extract_batch([R, L])
+    ur2, dp2, di2, kept2 = eL.stereo_match(eR, 386.1448, frame_left=1, frame_right=0)
+    assert kept2 == kept and np.array_equal(ur2, ur) and np.array_equal(dp2, dp) and np.array_equal(di2, di)
+    with pytest.raises(orb.OrbxError):
+        eL.stereo_match(orb.ORBextractor(params[0], 1.2, params[2] - 1, 20, 7), 386.1448)
+
+
 def test_full_size_properties(orb, oracle_mod):
     """BASELINE configs 3 and 5 at full size: one frame each against the oracle (seconds on the CPU),
     and size-independent properties on the batch: determinism, self-match, level-major ordering, bounds."""

@@ -151,3 +151,33 @@ def test_rotation_filter_port_vs_reference(oracle_mod):
         if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_rotation_filter"):
             r_acc, r_hist, r_top3 = oracle_mod.RefExtractor.rotation_filter(idx, acc, a, b)
             assert np.array_equal(r_acc, k_acc) and np.array_equal(r_hist, hist) and np.array_equal(r_top3, top3)
+
+
+def _stereo_inputs(oracle_mod, seed, h, w, params):
+    from multimot_track_b200.synth import stereo_pair
+    L, R = stereo_pair(seed, h, w)
+    oL, oR = oracle_mod.Oracle(*params), oracle_mod.Oracle(*params)
+    kL, dL = oL(L); kR, dR = oR(R)
+    t = oL.tables()
+    pyrL = [oL.level_image(l) for l in range(params[2])]; pyrR = [oR.level_image(l) for l in range(params[2])]
+    return L, R, kL, dL, kR, dR, t, pyrL, pyrR
+
+
+@pytest.mark.parametrize("seed,shape,params", [(3, (375, 1242), (2000, 1.2, 8, 20, 7)), (5, (240, 400), (600, 1.2, 4, 20, 7))])
+def test_stereo_port_vs_reference(oracle_mod, seed, shape, params):
+    """Frame::ComputeStereoMatches: the C port against the reference's own compiled function body (src/Frame.cc:849-1038
+    excerpted unmodified, oracle/Makefile) on a synthetic rectified pair; bit-identical mvuRight / mvDepth / vDescIndex."""
+    _, _, kL, dL, kR, dR, t, pyrL, pyrR = _stereo_inputs(oracle_mod, seed, shape[0], shape[1], params)
+    a = oracle_mod.Oracle.stereo_matches(kL, dL, kR, dR, t["scale"], t["inv_scale"], pyrL, pyrR, 386.1448)
+    assert a["kept"] > 30                                  # the pair really produces stereo matches
+    m = a["u_right"] >= 0
+    disp = kL["x"][m] - a["u_right"][m]
+    assert (disp > 0).all() and (disp < 200).all() and np.allclose(a["depth"][m], np.float32(386.1448) / disp, rtol=1e-6)
+    assert (a["desc_index"] != 0).all()                    # the `bestIdxR != 0` quirk (:948)
+    assert ((a["sad"] >= 0) >= m).all() and (a["u_right"][a["best_dist"] >= 75] < 0).all()
+    if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_stereo_matches"):
+        b = oracle_mod.RefExtractor.stereo_matches(kL, dL, kR, dR, t["scale"], t["inv_scale"], pyrL, pyrR, 386.1448)
+        assert b["kept"] == a["kept"]
+        assert np.array_equal(a["u_right"].view(np.uint32), b["u_right"].view(np.uint32))
+        assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+        assert np.array_equal(a["desc_index"], b["desc_index"])
