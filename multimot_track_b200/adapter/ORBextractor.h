@@ -52,6 +52,10 @@ public:
     // Last error text from the GPU library (empty when the last call succeeded).
     const char *LastError() const;
 
+    // B200 extension: the GPU handle that still holds the last frame's keypoints, descriptors and pyramid on the
+    // device (for ComputeStereoMatchesGPU / BruteForceMatch without a round trip through the host).
+    orbx_handle *Handle() const { return mpHandle; }
+
 protected:
     ORBextractor(const ORBextractor &);              // a handle owns GPU memory: not copyable
     ORBextractor &operator=(const ORBextractor &);

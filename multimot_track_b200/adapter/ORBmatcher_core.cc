@@ -32,4 +32,30 @@ int BruteForceMatch(orbx_handle *handle, const cv::Mat &descA, const cv::Mat &de
     return rc;
 }
 
+int RotationConsistencyFilter(orbx_handle *handle, const std::vector<int> &bestIdx, std::vector<unsigned char> &accepted,
+                              const std::vector<float> &anglesA, const std::vector<float> &anglesB)
+{
+    const int nA = (int)bestIdx.size();
+    if ((int)accepted.size() != nA || (int)anglesA.size() != nA)
+        throw std::invalid_argument("RotationConsistencyFilter: bestIdx, accepted and anglesA need one entry per query");
+    if (nA == 0) return 0;
+    const int rc = orbx_rotation_filter(handle, nA, bestIdx.data(), accepted.data(), anglesA.data(), anglesB.data(), (int)anglesB.size(),
+                                        nullptr, nullptr);
+    if (rc < 0) throw std::runtime_error(std::string("orbx_rotation_filter: ") + orbx_last_error(handle));
+    return rc;
+}
+
+int ComputeStereoMatchesGPU(orbx_handle *left, orbx_handle *right, float mbf, std::vector<float> &mvuRight,
+                            std::vector<float> &mvDepth, std::vector<int> &vDescIndex)
+{
+    int n = 0;
+    int rc = orbx_stereo_match(left, right, 0, 0, mbf, nullptr, nullptr, nullptr, 0, &n);      // N = left keypoints
+    if (rc < 0) throw std::runtime_error(std::string("orbx_stereo_match: ") + orbx_last_error(left));
+    mvuRight.assign(n, -1.0f); mvDepth.assign(n, -1.0f); vDescIndex.assign(n, -1);             // src/Frame.cc:852-854
+    if (n == 0) return 0;
+    rc = orbx_stereo_match(left, right, 0, 0, mbf, mvuRight.data(), mvDepth.data(), vDescIndex.data(), n, &n);
+    if (rc < 0) throw std::runtime_error(std::string("orbx_stereo_match: ") + orbx_last_error(left));
+    return rc;
+}
+
 } // namespace ORB_SLAM2

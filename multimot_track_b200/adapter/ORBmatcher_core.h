@@ -33,6 +33,20 @@ int BruteForceMatch(orbx_handle *handle, const cv::Mat &descA, const cv::Mat &de
                     std::vector<int> &bestIdx, std::vector<int> &bestDist, std::vector<int> &secondDist,
                     std::vector<unsigned char> &accepted);
 
+// mbCheckOrientation of the matchers (src/ORBmatcher.cc:610-620 histogram, :2233-2274 ComputeThreeMaxima, :641-660
+// pruning) for the matches of BruteForceMatch: accepted[i] is cleared when the rotation anglesA[i] - anglesB[bestIdx[i]]
+// does not fall into one of the three most populated bins.  Returns the matches kept.
+int RotationConsistencyFilter(orbx_handle *handle, const std::vector<int> &bestIdx, std::vector<unsigned char> &accepted,
+                              const std::vector<float> &anglesA, const std::vector<float> &anglesB);
+
+// Frame::ComputeStereoMatches (src/Frame.cc:849-1038) on the GPU, from the device-resident results of the two
+// extractors that just processed the left and the right image (Frame::Frame stereo constructor, src/Frame.cc:96-104).
+// Fills mvuRight, mvDepth and vDescIndex exactly as the reference does (N = number of left keypoints); mbf as in Frame.
+// Returns the number of stereo matches kept.  The body of Frame::ComputeStereoMatches becomes
+//     ComputeStereoMatchesGPU(mpORBextractorLeft->Handle(), mpORBextractorRight->Handle(), mbf, mvuRight, mvDepth, vDescIndex);
+int ComputeStereoMatchesGPU(orbx_handle *left, orbx_handle *right, float mbf, std::vector<float> &mvuRight,
+                            std::vector<float> &mvDepth, std::vector<int> &vDescIndex);
+
 } // namespace ORB_SLAM2
 
 #endif

@@ -36,6 +36,24 @@ int main(int argc, char **argv)
         for (int y = -19; y < lh + 19; ++y) std::fwrite(m.data + (long)y * (long)m.step - 19, 1, lw + 38, o);
     }
     std::fclose(o);
+    // stereo constructor shape (src/Frame.cc:96-104): a second extractor on the same image, then ComputeStereoMatches
+    ORB_SLAM2::ORBextractor *right = new ORB_SLAM2::ORBextractor(std::atoi(argv[4]), (float)std::atof(argv[5]), std::atoi(argv[6]),
+                                                                std::atoi(argv[7]), std::atoi(argv[8]));
+    std::vector<cv::KeyPoint> mvKeysRight;
+    cv::Mat mDescriptorsRight;
+    (*right)(im, cv::Mat(), mvKeysRight, mDescriptorsRight);
+    std::vector<float> mvuRight, mvDepth;
+    std::vector<int> vDescIndex;
+    const int nstereo = ORB_SLAM2::ComputeStereoMatchesGPU(extractor->Handle(), right->Handle(), 386.1448f, mvuRight, mvDepth, vDescIndex);
+    std::vector<int> bi, bd, sd;
+    std::vector<unsigned char> acc;
+    const int nm = ORB_SLAM2::BruteForceMatch(extractor->Handle(), mDescriptors, mDescriptorsRight, ORB_SLAM2::ORBmatcher::TH_HIGH, 0.9f, bi, bd, sd, acc);
+    std::vector<float> angL(n), angR(mvKeysRight.size());
+    for (int i = 0; i < n; ++i) angL[i] = mvKeys[i].angle;
+    for (size_t i = 0; i < mvKeysRight.size(); ++i) angR[i] = mvKeysRight[i].angle;
+    const int nrot = ORB_SLAM2::RotationConsistencyFilter(extractor->Handle(), bi, acc, angL, angR);
+    std::printf("stereo on identical images: %d of %d matched (%d sized outputs); %d brute-force matches, %d after the rotation check\n",
+                nstereo, n, (int)mvuRight.size(), nm, nrot);
     int self = n > 1 ? ORB_SLAM2::ORBmatcher::DescriptorDistance(mDescriptors.row(0), mDescriptors.row(0)) : 0;
     std::printf("%d keypoints, self distance %d, TH_LOW %d TH_HIGH %d\n", n, self, ORB_SLAM2::ORBmatcher::TH_LOW, ORB_SLAM2::ORBmatcher::TH_HIGH);
     return 0;

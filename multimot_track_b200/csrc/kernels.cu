@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 
 namespace orbx {
@@ -500,7 +501,8 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
     static const BlurMaps zero_maps = {};
     const int total = hP.n_blur_work * nframes;
     if (total <= 0) return cudaSuccess;
-    const int grid = total < 148 * 4 ? total : 148 * 4;               // 4 resident CTAs per SM (64 registers x 256 threads)
+    static const int per_sm = std::getenv("ORBX_BLUR_CTAS_PER_SM") ? std::atoi(std::getenv("ORBX_BLUR_CTAS_PER_SM")) : 4;
+    const int grid = total < 148 * per_sm ? total : 148 * per_sm;     // <= 4 resident CTAs per SM (64 registers x 256 threads)
     k_blur<<<grid, 256, 0, st>>>(dP, s0, maps ? *maps : zero_maps, maps ? tma_levels : 0u, total);
     ls->launches++;
     return cudaGetLastError();
@@ -750,6 +752,30 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, MINB) k_fast_fused(co
     ff_process<CELL>(P, J, tile, list, lane);
 }
 
+// ---- persistent variant: a fixed grid of CTAs walks the (job, frame) items, so the kernel occupies only part of every
+// SM and the latency-bound kernels of the other handles (pyramid, octree, orientation) stay co-resident with it.
+template <int CELL, int UNR = 12>
+__global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, 4)
+k_fast_fused_persist(const DevParams *__restrict__ P, Src0 s0, int work_off, int work_end, int nframes)
+{
+    using C = FfCfg<CELL>;
+    extern __shared__ __align__(16) uint32_t ff_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *tile = ff_smem + (size_t)warp * C::WARP_WORDS;
+    uint32_t *list = tile + C::ROWS * C::PITCH;
+    const int njobs = work_end - work_off, total = njobs * nframes, stride = gridDim.x * C::WARPS;
+    for (int item = blockIdx.x * C::WARPS + warp; item < total; item += stride) {
+        const int frame = item / njobs;
+        const FfJob J = ff_job(P, work_off + item - frame * njobs, frame);
+        int sp;
+        const uint8_t *img = level_ptr(P, s0, frame, J.level, &sp);
+        ff_stage<CELL, false, UNR>(img, sp, 0, 0, P->lv[J.level].h - 1, (sp >> 2) - 1, J, tile, lane);
+        __syncwarp();
+        ff_process<CELL>(P, J, tile, list, lane);
+        __syncwarp();
+    }
+}
+
 // ---- persistent TMA variant: every warp walks (job, frame) items; the raw pixel box of the NEXT item (96 bytes x
 // h_cell+6 rows, 16-byte aligned origin) is fetched by cp.async.bulk.tensor while the current item is scored.
 template <int CELL>
@@ -850,6 +876,13 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
         const dim3 grid((n_small + C::WARPS - 1) / C::WARPS, nframes);
 #define FF_GO(...) do { cudaFuncSetAttribute(k_fast_fused<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); \
                         k_fast_fused<__VA_ARGS__><<<grid, C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small); } while (0)
+        static const int persist = std::getenv("ORBX_FF_CTAS_PER_SM") ? std::atoi(std::getenv("ORBX_FF_CTAS_PER_SM")) : 0;
+        if (persist > 0) {
+            cudaFuncSetAttribute(k_fast_fused_persist<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+            const int total_ctas = (n_small * nframes + C::WARPS - 1) / C::WARPS;
+            k_fast_fused_persist<44><<<std::min(148 * persist, total_ctas), C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small, nframes);
+            ls->launches++;
+        } else
         switch (variant) {
         case 1: FF_GO(44, 5, 4); break;
         case 2: FF_GO(44, 4, 12); break;
@@ -858,7 +891,7 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
         default: FF_GO(44, 4, 12); break;
         }
 #undef FF_GO
-        ls->launches++;
+        if (persist <= 0) ls->launches++;
     }
     if (hP.n_ffast_work > n_small) {
         using C = FfCfg<64>;
@@ -1659,7 +1692,8 @@ cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0
             attr_set = true;
         }
         // 3 CTAs of 8 warps per SM resident; every warp walks several keypoints of its frame
-        int per_frame = 148 * 3 / nframes;                             // one wave: never more CTAs than resident slots
+        static const int od_per_sm = std::getenv("ORBX_OD_CTAS_PER_SM") ? std::atoi(std::getenv("ORBX_OD_CTAS_PER_SM")) : 3;
+        int per_frame = 148 * od_per_sm / nframes;                     // one wave: never more CTAs than resident slots
         const int max_useful = (hP.kp_frame_cap + kOdWarps - 1) / kOdWarps;
         if (per_frame > max_useful) per_frame = max_useful;
         if (per_frame < 1) per_frame = 1;
