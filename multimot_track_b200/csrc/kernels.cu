@@ -181,33 +181,90 @@ __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P,
     resize_tile(P, S, sp, dst, level, blockIdx.x * kRzTW, y0, min(y0 + kRzTH, D.h), ssrc);
 }
 
-// ---- TMA-staged variant: the source window of a tile is one cp.async.bulk.tensor box ------------------------
+// ---- TMA-staged, separable variant.  Persistent CTAs walk the 128x32 destination tiles of one frame; the source
+// window of the NEXT tile is in flight as one cp.async.bulk.tensor box (double buffer) while this one is resampled.
+// The horizontal interpolation is done ONCE per source row of the window (H >> 4, as cv::resize keeps it) into shared
+// memory, then the vertical pass combines two of those rows per destination row -- half the multiplies and a third of
+// the byte loads of the direct form, with identical integer results.
 __global__ void __launch_bounds__(256)
-k_resize_tma(const DevParams *__restrict__ P, const __grid_constant__ CUtensorMap tmap, int level, int box_w, int box_h)
+k_resize_sep(const DevParams *__restrict__ P, const __grid_constant__ CUtensorMap tmap, int level, int box_w, int box_h, int box_bytes,
+             int ntx, int ntiles)
 {
-    extern __shared__ __align__(128) uint8_t sbox[];               // [box_h][box_w] source bytes, dense
-    __shared__ __align__(8) uint64_t mbar;
+    extern __shared__ __align__(128) uint8_t rs_smem[];            // [2][box_bytes] source boxes, then int Hs[box_h][128]
+    __shared__ __align__(8) uint64_t mbar[2];
     const LevelGeom &D = P->lv[level];
-    const int x0 = blockIdx.x * kRzTW, y0 = blockIdx.y * kRzTH, frame = blockIdx.z;
-    const int y_end = min(y0 + kRzTH, D.h);
     const ResizeTab *xt = P->xtab + P->xtab_off[level], *yt = P->ytab + P->ytab_off[level];
-    const int sx_lo = xt[x0].s0 & ~15, sy_lo = yt[y0].s0;         // 16-byte aligned box origin
-    const int tid = threadIdx.x + threadIdx.y * 32;
+    int *Hs = reinterpret_cast<int *>(rs_smem + 2 * box_bytes);
+    const int frame = blockIdx.y, tid = threadIdx.x + threadIdx.y * 32, q = threadIdx.x, g = threadIdx.y;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(box_w * box_h) : "memory");
+    auto issue = [&](int t, int b) {                                // thread 0
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int sx_lo = xt[tx * kRzTW].s0 & ~15, sy_lo = yt[ty * kRzTH].s0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar[b])), "r"(box_w * box_h) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     :: "r"(smem_u32(sbox)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar)),
+                     :: "r"(smem_u32(rs_smem + b * box_bytes)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar[b])),
                         "r"(sx_lo), "r"(sy_lo), "r"(frame) : "memory");
-    }
-    mbar_wait_parity(&mbar, 0);
+    };
+    int t = blockIdx.x;
+    if (tid == 0 && t < ntiles) issue(t, 0);
     uint8_t *dst = P->pyr + (long long)frame * P->pyr_frame_bytes + D.img_off;
-    resize_rows(P, level, sbox, box_w, sx_lo, sy_lo, x0, y0, y_end, dst);
+    unsigned phase = 0;
+    for (int n = 0; t < ntiles; t += gridDim.x, ++n) {
+        const int b = n & 1;
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, b ^ 1);
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int x0 = tx * kRzTW, y0 = ty * kRzTH, y_end = min(y0 + kRzTH, D.h);
+        const int sx_lo = xt[x0].s0 & ~15, sy_lo = yt[y0].s0, nrows = yt[y_end - 1].s1 - sy_lo + 1;
+        const int x4 = x0 + 4 * q;
+        const bool col_ok = x4 < D.w;
+        int o0[4], o1[4], c0[4], c1[4];
+        if (col_ok) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                              // tables are padded to a multiple of 4 entries
+                const ResizeTab e = xt[x4 + k];
+                o0[k] = e.s0 - sx_lo; o1[k] = e.s1 - sx_lo; c0[k] = e.c0; c1[k] = e.c1;
+            }
+        }
+        mbar_wait_parity(&mbar[b], (phase >> b) & 1u);
+        phase ^= 1u << b;
+        // ---- horizontal pass: source rows of the window -> Hs[r][x] = (S[s0]*a0 + S[s1]*a1) >> 4
+        if (col_ok) {
+            const uint8_t *sb = rs_smem + b * box_bytes;
+            for (int r = g; r < nrows; r += 8) {
+                const uint8_t *row = sb + r * box_w;
+                int4 h;
+                h.x = (row[o0[0]] * c0[0] + row[o1[0]] * c1[0]) >> 4;
+                h.y = (row[o0[1]] * c0[1] + row[o1[1]] * c1[1]) >> 4;
+                h.z = (row[o0[2]] * c0[2] + row[o1[2]] * c1[2]) >> 4;
+                h.w = (row[o0[3]] * c0[3] + row[o1[3]] * c1[3]) >> 4;
+                *reinterpret_cast<int4 *>(Hs + r * kRzTW + 4 * q) = h;
+            }
+        }
+        __syncthreads();
+        // ---- vertical pass: out = (((b0*H0) >> 16) + ((b1*H1) >> 16) + 2) >> 2; no clamp needed (see resize_rows)
+        if (col_ok) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int y = y0 + g + 8 * rr;
+                if (y < y_end) {
+                    const ResizeTab e = yt[y];
+                    const int4 h0 = *reinterpret_cast<const int4 *>(Hs + (e.s0 - sy_lo) * kRzTW + 4 * q);
+                    const int4 h1 = *reinterpret_cast<const int4 *>(Hs + (e.s1 - sy_lo) * kRzTW + 4 * q);
+                    const int b0 = e.c0, b1 = e.c1;
+                    const uint32_t v0 = (((b0 * h0.x) >> 16) + ((b1 * h1.x) >> 16) + 2) >> 2, v1 = (((b0 * h0.y) >> 16) + ((b1 * h1.y) >> 16) + 2) >> 2;
+                    const uint32_t v2 = (((b0 * h0.z) >> 16) + ((b1 * h1.z) >> 16) + 2) >> 2, v3 = (((b0 * h0.w) >> 16) + ((b1 * h1.w) >> 16) + 2) >> 2;
+                    *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = v0 | v1 << 8 | v2 << 16 | v3 << 24;   // pitch % 64 == 0
+                }
+            }
+        }
+        __syncthreads();                                               // Hs and box b are free again
+    }
 }
 
 void resize_box(const LevelGeom &src, const LevelGeom &dst, int *box_w, int *box_h)
@@ -310,9 +367,26 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
         for (int l = 1; l < hP.nlevels; ++l) {
             const LevelGeom &D = hP.lv[l];
             const dim3 grid((D.w + kRzTW - 1) / kRzTW, (D.h + kRzTH - 1) / kRzTH, nframes);
-            if (tma && tma->ok[l])                                 // source window by TMA (cp.async.bulk.tensor)
-                k_resize_tma<<<grid, dim3(32, 8), (size_t)tma->box_w[l] * tma->box_h[l], st>>>(dP, tma->src[l], l, tma->box_w[l], tma->box_h[l]);
-            else
+            if (tma && tma->ok[l]) {                               // source windows by TMA, persistent separable kernel
+                const int bw = tma->box_w[l], bh = tma->box_h[l];
+                const int box_bytes = (bw * bh + 127) / 128 * 128;
+                const size_t smem = 2 * (size_t)box_bytes + (size_t)bh * kRzTW * sizeof(int);
+                static size_t attr = 40 * 1024;                    // static + dynamic above 48 KB needs the opt-in attribute
+                if (smem > attr) {
+                    cudaError_t e = cudaFuncSetAttribute(k_resize_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    attr = smem;
+                }
+                const int ntx = grid.x, ntiles = grid.x * grid.y;
+                int per_sm = (int)((227 * 1024) / (smem + 1024));
+                per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
+                const int cap = std::max(1, 148 * per_sm / nframes);      // resident CTAs available to one frame
+                static const int force_iters = std::getenv("ORBX_RZ_ITERS") ? std::atoi(std::getenv("ORBX_RZ_ITERS")) : 0;
+                const int iters = force_iters > 0 ? force_iters : (ntiles + cap - 1) / cap;
+                k_resize_sep<<<dim3((ntiles + iters - 1) / iters, nframes), dim3(32, 8), smem, st>>>(dP, tma->src[l], l, bw, bh, box_bytes, ntx, ntiles);
+                const cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+            } else
                 k_resize<<<grid, dim3(32, 8), 0, st>>>(dP, s0, l);
             ls->launches++;
         }
