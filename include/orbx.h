@@ -212,6 +212,17 @@ int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, uint8_t *ac
 int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA,
                                 const float *d_angleB, int32_t *d_hist, int32_t *d_top3, int32_t *d_kept);
 
+/* ---- representative descriptors of map points -------------- */
+
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-306), batched: map point p has the observed descriptors
+ * desc[offsets[p] .. offsets[p+1]) (32 bytes each, gathered by the caller as :263-270 does); for each point the
+ * all-pairs Hamming distances, the median of every row (sorted row[(int)(0.5*(n-1))], :291) and the FIRST row with the
+ * least median (:293-297).  best_idx[p] is relative to the point's first row (-1 for a point without descriptors);
+ * best_median (may be NULL) receives that median.  Host pointers; at most 1024 observations per point.
+ * Returns ORBX_OK or a negative status. */
+int orbx_distinctive_descriptors(orbx_handle *h, const uint8_t *desc, const int32_t *offsets, int npoints,
+                                 int32_t *best_idx, int32_t *best_median);
+
 /* ---- stereo association ------------------------------------- */
 
 /* Frame::ComputeStereoMatches (src/Frame.cc:849-1038) on the results of two extractors that are still resident on the

@@ -59,6 +59,7 @@ SIGNATURES = {
     "orbx_match_device": (_I, [_VP, _VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP]),
     "orbx_rotation_filter": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "orbx_rotation_filter_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "orbx_distinctive_descriptors": (_I, [_VP, _VP, _VP, _I, _VP, _VP]),
     "orbx_stereo_match": (_I, [_VP, _VP, _I, _I, _F, _VP, _VP, _VP, _I, _VP]),
     "orbx_set_profiling": (_I, [_VP, _I]),
     "orbx_get_stage_ms": (_I, [_VP, _VP, _I]),

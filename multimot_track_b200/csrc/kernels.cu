@@ -1926,6 +1926,75 @@ cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_acce
     return cudaGetLastError();
 }
 
+// ------------------------------------------------- distinctive descriptors
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301), batched over map points: one CTA per map point,
+// its n observed descriptors staged in shared memory; a warp owns a row i, builds the 257-bin histogram of the
+// distances d(i, .) (d(i,i) = 0) with shared-memory atomics and reads the median off the running count
+// (sorted[(int)(0.5*(n-1))]); the point keeps the FIRST row with the least median (atomicMin on median << 16 | i).
+constexpr int kDdWarps = 4, kDdMaxObs = 1024;
+
+__global__ void __launch_bounds__(kDdWarps * 32)
+k_distinctive(const uint8_t *__restrict__ desc, const int32_t *__restrict__ offsets, int npoints, int32_t *__restrict__ best_idx,
+              int32_t *__restrict__ best_median)
+{
+    extern __shared__ __align__(16) uint8_t dd_smem[];               // [n][32] descriptors, then kDdWarps x 264 histogram words
+    __shared__ unsigned s_best;
+    const int p = blockIdx.x;
+    if (p >= npoints) return;
+    const int o0 = offsets[p], n = offsets[p + 1] - o0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (n <= 0) { if (threadIdx.x == 0) { best_idx[p] = -1; if (best_median) best_median[p] = -1; } return; }
+    uint4 *sd = reinterpret_cast<uint4 *>(dd_smem);
+    int *hist = reinterpret_cast<int *>(dd_smem + (size_t)n * 32) + warp * 264;
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) sd[i] = reinterpret_cast<const uint4 *>(desc + (long long)o0 * 32)[i];
+    if (threadIdx.x == 0) s_best = 0xffffffffu;
+    __syncthreads();
+    const int mpos = (int)(0.5 * (n - 1));                           // index of the median in the sorted row
+    for (int i = warp; i < n; i += kDdWarps) {
+        for (int k = lane; k < 264; k += 32) hist[k] = 0;
+        __syncwarp();
+        const uint4 a0 = sd[2 * i], a1 = sd[2 * i + 1];
+        for (int j = lane; j < n; j += 32) {
+            const uint4 b0 = sd[2 * j], b1 = sd[2 * j + 1];
+            const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            atomicAdd(&hist[d], 1);                                   // d(i,i) = 0 falls out of the XOR
+        }
+        __syncwarp();
+        // median = smallest v with count(d <= v) > mpos: lane l owns bins 9l .. 9l+8 (288 >= 257)
+        int c[9], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const int b = 9 * lane + k; c[k] = b < 257 ? hist[b] : 0; sum += c[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, ofs); if (lane >= ofs) incl += t; }
+        int run = incl - sum, med = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { run += c[k]; if (run > mpos && med == 0x7fffffff) med = 9 * lane + k; }
+        med = __reduce_min_sync(0xffffffffu, med);
+        if (lane == 0) atomicMin(&s_best, (unsigned)med << 16 | (unsigned)i);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { best_idx[p] = (int)(s_best & 0xffffu); if (best_median) best_median[p] = (int)(s_best >> 16); }
+}
+
+cudaError_t launch_distinctive(const uint8_t *d_desc, const int32_t *d_offsets, int npoints, int max_obs, int32_t *d_best_idx,
+                               int32_t *d_best_median, cudaStream_t st, LaunchStats *ls)
+{
+    if (npoints <= 0) return cudaSuccess;
+    const size_t smem = (size_t)max_obs * 32 + kDdWarps * 264 * sizeof(int);
+    static size_t attr = 40 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    k_distinctive<<<npoints, kDdWarps * 32, smem, st>>>(d_desc, d_offsets, npoints, d_best_idx, d_best_median);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------- stereo
 // Frame::ComputeStereoMatches (src/Frame.cc:849-1038) on the device-resident results of a left and a right extractor.
 // One warp per left keypoint: (1) scan of ALL right keypoints with the reference's row-band / octave / disparity gates

@@ -86,6 +86,9 @@ cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB,
                          int4 *d_partial, int nchunks, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA, const float *d_angleB,
                                    int32_t *d_hist, int32_t *d_top3, int *d_kept, cudaStream_t st, LaunchStats *ls);
+constexpr int kDistinctiveMaxObs = 1024;      // observations of one map point that fit the CTA's shared memory
+cudaError_t launch_distinctive(const uint8_t *d_desc, const int32_t *d_offsets, int npoints, int max_obs, int32_t *d_best_idx,
+                               int32_t *d_best_median, cudaStream_t st, LaunchStats *ls);
 struct StereoScales { float scale[kMaxLevels], inv_scale[kMaxLevels]; };     // mvScaleFactors / mvInvScaleFactors
 cudaError_t launch_stereo(const DevParams *dPL, Src0 s0L, int frameL, const DevParams *dPR, Src0 s0R, int frameR, const StereoScales &sc, float bf,
                           int capL, float *d_u_right, float *d_depth, int32_t *d_desc_index, int32_t *d_sad, int *d_kept, cudaStream_t st, LaunchStats *ls);

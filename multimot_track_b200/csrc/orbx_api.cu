@@ -681,6 +681,43 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     return res[33];
 }
 
+// ------------------------------------------------- distinctive descriptors
+
+extern "C" int orbx_distinctive_descriptors(orbx_handle *h, const uint8_t *desc, const int32_t *offsets, int npoints,
+                                            int32_t *best_idx, int32_t *best_median)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (npoints < 0 || (npoints > 0 && (!offsets || !best_idx))) return fail(h, ORBX_ERR_BAD_ARG, "orbx_distinctive_descriptors: bad argument");
+    if (npoints == 0) return ORBX_OK;
+    int max_obs = 0;
+    for (int p = 0; p < npoints; ++p) {
+        const int n = offsets[p + 1] - offsets[p];
+        if (n < 0 || offsets[p] < 0) return fail(h, ORBX_ERR_BAD_ARG, "orbx_distinctive_descriptors: offsets must be non-negative and ascending");
+        max_obs = std::max(max_obs, n);
+    }
+    if (max_obs > kDistinctiveMaxObs) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_distinctive_descriptors: more than 1024 observations of one map point");
+    const int total = offsets[npoints];
+    if (total > 0 && !desc) return fail(h, ORBX_ERR_BAD_ARG, "orbx_distinctive_descriptors: NULL desc");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    uint8_t *d = nullptr;
+    const size_t desc_bytes = ((size_t)std::max(total, 1) * 32 + 255) / 256 * 256, off_bytes = ((size_t)(npoints + 1) * 4 + 255) / 256 * 256;
+    CU(cudaMalloc(&d, desc_bytes + off_bytes + (size_t)npoints * 8));
+    int32_t *d_off = (int32_t *)(d + desc_bytes), *d_best = (int32_t *)(d + desc_bytes + off_bytes), *d_med = d_best + npoints;
+    auto body = [&]() -> int {
+        if (total > 0) CU(cudaMemcpyAsync(d, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_off, offsets, (size_t)(npoints + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(launch_distinctive(d, d_off, npoints, std::max(max_obs, 1), d_best, d_med, st, &h->stats));
+        CU(cudaMemcpyAsync(best_idx, d_best, (size_t)npoints * 4, cudaMemcpyDeviceToHost, st));
+        if (best_median) CU(cudaMemcpyAsync(best_median, d_med, (size_t)npoints * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return ORBX_OK;
+    };
+    const int rc = body();
+    cudaFree(d);
+    return rc;
+}
+
 // ------------------------------------------------------------------- stereo
 
 extern "C" int orbx_stereo_match(orbx_handle *L, orbx_handle *R, int frame_left, int frame_right, float bf,

@@ -254,3 +254,13 @@ class ORBextractor:
                                          di.ctypes.data, cap, ctypes.byref(n))
         self._ck(rc)
         return ur[:n.value].copy(), dp[:n.value].copy(), di[:n.value].copy(), rc
+
+    def distinctive_descriptors(self, desc, offsets):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-306) for a batch of map points: point p owns
+        desc[offsets[p]:offsets[p+1]].  Returns (best_idx[np] relative to the point's first row, best_median[np])."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, np.int32)
+        npts = len(off) - 1
+        best = np.zeros(max(npts, 0), np.int32); med = np.zeros(max(npts, 0), np.int32)
+        self._ck(self._lib.orbx_distinctive_descriptors(self._h, d.ctypes.data, off.ctypes.data, npts, best.ctypes.data, med.ctypes.data))
+        return best, med

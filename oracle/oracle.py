@@ -150,6 +150,21 @@ class Oracle:
         return idx, d1, d2, acc.astype(bool)
 
     @classmethod
+    def distinctive_descriptors(cls, desc, offsets):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301) for a batch of map points: point p owns
+        desc[offsets[p]:offsets[p+1]].  Returns (best_idx[np] relative to the point's first row, best_median[np])."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.asarray(offsets, np.int64)
+        L = cls.lib()
+        L.orbo_distinctive_descriptor.argtypes = [_VP, _I, _VP]
+        best = np.zeros(len(off) - 1, np.int32); med = np.zeros(len(off) - 1, np.int32)
+        for p in range(len(off) - 1):
+            m = ctypes.c_int32(0)
+            n = int(off[p + 1] - off[p])
+            best[p] = L.orbo_distinctive_descriptor(d[off[p]:].ctypes.data, n, ctypes.byref(m)) if n > 0 else -1
+            med[p] = m.value if n > 0 else -1
+        return best, med
+
+    @classmethod
     def stereo_matches(cls, kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR, bf):
         """Frame::ComputeStereoMatches (src/Frame.cc:849-1038).  pyrL / pyrR: lists of un-padded level images.
         Returns dict(u_right, depth, desc_index, best_dist, best_idx, sad, kept)."""
@@ -276,6 +291,15 @@ class RefExtractor:
     def descriptor_distance(cls, a, b, variant="canon"):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return cls.lib(variant).orbref_descriptor_distance(a.ctypes.data, b.ctypes.data)
+
+    @classmethod
+    def distinctive_descriptor(cls, desc, variant="canon"):
+        """The reference's own loop (src/MapPoint.cc:272-301) on one map point's descriptors: (best index, its median)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        L = cls.lib(variant)
+        L.orbref_distinctive_descriptor.argtypes = [_VP, _I, _VP]
+        m = ctypes.c_int(0)
+        return L.orbref_distinctive_descriptor(d.ctypes.data, len(d), ctypes.byref(m)), m.value
 
     @classmethod
     def stereo_matches(cls, kpsL, descL, kpsR, descR, scale, inv_scale, pyrL, pyrR, bf, variant="canon"):

@@ -578,6 +578,24 @@ int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const floa
     return kept;
 }
 
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:272-301: all-pairs Hamming distances of a map point's n
+ * observed descriptors, per-row median = sorted row[(int)(0.5*(n-1))], first row with the least median. */
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+int orbo_distinctive_descriptor(const uint8_t *desc, int n, int32_t *best_median)
+{
+    int best = INT_MAX, best_idx = 0;
+    int *row = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) row[j] = i == j ? 0 : orbo_hamming256(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+        qsort(row, (size_t)n, sizeof(int), cmp_int);
+        const int median = row[(int)(0.5 * (n - 1))];
+        if (median < best) { best = median; best_idx = i; }
+    }
+    free(row);
+    if (best_median) *best_median = best;
+    return best_idx;
+}
+
 /* ------------------------------------------------------------------ stereo
  * Frame::ComputeStereoMatches, src/Frame.cc:849-1038 of the reference (this fork: minD = 0, maxD = 200, row band
  * r = 1.2 * scale, patches normalised by their centre pixel, vDescIndex with its `bestIdxR != 0` quirk).

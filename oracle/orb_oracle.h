@@ -76,6 +76,8 @@ int orbo_match(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int t
 int orbo_rotation_bin(float angle_a, float angle_b);
 int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
                          int32_t *hist, int32_t *top3);
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301) for one map point: index of the representative descriptor */
+int orbo_distinctive_descriptor(const uint8_t *desc, int n, int32_t *best_median);
 /* Frame::ComputeStereoMatches (src/Frame.cc:849-1038).  pyr*[l]: un-padded level images (pitch[l], lw[l] x lh[l]).
  * Outputs per left keypoint: mvuRight, mvDepth, vDescIndex; optional debug: best Hamming distance / index, SAD of the
  * pushed matches (-1 otherwise).  Returns the matches kept, or -1 when none was pushed (the reference then reads an

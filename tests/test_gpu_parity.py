@@ -243,6 +243,28 @@ def test_stereo_matches_vs_oracle(orb, oracle_mod, seed, shape, params):
         eL.stereo_match(orb.ORBextractor(params[0], 1.2, params[2] - 1, 20, 7), 386.1448)
 
 
+def test_distinctive_descriptors_vs_oracle(orb, oracle_mod):
+    """MapPoint::ComputeDistinctiveDescriptors batched over map points (src/MapPoint.cc:242-306): representative row and
+    its median identical to the oracle, on constructed cases and on tracks built from real descriptors."""
+    from test_oracle_vs_ref import _distinctive_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    for desc, off in (_distinctive_cases(23), _distinctive_cases(99)):
+        best, med = ext.distinctive_descriptors(desc, off)
+        ob, om_ = oracle_mod.Oracle.distinctive_descriptors(desc, off)
+        assert np.array_equal(best, ob) and np.array_equal(med, om_)
+    # "map points" = groups of descriptors of one frame that are close to each other, 3000 of them
+    _, d = ext(synth(0, 375, 1242))
+    rng = np.random.default_rng(5)
+    sizes = rng.integers(1, 40, 3000)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    rows = d[rng.integers(0, len(d), off[-1])]
+    best, med = ext.distinctive_descriptors(rows, off)
+    ob, om_ = oracle_mod.Oracle.distinctive_descriptors(rows, off)
+    assert np.array_equal(best, ob) and np.array_equal(med, om_)
+    with pytest.raises(orb.OrbxError):
+        ext.distinctive_descriptors(np.zeros((1100, 32), np.uint8), [0, 1100])
+
+
 def test_full_size_properties(orb, oracle_mod):
     """BASELINE configs 3 and 5 at full size: one frame each against the oracle (seconds on the CPU),
     and size-independent properties on the batch: determinism, self-match, level-major ordering, bounds."""

@@ -181,3 +181,37 @@ def test_stereo_port_vs_reference(oracle_mod, seed, shape, params):
         assert np.array_equal(a["u_right"].view(np.uint32), b["u_right"].view(np.uint32))
         assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
         assert np.array_equal(a["desc_index"], b["desc_index"])
+
+
+def _distinctive_cases(seed=23):
+    """Map points with 0..70 observations: noisy copies of a base descriptor, plus ties and identical rows."""
+    rng = np.random.default_rng(seed)
+    rows, offsets = [], [0]
+    for n in (1, 2, 3, 4, 5, 8, 13, 0, 33, 64, 70, 2, 6):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.repeat(base[None, :], n, 0).copy()
+        for i in range(n):
+            for f in rng.integers(0, 256, rng.integers(0, 14)):
+                d[i, f % 32] ^= np.uint8(1 << (f % 8))
+        if n == 6:
+            d[3] = d[1]; d[5] = d[0]                      # exact duplicates: equal medians, the first row must win
+        rows.append(d); offsets.append(offsets[-1] + n)
+    return np.concatenate(rows), np.array(offsets, np.int32)
+
+
+def test_distinctive_descriptors_port_vs_reference(oracle_mod):
+    """MapPoint::ComputeDistinctiveDescriptors: the port against numpy and against the reference's own loop
+    (src/MapPoint.cc:272-301 excerpted unmodified, oracle/Makefile)."""
+    desc, off = _distinctive_cases()
+    best, med = oracle_mod.Oracle.distinctive_descriptors(desc, off)
+    for p in range(len(off) - 1):
+        d = desc[off[p]:off[p + 1]]
+        n = len(d)
+        if n == 0:
+            assert best[p] == -1
+            continue
+        D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(axis=2)
+        medians = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+        assert best[p] == int(np.argmin(medians)) and med[p] == medians.min()
+        if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_distinctive_descriptor"):
+            assert oracle_mod.RefExtractor.distinctive_descriptor(d) == (best[p], med[p])
