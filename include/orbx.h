@@ -135,6 +135,13 @@ int orbx_make_plan(const orbx_config *cfg, int width, int height, orbx_plan *out
 int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int stride_bytes,
                  orbx_keypoint *kps, uint8_t *desc, int cap, int *n_out);
 
+/* The colour image as the drivers hand it to Tracking::GrabImageRGBD / Stereo / Monocular: 3 or 4 interleaved 8-bit
+ * channels, converted to grey ON THE DEVICE exactly like cvtColor(CV_RGB2GRAY | CV_BGR2GRAY | CV_RGBA2GRAY |
+ * CV_BGRA2GRAY) at src/Tracking.cc:459-472 (rgb_order = Camera.RGB of the settings file, :192-193), then extracted.
+ * channels == 1 behaves like orbx_extract.  The grey image is level 0 of the pyramid (orbx_get_pyramid_level). */
+int orbx_extract_color(orbx_handle *h, const uint8_t *image, int width, int height, int stride_bytes, int channels,
+                       int rgb_order, orbx_keypoint *kps, uint8_t *desc, int cap, int *n_out);
+
 /* A batch of equally sized frames given as host pointers.  Outputs are laid out
  * frame-major: frame f writes kps[f*cap_per_frame ...], desc[f*cap_per_frame*32 ...],
  * n_out[f].  Pinned (page-locked) host buffers are used directly by the copy engine;

@@ -45,6 +45,7 @@ SIGNATURES = {
     "orbx_max_keypoints": (_I, [_VP, _I, _I]),
     "orbx_make_plan": (_I, [ctypes.POINTER(OrbxConfig), _I, _I, ctypes.POINTER(OrbxPlan)]),
     "orbx_extract": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _I, _VP]),
+    "orbx_extract_color": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP]),
     "orbx_extract_batch": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _I, _VP]),
     "orbx_submit_device": (_I, [_VP, _VP, _I, _I, _I, _I, _SZ]),
     "orbx_submit_host": (_I, [_VP, _VP, _I, _I, _I, _I]),

@@ -313,6 +313,35 @@ __global__ void k_repack(const uint8_t *__restrict__ src, long long src_frame_st
     *reinterpret_cast<uint32_t *>(dst + f * dst_frame_stride + (long long)y * dst_pitch + x4) = v;
 }
 
+// cv::cvtColor(..., CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) of Tracking::GrabImage* (src/Tracking.cc:459-472)
+// straight into the 64-byte-pitched level-0 slots: (c0*k0 + c1*19235 + c2*k2 + 2^14) >> 15 with (k0, k2) = (9798, 3735) for
+// RGB order, swapped for BGR.  Four pixels per thread, one 32-bit store.
+__global__ void k_gray(const uint8_t *__restrict__ src, long long src_frame_stride, int src_pitch, int channels, int k0, int k2,
+                       uint8_t *__restrict__ dst, long long dst_frame_stride, int dst_pitch, int w, int h)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= w) return;
+    const uint8_t *s = src + f * src_frame_stride + (long long)y * src_pitch + (long long)x4 * channels;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (x4 + k < w) {
+            const uint8_t *p = s + k * channels;
+            v |= (uint32_t)((p[0] * k0 + p[1] * 19235 + p[2] * k2 + (1 << 14)) >> 15) << (8 * k);
+        }
+    *reinterpret_cast<uint32_t *>(dst + f * dst_frame_stride + (long long)y * dst_pitch + x4) = v;
+}
+
+cudaError_t launch_gray(const uint8_t *src, long long src_frame_stride, int src_pitch, int channels, int rgb_order, uint8_t *dst,
+                        long long dst_frame_stride, int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls)
+{
+    dim3 block(128), grid((w + 511) / 512, h, nframes);
+    k_gray<<<grid, block, 0, st>>>(src, src_frame_stride, src_pitch, channels, rgb_order ? 9798 : 3735, rgb_order ? 3735 : 9798, dst,
+                                   dst_frame_stride, dst_pitch, w, h);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
                           int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls)
 {

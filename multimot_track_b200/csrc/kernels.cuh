@@ -61,6 +61,8 @@ void resize_box(const LevelGeom &src, const LevelGeom &dst, int *box_w, int *box
 
 cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, int nframes, cudaStream_t st, LaunchStats *ls,
                            const TmaMaps *tma = nullptr);
+cudaError_t launch_gray(const uint8_t *src, long long src_frame_stride, int src_pitch, int channels, int rgb_order, uint8_t *dst,
+                        long long dst_frame_stride, int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_repack(const uint8_t *src, long long src_frame_stride, int src_pitch, uint8_t *dst, long long dst_frame_stride,
                           int dst_pitch, int w, int h, int nframes, cudaStream_t st, LaunchStats *ls);
 // maps->m[l]: the level-l images of this batch (level 0 = the caller's frames or our level-0 slots); bit l of tma_levels

@@ -395,11 +395,14 @@ extern "C" int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int n
     return enqueue_pipeline(h, s0, nframes);
 }
 
-extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height, int stride_bytes)
+// channels == 1: grey frames; 3 / 4: colour frames converted on the device (rgb_order as Camera.RGB, src/Tracking.cc:192-193)
+static int submit_host_frames(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height, int stride_bytes,
+                              int channels, int rgb_order)
 {
     if (!h) return ORBX_ERR_BAD_ARG;
     if (!frames) return fail(h, ORBX_ERR_BAD_ARG, "NULL frame array");
-    int rc = check_shape(h, nframes, width, height, stride_bytes);
+    if (channels != 1 && channels != 3 && channels != 4) return fail(h, ORBX_ERR_BAD_ARG, "channels must be 1, 3 or 4");
+    int rc = check_shape(h, nframes, width, height, stride_bytes / channels);
     if (rc != ORBX_OK) return rc;
     for (int f = 0; f < nframes; ++f) if (!frames[f]) return fail(h, ORBX_ERR_BAD_ARG, "NULL frame pointer");
     CU(cudaSetDevice(h->device));
@@ -410,7 +413,7 @@ extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, in
     const LevelGeom &L0 = h->geo.lv[0];
     // H2D as plain 1-D copies (one per frame, or one for the whole batch when the frames are
     // contiguous in host memory), then a device kernel re-pitches rows into the aligned level-0 slots
-    const size_t frame_bytes = (size_t)stride_bytes * (size_t)(height - 1) + (size_t)width;
+    const size_t frame_bytes = (size_t)stride_bytes * (size_t)(height - 1) + (size_t)width * channels;
     const size_t slot = (size_t)stride_bytes * (size_t)height;
     if (slot * (size_t)nframes > h->in_bytes) {
         CU(cudaStreamSynchronize(h->stream));
@@ -425,11 +428,32 @@ extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, in
     else
         for (int f = 0; f < nframes; ++f)
             CU(cudaMemcpyAsync(h->d_in + (size_t)f * slot, frames[f], frame_bytes, cudaMemcpyHostToDevice, h->stream));
-    CU(launch_repack(h->d_in, (long long)slot, stride_bytes, h->d_pyr + L0.img_off, h->geo.pyr_frame_bytes, L0.pitch, width, height,
-                     nframes, h->stream, &h->stats));
+    if (channels == 1)
+        CU(launch_repack(h->d_in, (long long)slot, stride_bytes, h->d_pyr + L0.img_off, h->geo.pyr_frame_bytes, L0.pitch, width, height,
+                         nframes, h->stream, &h->stats));
+    else
+        CU(launch_gray(h->d_in, (long long)slot, stride_bytes, channels, rgb_order, h->d_pyr + L0.img_off, h->geo.pyr_frame_bytes, L0.pitch,
+                       width, height, nframes, h->stream, &h->stats));
     Src0 s0;
     s0.ptr = h->d_pyr + L0.img_off; s0.pitch = L0.pitch; s0.frame_stride = h->geo.pyr_frame_bytes;
     return enqueue_pipeline(h, s0, nframes);
+}
+
+extern "C" int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height, int stride_bytes)
+{
+    return submit_host_frames(h, frames, nframes, width, height, stride_bytes, 1, 0);
+}
+
+extern "C" int orbx_extract_color(orbx_handle *h, const uint8_t *image, int width, int height, int stride_bytes, int channels, int rgb_order,
+                                  orbx_keypoint *kps, uint8_t *desc, int cap, int *n_out)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!n_out) return fail(h, ORBX_ERR_BAD_ARG, "NULL n_out");
+    if (!image || width <= 0 || height <= 0) { *n_out = 0; return ORBX_OK; }      // empty image: silent return (src/ORBextractor.cc:1049)
+    const uint8_t *frames[1] = {image};
+    int rc = submit_host_frames(h, frames, 1, width, height, stride_bytes, channels, rgb_order);
+    if (rc != ORBX_OK) return rc;
+    return orbx_collect(h, kps, desc, cap, n_out);
 }
 
 extern "C" int orbx_collect_view(orbx_handle *h, const orbx_keypoint **kps, const uint8_t **desc, const int **n_out, int *cap_per_frame)

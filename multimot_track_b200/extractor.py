@@ -264,3 +264,18 @@ class ORBextractor:
         best = np.zeros(max(npts, 0), np.int32); med = np.zeros(max(npts, 0), np.int32)
         self._ck(self._lib.orbx_distinctive_descriptors(self._h, d.ctypes.data, off.ctypes.data, npts, best.ctypes.data, med.ctypes.data))
         return best, med
+
+    def extract_color(self, image, rgb=True):
+        """Colour image [H, W, 3 or 4] uint8 -> (keypoints, descriptors); the grey conversion of Tracking::GrabImage*
+        (src/Tracking.cc:459-472, `rgb` = Camera.RGB) runs on the device."""
+        a = np.ascontiguousarray(image, np.uint8)
+        if a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise ValueError("expected an [H, W, 3 or 4] uint8 image")
+        h, w, c = a.shape
+        cap = self.max_keypoints(w, h)
+        kps = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = ctypes.c_int(0)
+        self._ck(self._lib.orbx_extract_color(self._h, a.ctypes.data, w, h, a.strides[0], c, int(bool(rgb)), kps.ctypes.data, desc.ctypes.data,
+                                              cap, ctypes.byref(n)))
+        self._last_batch = 1
+        return kps[:n.value], desc[:n.value]

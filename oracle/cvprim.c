@@ -258,3 +258,16 @@ float cvp_fast_atan2(float y, float x)
     if (y < 0) a = 360.f - a;
     return a;
 }
+
+/* cv::cvtColor(src, dst, CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) on 8-bit images (called from
+ * Tracking::GrabImage*, src/Tracking.cc:459-472): 15-bit fixed point, R 9798, G 19235, B 3735, round to nearest. */
+void cvp_cvt_gray_u8(const uint8_t *src, int w, int h, int stride, int channels, int rgb_order, uint8_t *dst, int dstride)
+{
+    const int c0 = rgb_order ? 9798 : 3735, c2 = rgb_order ? 3735 : 9798;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *s = src + (size_t)y * stride;
+        uint8_t *d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x, s += channels)
+            d[x] = (uint8_t)((s[0] * c0 + s[1] * 19235 + s[2] * c2 + (1 << 14)) >> 15);
+    }
+}

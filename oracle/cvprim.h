@@ -58,6 +58,9 @@ int cvp_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold,
 /* cv::fastAtan2(y, x): degrees in [0, 360), 7th-order polynomial, fp32. */
 float cvp_fast_atan2(float y, float x);
 
+/* cv::cvtColor to grey, 8-bit, 3 or 4 channels; rgb_order != 0: first channel is R (CV_RGB[A]2GRAY), else B (CV_BGR[A]2GRAY) */
+void cvp_cvt_gray_u8(const uint8_t *src, int w, int h, int stride, int channels, int rgb_order, uint8_t *dst, int dstride);
+
 #ifdef __cplusplus
 }
 #endif

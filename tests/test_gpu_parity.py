@@ -243,6 +243,26 @@ def test_stereo_matches_vs_oracle(orb, oracle_mod, seed, shape, params):
         eL.stereo_match(orb.ORBextractor(params[0], 1.2, params[2] - 1, 20, 7), 386.1448)
 
 
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_color_input_vs_oracle(orb, oracle_mod, channels, rgb):
+    """Colour frames as Tracking::GrabImageRGBD receives them: device-side cvtColor (src/Tracking.cc:459-472) + extraction
+    equal the oracle's grey conversion (checked against cv2 in tests/test_oracle_cvprim.py) + extraction."""
+    import ctypes
+    rng = np.random.default_rng(41)
+    base = np.stack([synth(60 + c, 300, 501) for c in range(channels)], axis=2)        # odd width: ragged last quad
+    img = np.ascontiguousarray(np.clip(base.astype(np.int16) + rng.integers(-3, 4, base.shape), 0, 255).astype(np.uint8))
+    L = oracle_mod.Oracle.lib()
+    gray = np.zeros(img.shape[:2], np.uint8)
+    L.cvp_cvt_gray_u8(ctypes.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], channels, int(rgb),
+                      ctypes.c_void_p(gray.ctypes.data), gray.strides[0])
+    params = (1000, 1.2, 6, 20, 7)
+    ext, o = orb.ORBextractor(*params), oracle_mod.Oracle(*params)
+    kps, desc = ext.extract_color(img, rgb=rgb)
+    ok, od = o(gray)
+    assert np.array_equal(ext.pyramid_level(0), gray)
+    assert kps_equal_exact(kps, ok) and np.array_equal(kps["angle"], ok["angle"]) and np.array_equal(desc, od)
+
+
 def test_distinctive_descriptors_vs_oracle(orb, oracle_mod):
     """MapPoint::ComputeDistinctiveDescriptors batched over map points (src/MapPoint.cc:242-306): representative row and
     its median identical to the oracle, on constructed cases and on tracks built from real descriptors."""

@@ -92,3 +92,22 @@ def test_primitives_against_live_cv2(L):
         det = cv2.FastFeatureDetector_create(threshold=12, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
         ref = np.array([(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in det.detect(img)], np.int32).reshape(-1, 3)
         assert np.array_equal(_fast(L, img, 12, 1), ref)
+
+
+def _gray(L, img, rgb_order):
+    h, w, c = img.shape
+    out = np.zeros((h, w), np.uint8)
+    L.cvp_cvt_gray_u8(ctypes.c_void_p(img.ctypes.data), w, h, img.strides[0], c, int(rgb_order), ctypes.c_void_p(out.ctypes.data), out.strides[0])
+    return out
+
+
+def test_gray_conversion_against_live_cv2(L):
+    """cvtColor(…, CV_RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) as Tracking::GrabImage* calls it (src/Tracking.cc:459-472)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(9)
+    for c in (3, 4):
+        img = rng.integers(0, 256, (57, 131, c), dtype=np.uint8)
+        img[0, :8] = [[0] * c, [255] * c, [255, 0, 0, 9][:c], [0, 255, 0, 9][:c], [0, 0, 255, 9][:c], [1, 1, 1, 1][:c], [254, 255, 253, 0][:c], [128] * c]
+        codes = {(3, 1): cv2.COLOR_RGB2GRAY, (3, 0): cv2.COLOR_BGR2GRAY, (4, 1): cv2.COLOR_RGBA2GRAY, (4, 0): cv2.COLOR_BGRA2GRAY}
+        for rgb in (1, 0):
+            assert np.array_equal(_gray(L, img, rgb), cv2.cvtColor(img, codes[(c, rgb)]))
