@@ -186,64 +186,74 @@ __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P,
 // The horizontal interpolation is done ONCE per source row of the window (H >> 4, as cv::resize keeps it) into shared
 // memory, then the vertical pass combines two of those rows per destination row -- half the multiplies and a third of
 // the byte loads of the direct form, with identical integer results.
+struct ResizeArgs {                  // everything the kernel needs, resolved on the host (no dependent parameter loads)
+    const ResizeTab *xt, *yt;        // tables of this level
+    uint8_t *dst;                    // level image of frame 0
+    long long frame_stride;
+    int w, h, pitch;                 // destination level
+    int box_w, box_h, box_bytes;
+    int ntx, nty, nchunks;           // tiles per row / column; a CTA owns column tx and the tile rows chunk, chunk + nchunks, ...
+};
+
 __global__ void __launch_bounds__(256)
-k_resize_sep(const DevParams *__restrict__ P, const __grid_constant__ CUtensorMap tmap, int level, int box_w, int box_h, int box_bytes,
-             int ntx, int ntiles)
+k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
 {
     extern __shared__ __align__(128) uint8_t rs_smem[];            // [2][box_bytes] source boxes, then int Hs[box_h][128]
     __shared__ __align__(8) uint64_t mbar[2];
-    const LevelGeom &D = P->lv[level];
-    const ResizeTab *xt = P->xtab + P->xtab_off[level], *yt = P->ytab + P->ytab_off[level];
-    int *Hs = reinterpret_cast<int *>(rs_smem + 2 * box_bytes);
+    int *Hs = reinterpret_cast<int *>(rs_smem + 2 * A.box_bytes);
     const int frame = blockIdx.y, tid = threadIdx.x + threadIdx.y * 32, q = threadIdx.x, g = threadIdx.y;
+    const int chunk = blockIdx.x / A.ntx, tx = blockIdx.x - chunk * A.ntx;
+    const int x0 = tx * kRzTW, x4 = x0 + 4 * q;
+    const bool col_ok = x4 < A.w;
+    const int sx_lo = A.xt[x0].s0 & ~15;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[0])), "r"(1) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int t, int b) {                                // thread 0
-        const int ty = t / ntx, tx = t - ty * ntx;
-        const int sx_lo = xt[tx * kRzTW].s0 & ~15, sy_lo = yt[ty * kRzTH].s0;
+    auto issue = [&](int ty, int b) {                               // thread 0
+        const int sy_lo = A.yt[ty * kRzTH].s0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar[b])), "r"(box_w * box_h) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar[b])), "r"(A.box_w * A.box_h) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     :: "r"(smem_u32(rs_smem + b * box_bytes)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar[b])),
+                     :: "r"(smem_u32(rs_smem + b * A.box_bytes)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar[b])),
                         "r"(sx_lo), "r"(sy_lo), "r"(frame) : "memory");
     };
-    int t = blockIdx.x;
-    if (tid == 0 && t < ntiles) issue(t, 0);
-    uint8_t *dst = P->pyr + (long long)frame * P->pyr_frame_bytes + D.img_off;
-    unsigned phase = 0;
-    for (int n = 0; t < ntiles; t += gridDim.x, ++n) {
-        const int b = n & 1;
-        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, b ^ 1);
-        const int ty = t / ntx, tx = t - ty * ntx;
-        const int x0 = tx * kRzTW, y0 = ty * kRzTH, y_end = min(y0 + kRzTH, D.h);
-        const int sx_lo = xt[x0].s0 & ~15, sy_lo = yt[y0].s0, nrows = yt[y_end - 1].s1 - sy_lo + 1;
-        const int x4 = x0 + 4 * q;
-        const bool col_ok = x4 < D.w;
-        int o0[4], o1[4], c0[4], c1[4];
-        if (col_ok) {
+    int ty = chunk;
+    if (tid == 0 && ty < A.nty) issue(ty, 0);
+    // the four destination columns of this thread: source offsets inside the box and 11-bit weights (fixed for the CTA)
+    int o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0}, c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+    if (col_ok) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                              // tables are padded to a multiple of 4 entries
-                const ResizeTab e = xt[x4 + k];
-                o0[k] = e.s0 - sx_lo; o1[k] = e.s1 - sx_lo; c0[k] = e.c0; c1[k] = e.c1;
-            }
+        for (int k = 0; k < 4; ++k) {                                  // tables are padded to a multiple of 4 entries
+            const ResizeTab e = A.xt[x4 + k];
+            o0[k] = e.s0 - sx_lo; o1[k] = e.s1 - sx_lo; c0[k] = e.c0; c1[k] = e.c1;
         }
+    }
+    uint8_t *dcol = A.dst + (long long)frame * A.frame_stride + x4;
+    unsigned phase = 0;
+    for (int n = 0; ty < A.nty; ty += A.nchunks, ++n) {
+        const int b = n & 1;
+        if (tid == 0 && ty + A.nchunks < A.nty) issue(ty + A.nchunks, b ^ 1);
+        const int y0 = ty * kRzTH, y_end = min(y0 + kRzTH, A.h);
+        const int sy_lo = A.yt[y0].s0, nrows = A.yt[y_end - 1].s1 - sy_lo + 1;
+        ResizeTab ey[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) ey[rr] = A.yt[min(y0 + g + 8 * rr, y_end - 1)];
         mbar_wait_parity(&mbar[b], (phase >> b) & 1u);
         phase ^= 1u << b;
         // ---- horizontal pass: source rows of the window -> Hs[r][x] = (S[s0]*a0 + S[s1]*a1) >> 4
         if (col_ok) {
-            const uint8_t *sb = rs_smem + b * box_bytes;
-            for (int r = g; r < nrows; r += 8) {
-                const uint8_t *row = sb + r * box_w;
+            const uint8_t *row = rs_smem + b * A.box_bytes + g * A.box_w;
+            int *hrow = Hs + g * kRzTW + 4 * q;
+            for (int r = g; r < nrows; r += 8, row += 8 * A.box_w, hrow += 8 * kRzTW) {
                 int4 h;
                 h.x = (row[o0[0]] * c0[0] + row[o1[0]] * c1[0]) >> 4;
                 h.y = (row[o0[1]] * c0[1] + row[o1[1]] * c1[1]) >> 4;
                 h.z = (row[o0[2]] * c0[2] + row[o1[2]] * c1[2]) >> 4;
                 h.w = (row[o0[3]] * c0[3] + row[o1[3]] * c1[3]) >> 4;
-                *reinterpret_cast<int4 *>(Hs + r * kRzTW + 4 * q) = h;
+                *reinterpret_cast<int4 *>(hrow) = h;
             }
         }
         __syncthreads();
@@ -253,13 +263,13 @@ k_resize_sep(const DevParams *__restrict__ P, const __grid_constant__ CUtensorMa
             for (int rr = 0; rr < 4; ++rr) {
                 const int y = y0 + g + 8 * rr;
                 if (y < y_end) {
-                    const ResizeTab e = yt[y];
+                    const ResizeTab e = ey[rr];
                     const int4 h0 = *reinterpret_cast<const int4 *>(Hs + (e.s0 - sy_lo) * kRzTW + 4 * q);
                     const int4 h1 = *reinterpret_cast<const int4 *>(Hs + (e.s1 - sy_lo) * kRzTW + 4 * q);
                     const int b0 = e.c0, b1 = e.c1;
                     const uint32_t v0 = (((b0 * h0.x) >> 16) + ((b1 * h1.x) >> 16) + 2) >> 2, v1 = (((b0 * h0.y) >> 16) + ((b1 * h1.y) >> 16) + 2) >> 2;
                     const uint32_t v2 = (((b0 * h0.z) >> 16) + ((b1 * h1.z) >> 16) + 2) >> 2, v3 = (((b0 * h0.w) >> 16) + ((b1 * h1.w) >> 16) + 2) >> 2;
-                    *reinterpret_cast<uint32_t *>(dst + (long long)y * D.pitch + x4) = v0 | v1 << 8 | v2 << 16 | v3 << 24;   // pitch % 64 == 0
+                    *reinterpret_cast<uint32_t *>(dcol + (long long)y * A.pitch) = v0 | v1 << 8 | v2 << 16 | v3 << 24;   // pitch % 64 == 0
                 }
             }
         }
@@ -406,13 +416,17 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
                     if (e != cudaSuccess) return e;
                     attr = smem;
                 }
-                const int ntx = grid.x, ntiles = grid.x * grid.y;
                 int per_sm = (int)((227 * 1024) / (smem + 1024));
                 per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
-                const int cap = std::max(1, 148 * per_sm / nframes);      // resident CTAs available to one frame
-                static const int force_iters = std::getenv("ORBX_RZ_ITERS") ? std::atoi(std::getenv("ORBX_RZ_ITERS")) : 0;
-                const int iters = force_iters > 0 ? force_iters : (ntiles + cap - 1) / cap;
-                k_resize_sep<<<dim3((ntiles + iters - 1) / iters, nframes), dim3(32, 8), smem, st>>>(dP, tma->src[l], l, bw, bh, box_bytes, ntx, ntiles);
+                const int ntx = grid.x, nty = grid.y;
+                const int cap = std::max(1, 148 * per_sm / nframes / ntx);   // resident CTAs available to one tile column of one frame
+                const int iters = (nty + cap - 1) / cap;
+                ResizeArgs A;
+                A.xt = hP.xtab + hP.xtab_off[l]; A.yt = hP.ytab + hP.ytab_off[l];
+                A.dst = hP.pyr + D.img_off; A.frame_stride = hP.pyr_frame_bytes;
+                A.w = D.w; A.h = D.h; A.pitch = D.pitch; A.box_w = bw; A.box_h = bh; A.box_bytes = box_bytes;
+                A.ntx = ntx; A.nty = nty; A.nchunks = (nty + iters - 1) / iters;
+                k_resize_sep<<<dim3(ntx * A.nchunks, nframes), dim3(32, 8), smem, st>>>(tma->src[l], A);
                 const cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return e;
             } else
