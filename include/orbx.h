@@ -219,6 +219,34 @@ int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, uint8_t *ac
 int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA,
                                 const float *d_angleB, int32_t *d_hist, int32_t *d_top3, int32_t *d_kept);
 
+/* ---- bag-of-words vocabulary -------------------------------- */
+
+/* The DBoW2 vocabulary tree of the reference (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,
+ * include/ORBVocabulary.h; loaded by System at src/System.cc:66-67, used by Frame::ComputeBoW, src/Frame.cc:778-785).
+ * The tree lives on the handle's device; the per-descriptor descent (TemplatedVocabulary.h:1205-1250) runs on the GPU,
+ * the BowVector / FeatureVector bookkeeping (:1127-1195) on the host in DBoW2's double arithmetic. */
+typedef struct orbx_vocabulary orbx_vocabulary;
+
+/* ORBVocabulary::loadFromTextFile (TemplatedVocabulary.h:1338-1418): header `k L scoring weighting`, then one node per
+ * line `parent isLeaf d0 .. d31 weight`.  Returns ORBX_OK or a negative status (message in orbx_last_error(h)). */
+int orbx_voc_load_text(orbx_handle *h, const char *path, orbx_vocabulary **out);
+/* The same tree from arrays: node i+1 of the file order has parent[i], is_leaf[i], desc[i][32], weight[i]. */
+int orbx_voc_create(orbx_handle *h, int k, int L, int scoring, int weighting, int nnodes, const int32_t *parent,
+                    const uint8_t *is_leaf, const uint8_t *desc, const double *weight, orbx_vocabulary **out);
+void orbx_voc_destroy(orbx_vocabulary *voc);
+int orbx_voc_info(const orbx_vocabulary *voc, int *k, int *L, int *nodes, int *words);
+
+/* Per descriptor (host pointers, n x 32 bytes): word id, node id at level L - levelsup (0 when that level is <= 0) and
+ * the word's weight, as TemplatedVocabulary::transform(feature, id, weight, &nid, levelsup) returns them. */
+int orbx_voc_transform(orbx_handle *h, const orbx_vocabulary *voc, const uint8_t *desc, int n, int levelsup,
+                       int32_t *word, int32_t *node, double *weight);
+
+/* BowVector and FeatureVector of transform(features, v, fv, levelsup) from the per-descriptor results, flattened in map
+ * order: bow_ids / bow_vals (ascending word id, *n_bow entries, at most n), fv_nodes[j] owns the feature indices
+ * fv_feats[fv_off[j] .. fv_off[j+1]) (ascending node id, *n_fv nodes; fv_off needs n + 1 entries).  Host only. */
+int orbx_voc_bow(const orbx_vocabulary *voc, int n, const int32_t *word, const int32_t *node, const double *weight,
+                 int32_t *bow_ids, double *bow_vals, int *n_bow, int32_t *fv_nodes, int32_t *fv_off, int32_t *fv_feats, int *n_fv);
+
 /* ---- representative descriptors of map points -------------- */
 
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-306), batched: map point p has the observed descriptors

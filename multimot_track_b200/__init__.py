@@ -8,5 +8,6 @@ There is no CPU fallback: importing works anywhere, computing needs a CUDA devic
 from ._lib import OrbxError, lib_path, load_library  # noqa: F401
 from .extractor import KEYPOINT_DTYPE, ORBextractor  # noqa: F401
 from .matcher import ORBmatcher  # noqa: F401
+from .vocabulary import ORBVocabulary  # noqa: F401
 
-__all__ = ["ORBextractor", "ORBmatcher", "KEYPOINT_DTYPE", "OrbxError", "load_library", "lib_path"]
+__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "KEYPOINT_DTYPE", "OrbxError", "load_library", "lib_path"]

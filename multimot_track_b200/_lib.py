@@ -60,6 +60,12 @@ SIGNATURES = {
     "orbx_match_device": (_I, [_VP, _VP, _I, _VP, _I, _I, _F, _VP, _VP, _VP, _VP]),
     "orbx_rotation_filter": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "orbx_rotation_filter_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "orbx_voc_load_text": (_I, [_VP, ctypes.c_char_p, ctypes.POINTER(_VP)]),
+    "orbx_voc_create": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, ctypes.POINTER(_VP)]),
+    "orbx_voc_destroy": (None, [_VP]),
+    "orbx_voc_info": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "orbx_voc_transform": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
+    "orbx_voc_bow": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "orbx_distinctive_descriptors": (_I, [_VP, _VP, _VP, _I, _VP, _VP]),
     "orbx_stereo_match": (_I, [_VP, _VP, _I, _I, _F, _VP, _VP, _VP, _I, _VP]),
     "orbx_set_profiling": (_I, [_VP, _I]),

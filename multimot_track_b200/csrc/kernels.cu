@@ -1969,6 +1969,50 @@ cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_acce
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------- BoW descent
+// TemplatedVocabulary::transform(feature, word, weight, nid, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1205-1250),
+// one warp per descriptor: lane c takes child c of the current node (k <= 32), FORB::distance by __popc (FORB.cpp:81-101),
+// the FIRST child with the least distance wins (redux.min on distance << 8 | child position), down to a node without
+// children; the node id of level L - levelsup is recorded on the way.
+__global__ void __launch_bounds__(256)
+k_bow_descent(const uint8_t *__restrict__ feat, int n, const int32_t *__restrict__ child_off, const int32_t *__restrict__ child_ids,
+              const uint4 *__restrict__ node_desc, const int32_t *__restrict__ word_id, int nid_level,
+              int32_t *__restrict__ word_out, int32_t *__restrict__ node_out, int32_t *__restrict__ final_out)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const uint4 a0 = reinterpret_cast<const uint4 *>(feat)[2 * (long long)warp], a1 = reinterpret_cast<const uint4 *>(feat)[2 * (long long)warp + 1];
+    int node = 0, level = 0, nid = 0;
+    int off = __ldg(child_off), cnt = __ldg(child_off + 1) - off;
+    do {
+        ++level;
+        unsigned key = 0xffffffffu;
+        int mine = 0;
+        if (lane < cnt) {
+            mine = __ldg(child_ids + off + lane);
+            const uint4 b0 = __ldg(node_desc + 2 * (long long)mine), b1 = __ldg(node_desc + 2 * (long long)mine + 1);
+            const unsigned d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                               __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            key = d << 8 | (unsigned)lane;
+        }
+        key = __reduce_min_sync(0xffffffffu, key);
+        node = __shfl_sync(0xffffffffu, mine, (int)(key & 0xffu));
+        if (level == nid_level) nid = node;
+        off = __ldg(child_off + node); cnt = __ldg(child_off + node + 1) - off;
+    } while (cnt > 0);
+    if (lane == 0) { word_out[warp] = __ldg(word_id + node); node_out[warp] = nid; final_out[warp] = node; }
+}
+
+cudaError_t launch_bow_descent(const uint8_t *d_feat, int n, const int32_t *d_child_off, const int32_t *d_child_ids, const uint8_t *d_node_desc,
+                               const int32_t *d_word_id, int nid_level, int32_t *d_word, int32_t *d_node, int32_t *d_final, cudaStream_t st, LaunchStats *ls)
+{
+    if (n <= 0) return cudaSuccess;
+    k_bow_descent<<<(n + 7) / 8, 256, 0, st>>>(d_feat, n, d_child_off, d_child_ids, reinterpret_cast<const uint4 *>(d_node_desc), d_word_id, nid_level,
+                                                 d_word, d_node, d_final);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------- distinctive descriptors
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301), batched over map points: one CTA per map point,
 // its n observed descriptors staged in shared memory; a warp owns a row i, builds the 257-bin histogram of the

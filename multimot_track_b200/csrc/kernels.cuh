@@ -88,6 +88,8 @@ cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB,
                          int4 *d_partial, int nchunks, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA, const float *d_angleB,
                                    int32_t *d_hist, int32_t *d_top3, int *d_kept, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_bow_descent(const uint8_t *d_feat, int n, const int32_t *d_child_off, const int32_t *d_child_ids, const uint8_t *d_node_desc,
+                               const int32_t *d_word_id, int nid_level, int32_t *d_word, int32_t *d_node, int32_t *d_final, cudaStream_t st, LaunchStats *ls);
 constexpr int kDistinctiveMaxObs = 1024;      // observations of one map point that fit the CTA's shared memory
 cudaError_t launch_distinctive(const uint8_t *d_desc, const int32_t *d_offsets, int npoints, int max_obs, int32_t *d_best_idx,
                                int32_t *d_best_median, cudaStream_t st, LaunchStats *ls);

@@ -705,6 +705,120 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     return res[33];
 }
 
+// --------------------------------------------------------------- vocabulary
+
+struct orbx_vocabulary {
+    VocHost host;
+    int device = 0;
+    int32_t *d_child_off = nullptr, *d_child_ids = nullptr, *d_word_id = nullptr;
+    uint8_t *d_desc = nullptr;
+};
+
+static int voc_upload(orbx_handle *h, orbx_vocabulary *v)
+{
+    const VocHost &H = v->host;
+    v->device = h->device;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMalloc(&v->d_child_off, H.child_off.size() * 4));
+    CU(cudaMalloc(&v->d_child_ids, std::max<size_t>(H.child_ids.size(), 1) * 4));
+    CU(cudaMalloc(&v->d_word_id, H.word_id.size() * 4));
+    CU(cudaMalloc(&v->d_desc, H.desc.size()));
+    CU(cudaMemcpy(v->d_child_off, H.child_off.data(), H.child_off.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(v->d_child_ids, H.child_ids.data(), H.child_ids.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(v->d_word_id, H.word_id.data(), H.word_id.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(v->d_desc, H.desc.data(), H.desc.size(), cudaMemcpyHostToDevice));
+    return ORBX_OK;
+}
+
+extern "C" void orbx_voc_destroy(orbx_vocabulary *v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    dfree(v->d_child_off); dfree(v->d_child_ids); dfree(v->d_word_id); dfree(v->d_desc);
+    delete v;
+}
+
+static int voc_finish(orbx_handle *h, orbx_vocabulary *v, int rc, const std::string &err, orbx_vocabulary **out)
+{
+    if (rc == ORBX_OK) rc = voc_upload(h, v); else fail(h, rc, err);
+    if (rc != ORBX_OK) { orbx_voc_destroy(v); return rc; }
+    *out = v;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_voc_load_text(orbx_handle *h, const char *path, orbx_vocabulary **out)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!path || !out) return fail(h, ORBX_ERR_BAD_ARG, "orbx_voc_load_text: NULL argument");
+    *out = nullptr;
+    orbx_vocabulary *v = new (std::nothrow) orbx_vocabulary();
+    if (!v) return fail(h, ORBX_ERR_OOM, "host allocation failed");
+    std::string err;
+    const int rc = voc_load_text(path, &v->host, &err);
+    return voc_finish(h, v, rc, err, out);
+}
+
+extern "C" int orbx_voc_create(orbx_handle *h, int k, int L, int scoring, int weighting, int nnodes, const int32_t *parent,
+                               const uint8_t *is_leaf, const uint8_t *desc, const double *weight, orbx_vocabulary **out)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!parent || !is_leaf || !desc || !weight || !out) return fail(h, ORBX_ERR_BAD_ARG, "orbx_voc_create: NULL argument");
+    *out = nullptr;
+    orbx_vocabulary *v = new (std::nothrow) orbx_vocabulary();
+    if (!v) return fail(h, ORBX_ERR_OOM, "host allocation failed");
+    std::string err;
+    const int rc = voc_build(k, L, scoring, weighting, nnodes, parent, is_leaf, desc, weight, &v->host, &err);
+    return voc_finish(h, v, rc, err, out);
+}
+
+extern "C" int orbx_voc_info(const orbx_vocabulary *v, int *k, int *L, int *nodes, int *words)
+{
+    if (!v) return ORBX_ERR_BAD_ARG;
+    if (k) *k = v->host.k;
+    if (L) *L = v->host.L;
+    if (nodes) *nodes = v->host.nnodes;
+    if (words) *words = v->host.nwords;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_voc_transform(orbx_handle *h, const orbx_vocabulary *v, const uint8_t *desc, int n, int levelsup,
+                                  int32_t *word, int32_t *node, double *weight)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!v || n < 0 || (n > 0 && (!desc || !word || !node || !weight))) return fail(h, ORBX_ERR_BAD_ARG, "orbx_voc_transform: bad argument");
+    if (v->device != h->device) return fail(h, ORBX_ERR_BAD_ARG, "orbx_voc_transform: the vocabulary lives on another device");
+    if (n == 0) return ORBX_OK;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    uint8_t *d = nullptr;
+    const size_t feat_bytes = ((size_t)n * 32 + 255) / 256 * 256;
+    CU(cudaMalloc(&d, feat_bytes + (size_t)n * 12));
+    int32_t *d_word = (int32_t *)(d + feat_bytes), *d_node = d_word + n, *d_final = d_node + n;
+    std::vector<int32_t> final_id((size_t)n);
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(d, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        CU(launch_bow_descent(d, n, v->d_child_off, v->d_child_ids, v->d_desc, v->d_word_id, v->host.L - levelsup, d_word, d_node, d_final, st, &h->stats));
+        CU(cudaMemcpyAsync(word, d_word, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(node, d_node, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(final_id.data(), d_final, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return ORBX_OK;
+    };
+    const int rc = body();
+    cudaFree(d);
+    if (rc != ORBX_OK) return rc;
+    for (int i = 0; i < n; ++i) weight[i] = v->host.weight[final_id[i]];          // the word's weight (a double), looked up on the host
+    return ORBX_OK;
+}
+
+extern "C" int orbx_voc_bow(const orbx_vocabulary *v, int n, const int32_t *word, const int32_t *node, const double *weight,
+                            int32_t *bow_ids, double *bow_vals, int *n_bow, int32_t *fv_nodes, int32_t *fv_off, int32_t *fv_feats, int *n_fv)
+{
+    if (!v || n < 0 || !n_bow || !n_fv || !fv_off || (n > 0 && (!word || !node || !weight || !bow_ids || !bow_vals || !fv_nodes || !fv_feats)))
+        return ORBX_ERR_BAD_ARG;
+    return voc_bow(v->host, n, word, node, weight, bow_ids, bow_vals, n_bow, fv_nodes, fv_off, fv_feats, n_fv);
+}
+
 // ------------------------------------------------- distinctive descriptors
 
 extern "C" int orbx_distinctive_descriptors(orbx_handle *h, const uint8_t *desc, const int32_t *offsets, int npoints,

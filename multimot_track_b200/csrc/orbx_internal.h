@@ -85,6 +85,19 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
 
 constexpr int kBlurTileW = 128, kBlurTileH = 64;
 
+// DBoW2 vocabulary tree (vocabulary.cpp): node 0 is the root, children of node i are child_ids[child_off[i] .. child_off[i+1])
+struct VocHost {
+    int k = 0, L = 0, scoring = 0, weighting = 0, nnodes = 0, nwords = 0;
+    std::vector<int32_t> child_off, child_ids, word_id;
+    std::vector<uint8_t> desc;           // [nnodes][32]
+    std::vector<double> weight;
+};
+int voc_build(int k, int L, int scoring, int weighting, int nfile, const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc,
+              const double *weight, VocHost *v, std::string *err);
+int voc_load_text(const char *path, VocHost *v, std::string *err);
+int voc_bow(const VocHost &v, int n, const int32_t *word, const int32_t *node, const double *weight, int32_t *bow_ids, double *bow_vals,
+            int *n_bow, int32_t *fv_nodes, int32_t *fv_off, int32_t *fv_feats, int *n_fv);
+
 } // namespace orbx
 
 #endif

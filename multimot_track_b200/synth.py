@@ -37,3 +37,38 @@ def stereo_pair(seed, h, w, max_disp=60.0):
     right = cv2.remap(left_wide, xs + disp, ys, cv2.INTER_LINEAR)
     right = np.clip(right.astype(np.int16) + rng.integers(-2, 3, (h, w), dtype=np.int16), 0, 255).astype(np.uint8)
     return np.ascontiguousarray(left_wide[:, :w]), right
+
+
+def write_synthetic_vocabulary(path, k=10, levels=4, seed=0, scoring=0, weighting=0, seeds=None, stop_fraction=0.02):
+    """A complete k-ary vocabulary tree in the ORBvoc text format (`k L scoring weighting`, then per node
+    `parent isLeaf d0 .. d31 weight`, TemplatedVocabulary.h:1338-1418 / saveToTextFile :1423-1448), written in the
+    creation order of DBoW2's HKmeans (children of a node consecutive, depth first).  Node descriptors are their
+    parent's with a shrinking number of random bit flips (children of the root: `seeds`, real descriptors, if given);
+    leaf weights are idf-like positive doubles, a few of them 0 (stopped words)."""
+    rng = np.random.default_rng(seed)
+    rows = []
+
+    def grow(parent_id, parent_desc, level):
+        ids = []
+        for c in range(k):
+            if level == 1 and seeds is not None:
+                d = np.array(seeds[rng.integers(0, len(seeds))], np.uint8).copy()
+            else:
+                d = parent_desc.copy()
+                for f in rng.integers(0, 256, max(2, 96 >> level)):
+                    d[f % 32] ^= np.uint8(1 << (f % 8))
+            leaf = level == levels
+            w = 0.0 if (leaf and rng.random() < stop_fraction) else (float(rng.random() * 9 + 0.5) if leaf else 0.0)
+            rows.append((parent_id, int(leaf), d, w))
+            ids.append(len(rows))
+        if level < levels:
+            for nid in ids:
+                grow(nid, rows[nid - 1][2], level + 1)
+
+    # DBoW2 numbers the k children of a node consecutively and then recurses into each of them
+    grow(0, rng.integers(0, 256, 32, dtype=np.uint8), 1)
+    # no newline after the last node: DBoW2's loader loops on !eof() and would read an empty line as one more node
+    with open(path, "w") as f:
+        f.write("%d %d %d %d\n" % (k, levels, scoring, weighting))
+        f.write("\n".join("%d %d %s %s" % (parent_id, leaf, " ".join(str(int(v)) for v in d), repr(w)) for parent_id, leaf, d, w in rows))
+    return len(rows) + 1

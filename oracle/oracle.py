@@ -333,3 +333,107 @@ class RefExtractor:
         s = cls.lib(variant).orbref_extract_many(int(params[0]), float(params[1]), int(params[2]), int(params[3]), int(params[4]),
                                                  f.ctypes.data, f.shape[0], f.shape[2], f.shape[1], int(threads), ctypes.byref(tot))
         return s, tot.value
+
+
+def parse_voc_text(path):
+    """Rows of an ORBvoc text file (TemplatedVocabulary.h:1338-1418): header `k L scoring weighting`, then per node
+    `parent isLeaf d0 .. d31 weight` in file order (node ids 1, 2, ...)."""
+    with open(path) as f:
+        k, L, scoring, weighting = (int(v) for v in f.readline().split())
+        rows = [ln.split() for ln in f if ln.strip()]
+    parent = np.array([int(r[0]) for r in rows], np.int32)
+    leaf = np.array([int(r[1]) > 0 for r in rows], np.uint8)
+    desc = np.array([[int(v) for v in r[2:34]] for r in rows], np.uint8).reshape(-1, 32)
+    weight = np.array([float(r[34]) for r in rows], np.float64)
+    return k, L, scoring, weighting, parent, leaf, desc, weight
+
+
+class _VocBase:
+    def transform(self, desc, levelsup=4):
+        """Frame::ComputeBoW shape: returns (bow_ids, bow_vals, fv_nodes, fv_off, fv_feats)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        word, node, weight = self.transform_each(d, levelsup)
+        return self.bow(word, node, weight)
+
+
+class OracleVocabulary(_VocBase):
+    """The C port of the DBoW2 tree (oracle/orb_oracle.c)."""
+
+    def __init__(self, path):
+        L = Oracle.lib()
+        k, lv, sc, wt, parent, leaf, desc, weight = parse_voc_text(path)
+        L.orbo_voc_create.restype = _VP
+        L.orbo_voc_create.argtypes = [_I, _I, _I, _I, _I, _VP, _VP, _VP, _VP]
+        L.orbo_voc_destroy.argtypes = [_VP]
+        L.orbo_voc_transform_each.argtypes = [_VP, _VP, _I, _I, _VP, _VP, _VP]
+        L.orbo_voc_bow.argtypes = [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]
+        self.L, self.k, self.levels, self.nodes, self.words = L, k, lv, len(parent) + 1, int(leaf.sum())
+        self.h = L.orbo_voc_create(k, lv, sc, wt, len(parent), parent.ctypes.data, leaf.ctypes.data, desc.ctypes.data, weight.ctypes.data)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orbo_voc_destroy(self.h); self.h = None
+
+    def transform_each(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word = np.zeros(n, np.int32); node = np.zeros(n, np.int32); weight = np.zeros(n, np.float64)
+        self.L.orbo_voc_transform_each(self.h, d.ctypes.data, n, int(levelsup), word.ctypes.data, node.ctypes.data, weight.ctypes.data)
+        return word, node, weight
+
+    def bow(self, word, node, weight):
+        n = len(word)
+        bi = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64)
+        fn = np.zeros(max(n, 1), np.int32); fo = np.zeros(n + 2, np.int32); ff = np.zeros(max(n, 1), np.int32)
+        nf = _I(0)
+        nb = self.L.orbo_voc_bow(self.h, n, np.ascontiguousarray(word, np.int32).ctypes.data, np.ascontiguousarray(node, np.int32).ctypes.data,
+                                 np.ascontiguousarray(weight, np.float64).ctypes.data, bi.ctypes.data, bv.ctypes.data, fn.ctypes.data, fo.ctypes.data,
+                                 ff.ctypes.data, ctypes.byref(nf))
+        return bi[:nb].copy(), bv[:nb].copy(), fn[:nf.value].copy(), fo[:nf.value + 1].copy(), ff[:fo[nf.value]].copy()
+
+
+class RefVocabulary(_VocBase):
+    """The reference's vendored DBoW2 (Thirdparty/DBoW2) compiled unmodified: oracle/_ref/liborbref_bow.so."""
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(HERE, "_ref", "liborbref_bow.so"))
+
+    def __init__(self, path):
+        if RefVocabulary._lib is None:
+            L = _load(os.path.join(HERE, "_ref", "liborbref_bow.so"))
+            L.orbref_voc_load.restype = _VP
+            L.orbref_voc_load.argtypes = [ctypes.c_char_p]
+            L.orbref_voc_free.argtypes = [_VP]
+            L.orbref_voc_info.argtypes = [_VP] * 5
+            L.orbref_voc_transform_each.argtypes = [_VP, _VP, _I, _I, _VP, _VP, _VP]
+            L.orbref_voc_transform.argtypes = [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]
+            RefVocabulary._lib = L
+        self.L = RefVocabulary._lib
+        self.h = self.L.orbref_voc_load(path.encode())
+        assert self.h, "DBoW2 could not load " + path
+        k, lv, nn, nw = _I(), _I(), _I(), _I()
+        self.L.orbref_voc_info(self.h, ctypes.byref(k), ctypes.byref(lv), ctypes.byref(nn), ctypes.byref(nw))
+        self.k, self.levels, self.nodes, self.words = k.value, lv.value, nn.value, nw.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orbref_voc_free(self.h); self.h = None
+
+    def transform_each(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word = np.zeros(n, np.int32); node = np.zeros(n, np.int32); weight = np.zeros(n, np.float64)
+        self.L.orbref_voc_transform_each(self.h, d.ctypes.data, n, int(levelsup), word.ctypes.data, node.ctypes.data, weight.ctypes.data)
+        return word, node, weight
+
+    def transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        bi = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64)
+        fn = np.zeros(max(n, 1), np.int32); fo = np.zeros(n + 2, np.int32); ff = np.zeros(max(n, 1), np.int32)
+        nf = _I(0)
+        nb = self.L.orbref_voc_transform(self.h, d.ctypes.data, n, int(levelsup), bi.ctypes.data, bv.ctypes.data, fn.ctypes.data, fo.ctypes.data,
+                                         ff.ctypes.data, ctypes.byref(nf))
+        return bi[:nb].copy(), bv[:nb].copy(), fn[:nf.value].copy(), fo[:nf.value + 1].copy(), ff[:fo[nf.value]].copy()

@@ -596,6 +596,122 @@ int orbo_distinctive_descriptor(const uint8_t *desc, int n, int32_t *best_median
     return best_idx;
 }
 
+/* ------------------------------------------------------------- vocabulary
+ * DBoW2 as vendored by the reference (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the tree built the way
+ * loadFromTextFile builds it (:1338-1418: node ids in file order, children in file order, word ids in order of the
+ * leaf flag), the per-feature descent (:1205-1250: first child with the least FORB::distance, stop at a node without
+ * children, node id recorded at level L - levelsup) and the BowVector / FeatureVector assembly of transform(features)
+ * (:1127-1195) with BowVector::addWeight / addIfNotExist / normalize (BowVector.cpp:32-86) in double. */
+struct orbo_voc {
+    int k, L, scoring, weighting, nnodes;        /* nnodes includes the root (id 0) */
+    int *child_off, *child_ids, *word_id;
+    uint8_t *desc; double *weight;
+};
+
+orbo_voc *orbo_voc_create(int k, int L, int scoring, int weighting, int nfile, const int32_t *parent, const uint8_t *is_leaf,
+                          const uint8_t *desc, const double *weight)
+{
+    orbo_voc *v = (orbo_voc *)calloc(1, sizeof(orbo_voc));
+    const int n = nfile + 1;
+    v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->nnodes = n;
+    v->child_off = (int *)calloc((size_t)n + 1, sizeof(int));
+    v->child_ids = (int *)calloc((size_t)n, sizeof(int));
+    v->word_id = (int *)malloc(sizeof(int) * (size_t)n);
+    v->desc = (uint8_t *)calloc((size_t)n, 32);
+    v->weight = (double *)calloc((size_t)n, sizeof(double));
+    int *cnt = (int *)calloc((size_t)n, sizeof(int));
+    for (int i = 0; i < nfile; ++i) cnt[parent[i]]++;
+    for (int i = 0; i < n; ++i) v->child_off[i + 1] = v->child_off[i] + cnt[i];
+    memset(cnt, 0, sizeof(int) * (size_t)n);
+    int words = 0;
+    v->word_id[0] = -1;
+    for (int i = 0; i < nfile; ++i) {
+        const int nid = i + 1, pid = parent[i];
+        v->child_ids[v->child_off[pid] + cnt[pid]++] = nid;
+        memcpy(v->desc + 32 * (size_t)nid, desc + 32 * (size_t)i, 32);
+        v->weight[nid] = weight[i];
+        v->word_id[nid] = is_leaf[i] ? words++ : -1;
+    }
+    free(cnt);
+    return v;
+}
+
+void orbo_voc_destroy(orbo_voc *v)
+{
+    if (!v) return;
+    free(v->child_off); free(v->child_ids); free(v->word_id); free(v->desc); free(v->weight); free(v);
+}
+
+void orbo_voc_transform_each(const orbo_voc *v, const uint8_t *desc, int n, int levelsup, int32_t *word, int32_t *node, double *weight)
+{
+    const int nid_level = v->L - levelsup;
+    for (int i = 0; i < n; ++i) {
+        const uint8_t *f = desc + 32 * (size_t)i;
+        int final_id = 0, current_level = 0, nid = 0;
+        do {
+            ++current_level;
+            const int *ch = v->child_ids + v->child_off[final_id];
+            const int nc = v->child_off[final_id + 1] - v->child_off[final_id];
+            final_id = ch[0];
+            int best_d = orbo_hamming256(f, v->desc + 32 * (size_t)final_id);
+            for (int c = 1; c < nc; ++c) {
+                const int d = orbo_hamming256(f, v->desc + 32 * (size_t)ch[c]);
+                if (d < best_d) { best_d = d; final_id = ch[c]; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (v->child_off[final_id + 1] - v->child_off[final_id] > 0);
+        word[i] = v->word_id[final_id]; node[i] = nid; weight[i] = v->weight[final_id];
+    }
+}
+
+typedef struct { int32_t key; int32_t idx; } kv_pair;
+static int cmp_kv(const void *a, const void *b)
+{
+    const kv_pair *x = (const kv_pair *)a, *y = (const kv_pair *)b;
+    return x->key != y->key ? (x->key < y->key ? -1 : 1) : (x->idx < y->idx ? -1 : (x->idx > y->idx));
+}
+
+int orbo_voc_bow(const orbo_voc *v, int n, const int32_t *word, const int32_t *node, const double *weight,
+                 int32_t *bow_ids, double *bow_vals, int32_t *fv_nodes, int32_t *fv_off, int32_t *fv_feats, int *n_fv)
+{
+    /* scoring -> (must normalize, norm): L1, L2, CHI_SQUARE, KL, BHATTACHARYYA normalize (L2 with the L2 norm), DOT_PRODUCT not */
+    const int must = v->scoring != 5, l2 = v->scoring == 1;
+    kv_pair *kw = (kv_pair *)malloc(sizeof(kv_pair) * (size_t)(n > 0 ? n : 1)), *kn = (kv_pair *)malloc(sizeof(kv_pair) * (size_t)(n > 0 ? n : 1));
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (weight[i] > 0) { kw[m].key = word[i]; kw[m].idx = i; kn[m].key = node[i]; kn[m].idx = i; ++m; }
+    qsort(kw, (size_t)m, sizeof(kv_pair), cmp_kv);                          /* by word, then feature order: the order addWeight sees */
+    qsort(kn, (size_t)m, sizeof(kv_pair), cmp_kv);
+    int nb = 0;
+    for (int i = 0; i < m;) {
+        int j = i;
+        double acc = weight[kw[i].idx];                                     /* insert(id, v) */
+        for (j = i + 1; j < m && kw[j].key == kw[i].key; ++j)
+            if (v->weighting == 0 || v->weighting == 1) acc += weight[kw[j].idx];   /* TF_IDF, TF: addWeight; IDF, BINARY: addIfNotExist */
+        bow_ids[nb] = kw[i].key; bow_vals[nb] = acc; ++nb;
+        i = j;
+    }
+    if ((v->weighting == 0 || v->weighting == 1) && nb > 0 && !must) {
+        const double nd = nb;
+        for (int i = 0; i < nb; ++i) bow_vals[i] /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (!l2) for (int i = 0; i < nb; ++i) norm += fabs(bow_vals[i]);
+        else { for (int i = 0; i < nb; ++i) norm += bow_vals[i] * bow_vals[i]; norm = sqrt(norm); }
+        if (norm > 0.0) for (int i = 0; i < nb; ++i) bow_vals[i] /= norm;
+    }
+    int nf = 0, o = 0;
+    for (int i = 0; i < m;) {
+        int j = i;
+        fv_nodes[nf] = kn[i].key; fv_off[nf] = o;
+        for (j = i; j < m && kn[j].key == kn[i].key; ++j) fv_feats[o++] = kn[j].idx;
+        ++nf; i = j;
+    }
+    fv_off[nf] = o; *n_fv = nf;
+    free(kw); free(kn);
+    return nb;
+}
+
 /* ------------------------------------------------------------------ stereo
  * Frame::ComputeStereoMatches, src/Frame.cc:849-1038 of the reference (this fork: minD = 0, maxD = 200, row band
  * r = 1.2 * scale, patches normalised by their centre pixel, vDescIndex with its `bestIdxR != 0` quirk).

@@ -76,6 +76,17 @@ int orbo_match(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int t
 int orbo_rotation_bin(float angle_a, float angle_b);
 int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
                          int32_t *hist, int32_t *top3);
+/* DBoW2 vocabulary tree as the reference vendors it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): built from the rows
+ * of an ORBvoc text file (parent id, leaf flag, 32 descriptor bytes, weight per node, file order), descent per feature,
+ * BowVector / FeatureVector assembly.  scoring: 0 L1, 1 L2, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT;
+ * weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY (BowVector.h). */
+typedef struct orbo_voc orbo_voc;
+orbo_voc *orbo_voc_create(int k, int L, int scoring, int weighting, int nfile, const int32_t *parent, const uint8_t *is_leaf,
+                          const uint8_t *desc, const double *weight);
+void orbo_voc_destroy(orbo_voc *v);
+void orbo_voc_transform_each(const orbo_voc *v, const uint8_t *desc, int n, int levelsup, int32_t *word, int32_t *node, double *weight);
+int orbo_voc_bow(const orbo_voc *v, int n, const int32_t *word, const int32_t *node, const double *weight,
+                 int32_t *bow_ids, double *bow_vals, int32_t *fv_nodes, int32_t *fv_off, int32_t *fv_feats, int *n_fv);
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301) for one map point: index of the representative descriptor */
 int orbo_distinctive_descriptor(const uint8_t *desc, int n, int32_t *best_median);
 /* Frame::ComputeStereoMatches (src/Frame.cc:849-1038).  pyr*[l]: un-padded level images (pitch[l], lw[l] x lh[l]).

@@ -263,6 +263,32 @@ def test_color_input_vs_oracle(orb, oracle_mod, channels, rgb):
     assert kps_equal_exact(kps, ok) and np.array_equal(kps["angle"], ok["angle"]) and np.array_equal(desc, od)
 
 
+def test_vocabulary_transform_vs_oracle(orb, oracle_mod, tmp_path):
+    """Frame::ComputeBoW (src/Frame.cc:778-785): ORBVocabulary::loadFromTextFile + transform on the GPU against the oracle
+    port (pinned to the reference's DBoW2): words, nodes, weights per descriptor; BowVector values bit-identical."""
+    from test_oracle_vs_ref import _voc_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    _, d = ext(synth(2, 375, 1242))
+    for path, k, L in _voc_cases(tmp_path, d):
+        voc = orb.ORBVocabulary(ext)
+        assert voc.loadFromTextFile(path)
+        o = oracle_mod.OracleVocabulary(path)
+        assert voc.info() == dict(k=o.k, L=o.levels, nodes=o.nodes, words=o.words)
+        for lu in (4, 2, 0):
+            for x, y in zip(voc.transform_each(d, lu), o.transform_each(d, lu)):
+                assert np.array_equal(x, y)
+            tg, to = voc.transform(d, lu), o.transform(d, lu)
+            assert np.array_equal(tg[1].view(np.uint64), to[1].view(np.uint64))
+            for x, y in zip(tg, to):
+                assert np.array_equal(x, y)
+        e = voc.transform(np.zeros((0, 32), np.uint8), 4)
+        assert all(len(a) == 0 for a in e[:3])
+    bad = tmp_path / "bad.txt"
+    bad.write_text("99 3 0 0\n0 1 " + " ".join(["0"] * 32) + " 1.0")
+    with pytest.raises(orb.OrbxError):
+        orb.ORBVocabulary(ext).loadFromTextFile(str(bad))
+
+
 def test_distinctive_descriptors_vs_oracle(orb, oracle_mod):
     """MapPoint::ComputeDistinctiveDescriptors batched over map points (src/MapPoint.cc:242-306): representative row and
     its median identical to the oracle, on constructed cases and on tracks built from real descriptors."""

@@ -215,3 +215,38 @@ def test_distinctive_descriptors_port_vs_reference(oracle_mod):
         assert best[p] == int(np.argmin(medians)) and med[p] == medians.min()
         if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_distinctive_descriptor"):
             assert oracle_mod.RefExtractor.distinctive_descriptor(d) == (best[p], med[p])
+
+
+def _voc_cases(tmp_path, seeds):
+    from multimot_track_b200.synth import write_synthetic_vocabulary
+    cases = []
+    for i, (k, L, sc, wt) in enumerate([(10, 3, 0, 0), (9, 3, 1, 1), (6, 4, 5, 0), (10, 2, 0, 2), (4, 5, 2, 3)]):
+        path = str(tmp_path / ("voc%d.txt" % i))
+        write_synthetic_vocabulary(path, k, L, seed=50 + i, scoring=sc, weighting=wt, seeds=seeds)
+        cases.append((path, k, L))
+    return cases
+
+
+def test_vocabulary_port_vs_dbow2(oracle_mod, tmp_path):
+    """Frame::ComputeBoW's vocabulary (DBoW2): the C port against the reference's vendored DBoW2 compiled unmodified
+    (oracle/_ref/liborbref_bow.so): word / node / weight per descriptor, BowVector values as bit patterns, FeatureVector."""
+    from multimot_track_b200.synth import value_noise_frame
+    _, d = oracle_mod.Oracle(800, 1.2, 6, 20, 7)(value_noise_frame(2, 300, 600))
+    for path, k, L in _voc_cases(tmp_path, d):
+        a = oracle_mod.OracleVocabulary(path)
+        assert (a.k, a.levels, a.nodes) == (k, L, (k ** (L + 1) - 1) // (k - 1)) and a.words == k ** L
+        word, node, weight = a.transform_each(d, 4)
+        assert (word >= 0).all() and (word < a.words).all() and (weight >= 0).all()
+        bi, bv, fn, fo, ff = a.transform(d, 2)
+        assert (np.diff(bi) > 0).all() and (np.diff(fn) > 0).all() and sorted(ff.tolist()) == sorted(np.nonzero(a.transform_each(d, 2)[2] > 0)[0].tolist())
+        if not oracle_mod.RefVocabulary.available():
+            continue
+        b = oracle_mod.RefVocabulary(path)
+        assert (b.k, b.levels, b.nodes, b.words) == (a.k, a.levels, a.nodes, a.words)
+        for lu in (4, 2, 1, 0):
+            for x, y in zip(a.transform_each(d, lu), b.transform_each(d, lu)):
+                assert np.array_equal(x, y)
+            ta, tb = a.transform(d, lu), b.transform(d, lu)
+            assert np.array_equal(ta[1].view(np.uint64), tb[1].view(np.uint64))
+            for x, y in zip(ta, tb):
+                assert np.array_equal(x, y)
