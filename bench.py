@@ -322,6 +322,47 @@ def main():
     except Exception as ex:                                            # the headline metric must still print
         matcher = {"error": repr(ex)}
 
+    # ---- the "next" rows of SURVEY 8f, timed end to end through the C ABI (host wall clock, results on the host)
+    extras = None
+    if rank == 0:
+        try:
+            import tempfile
+            from multimot_track_b200.synth import stereo_pair, write_synthetic_vocabulary
+            eL, eR = orb.ORBextractor(*params, device_id=local), orb.ORBextractor(*params, device_id=local)
+            Ls, Rs = stereo_pair(3, H, W)
+            kL, dL = eL(Ls); kR, dR = eR(Rs)
+            eL.stereo_match(eR, 386.1448)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ur, dp, di, kept = eL.stereo_match(eR, 386.1448)
+            t_stereo = (time.perf_counter() - t0) / 20
+            with tempfile.TemporaryDirectory() as td:
+                vp = os.path.join(td, "voc.txt")
+                write_synthetic_vocabulary(vp, 10, 4, seed=1, seeds=dL)
+                voc = orb.ORBVocabulary(eL)
+                voc.loadFromTextFile(vp)
+            voc.transform(dL, 4)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                voc.transform(dL, 4)
+            t_bow = (time.perf_counter() - t0) / 20
+            rng2 = np.random.default_rng(5)
+            sizes = rng2.integers(2, 40, 5000)
+            off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+            rows = dL[rng2.integers(0, len(dL), off[-1])]
+            eL.distinctive_descriptors(rows, off)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                eL.distinctive_descriptors(rows, off)
+            t_dd = (time.perf_counter() - t0) / 10
+            extras = {"stereo_match": {"workload": "Frame::ComputeStereoMatches, %d x %d keypoints, %dx%d pair" % (len(kL), len(kR), W, H),
+                                       "ms_per_pair": 1e3 * t_stereo, "matches_kept": int(kept)},
+                      "bow_transform": {"workload": "ORBVocabulary::transform, %d descriptors, synthetic k=10 L=4 tree" % len(dL), "ms_per_frame": 1e3 * t_bow},
+                      "distinctive_descriptors": {"workload": "5000 map points, %d observations" % int(off[-1]), "ms_per_batch": 1e3 * t_dd},
+                      "note": "host wall clock through the synchronous C-ABI calls, H2D / D2H of the small arrays included"}
+        except Exception as ex:
+            extras = {"error": repr(ex)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's ORBextractor on all host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -353,7 +394,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": batch * H * W, "d2h_bytes_per_step": batch * (cap * 60 + 4),
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "matcher": matcher}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "matcher": matcher, "next_rows": extras}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
