@@ -136,11 +136,30 @@ def run_reference(args, H, W, nfeat, nlev, batch, desc):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Multi-rank runs: pin this process (and the pinned host buffers it allocates afterwards) to the CPUs of the NUMA
+    node its GPU hangs off, so launches and the D2H of the results do not cross sockets.  Best effort."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="k1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -160,6 +179,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(torch, local) if world > 1 and not os.environ.get("ORBX_NO_NUMA_BIND") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.warmup < 3:
@@ -245,11 +265,14 @@ def main():
         return ms, kp, nl, (t0, t1)
 
     # ---- value: device-resident inputs
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
+    # clocks / throttle reasons: rank 0 samples its own GPU (one nvidia-smi poller per rank takes driver locks that stall
+    # the other ranks' launches and costs ~10 % at N = 8)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
     ms_dev, kp_dev, launches, (t0, t1) = timed(submit_dev, args.steps, args.warmup)
-    clocks = sampler.stop(t0, t1)
+    clocks = sampler.stop(t0, t1) if sampler else None
     # ---- e2e: host buffers through the plugin entry point
     ms_e2e, kp_e2e, _, _ = timed(submit_host, args.steps, args.warmup)
 
@@ -387,7 +410,7 @@ def main():
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": desc, "nfeatures": nfeat, "nlevels": nlev, "scale_factor": 1.2, "ini_th_fast": 20, "min_th_fast": 7,
-                           "batch_per_gpu": batch, "global_batch": batch * world, "sharding": "frame-parallel, no collective",
+                           "batch_per_gpu": batch, "global_batch": batch * world, "sharding": "frame-parallel, no collective", "numa_bind": numa_cpus,
                            "handles_in_flight": len(handles),
                            "l2": "inputs larger than L2: %d frame slots = %.0f MB in HBM, walked cyclically" % (nslots, nslots * H * pitch / 2 ** 20),
                            "input_row_pitch": pitch, "keypoints_per_step": kp_dev / max(1, args.steps)},
