@@ -265,8 +265,7 @@ def main():
         return ms, kp, nl, (t0, t1)
 
     # ---- value: device-resident inputs
-    # clocks / throttle reasons: rank 0 samples its own GPU (one nvidia-smi poller per rank takes driver locks that stall
-    # the other ranks' launches and costs ~10 % at N = 8)
+    # clocks / throttle reasons: rank 0 samples its own GPU (one nvidia-smi poller per job is enough)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
