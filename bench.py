@@ -353,6 +353,10 @@ def main():
             eL, eR = orb.ORBextractor(*params, device_id=local), orb.ORBextractor(*params, device_id=local)
             Ls, Rs = stereo_pair(3, H, W)
             kL, dL = eL(Ls); kR, dR = eR(Rs)
+            t0 = time.perf_counter()
+            for _ in range(50):
+                eR(Rs)
+            t_single = (time.perf_counter() - t0) / 50
             eL.stereo_match(eR, 386.1448)
             t0 = time.perf_counter()
             for _ in range(20):
@@ -377,7 +381,9 @@ def main():
             for _ in range(10):
                 eL.distinctive_descriptors(rows, off)
             t_dd = (time.perf_counter() - t0) / 10
-            extras = {"stereo_match": {"workload": "Frame::ComputeStereoMatches, %d x %d keypoints, %dx%d pair" % (len(kL), len(kR), W, H),
+            extras = {"single_frame_call": {"workload": "ORBextractor::operator() on one %dx%d host frame (H2D, extract, D2H), the shape Frame::ExtractORB calls" % (W, H),
+                                            "ms_per_frame": 1e3 * t_single},
+                      "stereo_match": {"workload": "Frame::ComputeStereoMatches, %d x %d keypoints, %dx%d pair" % (len(kL), len(kR), W, H),
                                        "ms_per_pair": 1e3 * t_stereo, "matches_kept": int(kept)},
                       "bow_transform": {"workload": "ORBVocabulary::transform, %d descriptors, synthetic k=10 L=4 tree" % len(dL), "ms_per_frame": 1e3 * t_bow},
                       "distinctive_descriptors": {"workload": "5000 map points, %d observations" % int(off[-1]), "ms_per_batch": 1e3 * t_dd},

@@ -20,6 +20,8 @@
 
 namespace orbx {
 
+constexpr int kMaxOptInSmem = 224 * 1024;     // dynamic shared memory opt-in cap (227 KB per CTA on sm_100, minus room for static)
+
 // ------------------------------------------------------------------ helpers
 
 __device__ __forceinline__ const uint8_t *level_ptr(const DevParams *P, const Src0 &s0, int frame, int level, int *pitch)
@@ -128,46 +130,6 @@ __device__ __forceinline__ void resize_tile(const DevParams *__restrict__ P, con
     }
     __syncthreads();
     resize_rows(P, level, reinterpret_cast<const uint8_t *>(&ssrc[0][0]), kRzSrcWords * 4, sx_lo, sy_lo, x0, y0, y_end, dst);
-}
-
-// All levels in ONE launch.  The level chain (level l is resized from level l-1, :1124) is
-// kept inside a CTA: CTA (band, frame) owns a horizontal band of every level and also
-// computes the few extra rows of level l that its band of level l+1 reads, so it only
-// ever consumes rows it produced itself (made visible by the block barrier).  Halo rows
-// are computed redundantly by neighbouring bands with identical results.
-__global__ void __launch_bounds__(256) k_pyramid_fused(const DevParams *__restrict__ P, Src0 s0, int nbands)
-{
-    __shared__ uint32_t ssrc[kRzSrcRows][kRzSrcWords];
-    __shared__ int c_lo[kMaxLevels], c_hi[kMaxLevels];
-    const int band = blockIdx.x, frame = blockIdx.y, L = P->nlevels;
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        for (int l = L - 1; l >= 1; --l) {
-            const int h = P->lv[l].h;
-            int lo = (int)((long long)h * band / nbands), hi = (int)((long long)h * (band + 1) / nbands);
-            if (l < L - 1 && c_hi[l + 1] > c_lo[l + 1]) {
-                const ResizeTab *yt = P->ytab + P->ytab_off[l + 1];
-                lo = min(lo, (int)yt[c_lo[l + 1]].s0);
-                hi = max(hi, (int)yt[c_hi[l + 1] - 1].s1 + 1);
-            }
-            c_lo[l] = lo; c_hi[l] = hi;
-        }
-    }
-    __syncthreads();
-    for (int l = 1; l < L; ++l) {
-        const LevelGeom &D = P->lv[l];
-        int sp;
-        const uint8_t *S = level_ptr(P, s0, frame, l - 1, &sp);
-        uint8_t *dst = P->pyr + (long long)frame * P->pyr_frame_bytes + D.img_off;
-        const int lo = c_lo[l], hi = c_hi[l];
-        const int ntx = (D.w + kRzTW - 1) / kRzTW, nty = (hi - lo + kRzTH - 1) / kRzTH;
-        for (int t = 0; t < ntx * nty; ++t) {
-            const int ty = t / ntx, tx = t - ty * ntx;
-            const int y0 = lo + ty * kRzTH;
-            resize_tile(P, S, sp, dst, l, tx * kRzTW, y0, min(y0 + kRzTH, hi), ssrc);
-        }
-        __threadfence_block();
-        __syncthreads();                                           // level l of this band is visible before level l+1 reads it
-    }
 }
 
 __global__ void __launch_bounds__(256) k_resize(const DevParams *__restrict__ P, Src0 s0, int level)
@@ -410,11 +372,9 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
                 const int bw = tma->box_w[l], bh = tma->box_h[l];
                 const int box_bytes = (bw * bh + 127) / 128 * 128;
                 const size_t smem = 2 * (size_t)box_bytes + (size_t)bh * kRzTW * sizeof(int);
-                static size_t attr = 40 * 1024;                    // static + dynamic above 48 KB needs the opt-in attribute
-                if (smem > attr) {
-                    cudaError_t e = cudaFuncSetAttribute(k_resize_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (smem > 40 * 1024) {                            // static + dynamic above 48 KB needs the opt-in (per device: set every time)
+                    cudaError_t e = cudaFuncSetAttribute(k_resize_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
                     if (e != cudaSuccess) return e;
-                    attr = smem;
                 }
                 int per_sm = (int)((227 * 1024) / (smem + 1024));
                 per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
@@ -618,8 +578,7 @@ cudaError_t launch_blur(const DevParams *dP, const DevParams &hP, Src0 s0, int n
     static const BlurMaps zero_maps = {};
     const int total = hP.n_blur_work * nframes;
     if (total <= 0) return cudaSuccess;
-    static const int per_sm = std::getenv("ORBX_BLUR_CTAS_PER_SM") ? std::atoi(std::getenv("ORBX_BLUR_CTAS_PER_SM")) : 4;
-    const int grid = total < 148 * per_sm ? total : 148 * per_sm;     // <= 4 resident CTAs per SM (64 registers x 256 threads)
+    const int grid = total < 148 * 4 ? total : 148 * 4;               // 4 resident CTAs per SM (64 registers x 256 threads)
     k_blur<<<grid, 256, 0, st>>>(dP, s0, maps ? *maps : zero_maps, maps ? tma_levels : 0u, total);
     ls->launches++;
     return cudaGetLastError();
@@ -869,30 +828,6 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, MINB) k_fast_fused(co
     ff_process<CELL>(P, J, tile, list, lane);
 }
 
-// ---- persistent variant: a fixed grid of CTAs walks the (job, frame) items, so the kernel occupies only part of every
-// SM and the latency-bound kernels of the other handles (pyramid, octree, orientation) stay co-resident with it.
-template <int CELL, int UNR = 12>
-__global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, 4)
-k_fast_fused_persist(const DevParams *__restrict__ P, Src0 s0, int work_off, int work_end, int nframes)
-{
-    using C = FfCfg<CELL>;
-    extern __shared__ __align__(16) uint32_t ff_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *tile = ff_smem + (size_t)warp * C::WARP_WORDS;
-    uint32_t *list = tile + C::ROWS * C::PITCH;
-    const int njobs = work_end - work_off, total = njobs * nframes, stride = gridDim.x * C::WARPS;
-    for (int item = blockIdx.x * C::WARPS + warp; item < total; item += stride) {
-        const int frame = item / njobs;
-        const FfJob J = ff_job(P, work_off + item - frame * njobs, frame);
-        int sp;
-        const uint8_t *img = level_ptr(P, s0, frame, J.level, &sp);
-        ff_stage<CELL, false, UNR>(img, sp, 0, 0, P->lv[J.level].h - 1, (sp >> 2) - 1, J, tile, lane);
-        __syncwarp();
-        ff_process<CELL>(P, J, tile, list, lane);
-        __syncwarp();
-    }
-}
-
 // ---- persistent TMA variant: every warp walks (job, frame) items; the raw pixel box of the NEXT item (96 bytes x
 // h_cell+6 rows, 16-byte aligned origin) is fetched by cp.async.bulk.tensor while the current item is scored.
 template <int CELL>
@@ -989,26 +924,12 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
     }
     if (n_small > 0) {
         using C = FfCfg<44>;
-        static const int variant = std::getenv("ORBX_FF_VARIANT") ? std::atoi(std::getenv("ORBX_FF_VARIANT")) : 0;
         const dim3 grid((n_small + C::WARPS - 1) / C::WARPS, nframes);
-#define FF_GO(...) do { cudaFuncSetAttribute(k_fast_fused<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); \
-                        k_fast_fused<__VA_ARGS__><<<grid, C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small); } while (0)
-        static const int persist = std::getenv("ORBX_FF_CTAS_PER_SM") ? std::atoi(std::getenv("ORBX_FF_CTAS_PER_SM")) : 0;
-        if (persist > 0) {
-            cudaFuncSetAttribute(k_fast_fused_persist<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-            const int total_ctas = (n_small * nframes + C::WARPS - 1) / C::WARPS;
-            k_fast_fused_persist<44><<<std::min(148 * persist, total_ctas), C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small, nframes);
-            ls->launches++;
-        } else
-        switch (variant) {
-        case 1: FF_GO(44, 5, 4); break;
-        case 2: FF_GO(44, 4, 12); break;
-        case 3: FF_GO(44, 5, 12); break;
-        case 4: FF_GO(44, 4, 4); break;
-        default: FF_GO(44, 4, 12); break;
-        }
-#undef FF_GO
-        if (persist <= 0) ls->launches++;
+        // 4 CTAs / SM (104 registers) and a 12-deep staging unroll measured best; 5 CTAs at 96 registers, shallower unrolls,
+        // persistent CTAs and the TMA variant above were all slower
+        cudaFuncSetAttribute(k_fast_fused<44, 4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        k_fast_fused<44, 4, 12><<<grid, C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small);
+        ls->launches++;
     }
     if (hP.n_ffast_work > n_small) {
         using C = FfCfg<64>;
@@ -1366,11 +1287,9 @@ static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int
                                    int level_off = 0, int level_cnt = -1)
 {
     const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget);
-    static size_t attr = 0;                                          // the attribute is a maximum: raise it once per size
-    if (o.bytes > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o.bytes);
+    {                                                                // the attribute is a per-device maximum: cheap, set every time
+        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
         if (e != cudaSuccess) return e;
-        attr = o.bytes;
     }
     if (level_cnt < 0) level_cnt = hP.nlevels - level_off;
     k_octree<THREADS, IPT><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off);
@@ -1801,16 +1720,13 @@ cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0
 {
     ls->launches++;
     if (maps) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        {
             cudaError_t e = cudaFuncSetAttribute(k_orient_desc_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOdSmemBytes);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orient_desc_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOdSmemBytes);
             if (e != cudaSuccess) return e;
-            attr_set = true;
         }
         // 3 CTAs of 8 warps per SM resident; every warp walks several keypoints of its frame
-        static const int od_per_sm = std::getenv("ORBX_OD_CTAS_PER_SM") ? std::atoi(std::getenv("ORBX_OD_CTAS_PER_SM")) : 3;
-        int per_frame = 148 * od_per_sm / nframes;                     // one wave: never more CTAs than resident slots
+        int per_frame = 148 * 3 / nframes;                             // one wave: never more CTAs than resident slots
         const int max_useful = (hP.kp_frame_cap + kOdWarps - 1) / kOdWarps;
         if (per_frame > max_useful) per_frame = max_useful;
         if (per_frame < 1) per_frame = 1;
@@ -2071,11 +1987,9 @@ cudaError_t launch_distinctive(const uint8_t *d_desc, const int32_t *d_offsets, 
 {
     if (npoints <= 0) return cudaSuccess;
     const size_t smem = (size_t)max_obs * 32 + kDdWarps * 264 * sizeof(int);
-    static size_t attr = 40 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
         if (e != cudaSuccess) return e;
-        attr = smem;
     }
     k_distinctive<<<npoints, kDdWarps * 32, smem, st>>>(d_desc, d_offsets, npoints, d_best_idx, d_best_median);
     ls->launches++;
