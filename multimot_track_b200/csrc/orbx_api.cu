@@ -40,6 +40,7 @@ struct orbx_handle {
     uint8_t *d_out_desc = nullptr;
     int *d_out_n = nullptr;
     uint8_t *d_pad = nullptr; size_t pad_bytes = 0;
+    uint8_t *d_scratch = nullptr; size_t scratch_bytes = 0;      // grow-only scratch of the synchronous helper calls (matcher filters, stereo, BoW, ...)
     uint8_t *d_in = nullptr; size_t in_bytes = 0;       // H2D landing area for host frames before the repack kernel
     // pinned host staging of the results
     orbx_keypoint *p_kps = nullptr;
@@ -83,6 +84,22 @@ int fail(orbx_handle *h, int code, const std::string &msg) { if (h) h->err = msg
     } while (0)
 
 template <typename T> void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+// Grow-only device scratch of a handle (the calls that use it are synchronous, so one buffer is enough).
+int get_scratch(orbx_handle *h, size_t bytes, void **out)
+{
+    if (bytes > h->scratch_bytes) {
+        cudaStreamSynchronize(h->stream);
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr; h->scratch_bytes = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        const cudaError_t e = cudaMalloc(&h->d_scratch, want);
+        if (e != cudaSuccess) { h->err = std::string("scratch allocation failed: ") + cudaGetErrorString(e); return ORBX_ERR_OOM; }
+        h->scratch_bytes = want;
+    }
+    *out = h->d_scratch;
+    return ORBX_OK;
+}
 template <typename T> void hfree(T *&p) { if (p) cudaFreeHost(p); p = nullptr; }
 
 void free_batch_buffers(orbx_handle *h)
@@ -308,7 +325,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_batch_buffers(h);
     free_geo_tables(h);
-    dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad); dfree(h->d_in);
+    dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad); dfree(h->d_in); dfree(h->d_scratch);
     dfree(h->m_A); dfree(h->m_B); dfree(h->m_out); dfree(h->m_acc); dfree(h->m_nacc); dfree(h->m_partial);
     for (int i = 0; i <= ORBX_NUM_STAGES; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -680,7 +697,7 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     // one scratch block: idx | angleA | angleB | hist[30] top3[3] kept[1] | accept
     const size_t words = (size_t)nA * 2 + (size_t)nB + 34;
     uint32_t *d = nullptr;
-    CU(cudaMalloc(&d, words * 4 + (size_t)nA + 16));
+    { const int rcs = get_scratch(h, words * 4 + (size_t)nA + 16, (void **)&d); if (rcs != ORBX_OK) return rcs; }
     int32_t *d_idx = (int32_t *)d; float *d_a = (float *)(d + nA), *d_b = (float *)(d + 2 * (size_t)nA);
     int32_t *d_hist = (int32_t *)(d + 2 * (size_t)nA + nB); uint8_t *d_acc = (uint8_t *)(d + words);
     int32_t res[34];
@@ -698,7 +715,6 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
         return ORBX_OK;
     };
     const int rc = body();
-    cudaFree(d);
     if (rc != ORBX_OK) return rc;
     if (hist) std::memcpy(hist, res, 30 * sizeof(int32_t));
     if (top3) std::memcpy(top3, res + 30, 3 * sizeof(int32_t));
@@ -792,7 +808,7 @@ extern "C" int orbx_voc_transform(orbx_handle *h, const orbx_vocabulary *v, cons
     cudaStream_t st = h->stream;
     uint8_t *d = nullptr;
     const size_t feat_bytes = ((size_t)n * 32 + 255) / 256 * 256;
-    CU(cudaMalloc(&d, feat_bytes + (size_t)n * 12));
+    { const int rcs = get_scratch(h, feat_bytes + (size_t)n * 12, (void **)&d); if (rcs != ORBX_OK) return rcs; }
     int32_t *d_word = (int32_t *)(d + feat_bytes), *d_node = d_word + n, *d_final = d_node + n;
     std::vector<int32_t> final_id((size_t)n);
     auto body = [&]() -> int {
@@ -805,7 +821,6 @@ extern "C" int orbx_voc_transform(orbx_handle *h, const orbx_vocabulary *v, cons
         return ORBX_OK;
     };
     const int rc = body();
-    cudaFree(d);
     if (rc != ORBX_OK) return rc;
     for (int i = 0; i < n; ++i) weight[i] = v->host.weight[final_id[i]];          // the word's weight (a double), looked up on the host
     return ORBX_OK;
@@ -840,7 +855,7 @@ extern "C" int orbx_distinctive_descriptors(orbx_handle *h, const uint8_t *desc,
     cudaStream_t st = h->stream;
     uint8_t *d = nullptr;
     const size_t desc_bytes = ((size_t)std::max(total, 1) * 32 + 255) / 256 * 256, off_bytes = ((size_t)(npoints + 1) * 4 + 255) / 256 * 256;
-    CU(cudaMalloc(&d, desc_bytes + off_bytes + (size_t)npoints * 8));
+    { const int rcs = get_scratch(h, desc_bytes + off_bytes + (size_t)npoints * 8, (void **)&d); if (rcs != ORBX_OK) return rcs; }
     int32_t *d_off = (int32_t *)(d + desc_bytes), *d_best = (int32_t *)(d + desc_bytes + off_bytes), *d_med = d_best + npoints;
     auto body = [&]() -> int {
         if (total > 0) CU(cudaMemcpyAsync(d, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st));
@@ -851,9 +866,7 @@ extern "C" int orbx_distinctive_descriptors(orbx_handle *h, const uint8_t *desc,
         CU(cudaStreamSynchronize(st));
         return ORBX_OK;
     };
-    const int rc = body();
-    cudaFree(d);
-    return rc;
+    return body();
 }
 
 // ------------------------------------------------------------------- stereo
@@ -876,7 +889,7 @@ extern "C" int orbx_stereo_match(orbx_handle *L, orbx_handle *R, int frame_left,
     const int capL = L->geo.kp_frame_cap;
     // scratch: u_right | depth | desc_index | sad (capL each) | kept
     uint32_t *d = nullptr;
-    CU(cudaMalloc(&d, ((size_t)capL * 4 + 4) * sizeof(uint32_t)));
+    { const int rcs = get_scratch(L, ((size_t)capL * 4 + 4) * sizeof(uint32_t), (void **)&d); if (rcs != ORBX_OK) return rcs; }
     float *d_ur = (float *)d, *d_dp = d_ur + capL;
     int32_t *d_di = (int32_t *)(d_dp + capL), *d_sad = d_di + capL;
     int *d_kept = (int *)(d_sad + capL);
@@ -901,7 +914,6 @@ extern "C" int orbx_stereo_match(orbx_handle *L, orbx_handle *R, int frame_left,
         return ORBX_OK;
     };
     rc = body();
-    cudaFree(d);
     if (rc != ORBX_OK) return rc;
     return kept < 0 ? 0 : kept;
 }
