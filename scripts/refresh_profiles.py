@@ -70,6 +70,40 @@ for rep, out in (("prof_%s_main.ncu-rep" % tag, "r1_ncu_full_main_kernels.txt"),
         name = r[kk].split("(")[0].replace("void ", "").split("<")[0]
         val = float(r[a]) * mult[units[a]] + float(r[b]) * mult[units[b]]
         traffic.setdefault(name, []).append(val)
+# ---- one table: per kernel duration, DRAM traffic and throughput, pipe utilisation (north_star: HBM GB/s + integer pipe)
+want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd"), ("dram__bytes_write.sum", "wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu%"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma%"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("smsp__inst_executed.sum", "inst"), ("launch__registers_per_thread", "regs")]
+lines = ["# per-kernel summary of the `ncu --set full` captures (one mid capture per kernel; batch of 32 frames, 1242x375)",
+         "# DRAM GB/s = (dram read + write) / duration; peak copy bandwidth on this pod 6545 GB/s (MEASURED_PEAKS.json); alu% = integer ALU pipe",
+         "%-28s %9s %9s %9s %7s %6s %6s %7s %6s %10s %5s" % ("kernel", "us", "dram MB", "DRAM GB/s", "dram%", "alu%", "fma%", "issue%", "occ%", "warp-inst", "regs")]
+for rep in ("prof_%s_main.ncu-rep" % tag, "prof_%s_resize.ncu-rep" % tag):
+    path = os.path.join(G, rep)
+    if not os.path.exists(path):
+        continue
+    rr = list(csv.reader(subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    h, units = rr[0], rr[1]
+    kk = h.index("Kernel Name")
+    groups = collections.OrderedDict()
+    for r in rr[2:]:
+        groups.setdefault(r[kk].split("(")[0].replace("void ", ""), []).append(r)
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+    for name, rs in groups.items():
+        picks = rs if name.startswith("k_resize") else [rs[len(rs) // 2]]
+        for r in picks:
+            v = {}
+            for m, short in want:
+                if m in h:
+                    i = h.index(m)
+                    v[short] = float(r[i].replace(",", "")) * mult.get(units[i], 1.0)
+            mb = (v.get("rd", 0) + v.get("wr", 0)) / 1e6
+            lines.append("%-28s %9.1f %9.2f %9.0f %7.1f %6.1f %6.1f %7.1f %6.1f %10.0f %5.0f" % (
+                name[:28], v.get("us", 0), mb, mb * 1e6 / (v.get("us", 1) * 1e-6) / 1e9, v.get("dram%", 0), v.get("alu%", 0), v.get("fma%", 0),
+                v.get("issue%", 0), v.get("occ%", 0), v.get("inst", 0), v.get("regs", 0)))
+open(os.path.join(P, "r1_kernel_table.txt"), "w").write("\n".join(lines) + "\n")
+print("\n".join(lines))
+
 tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes), mean over the captured launches, from `ncu --set full "
                   "--clock-control none` of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (batch of 32 frames, 1242x375); "
                   "k_resize_tma is the SUM over the 7 level launches; sources: profiles/r1_ncu_full_*.txt",
