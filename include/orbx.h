@@ -219,6 +219,34 @@ int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, uint8_t *ac
 int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA,
                                 const float *d_angleB, int32_t *d_hist, int32_t *d_top3, int32_t *d_kept);
 
+/* ---- windowed projection matcher ---------------------------- */
+
+/* Camera / pose block of the two frames: Frame::fx, fy, cx, cy, mbf, mb, the undistorted image bounds mnMinX .. mnMaxY
+ * (src/Frame.cc:113-136) and mTcw of the current and of the last frame, row-major 4x4. */
+typedef struct orbx_projection_setup {
+    float fx, fy, cx, cy, bf, b;
+    float min_x, max_x, min_y, max_y;
+    float Tcw_cur[16], Tcw_last[16];
+} orbx_projection_setup;
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1958-2102), the
+ * matcher of Tracking::TrackWithMotionModel (src/Tracking.cc:2986-2992), with the 64x48 grid of the current frame
+ * (Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid, src/Frame.cc:601-616, 710-776).
+ * Last frame, per keypoint i < n_last: world_pos[i][3] and mp_desc[i][32] of its map point (MapPoint::GetWorldPos /
+ * GetDescriptor), valid[i] (a map point is there and mvbOutlier[i] is false), nobs[i] (MapPoint::Observations()),
+ * last_octave[i], last_angle[i] (mvKeys / mvKeysUn).  Current frame, per feature j < n_cur: cur_xy[j][2] (mvKeysUn),
+ * cur_octave, cur_angle, cur_uright (mvuRight, <= 0 when absent), cur_desc[j][32].  The scale factors are the handle's.
+ * cur_match[j] receives the index i of the last-frame point whose map point feature j holds when the function returns
+ * (CurrentFrame.mvpMapPoints[j]), -1 for none; with check_orientation the rotation histogram pruning is applied.
+ * The projections, window tests and Hamming distances run on the GPU; the greedy claim bookkeeping, sequential in the
+ * reference (:2028-2030, :2053), is replayed on the host over the candidate lists.  Host pointers.
+ * Returns nmatches (>= 0) or a negative status (ORBX_ERR_UNSUPPORTED when one window holds more than 512 candidates). */
+int orbx_search_by_projection(orbx_handle *h, const orbx_projection_setup *setup,
+                              int n_last, const float *world_pos, const uint8_t *mp_desc, const uint8_t *valid, const int32_t *nobs,
+                              const int32_t *last_octave, const float *last_angle,
+                              int n_cur, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
+                              const uint8_t *cur_desc, float th, int mono, int check_orientation, int32_t *cur_match);
+
 /* ---- bag-of-words vocabulary -------------------------------- */
 
 /* The DBoW2 vocabulary tree of the reference (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,

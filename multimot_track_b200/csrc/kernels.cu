@@ -1885,6 +1885,103 @@ cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_acce
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------ projection matcher
+// The parallel part of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1958-2102): one warp
+// per last-frame map point projects it into the current frame (OpenCV's CV_32F gemm semantics: float accumulation, k ascending,
+// then + t; 1.0 / z in double), derives the search window and the cell range of Frame::GetFeaturesInArea (src/Frame.cc:710-763),
+// and tests EVERY current feature against the cell range (PosInGrid rounding, :765-776), the level range, the |dx|, |dy| < r
+// window and the stereo gate (:2032-2038); survivors leave as (cell << 32 | index << 16 | Hamming distance), the order the
+// reference would visit them in.  The claim bookkeeping, which is sequential in the reference, follows on the host.
+__global__ void __launch_bounds__(256)
+k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_pos, const uint8_t *__restrict__ mp_desc,
+                     const uint8_t *__restrict__ valid, const int32_t *__restrict__ last_octave, int n_cur,
+                     const float *__restrict__ cur_xy, const int32_t *__restrict__ cur_octave, const float *__restrict__ cur_uright,
+                     const uint8_t *__restrict__ cur_desc, int cap, unsigned long long *__restrict__ cand, int *__restrict__ count)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_last) return;
+    int n_out = 0;
+    bool live = valid[i] != 0;
+    float u = 0, v = 0, invzc = 0, radius = 0;
+    int min_cx = 0, max_cx = -1, min_cy = 0, max_cy = -1, min_level = 0, max_level = -1;
+    if (live) {
+        const float x0 = world_pos[3 * i], x1 = world_pos[3 * i + 1], x2 = world_pos[3 * i + 2];
+        float p[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float s = __fadd_rn(0.f, __fmul_rn(S.Tc[4 * r], x0));
+            s = __fadd_rn(s, __fmul_rn(S.Tc[4 * r + 1], x1));
+            s = __fadd_rn(s, __fmul_rn(S.Tc[4 * r + 2], x2));
+            p[r] = __fadd_rn(s, S.Tc[4 * r + 3]);
+        }
+        invzc = __double2float_rn(__ddiv_rn(1.0, (double)p[2]));
+        u = __fadd_rn(__fmul_rn(__fmul_rn(S.fx, p[0]), invzc), S.cx);
+        v = __fadd_rn(__fmul_rn(__fmul_rn(S.fy, p[1]), invzc), S.cy);
+        live = !(invzc < 0) && !(u < S.min_x || u > S.max_x) && !(v < S.min_y || v > S.max_y);
+    }
+    if (live) {
+        const int oct = last_octave[i];
+        radius = __fmul_rn(S.th, S.scale[oct]);
+        if (S.forward) { min_level = oct; max_level = -1; }
+        else if (S.backward) { min_level = 0; max_level = oct; }
+        else { min_level = oct - 1; max_level = oct + 1; }
+        min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, S.min_x), radius), S.w_inv)));
+        max_cx = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, S.min_x), radius), S.w_inv)));
+        min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
+        max_cy = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
+        live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
+    }
+    if (live) {
+        const bool check_levels = min_level > 0 || max_level >= 0;
+        const uint4 a0 = reinterpret_cast<const uint4 *>(mp_desc)[2 * (long long)i], a1 = reinterpret_cast<const uint4 *>(mp_desc)[2 * (long long)i + 1];
+        const float ur = __fsub_rn(u, __fmul_rn(S.bf, invzc));
+        for (int base = 0; base < n_cur; base += 32) {
+            const int i2 = base + lane;
+            bool ok = i2 < n_cur;
+            unsigned long long key = 0;
+            if (ok) {
+                const float x = cur_xy[2 * i2], y = cur_xy[2 * i2 + 1];
+                const int px = (int)roundf(__fmul_rn(__fsub_rn(x, S.min_x), S.w_inv)), py = (int)roundf(__fmul_rn(__fsub_rn(y, S.min_y), S.h_inv));
+                ok = px >= min_cx && px <= max_cx && py >= min_cy && py <= max_cy && px < 64 && py < 48;     // in a visited grid cell (PosInGrid)
+                if (ok && check_levels) {
+                    const int lv = cur_octave[i2];
+                    ok = !(lv < min_level) && !(max_level >= 0 && lv > max_level);
+                }
+                ok = ok && fabsf(__fsub_rn(x, u)) < radius && fabsf(__fsub_rn(y, v)) < radius;
+                if (ok) {
+                    const float urt = cur_uright[i2];
+                    if (urt > 0 && fabsf(__fsub_rn(ur, urt)) > radius) ok = false;
+                }
+                if (ok) {
+                    const uint4 b0 = reinterpret_cast<const uint4 *>(cur_desc)[2 * (long long)i2], b1 = reinterpret_cast<const uint4 *>(cur_desc)[2 * (long long)i2 + 1];
+                    const unsigned d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                       __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                    key = (unsigned long long)(px * 48 + py) << 32 | (unsigned long long)i2 << 16 | d;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int at = n_out + __popc(m & lanemask_lt());
+                if (at < cap) cand[(long long)i * cap + at] = key;
+            }
+            n_out += __popc(m);
+        }
+    }
+    if (lane == 0) count[i] = n_out;                                    // may exceed cap: the caller reports it
+}
+
+cudaError_t launch_project_candidates(const ProjSetup &S, int n_last, const float *d_world, const uint8_t *d_mp_desc, const uint8_t *d_valid,
+                                      const int32_t *d_last_octave, int n_cur, const float *d_cur_xy, const int32_t *d_cur_octave,
+                                      const float *d_cur_uright, const uint8_t *d_cur_desc, int cap, unsigned long long *d_cand, int *d_count,
+                                      cudaStream_t st, LaunchStats *ls)
+{
+    if (n_last <= 0) return cudaSuccess;
+    k_project_candidates<<<(n_last + 7) / 8, 256, 0, st>>>(S, n_last, d_world, d_mp_desc, d_valid, d_last_octave, n_cur, d_cur_xy, d_cur_octave,
+                                                          d_cur_uright, d_cur_desc, cap, d_cand, d_count);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------- BoW descent
 // TemplatedVocabulary::transform(feature, word, weight, nid, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1205-1250),
 // one warp per descriptor: lane c takes child c of the current node (k <= 32), FORB::distance by __popc (FORB.cpp:81-101),

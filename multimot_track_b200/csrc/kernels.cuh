@@ -88,6 +88,17 @@ cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB,
                          int4 *d_partial, int nchunks, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA, const float *d_angleB,
                                    int32_t *d_hist, int32_t *d_top3, int *d_kept, cudaStream_t st, LaunchStats *ls);
+struct ProjSetup {                   // camera, current pose and window parameters of SearchByProjection, by value
+    float fx, fy, cx, cy, bf, b, min_x, max_x, min_y, max_y, w_inv, h_inv;
+    float Tc[16];
+    float scale[kMaxLevels];
+    float th;
+    int forward, backward;
+};
+cudaError_t launch_project_candidates(const ProjSetup &S, int n_last, const float *d_world, const uint8_t *d_mp_desc, const uint8_t *d_valid,
+                                      const int32_t *d_last_octave, int n_cur, const float *d_cur_xy, const int32_t *d_cur_octave,
+                                      const float *d_cur_uright, const uint8_t *d_cur_desc, int cap, unsigned long long *d_cand, int *d_count,
+                                      cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_bow_descent(const uint8_t *d_feat, int n, const int32_t *d_child_off, const int32_t *d_child_ids, const uint8_t *d_node_desc,
                                const int32_t *d_word_id, int nid_level, int32_t *d_word, int32_t *d_node, int32_t *d_final, cudaStream_t st, LaunchStats *ls);
 constexpr int kDistinctiveMaxObs = 1024;      // observations of one map point that fit the CTA's shared memory

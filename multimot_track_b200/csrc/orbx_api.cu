@@ -721,6 +721,76 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     return res[33];
 }
 
+// ------------------------------------------------------- projection matcher
+
+extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_setup *cam,
+                                         int n_last, const float *world_pos, const uint8_t *mp_desc, const uint8_t *valid, const int32_t *nobs,
+                                         const int32_t *last_octave, const float *last_angle,
+                                         int n_cur, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
+                                         const uint8_t *cur_desc, float th, int mono, int check_orientation, int32_t *cur_match)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!cam || n_last < 0 || n_cur < 0 || n_cur > 65535 ||
+        (n_last > 0 && (!world_pos || !mp_desc || !valid || !nobs || !last_octave || !last_angle)) ||
+        (n_cur > 0 && (!cur_xy || !cur_octave || !cur_angle || !cur_uright || !cur_desc || !cur_match)))
+        return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_projection: bad argument (at most 65535 current features)");
+    for (int i = 0; i < n_last; ++i)
+        if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= h->tab.nlevels)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_projection: octave out of range");
+    for (int j = 0; j < n_cur; ++j) cur_match[j] = -1;
+    if (n_last == 0 || n_cur == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    ProjSetup S;
+    S.fx = cam->fx; S.fy = cam->fy; S.cx = cam->cx; S.cy = cam->cy; S.bf = cam->bf; S.b = cam->b;
+    S.min_x = cam->min_x; S.max_x = cam->max_x; S.min_y = cam->min_y; S.max_y = cam->max_y;
+    S.w_inv = 64.0f / (cam->max_x - cam->min_x); S.h_inv = 48.0f / (cam->max_y - cam->min_y);      // src/Frame.cc:126-127
+    std::memcpy(S.Tc, cam->Tcw_cur, sizeof(S.Tc));
+    for (int l = 0; l < kMaxLevels; ++l) S.scale[l] = l < h->tab.nlevels ? h->tab.scale[l] : 1.f;
+    S.th = th;
+    {   // bForward / bBackward, :1968-1979: twc = -Rcw.t()*tcw (gemm with GEMM_1_T: double accumulation), tlc = Rlw*twc + tlw (float)
+        const float *Tc = cam->Tcw_cur, *Tl = cam->Tcw_last;
+        float twc[3], tlc2;
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += (double)Tc[4 * k + r] * (double)Tc[4 * k + 3];
+            twc[r] = (float)(s * -1.0);
+        }
+        volatile float s = 0.f;                                            // keep the float accumulation un-contracted
+        for (int k = 0; k < 3; ++k) { volatile float p = Tl[4 * 2 + k] * twc[k]; s = s + p; }
+        tlc2 = s + Tl[4 * 2 + 3];
+        S.forward = tlc2 > cam->b && !mono; S.backward = -tlc2 > cam->b && !mono;
+    }
+    constexpr int kCap = 512;
+    // scratch: world | last_octave | cur_xy | cur_octave | cur_uright | count | mp_desc | cur_desc | valid | cand
+    const size_t a4 = 16;
+    auto up = [&](size_t v) { return (v + a4 - 1) / a4 * a4; };
+    const size_t o_world = 0, o_loct = o_world + up((size_t)n_last * 12), o_xy = o_loct + up((size_t)n_last * 4), o_coct = o_xy + up((size_t)n_cur * 8),
+                 o_ur = o_coct + up((size_t)n_cur * 4), o_cnt = o_ur + up((size_t)n_cur * 4), o_mpd = o_cnt + up((size_t)n_last * 4),
+                 o_cd = o_mpd + up((size_t)n_last * 32), o_val = o_cd + up((size_t)n_cur * 32), o_cand = o_val + up((size_t)n_last),
+                 total = o_cand + (size_t)n_last * kCap * 8;
+    uint8_t *d = nullptr;
+    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+    cudaStream_t st = h->stream;
+    std::vector<unsigned long long> cand((size_t)n_last * kCap);
+    std::vector<int> count((size_t)n_last);
+    CU(cudaMemcpyAsync(d + o_world, world_pos, (size_t)n_last * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_loct, last_octave, (size_t)n_last * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_xy, cur_xy, (size_t)n_cur * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_coct, cur_octave, (size_t)n_cur * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_ur, cur_uright, (size_t)n_cur * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_mpd, mp_desc, (size_t)n_last * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_cd, cur_desc, (size_t)n_cur * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_last, cudaMemcpyHostToDevice, st));
+    CU(launch_project_candidates(S, n_last, (const float *)(d + o_world), d + o_mpd, d + o_val, (const int32_t *)(d + o_loct), n_cur,
+                                 (const float *)(d + o_xy), (const int32_t *)(d + o_coct), (const float *)(d + o_ur), d + o_cd, kCap,
+                                 (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), st, &h->stats));
+    CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n_last * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)n_last * kCap * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_last; ++i)
+        if (count[i] > kCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_by_projection: a search window holds more than 512 candidates");
+    return resolve_projection_matches(n_last, n_cur, cand.data(), count.data(), kCap, nobs, last_angle, cur_angle, check_orientation, cur_match);
+}
+
 // --------------------------------------------------------------- vocabulary
 
 struct orbx_vocabulary {

@@ -46,3 +46,23 @@ class ORBmatcher:
             return idx, d1, d2, acc, np.zeros(30, np.int32), np.full(3, -1, np.int32)
         acc, hist, top3 = self._ext.rotation_filter(idx, acc, anglesA, anglesB)
         return idx, d1, d2, acc, hist, top3
+
+    def SearchByProjection(self, case):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1958-2102).  `case` is a dict with
+        the arrays of include/orbx.h's orbx_search_by_projection (see multimot_track_b200.synth.projection_case): cam (fx fy cx cy
+        mbf mb mnMinX mnMaxX mnMinY mnMaxY), Tcw_cur, Tcw_last, world_pos, mp_desc, valid, nobs, last_octave, last_angle, cur_xy,
+        cur_octave, cur_angle, cur_uright, cur_desc, th, mono, check_orientation.  Returns (cur_match[n_cur], nmatches)."""
+        import ctypes
+        c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+        setup = np.concatenate([c["cam"].astype(np.float32), c["Tcw_cur"].astype(np.float32).reshape(-1), c["Tcw_last"].astype(np.float32).reshape(-1)])
+        setup = np.ascontiguousarray(setup, np.float32)
+        n_cur = len(c["cur_xy"])
+        out = np.full(n_cur, -1, np.int32)
+        ext = self._ext
+        rc = ext._lib.orbx_search_by_projection(ext._h, setup.ctypes.data, len(c["world_pos"]), c["world_pos"].ctypes.data, c["mp_desc"].ctypes.data,
+                                                c["valid"].ctypes.data, c["nobs"].ctypes.data, c["last_octave"].ctypes.data, c["last_angle"].ctypes.data,
+                                                n_cur, c["cur_xy"].ctypes.data, c["cur_octave"].ctypes.data, c["cur_angle"].ctypes.data,
+                                                c["cur_uright"].ctypes.data, c["cur_desc"].ctypes.data, float(case["th"]), int(case["mono"]),
+                                                int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), out.ctypes.data)
+        ext._ck(rc)
+        return out, rc

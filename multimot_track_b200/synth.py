@@ -72,3 +72,51 @@ def write_synthetic_vocabulary(path, k=10, levels=4, seed=0, scoring=0, weightin
         f.write("%d %d %d %d\n" % (k, levels, scoring, weighting))
         f.write("\n".join("%d %d %s %s" % (parent_id, leaf, " ".join(str(int(v)) for v in d), repr(w)) for parent_id, leaf, d, w in rows))
     return len(rows) + 1
+
+
+def projection_case(seed, kps, desc, scale, th=15.0, mono=False, forward=0.0, distractors=None):
+    """A TrackWithMotionModel-shaped input for ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono):
+    the last frame = the given keypoints / descriptors with random depths, back-projected to world points through
+    KITTI-like intrinsics (Tcw_last = identity); the current frame = those points seen from a slightly moved camera,
+    +-1.5 px of noise, a few descriptor bits flipped, octaves occasionally off by one, shuffled, plus distractor features;
+    mvuRight consistent with the depth for two thirds of them.  10 % of the last-frame points carry no usable map point,
+    a third of the map points have no observation yet (temporal points)."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    fx, fy, cx, cy, bf = 718.856, 718.856, 607.1928, 185.2157, 386.1448
+    w, h = 1242.0, 375.0
+    z = rng.uniform(4.0, 60.0, n).astype(np.float32)
+    xw = ((kps["x"] - np.float32(cx)) * z / np.float32(fx)).astype(np.float32)
+    yw = ((kps["y"] - np.float32(cy)) * z / np.float32(fy)).astype(np.float32)
+    world = np.stack([xw, yw, z], 1).astype(np.float32)
+    ang = np.deg2rad(rng.uniform(-1.5, 1.5, 3))
+    Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+    Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+    Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = Rx @ Ry @ Rz
+    T[:3, 3] = [rng.uniform(-0.2, 0.2), rng.uniform(-0.05, 0.05), -forward + rng.uniform(-0.1, 0.1)]
+    Tc = T.astype(np.float32)
+    pc = (Tc[:3, :3].astype(np.float64) @ world.T.astype(np.float64) + Tc[:3, 3:4].astype(np.float64)).T
+    u = fx * pc[:, 0] / pc[:, 2] + cx + rng.uniform(-1.5, 1.5, n)
+    v = fy * pc[:, 1] / pc[:, 2] + cy + rng.uniform(-1.5, 1.5, n)
+    cd = desc.copy()
+    for i in range(n):
+        for f in rng.integers(0, 256, rng.integers(0, 25)):
+            cd[i, f % 32] ^= np.uint8(1 << (f % 8))
+    coct = np.clip(kps["octave"] + rng.choice([-1, 0, 0, 0, 0, 1], n), 0, len(scale) - 1).astype(np.int32)
+    cang = ((kps["angle"] + rng.normal(0, 4, n)) % 360).astype(np.float32)
+    ur = np.where(rng.random(n) < 0.66, u - bf / pc[:, 2] + rng.uniform(-1, 1, n), -1.0)
+    if distractors is not None and len(distractors):
+        m = len(distractors)
+        u = np.concatenate([u, rng.uniform(20, w - 20, m)]); v = np.concatenate([v, rng.uniform(20, h - 20, m)])
+        cd = np.concatenate([cd, distractors]); coct = np.concatenate([coct, rng.integers(0, len(scale), m).astype(np.int32)])
+        cang = np.concatenate([cang, rng.uniform(0, 360, m).astype(np.float32)]); ur = np.concatenate([ur, np.full(m, -1.0)])
+    perm = rng.permutation(len(u))
+    return dict(cam=np.array([fx, fy, cx, cy, bf, bf / fx, 0.0, w, 0.0, h], np.float32), Tcw_cur=Tc.reshape(-1).copy(),
+                Tcw_last=np.eye(4, dtype=np.float32).reshape(-1).copy(), world_pos=world, mp_desc=np.ascontiguousarray(desc),
+                valid=(rng.random(n) < 0.9).astype(np.uint8), nobs=np.where(rng.random(n) < 0.33, 0, rng.integers(1, 9, n)).astype(np.int32),
+                last_octave=kps["octave"].astype(np.int32), last_angle=kps["angle"].astype(np.float32),
+                cur_xy=np.stack([u, v], 1).astype(np.float32)[perm], cur_octave=coct[perm].astype(np.int32), cur_angle=cang[perm].astype(np.float32),
+                cur_uright=ur.astype(np.float32)[perm], cur_desc=np.ascontiguousarray(cd[perm]), scale=np.asarray(scale, np.float32),
+                th=float(th), mono=bool(mono), check_orientation=True)

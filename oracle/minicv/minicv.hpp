@@ -90,6 +90,8 @@ public:
 // row-range view of the output matrix (src/ORBextractor.cc:1037) and then
 // writes the descriptors through it.
 struct MatExpr { int rows, cols, type; };
+class Mat;
+struct MatTExpr { const Mat *a; double alpha; };      // alpha * A^T, see the product operators below
 
 class Mat {
 public:
@@ -148,6 +150,10 @@ public:
     }
     Mat operator()(const Rect &r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
     Mat row(int y) const { return rowRange(y, y + 1); }
+    Mat col(int x) const { return colRange(x, x + 1); }
+    MatTExpr t() const { MatTExpr e = {this, 1.0}; return e; }
+    template <typename T> T &at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }              // vector element
+    template <typename T> const T &at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
 
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return type_; }
@@ -171,6 +177,41 @@ private:
     size_t esz_;
     std::shared_ptr<uchar> buf_;
 };
+
+// CV_32F matrix products as the projection matchers write them (src/ORBmatcher.cc:1968-1976, 1990-1991):
+//   A*B + C  and  A*B   -> cv::gemm with A not transposed: OpenCV 4.13 accumulates in FLOAT, k ascending, every product and
+//                          sum rounded separately, alpha / beta applied in float (pinned against live cv2, tests/test_oracle_cvprim.py)
+//   -A.t()*B            -> cv::gemm with GEMM_1_T and alpha = -1: DOUBLE accumulation, one rounding
+// Compile users of these with -ffp-contract=off.
+struct MatMulExpr { const Mat *a, *b; };
+static inline MatTExpr operator-(const MatTExpr &e) { MatTExpr r = {e.a, -e.alpha}; return r; }
+static inline Mat mat_mul_eval(const Mat &A, const Mat &B, const Mat *C)
+{
+    assert(A.type() == CV_32F && B.type() == CV_32F && A.cols == B.rows);
+    Mat t(A.rows, B.cols, CV_32F);
+    for (int i = 0; i < A.rows; ++i)
+        for (int j = 0; j < B.cols; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < A.cols; ++k) { const float p = A.at<float>(i, k) * B.at<float>(k, j); s = s + p; }
+            t.at<float>(i, j) = C ? s + C->at<float>(i, j) : s;
+        }
+    return t;
+}
+static inline MatMulExpr operator*(const Mat &a, const Mat &b) { MatMulExpr e = {&a, &b}; return e; }
+static inline Mat operator+(const MatMulExpr &e, const Mat &c) { return mat_mul_eval(*e.a, *e.b, &c); }
+static inline Mat operator*(const MatTExpr &e, const Mat &B)
+{
+    const Mat &A = *e.a;
+    assert(A.type() == CV_32F && B.type() == CV_32F && A.rows == B.rows);
+    Mat t(A.cols, B.cols, CV_32F);
+    for (int i = 0; i < A.cols; ++i)
+        for (int j = 0; j < B.cols; ++j) {
+            double s = 0;
+            for (int k = 0; k < A.rows; ++k) s += (double)A.at<float>(k, i) * (double)B.at<float>(k, j);
+            t.at<float>(i, j) = (float)(s * e.alpha);
+        }
+    return t;
+}
 
 // CV_32F element-wise arithmetic used by Frame::ComputeStereoMatches (:951, :969, :971)
 enum { NORM_L1 = 2 };

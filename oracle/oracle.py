@@ -437,3 +437,34 @@ class RefVocabulary(_VocBase):
         nb = self.L.orbref_voc_transform(self.h, d.ctypes.data, n, int(levelsup), bi.ctypes.data, bv.ctypes.data, fn.ctypes.data, fo.ctypes.data,
                                          ff.ctypes.data, ctypes.byref(nf))
         return bi[:nb].copy(), bv[:nb].copy(), fn[:nf.value].copy(), fo[:nf.value + 1].copy(), ff[:fo[nf.value]].copy()
+
+
+def _projection_args(case):
+    c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+    return [c["cam"].ctypes.data, c["Tcw_cur"].ctypes.data, c["Tcw_last"].ctypes.data, len(c["world_pos"]), c["world_pos"].ctypes.data,
+            c["mp_desc"].ctypes.data, c["valid"].ctypes.data, c["nobs"].ctypes.data, c["last_octave"].ctypes.data, c["last_angle"].ctypes.data,
+            len(c["cur_xy"]), c["cur_xy"].ctypes.data, c["cur_octave"].ctypes.data, c["cur_angle"].ctypes.data, c["cur_uright"].ctypes.data,
+            c["cur_desc"].ctypes.data, c["scale"].ctypes.data, len(c["scale"]), float(case["th"]), int(case["mono"]), int(case["check_orientation"])], c
+
+
+_PROJ_ARGTYPES = [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _F, _I, _I, _VP]
+
+
+def search_by_projection_port(case):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, ...) by the C port: (cur_match[nC], nmatches)."""
+    L = Oracle.lib()
+    L.orbo_search_by_projection.argtypes = _PROJ_ARGTYPES
+    args, keep = _projection_args(case)
+    out = np.full(len(keep["cur_xy"]), -1, np.int32)
+    n = L.orbo_search_by_projection(*args, out.ctypes.data)
+    return out, n
+
+
+def search_by_projection_ref(case, variant="canon"):
+    """The reference's own compiled SearchByProjection + Frame grid (excerpts of src/ORBmatcher.cc:1958-2102, src/Frame.cc)."""
+    L = RefExtractor.lib(variant)
+    L.orbref_search_by_projection.argtypes = _PROJ_ARGTYPES
+    args, keep = _projection_args(case)
+    out = np.full(len(keep["cur_xy"]), -1, np.int32)
+    n = L.orbref_search_by_projection(*args, out.ctypes.data)
+    return out, n

@@ -596,6 +596,126 @@ int orbo_distinctive_descriptor(const uint8_t *desc, int n, int32_t *best_median
     return best_idx;
 }
 
+/* ------------------------------------------------------- projection matcher
+ * ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), src/ORBmatcher.cc:1958-2102, with the
+ * grid of the current frame (Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea, src/Frame.cc:601-616, 710-776).
+ * Matrix products follow OpenCV 4.13's gemm for CV_32F (A*B [+ C]: float accumulation, k ascending; -A.t()*B: double
+ * accumulation), every other float operation is one statement in the reference's order (-ffp-contract=off). */
+static void three_maxima(const int *cnt, int L, int *ind1, int *ind2, int *ind3);
+
+int orbo_search_by_projection(const float *cam, const float *Tc, const float *Tl,
+                              int nL, const float *world_pos, const uint8_t *mp_desc, const uint8_t *valid, const int32_t *nobs,
+                              const int32_t *last_octave, const float *last_angle,
+                              int nC, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
+                              const uint8_t *cur_desc, const float *scale, int nlevels, float th, int mono, int check_orientation,
+                              int32_t *cur_match)
+{
+    (void)nlevels;
+    const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], mbf = cam[4], mb = cam[5];
+    const float minX = cam[6], maxX = cam[7], minY = cam[8], maxY = cam[9];
+    const float wInv = 64.0f / (maxX - minX), hInv = 48.0f / (maxY - minY);
+    /* AssignFeaturesToGrid: cell lists in feature order */
+    int *cell = (int *)malloc(sizeof(int) * (size_t)(nC > 0 ? nC : 1));
+    int *off = (int *)calloc(64 * 48 + 1, sizeof(int)), *idx = (int *)malloc(sizeof(int) * (size_t)(nC > 0 ? nC : 1));
+    for (int i = 0; i < nC; ++i) {
+        const int px = (int)roundf((cur_xy[2 * i] - minX) * wInv), py = (int)roundf((cur_xy[2 * i + 1] - minY) * hInv);
+        cell[i] = (px < 0 || px >= 64 || py < 0 || py >= 48) ? -1 : px * 48 + py;
+        if (cell[i] >= 0) off[cell[i] + 1]++;
+    }
+    for (int c = 0; c < 64 * 48; ++c) off[c + 1] += off[c];
+    {
+        int *fill = (int *)calloc(64 * 48, sizeof(int));
+        for (int i = 0; i < nC; ++i) if (cell[i] >= 0) idx[off[cell[i]] + fill[cell[i]]++] = i;
+        free(fill);
+    }
+    /* camera geometry, :1968-1979 */
+    float twc[3], tlc[3];
+    for (int r = 0; r < 3; ++r) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += (double)Tc[4 * k + r] * (double)Tc[4 * k + 3];
+        twc[r] = (float)(s * -1.0);
+    }
+    for (int r = 0; r < 3; ++r) {
+        float s = 0.f;
+        for (int k = 0; k < 3; ++k) { const float p = Tl[4 * r + k] * twc[k]; s = s + p; }
+        tlc[r] = s + Tl[4 * r + 3];
+    }
+    const int bForward = tlc[2] > mb && !mono, bBackward = -tlc[2] > mb && !mono;
+    int *claim_obs = (int *)calloc((size_t)(nC > 0 ? nC : 1), sizeof(int));
+    for (int i = 0; i < nC; ++i) cur_match[i] = -1;
+    int *hist_items = (int *)malloc(sizeof(int) * (size_t)(nL > 0 ? nL : 1)), *hist_bin = (int *)malloc(sizeof(int) * (size_t)(nL > 0 ? nL : 1));
+    int nh = 0, nmatches = 0;
+    for (int i = 0; i < nL; ++i) {
+        if (!valid[i]) continue;
+        float xc3[3];
+        for (int r = 0; r < 3; ++r) {
+            float s = 0.f;
+            for (int k = 0; k < 3; ++k) { const float p = Tc[4 * r + k] * world_pos[3 * i + k]; s = s + p; }
+            xc3[r] = s + Tc[4 * r + 3];
+        }
+        const float xc = xc3[0], yc = xc3[1];
+        const float invzc = (float)(1.0 / (double)xc3[2]);
+        if (invzc < 0) continue;
+        float u = fx * xc; u = u * invzc; u = u + cx;
+        float v = fy * yc; v = v * invzc; v = v + cy;
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        const int oct = last_octave[i];
+        const float radius = th * scale[oct];
+        int minLevel, maxLevel;
+        if (bForward) { minLevel = oct; maxLevel = -1; }
+        else if (bBackward) { minLevel = 0; maxLevel = oct; }
+        else { minLevel = oct - 1; maxLevel = oct + 1; }
+        /* GetFeaturesInArea, src/Frame.cc:710-763 */
+        int nMinCellX = (int)floorf((u - minX - radius) * wInv); if (nMinCellX < 0) nMinCellX = 0;
+        if (nMinCellX >= 64) continue;
+        int nMaxCellX = (int)ceilf((u - minX + radius) * wInv); if (nMaxCellX > 63) nMaxCellX = 63;
+        if (nMaxCellX < 0) continue;
+        int nMinCellY = (int)floorf((v - minY - radius) * hInv); if (nMinCellY < 0) nMinCellY = 0;
+        if (nMinCellY >= 48) continue;
+        int nMaxCellY = (int)ceilf((v - minY + radius) * hInv); if (nMaxCellY > 47) nMaxCellY = 47;
+        if (nMaxCellY < 0) continue;
+        const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        int bestDist = 256, bestIdx2 = -1, any = 0;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+            for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+                for (int j = off[ix * 48 + iy]; j < off[ix * 48 + iy + 1]; ++j) {
+                    const int i2 = idx[j];
+                    if (bCheckLevels) {
+                        if (cur_octave[i2] < minLevel) continue;
+                        if (maxLevel >= 0 && cur_octave[i2] > maxLevel) continue;
+                    }
+                    const float distx = cur_xy[2 * i2] - u, disty = cur_xy[2 * i2 + 1] - v;
+                    if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+                    any = 1;                                                    /* member of vIndices2 */
+                    if (cur_match[i2] >= 0 && claim_obs[i2] > 0) continue;      /* :2028-2030 */
+                    if (cur_uright[i2] > 0) {
+                        const float t = mbf * invzc;
+                        const float ur = u - t;
+                        const float er = fabsf(ur - cur_uright[i2]);
+                        if (er > radius) continue;
+                    }
+                    const int dist = orbo_hamming256(mp_desc + 32 * (size_t)i, cur_desc + 32 * (size_t)i2);
+                    if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+                }
+        if (!any) continue;
+        if (bestDist <= 100) {
+            cur_match[bestIdx2] = i; claim_obs[bestIdx2] = nobs[i];
+            ++nmatches;
+            if (check_orientation) { hist_items[nh] = bestIdx2; hist_bin[nh] = orbo_rotation_bin(last_angle[i], cur_angle[bestIdx2]); ++nh; }
+        }
+    }
+    if (check_orientation) {
+        int cnt[30] = {0}, i1 = -1, i2 = -1, i3 = -1;
+        for (int k = 0; k < nh; ++k) cnt[hist_bin[k]]++;
+        three_maxima(cnt, 30, &i1, &i2, &i3);
+        for (int k = 0; k < nh; ++k)
+            if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3) { cur_match[hist_items[k]] = -1; --nmatches; }
+    }
+    free(cell); free(off); free(idx); free(claim_obs); free(hist_items); free(hist_bin);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------- vocabulary
  * DBoW2 as vendored by the reference (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the tree built the way
  * loadFromTextFile builds it (:1338-1418: node ids in file order, children in file order, word ids in order of the

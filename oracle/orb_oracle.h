@@ -76,6 +76,18 @@ int orbo_match(const uint8_t *descA, int nA, const uint8_t *descB, int nB, int t
 int orbo_rotation_bin(float angle_a, float angle_b);
 int orbo_rotation_filter(int nA, const int32_t *idx, uint8_t *accept, const float *angleA, const float *angleB,
                          int32_t *hist, int32_t *top3);
+/* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1958-2102).
+ * cam: fx fy cx cy mbf mb mnMinX mnMaxX mnMinY mnMaxY; Tc / Tl: mTcw of the current / last frame, row-major 4x4;
+ * last frame point i: world_pos, descriptor of its map point, valid (map point present and not an outlier), nobs
+ * (MapPoint::Observations()), octave and angle of its keypoint; current frame: undistorted positions, octaves, angles, mvuRight,
+ * descriptors.  cur_match[nC]: per current feature the last-frame point whose map point it holds at the end (-1 none).
+ * Returns nmatches. */
+int orbo_search_by_projection(const float *cam, const float *Tc, const float *Tl,
+                              int nL, const float *world_pos, const uint8_t *mp_desc, const uint8_t *valid, const int32_t *nobs,
+                              const int32_t *last_octave, const float *last_angle,
+                              int nC, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
+                              const uint8_t *cur_desc, const float *scale, int nlevels, float th, int mono, int check_orientation,
+                              int32_t *cur_match);
 /* DBoW2 vocabulary tree as the reference vendors it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): built from the rows
  * of an ORBvoc text file (parent id, leaf flag, 32 descriptor bytes, weight per node, file order), descent per feature,
  * BowVector / FeatureVector assembly.  scoring: 0 L1, 1 L2, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT;

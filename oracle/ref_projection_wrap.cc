@@ -1,0 +1,66 @@
+// oracle/ref_projection_wrap.cc -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// C-callable wrapper around the reference's own ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame,
+// th, bMono, ...) (src/ORBmatcher.cc:1958-2102) and the Frame grid it searches (src/Frame.cc:601-616, 710-776), all
+// excerpted unmodified at build time (oracle/Makefile) and compiled against oracle/stereo_shim.hpp + oracle/minicv.
+#include <cstring>
+
+#include "stereo_shim.hpp"
+
+namespace {
+void fill_frame(ORB_SLAM2::Frame &F, const float *cam, const float *Tcw, int n, const float *xy_un, const int32_t *octave, const float *angle,
+                const float *uright, const uint8_t *desc, const float *scale, int nlevels)
+{
+    F.fx = cam[0]; F.fy = cam[1]; F.cx = cam[2]; F.cy = cam[3]; F.mbf = cam[4]; F.mb = cam[5];
+    F.mnMinX = cam[6]; F.mnMaxX = cam[7]; F.mnMinY = cam[8]; F.mnMaxY = cam[9];
+    F.mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (F.mnMaxX - F.mnMinX);      // src/Frame.cc:126-127
+    F.mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (F.mnMaxY - F.mnMinY);
+    F.mTcw = cv::Mat(4, 4, CV_32F);
+    for (int i = 0; i < 16; ++i) F.mTcw.at<float>(i / 4, i % 4) = Tcw[i];
+    F.N = n;
+    F.mvKeys.resize((size_t)n); F.mvKeysUn.resize((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        F.mvKeysUn[i] = cv::KeyPoint(xy_un[2 * i], xy_un[2 * i + 1], 31.f, angle[i], 0.f, octave[i], -1);
+        F.mvKeys[i] = F.mvKeysUn[i];
+    }
+    F.mvuRight.assign(uright, uright + n);
+    F.mDescriptors = cv::Mat(n, 32, CV_8UC1, (void *)desc, 32);
+    F.mvScaleFactors.assign(scale, scale + nlevels);
+    F.mvpMapPoints.assign((size_t)n, (ORB_SLAM2::MapPoint *)0);
+    F.mvbOutlier.assign((size_t)n, false);
+}
+}
+
+extern "C" {
+
+// cam: fx fy cx cy mbf mb mnMinX mnMaxX mnMinY mnMaxY.  Last frame: world_pos [nL][3], mp_desc [nL][32], valid[i] = has a map point
+// and is not an outlier, nobs[i] = MapPoint::Observations().  cur_match[nC] receives, per current feature, the index of the last-frame
+// point whose MapPoint it ends up holding (-1 = none).  Returns nmatches.
+int orbref_search_by_projection(const float *cam, const float *Tcw_cur, const float *Tcw_last,
+                                int nL, const float *world_pos, const uint8_t *mp_desc, const uint8_t *valid, const int32_t *nobs,
+                                const int32_t *last_octave, const float *last_angle,
+                                int nC, const float *cur_xy_un, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
+                                const uint8_t *cur_desc, const float *scale, int nlevels, float th, int mono, int check_orientation,
+                                int32_t *cur_match)
+{
+    ORB_SLAM2::Frame Cur, Last;
+    std::vector<float> zeros((size_t)nL, -1.0f), xyl((size_t)nL * 2, 0.f);
+    fill_frame(Cur, cam, Tcw_cur, nC, cur_xy_un, cur_octave, cur_angle, cur_uright, cur_desc, scale, nlevels);
+    fill_frame(Last, cam, Tcw_last, nL, xyl.data(), last_octave, last_angle, zeros.data(), mp_desc, scale, nlevels);
+    Cur.AssignFeaturesToGrid();
+    std::vector<ORB_SLAM2::MapPoint> pts((size_t)nL);
+    for (int i = 0; i < nL; ++i) {
+        pts[i].mWorldPos = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) pts[i].mWorldPos.at<float>(k) = world_pos[3 * i + k];
+        pts[i].mDescriptor = cv::Mat(1, 32, CV_8UC1, (void *)(mp_desc + 32 * (size_t)i), 32);
+        pts[i].nObs = nobs[i];
+        if (valid[i]) Last.mvpMapPoints[i] = &pts[i];
+    }
+    ORB_SLAM2::ORBmatcher matcher(0.9f, check_orientation != 0);
+    std::vector<int> temporal;
+    const int n = matcher.SearchByProjection(Cur, Last, th, mono != 0, temporal);
+    for (int i = 0; i < nC; ++i) cur_match[i] = Cur.mvpMapPoints[i] ? (int32_t)(Cur.mvpMapPoints[i] - &pts[0]) : -1;
+    return n;
+}
+
+} // extern "C"

@@ -11,18 +11,7 @@
 
 #include "ORBextractor.h"
 
-namespace ORB_SLAM2 {
-// Same declaration shape as include/ORBmatcher.h:44,94-96 of the reference; the
-// definitions come from the excerpt of src/ORBmatcher.cc (lines 41-43, 2279-2295).
-class ORBmatcher {
-public:
-    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
-    static const int TH_LOW;
-    static const int TH_HIGH;
-    static const int HISTO_LENGTH;
-    void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);   // :2233-2274, protected there
-};
-}
+#include "stereo_shim.hpp"            // the ORBmatcher declaration shared by every oracle translation unit
 
 namespace {
 // DistributeOctTree is protected: reach it through a subclass, no source edits.

@@ -263,6 +263,26 @@ def test_color_input_vs_oracle(orb, oracle_mod, channels, rgb):
     assert kps_equal_exact(kps, ok) and np.array_equal(kps["angle"], ok["angle"]) and np.array_equal(desc, od)
 
 
+def test_search_by_projection_vs_oracle(orb, oracle_mod):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1958-2102): projections, windows and
+    Hamming distances on the GPU + the sequential claim walk on the host give the oracle's mvpMapPoints assignment and nmatches."""
+    from test_oracle_vs_ref import _projection_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    m = orb.ORBmatcher(0.9, True, extractor=ext)
+    for case in _projection_cases(oracle_mod):
+        exp, nexp = oracle_mod.search_by_projection_port(case)
+        got, n = m.SearchByProjection(case)
+        assert n == nexp and np.array_equal(got, exp)
+        no_ori = dict(case, check_orientation=False)
+        exp2, nexp2 = oracle_mod.search_by_projection_port(no_ori)
+        got2, n2 = m.SearchByProjection(no_ori)
+        assert n2 == nexp2 and np.array_equal(got2, exp2) and n2 >= n
+    empty = dict(case, world_pos=np.zeros((0, 3), np.float32), mp_desc=np.zeros((0, 32), np.uint8), valid=np.zeros(0, np.uint8),
+                 nobs=np.zeros(0, np.int32), last_octave=np.zeros(0, np.int32), last_angle=np.zeros(0, np.float32))
+    got, n = m.SearchByProjection(empty)
+    assert n == 0 and (got == -1).all()
+
+
 def test_vocabulary_transform_vs_oracle(orb, oracle_mod, tmp_path):
     """Frame::ComputeBoW (src/Frame.cc:778-785): ORBVocabulary::loadFromTextFile + transform on the GPU against the oracle
     port (pinned to the reference's DBoW2): words, nodes, weights per descriptor; BowVector values bit-identical."""

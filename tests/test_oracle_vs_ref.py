@@ -250,3 +250,45 @@ def test_vocabulary_port_vs_dbow2(oracle_mod, tmp_path):
             assert np.array_equal(ta[1].view(np.uint64), tb[1].view(np.uint64))
             for x, y in zip(ta, tb):
                 assert np.array_equal(x, y)
+
+
+def _projection_cases(oracle_mod):
+    from multimot_track_b200.synth import projection_case, value_noise_frame
+    o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
+    k, d = o(value_noise_frame(0, 375, 1242))
+    _, d2 = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)(value_noise_frame(1, 375, 1242))
+    sc = o.tables()["scale"]
+    # (seed, th, mono, forward motion): lateral / mono / forward (bForward) / backward (bBackward) / wide window
+    return [projection_case(s, k, d, sc, th, mono, fw, d2[:700]) for s, th, mono, fw in
+            ((1, 15.0, False, 0.0), (2, 7.0, True, 0.0), (3, 15.0, False, 1.2), (4, 30.0, False, -1.2), (5, 45.0, False, 0.0))]
+
+
+def test_minicv_float_gemm_against_live_cv2(oracle_mod):
+    """The projection matcher's `Rcw*x3Dw+tcw` and `-Rcw.t()*tcw` (src/ORBmatcher.cc:1968-1976, 1990-1991) go through cv::gemm;
+    the port's arithmetic (float accumulation for A*B+C, double for the transposed product) is pinned to cv2 4.13 here."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    for _ in range(3000):
+        R = rng.normal(size=(3, 3)).astype(np.float32); x = (rng.normal(size=(3, 1)) * 10).astype(np.float32); t = rng.normal(size=(3, 1)).astype(np.float32)
+        f = np.zeros(3, np.float32); tr = np.zeros(3, np.float32)
+        for r in range(3):
+            s = np.float32(0)
+            for k in range(3):
+                s = np.float32(s + np.float32(R[r, k] * x[k, 0]))
+            f[r] = np.float32(s + t[r, 0])
+            tr[r] = np.float32(-sum(float(R[k, r]) * float(t[k, 0]) for k in range(3)))
+        assert np.array_equal(cv2.gemm(R, x, 1.0, t, 1.0).ravel().view(np.uint32), f.view(np.uint32))
+        assert np.array_equal(cv2.gemm(R, t, -1.0, None, 0.0, flags=cv2.GEMM_1_T).ravel().view(np.uint32), tr.view(np.uint32))
+
+
+def test_search_by_projection_port_vs_reference(oracle_mod):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, ...): the C port against the reference's own function and Frame grid
+    (src/ORBmatcher.cc:1958-2102, src/Frame.cc:601-616, 710-776 excerpted unmodified): the final mvpMapPoints assignment and nmatches."""
+    for case in _projection_cases(oracle_mod):
+        a, na = oracle_mod.search_by_projection_port(case)
+        assert na > 1000 and (a >= 0).sum() > 1000
+        taken = a[a >= 0]
+        assert len(np.unique(taken)) == len(taken) and case["valid"][taken].all()          # one feature per map point, valid points only
+        if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_search_by_projection"):
+            b, nb = oracle_mod.search_by_projection_ref(case)
+            assert nb == na and np.array_equal(a, b)
