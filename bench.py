@@ -381,7 +381,17 @@ def main():
             for _ in range(10):
                 eL.distinctive_descriptors(rows, off)
             t_dd = (time.perf_counter() - t0) / 10
-            extras = {"single_frame_call": {"workload": "ORBextractor::operator() on one %dx%d host frame (H2D, extract, D2H), the shape Frame::ExtractORB calls" % (W, H),
+            from multimot_track_b200.synth import projection_case
+            mt = orb.ORBmatcher(0.9, True, extractor=eL)
+            pc = projection_case(1, kL, dL, eL.GetScaleFactors(), 15.0, False, 0.0, dR[:700])
+            mt.SearchByProjection(pc)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                _, nproj = mt.SearchByProjection(pc)
+            t_proj = (time.perf_counter() - t0) / 20
+            extras = {"search_by_projection": {"workload": "ORBmatcher::SearchByProjection(CurrentFrame, LastFrame), %d map points x %d features, th 15" % (len(kL), len(pc["cur_xy"])),
+                                               "ms_per_call": 1e3 * t_proj, "nmatches": int(nproj)},
+                      "single_frame_call": {"workload": "ORBextractor::operator() on one %dx%d host frame (H2D, extract, D2H), the shape Frame::ExtractORB calls" % (W, H),
                                             "ms_per_frame": 1e3 * t_single},
                       "stereo_match": {"workload": "Frame::ComputeStereoMatches, %d x %d keypoints, %dx%d pair" % (len(kL), len(kR), W, H),
                                        "ms_per_pair": 1e3 * t_stereo, "matches_kept": int(kept)},

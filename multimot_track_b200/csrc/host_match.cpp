@@ -24,8 +24,8 @@ int rotation_bin_host(float a, float b)                              // :2060-20
 }
 }
 
-// cand: n_last rows of `cap` packed candidates (order << 16 | dist, order = cell << 16 | feature index), count[i] valid entries
-int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, int cap, const int32_t *nobs,
+// cand: compact lists of packed candidates (cell << 32 | feature index << 16 | distance); point i owns cand[offset[i] .. + count[i])
+int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                                const float *last_angle, const float *cur_angle, int check_orientation, int32_t *cur_match)
 {
     std::vector<int> claim_obs((size_t)n_cur, 0), hist_item, hist_bin;
@@ -35,7 +35,7 @@ int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *
     for (int i = 0; i < n_last; ++i) {
         const int c = count[i];
         if (c <= 0) continue;
-        row.assign(cand + (size_t)i * cap, cand + (size_t)i * cap + c);
+        row.assign(cand + offset[i], cand + offset[i] + c);
         std::sort(row.begin(), row.end());                                   // GetFeaturesInArea order: cell column-major, then index
         int bestDist = 256, bestIdx2 = -1;
         for (int k = 0; k < c; ++k) {

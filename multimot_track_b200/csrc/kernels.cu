@@ -1896,9 +1896,11 @@ __global__ void __launch_bounds__(256)
 k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_pos, const uint8_t *__restrict__ mp_desc,
                      const uint8_t *__restrict__ valid, const int32_t *__restrict__ last_octave, int n_cur,
                      const float *__restrict__ cur_xy, const int32_t *__restrict__ cur_octave, const float *__restrict__ cur_uright,
-                     const uint8_t *__restrict__ cur_desc, int cap, unsigned long long *__restrict__ cand, int *__restrict__ count)
+                     const uint8_t *__restrict__ cur_desc, int cap, unsigned long long *__restrict__ cand, int *__restrict__ count,
+                     int *__restrict__ offset, int *__restrict__ total)
 {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ unsigned long long s_list[8][kProjCap];               // per-warp staging; the lists leave compacted (one atomicAdd per point)
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (i >= n_last) return;
     int n_out = 0;
     bool live = valid[i] != 0;
@@ -1962,22 +1964,27 @@ k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_po
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (ok) {
                 const int at = n_out + __popc(m & lanemask_lt());
-                if (at < cap) cand[(long long)i * cap + at] = key;
+                if (at < cap) s_list[warp][at] = key;
             }
             n_out += __popc(m);
         }
     }
-    if (lane == 0) count[i] = n_out;                                    // may exceed cap: the caller reports it
+    __syncwarp();
+    int base = 0;
+    const int keep = min(n_out, cap);
+    if (lane == 0) { base = keep ? atomicAdd(total, keep) : 0; count[i] = n_out; offset[i] = base; }   // count may exceed cap: the caller reports it
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < keep; k += 32) cand[base + k] = s_list[warp][k];
 }
 
 cudaError_t launch_project_candidates(const ProjSetup &S, int n_last, const float *d_world, const uint8_t *d_mp_desc, const uint8_t *d_valid,
                                       const int32_t *d_last_octave, int n_cur, const float *d_cur_xy, const int32_t *d_cur_octave,
-                                      const float *d_cur_uright, const uint8_t *d_cur_desc, int cap, unsigned long long *d_cand, int *d_count,
-                                      cudaStream_t st, LaunchStats *ls)
+                                      const float *d_cur_uright, const uint8_t *d_cur_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
+                                      int *d_total, cudaStream_t st, LaunchStats *ls)
 {
     if (n_last <= 0) return cudaSuccess;
     k_project_candidates<<<(n_last + 7) / 8, 256, 0, st>>>(S, n_last, d_world, d_mp_desc, d_valid, d_last_octave, n_cur, d_cur_xy, d_cur_octave,
-                                                          d_cur_uright, d_cur_desc, cap, d_cand, d_count);
+                                                          d_cur_uright, d_cur_desc, kProjCap, d_cand, d_count, d_offset, d_total);
     ls->launches++;
     return cudaGetLastError();
 }

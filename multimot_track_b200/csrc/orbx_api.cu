@@ -759,19 +759,19 @@ extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_s
         tlc2 = s + Tl[4 * 2 + 3];
         S.forward = tlc2 > cam->b && !mono; S.backward = -tlc2 > cam->b && !mono;
     }
-    constexpr int kCap = 512;
-    // scratch: world | last_octave | cur_xy | cur_octave | cur_uright | count | mp_desc | cur_desc | valid | cand
+    // scratch: world | last_octave | cur_xy | cur_octave | cur_uright | count | offset | total | mp_desc | cur_desc | valid | cand
     const size_t a4 = 16;
     auto up = [&](size_t v) { return (v + a4 - 1) / a4 * a4; };
     const size_t o_world = 0, o_loct = o_world + up((size_t)n_last * 12), o_xy = o_loct + up((size_t)n_last * 4), o_coct = o_xy + up((size_t)n_cur * 8),
-                 o_ur = o_coct + up((size_t)n_cur * 4), o_cnt = o_ur + up((size_t)n_cur * 4), o_mpd = o_cnt + up((size_t)n_last * 4),
-                 o_cd = o_mpd + up((size_t)n_last * 32), o_val = o_cd + up((size_t)n_cur * 32), o_cand = o_val + up((size_t)n_last),
-                 total = o_cand + (size_t)n_last * kCap * 8;
+                 o_ur = o_coct + up((size_t)n_cur * 4), o_cnt = o_ur + up((size_t)n_cur * 4), o_off = o_cnt + up((size_t)n_last * 4),
+                 o_tot = o_off + up((size_t)n_last * 4), o_mpd = o_tot + 16, o_cd = o_mpd + up((size_t)n_last * 32),
+                 o_val = o_cd + up((size_t)n_cur * 32), o_cand = o_val + up((size_t)n_last), total = o_cand + (size_t)n_last * kProjCap * 8;
     uint8_t *d = nullptr;
     { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
     cudaStream_t st = h->stream;
-    std::vector<unsigned long long> cand((size_t)n_last * kCap);
-    std::vector<int> count((size_t)n_last);
+    std::vector<int> count((size_t)n_last), offset((size_t)n_last);
+    int ncand = 0;
+    CU(cudaMemsetAsync(d + o_tot, 0, 4, st));
     CU(cudaMemcpyAsync(d + o_world, world_pos, (size_t)n_last * 12, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d + o_loct, last_octave, (size_t)n_last * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d + o_xy, cur_xy, (size_t)n_cur * 8, cudaMemcpyHostToDevice, st));
@@ -781,14 +781,20 @@ extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_s
     CU(cudaMemcpyAsync(d + o_cd, cur_desc, (size_t)n_cur * 32, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_last, cudaMemcpyHostToDevice, st));
     CU(launch_project_candidates(S, n_last, (const float *)(d + o_world), d + o_mpd, d + o_val, (const int32_t *)(d + o_loct), n_cur,
-                                 (const float *)(d + o_xy), (const int32_t *)(d + o_coct), (const float *)(d + o_ur), d + o_cd, kCap,
-                                 (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), st, &h->stats));
+                                 (const float *)(d + o_xy), (const int32_t *)(d + o_coct), (const float *)(d + o_ur), d + o_cd,
+                                 (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), (int *)(d + o_off), (int *)(d + o_tot), st, &h->stats));
     CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n_last * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)n_last * kCap * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(offset.data(), d + o_off, (size_t)n_last * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ncand, d + o_tot, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < n_last; ++i)
-        if (count[i] > kCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_by_projection: a search window holds more than 512 candidates");
-    return resolve_projection_matches(n_last, n_cur, cand.data(), count.data(), kCap, nobs, last_angle, cur_angle, check_orientation, cur_match);
+        if (count[i] > kProjCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_by_projection: a search window holds more than 512 candidates");
+    std::vector<unsigned long long> cand((size_t)std::max(ncand, 1));
+    if (ncand > 0) {
+        CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return resolve_projection_matches(n_last, n_cur, cand.data(), count.data(), offset.data(), nobs, last_angle, cur_angle, check_orientation, cur_match);
 }
 
 // --------------------------------------------------------------- vocabulary

@@ -86,7 +86,7 @@ int build_geometry(const Tables &t, int width, int height, Geometry *g, std::str
 constexpr int kBlurTileW = 128, kBlurTileH = 64;
 
 // host_match.cpp: the sequential walk of SearchByProjection over the GPU's candidate lists
-int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, int cap, const int32_t *nobs,
+int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                                const float *last_angle, const float *cur_angle, int check_orientation, int32_t *cur_match);
 
 // DBoW2 vocabulary tree (vocabulary.cpp): node 0 is the root, children of node i are child_ids[child_off[i] .. child_off[i+1])
