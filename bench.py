@@ -389,7 +389,16 @@ def main():
             for _ in range(20):
                 _, nproj = mt.SearchByProjection(pc)
             t_proj = (time.perf_counter() - t0) / 20
-            extras = {"search_by_projection": {"workload": "ORBmatcher::SearchByProjection(CurrentFrame, LastFrame), %d map points x %d features, th 15" % (len(kL), len(pc["cur_xy"])),
+            from multimot_track_b200.synth import initialization_case
+            ic = initialization_case(1, kL, dL, 100, 0.9, (6.0, -3.0), dR[:600])
+            mt.SearchForInitialization(ic)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                _, _, ninit = mt.SearchForInitialization(ic)
+            t_init = (time.perf_counter() - t0) / 20
+            extras = {"search_for_initialization": {"workload": "ORBmatcher::SearchForInitialization, %d x %d keypoints, window 100, ratio 0.9" % (len(kL), len(ic["xy2"])),
+                                                    "ms_per_call": 1e3 * t_init, "nmatches": int(ninit)},
+                      "search_by_projection": {"workload": "ORBmatcher::SearchByProjection(CurrentFrame, LastFrame), %d map points x %d features, th 15" % (len(kL), len(pc["cur_xy"])),
                                                "ms_per_call": 1e3 * t_proj, "nmatches": int(nproj)},
                       "single_frame_call": {"workload": "ORBextractor::operator() on one %dx%d host frame (H2D, extract, D2H), the shape Frame::ExtractORB calls" % (W, H),
                                             "ms_per_frame": 1e3 * t_single},

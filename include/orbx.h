@@ -247,6 +247,20 @@ int orbx_search_by_projection(orbx_handle *h, const orbx_projection_setup *setup
                               int n_cur, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
                               const uint8_t *cur_desc, float th, int mono, int check_orientation, int32_t *cur_match);
 
+/* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:780-895),
+ * the matcher of Tracking::MonocularInitialization (src/Tracking.cc:2622), over the 64x48 grid of F2 with the image bounds
+ * mnMinX .. mnMaxY (src/Frame.cc:113-136).  Frame 1, per keypoint i < n1: octave1, angle1 (mvKeysUn), desc1[i][32]; frame 2,
+ * per keypoint j < n2: xy2[j][2], octave2, angle2 (mvKeysUn), desc2[j][32]; prev_matched[i][2] = vbPrevMatched, read as the
+ * window centres and updated in place for the matched keypoints as the reference does (:888-891); nnratio = mfNNratio,
+ * check_orientation = mbCheckOrientation.  matches12[i] receives vnMatches12.  The window / level gates and the Hamming
+ * distances run on the GPU; the order-dependent vMatchedDistance / vnMatches21 bookkeeping (:819, :838-846) is replayed on the
+ * host over the candidate lists.  Host pointers.  Returns nmatches (>= 0) or a negative status (ORBX_ERR_UNSUPPORTED when one
+ * window holds more than 512 candidates). */
+int orbx_search_for_initialization(orbx_handle *h, float min_x, float max_x, float min_y, float max_y,
+                                   int n1, const int32_t *octave1, const float *angle1, const uint8_t *desc1,
+                                   int n2, const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2,
+                                   float *prev_matched, int window_size, float nnratio, int check_orientation, int32_t *matches12);
+
 /* ---- bag-of-words vocabulary -------------------------------- */
 
 /* The DBoW2 vocabulary tree of the reference (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,

@@ -5,6 +5,7 @@
 // first least distance in GetFeaturesInArea's candidate order wins (:2045-2049), a later temporal point overwrites -- and the
 // rotation histogram (:2058-2067, ComputeThreeMaxima :2233-2274, pruning :2075-2094).  It is O(candidates), a few microseconds.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <vector>
 
@@ -22,6 +23,61 @@ int rotation_bin_host(float a, float b)                              // :2060-20
     if (bin == ORBX_HISTO_LENGTH) bin = 0;
     return bin;
 }
+
+// ComputeThreeMaxima (src/ORBmatcher.cc:2233-2274) on bin counts
+void three_maxima_host(const int *cnt, int &i1, int &i2, int &i3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    i1 = i2 = i3 = -1;
+    for (int i = 0; i < ORBX_HISTO_LENGTH; ++i) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+        else if (s > max3) { max3 = s; i3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) i3 = -1;
+}
+}
+
+// The sequential part of ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:780-895) over the candidate lists of
+// k_window_candidates: a candidate already matched at a distance <= ours is skipped (:819), best / second best in
+// GetFeaturesInArea's order (:822-831), TH_LOW and the ratio test (:834-836), a better match steals the feature from its
+// previous owner (:838-842); rotHist keeps every push, stolen or not (:856), and the pruning clears what is still set (:872-885).
+int resolve_initialization_matches(int n1, int n2, const unsigned long long *cand, const int *count, const int *offset, const float *ang1,
+                                   const float *ang2, float nnratio, int check_orientation, int32_t *m12)
+{
+    std::vector<int> matched_dist((size_t)n2, INT_MAX), m21((size_t)n2, -1), hist_item, hist_bin;
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    int nmatches = 0;
+    std::vector<unsigned long long> row;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int c = count[i1];
+        if (c <= 0) continue;
+        row.assign(cand + offset[i1], cand + offset[i1] + c);
+        std::sort(row.begin(), row.end());
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < c; ++k) {
+            const int i2 = (int)((row[k] >> 16) & 0xffffu), dist = (int)(row[k] & 0xffffu);
+            if (matched_dist[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= ORBX_TH_LOW && (float)bestDist < (float)bestDist2 * nnratio) {
+            if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; --nmatches; }
+            m12[i1] = bestIdx2; m21[bestIdx2] = i1; matched_dist[bestIdx2] = bestDist;
+            ++nmatches;
+            if (check_orientation) { hist_item.push_back(i1); hist_bin.push_back(rotation_bin_host(ang1[i1], ang2[bestIdx2])); }
+        }
+    }
+    if (check_orientation) {
+        int cnt[ORBX_HISTO_LENGTH] = {0}, i1, i2, i3;
+        for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
+        three_maxima_host(cnt, i1, i2, i3);
+        for (size_t k = 0; k < hist_bin.size(); ++k)
+            if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3 && m12[hist_item[k]] >= 0) { m12[hist_item[k]] = -1; --nmatches; }
+    }
+    return nmatches;
 }
 
 // cand: compact lists of packed candidates (cell << 32 | feature index << 16 | distance); point i owns cand[offset[i] .. + count[i])
@@ -52,15 +108,8 @@ int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *
     if (check_orientation) {
         int cnt[ORBX_HISTO_LENGTH] = {0};
         for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
-        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
-        for (int i = 0; i < ORBX_HISTO_LENGTH; ++i) {
-            const int s = cnt[i];
-            if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
-            else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
-            else if (s > max3) { max3 = s; i3 = i; }
-        }
-        if ((float)max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
-        else if ((float)max3 < 0.1f * (float)max1) i3 = -1;
+        int i1, i2, i3;
+        three_maxima_host(cnt, i1, i2, i3);
         for (size_t k = 0; k < hist_bin.size(); ++k)
             if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3) { cur_match[hist_item[k]] = -1; --nmatches; }
     }

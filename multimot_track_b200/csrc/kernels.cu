@@ -1892,6 +1892,59 @@ cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_acce
 // and tests EVERY current feature against the cell range (PosInGrid rounding, :765-776), the level range, the |dx|, |dy| < r
 // window and the stereo gate (:2032-2038); survivors leave as (cell << 32 | index << 16 | Hamming distance), the order the
 // reference would visit them in.  The claim bookkeeping, which is sequential in the reference, follows on the host.
+// One warp: every feature of the searched frame against one query window (cell range of GetFeaturesInArea, level range,
+// |dx|, |dy| < r, optional stereo gate), Hamming distance of the survivors, compact write-out in arbitrary order (the packed
+// key carries the reference's visiting order).  count[i] may exceed cap; the caller reports that.
+__device__ __forceinline__ void window_scan(const ProjSetup &S, bool live, float u, float v, float radius, int min_cx, int max_cx, int min_cy, int max_cy,
+                                            int min_level, int max_level, bool stereo_gate, float ur, const uint8_t *qdesc, int n_cur,
+                                            const float *__restrict__ cur_xy, const int32_t *__restrict__ cur_octave, const float *__restrict__ cur_uright,
+                                            const uint8_t *__restrict__ cur_desc, int cap, unsigned long long *list, int lane, int i,
+                                            unsigned long long *__restrict__ cand, int *__restrict__ count, int *__restrict__ offset, int *__restrict__ total)
+{
+    int n_out = 0;
+    if (live) {
+        const bool check_levels = min_level > 0 || max_level >= 0;
+        const uint4 a0 = reinterpret_cast<const uint4 *>(qdesc)[0], a1 = reinterpret_cast<const uint4 *>(qdesc)[1];
+        for (int base = 0; base < n_cur; base += 32) {
+            const int i2 = base + lane;
+            bool ok = i2 < n_cur;
+            unsigned long long key = 0;
+            if (ok) {
+                const float x = cur_xy[2 * i2], y = cur_xy[2 * i2 + 1];
+                const int px = (int)roundf(__fmul_rn(__fsub_rn(x, S.min_x), S.w_inv)), py = (int)roundf(__fmul_rn(__fsub_rn(y, S.min_y), S.h_inv));
+                ok = px >= min_cx && px <= max_cx && py >= min_cy && py <= max_cy && px < 64 && py < 48;     // in a visited grid cell (PosInGrid)
+                if (ok && check_levels) {
+                    const int lv = cur_octave[i2];
+                    ok = !(lv < min_level) && !(max_level >= 0 && lv > max_level);
+                }
+                ok = ok && fabsf(__fsub_rn(x, u)) < radius && fabsf(__fsub_rn(y, v)) < radius;
+                if (ok && stereo_gate) {
+                    const float urt = cur_uright[i2];
+                    if (urt > 0 && fabsf(__fsub_rn(ur, urt)) > radius) ok = false;
+                }
+                if (ok) {
+                    const uint4 b0 = reinterpret_cast<const uint4 *>(cur_desc)[2 * (long long)i2], b1 = reinterpret_cast<const uint4 *>(cur_desc)[2 * (long long)i2 + 1];
+                    const unsigned d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                       __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                    key = (unsigned long long)(px * 48 + py) << 32 | (unsigned long long)i2 << 16 | d;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int at = n_out + __popc(m & lanemask_lt());
+                if (at < cap) list[at] = key;
+            }
+            n_out += __popc(m);
+        }
+    }
+    __syncwarp();
+    int base = 0;
+    const int keep = min(n_out, cap);
+    if (lane == 0) { base = keep ? atomicAdd(total, keep) : 0; count[i] = n_out; offset[i] = base; }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < keep; k += 32) cand[base + k] = list[k];
+}
+
 __global__ void __launch_bounds__(256)
 k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_pos, const uint8_t *__restrict__ mp_desc,
                      const uint8_t *__restrict__ valid, const int32_t *__restrict__ last_octave, int n_cur,
@@ -1902,7 +1955,6 @@ k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_po
     __shared__ unsigned long long s_list[8][kProjCap];               // per-warp staging; the lists leave compacted (one atomicAdd per point)
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (i >= n_last) return;
-    int n_out = 0;
     bool live = valid[i] != 0;
     float u = 0, v = 0, invzc = 0, radius = 0;
     int min_cx = 0, max_cx = -1, min_cy = 0, max_cy = -1, min_level = 0, max_level = -1;
@@ -1933,48 +1985,43 @@ k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_po
         max_cy = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
         live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
     }
+    window_scan(S, live, u, v, radius, min_cx, max_cx, min_cy, max_cy, min_level, max_level, true, __fsub_rn(u, __fmul_rn(S.bf, invzc)),
+                mp_desc + 32 * (long long)i, n_cur, cur_xy, cur_octave, cur_uright, cur_desc, cap, s_list[warp], lane, i, cand, count, offset, total);
+}
+
+// The window search of ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:797): octave-0 keypoints of F1 look around
+// vbPrevMatched[i1] in F2's grid, levels (level1, level1), radius = windowSize, no stereo gate.
+__global__ void __launch_bounds__(256)
+k_window_candidates(ProjSetup S, int n1, const float *__restrict__ prev_xy, const int32_t *__restrict__ oct1, const uint8_t *__restrict__ desc1,
+                    int n2, const float *__restrict__ xy2, const int32_t *__restrict__ oct2, const uint8_t *__restrict__ desc2, int cap,
+                    unsigned long long *__restrict__ cand, int *__restrict__ count, int *__restrict__ offset, int *__restrict__ total)
+{
+    __shared__ unsigned long long s_list[8][kProjCap];
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (i >= n1) return;
+    const int level1 = oct1[i];
+    bool live = !(level1 > 0);
+    const float u = prev_xy[2 * i], v = prev_xy[2 * i + 1], radius = S.th;
+    int min_cx = 0, max_cx = -1, min_cy = 0, max_cy = -1;
     if (live) {
-        const bool check_levels = min_level > 0 || max_level >= 0;
-        const uint4 a0 = reinterpret_cast<const uint4 *>(mp_desc)[2 * (long long)i], a1 = reinterpret_cast<const uint4 *>(mp_desc)[2 * (long long)i + 1];
-        const float ur = __fsub_rn(u, __fmul_rn(S.bf, invzc));
-        for (int base = 0; base < n_cur; base += 32) {
-            const int i2 = base + lane;
-            bool ok = i2 < n_cur;
-            unsigned long long key = 0;
-            if (ok) {
-                const float x = cur_xy[2 * i2], y = cur_xy[2 * i2 + 1];
-                const int px = (int)roundf(__fmul_rn(__fsub_rn(x, S.min_x), S.w_inv)), py = (int)roundf(__fmul_rn(__fsub_rn(y, S.min_y), S.h_inv));
-                ok = px >= min_cx && px <= max_cx && py >= min_cy && py <= max_cy && px < 64 && py < 48;     // in a visited grid cell (PosInGrid)
-                if (ok && check_levels) {
-                    const int lv = cur_octave[i2];
-                    ok = !(lv < min_level) && !(max_level >= 0 && lv > max_level);
-                }
-                ok = ok && fabsf(__fsub_rn(x, u)) < radius && fabsf(__fsub_rn(y, v)) < radius;
-                if (ok) {
-                    const float urt = cur_uright[i2];
-                    if (urt > 0 && fabsf(__fsub_rn(ur, urt)) > radius) ok = false;
-                }
-                if (ok) {
-                    const uint4 b0 = reinterpret_cast<const uint4 *>(cur_desc)[2 * (long long)i2], b1 = reinterpret_cast<const uint4 *>(cur_desc)[2 * (long long)i2 + 1];
-                    const unsigned d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-                                       __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-                    key = (unsigned long long)(px * 48 + py) << 32 | (unsigned long long)i2 << 16 | d;
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const int at = n_out + __popc(m & lanemask_lt());
-                if (at < cap) s_list[warp][at] = key;
-            }
-            n_out += __popc(m);
-        }
+        min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, S.min_x), radius), S.w_inv)));
+        max_cx = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, S.min_x), radius), S.w_inv)));
+        min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
+        max_cy = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
+        live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
     }
-    __syncwarp();
-    int base = 0;
-    const int keep = min(n_out, cap);
-    if (lane == 0) { base = keep ? atomicAdd(total, keep) : 0; count[i] = n_out; offset[i] = base; }   // count may exceed cap: the caller reports it
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (int k = lane; k < keep; k += 32) cand[base + k] = s_list[warp][k];
+    window_scan(S, live, u, v, radius, min_cx, max_cx, min_cy, max_cy, level1, level1, false, 0.f, desc1 + 32 * (long long)i, n2, xy2, oct2,
+                nullptr, desc2, cap, s_list[warp], lane, i, cand, count, offset, total);
+}
+
+cudaError_t launch_window_candidates(const ProjSetup &S, int n1, const float *d_prev_xy, const int32_t *d_oct1, const uint8_t *d_desc1, int n2,
+                                     const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, unsigned long long *d_cand, int *d_count,
+                                     int *d_offset, int *d_total, cudaStream_t st, LaunchStats *ls)
+{
+    if (n1 <= 0) return cudaSuccess;
+    k_window_candidates<<<(n1 + 7) / 8, 256, 0, st>>>(S, n1, d_prev_xy, d_oct1, d_desc1, n2, d_xy2, d_oct2, d_desc2, kProjCap, d_cand, d_count, d_offset, d_total);
+    ls->launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_project_candidates(const ProjSetup &S, int n_last, const float *d_world, const uint8_t *d_mp_desc, const uint8_t *d_valid,

@@ -797,6 +797,59 @@ extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_s
     return resolve_projection_matches(n_last, n_cur, cand.data(), count.data(), offset.data(), nobs, last_angle, cur_angle, check_orientation, cur_match);
 }
 
+extern "C" int orbx_search_for_initialization(orbx_handle *h, float min_x, float max_x, float min_y, float max_y,
+                                              int n1, const int32_t *octave1, const float *angle1, const uint8_t *desc1,
+                                              int n2, const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2,
+                                              float *prev_matched, int window_size, float nnratio, int check_orientation, int32_t *matches12)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (n1 < 0 || n2 < 0 || n2 > 65535 || !(max_x > min_x) || !(max_y > min_y) ||
+        (n1 > 0 && (!octave1 || !angle1 || !desc1 || !prev_matched || !matches12)) || (n2 > 0 && (!xy2 || !octave2 || !angle2 || !desc2)))
+        return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_for_initialization: bad argument (at most 65535 features in the second frame)");
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    ProjSetup S{};
+    S.min_x = min_x; S.max_x = max_x; S.min_y = min_y; S.max_y = max_y;
+    S.w_inv = 64.0f / (max_x - min_x); S.h_inv = 48.0f / (max_y - min_y);                           // src/Frame.cc:126-127
+    S.th = (float)window_size;                                                                      // const float &r of GetFeaturesInArea
+    // scratch: prev | oct1 | xy2 | oct2 | count | offset | total | desc1 | desc2 | cand
+    auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_prev = 0, o_o1 = o_prev + up((size_t)n1 * 8), o_xy = o_o1 + up((size_t)n1 * 4), o_o2 = o_xy + up((size_t)n2 * 8),
+                 o_cnt = o_o2 + up((size_t)n2 * 4), o_off = o_cnt + up((size_t)n1 * 4), o_tot = o_off + up((size_t)n1 * 4), o_d1 = o_tot + 16,
+                 o_d2 = o_d1 + up((size_t)n1 * 32), o_cand = o_d2 + up((size_t)n2 * 32), total = o_cand + (size_t)n1 * kProjCap * 8;
+    uint8_t *d = nullptr;
+    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+    cudaStream_t st = h->stream;
+    std::vector<int> count((size_t)n1), offset((size_t)n1);
+    int ncand = 0;
+    CU(cudaMemsetAsync(d + o_tot, 0, 4, st));
+    CU(cudaMemcpyAsync(d + o_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_o1, octave1, (size_t)n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_xy, xy2, (size_t)n2 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_o2, octave2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    CU(launch_window_candidates(S, n1, (const float *)(d + o_prev), (const int32_t *)(d + o_o1), d + o_d1, n2, (const float *)(d + o_xy),
+                                (const int32_t *)(d + o_o2), d + o_d2, (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), (int *)(d + o_off),
+                                (int *)(d + o_tot), st, &h->stats));
+    CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(offset.data(), d + o_off, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ncand, d + o_tot, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n1; ++i)
+        if (count[i] > kProjCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_for_initialization: a search window holds more than 512 candidates");
+    std::vector<unsigned long long> cand((size_t)std::max(ncand, 1));
+    if (ncand > 0) {
+        CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    const int n = resolve_initialization_matches(n1, n2, cand.data(), count.data(), offset.data(), angle1, angle2, nnratio, check_orientation, matches12);
+    for (int i = 0; i < n1; ++i)                                                                    // "Update prev matched", :888-891
+        if (matches12[i] >= 0) { prev_matched[2 * i] = xy2[2 * matches12[i]]; prev_matched[2 * i + 1] = xy2[2 * matches12[i] + 1]; }
+    return n;
+}
+
 // --------------------------------------------------------------- vocabulary
 
 struct orbx_vocabulary {

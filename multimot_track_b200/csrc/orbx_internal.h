@@ -89,6 +89,10 @@ constexpr int kBlurTileW = 128, kBlurTileH = 64;
 int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                                const float *last_angle, const float *cur_angle, int check_orientation, int32_t *cur_match);
 
+// ... and of SearchForInitialization (steal bookkeeping, ratio test, rotation histogram)
+int resolve_initialization_matches(int n1, int n2, const unsigned long long *cand, const int *count, const int *offset, const float *ang1,
+                                   const float *ang2, float nnratio, int check_orientation, int32_t *m12);
+
 // DBoW2 vocabulary tree (vocabulary.cpp): node 0 is the root, children of node i are child_ids[child_off[i] .. child_off[i+1])
 struct VocHost {
     int k = 0, L = 0, scoring = 0, weighting = 0, nnodes = 0, nwords = 0;

@@ -66,3 +66,21 @@ class ORBmatcher:
                                                 int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), out.ctypes.data)
         ext._ck(rc)
         return out, rc
+
+    def SearchForInitialization(self, case):
+        """ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:780-895).  `case`
+        (multimot_track_b200.synth.initialization_case): cam (.. mnMinX mnMaxX mnMinY mnMaxY at [6:10]), oct1, ang1, desc1, xy2, oct2,
+        ang2, desc2, prev_xy (vbPrevMatched), window, nnratio, check_orientation.
+        Returns (vnMatches12[n1], vbPrevMatched after the call, nmatches)."""
+        c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+        ext = self._ext
+        n1, n2 = len(c["oct1"]), len(c["xy2"])
+        prev = np.ascontiguousarray(c["prev_xy"], np.float32).copy()
+        m12 = np.full(n1, -1, np.int32)
+        b = [float(x) for x in c["cam"][6:10]]
+        rc = ext._lib.orbx_search_for_initialization(ext._h, b[0], b[1], b[2], b[3], n1, c["oct1"].ctypes.data, c["ang1"].ctypes.data, c["desc1"].ctypes.data,
+                                                     n2, c["xy2"].ctypes.data, c["oct2"].ctypes.data, c["ang2"].ctypes.data, c["desc2"].ctypes.data,
+                                                     prev.ctypes.data, int(case["window"]), float(case.get("nnratio", self.mfNNratio)),
+                                                     int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), m12.ctypes.data)
+        ext._ck(rc)
+        return m12, prev, rc

@@ -120,3 +120,37 @@ def projection_case(seed, kps, desc, scale, th=15.0, mono=False, forward=0.0, di
                 cur_xy=np.stack([u, v], 1).astype(np.float32)[perm], cur_octave=coct[perm].astype(np.int32), cur_angle=cang[perm].astype(np.float32),
                 cur_uright=ur.astype(np.float32)[perm], cur_desc=np.ascontiguousarray(cd[perm]), scale=np.asarray(scale, np.float32),
                 th=float(th), mono=bool(mono), check_orientation=True)
+
+
+def initialization_case(seed, kps, desc, window=100, nnratio=0.9, shift=(6.0, -3.0), distractors=None):
+    """Monocular initialisation input for ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize):
+    F2 = F1's keypoints moved by `shift` + noise with a few descriptor bits flipped, near-duplicates so that matches get stolen,
+    shuffled, plus distractors; vbPrevMatched = F1's positions (as Tracking::MonocularInitialization seeds it, src/Tracking.cc:2594-2596)."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    x2 = kps["x"] + np.float32(shift[0]) + rng.uniform(-2, 2, n).astype(np.float32)
+    y2 = kps["y"] + np.float32(shift[1]) + rng.uniform(-2, 2, n).astype(np.float32)
+    d2 = desc.copy()
+    for i in range(n):
+        for f in rng.integers(0, 256, rng.integers(0, 30)):
+            d2[i, f % 32] ^= np.uint8(1 << (f % 8))
+    o2 = kps["octave"].astype(np.int32).copy()
+    a2 = ((kps["angle"] + rng.normal(0, 5, n)) % 360).astype(np.float32)
+    dup = rng.choice(n, n // 6, replace=False)                     # a second feature near the true one with a similar descriptor
+    x2 = np.concatenate([x2, x2[dup] + rng.uniform(-8, 8, len(dup)).astype(np.float32)])
+    y2 = np.concatenate([y2, y2[dup] + rng.uniform(-8, 8, len(dup)).astype(np.float32)])
+    dd = d2[dup].copy()
+    for i in range(len(dup)):
+        for f in rng.integers(0, 256, rng.integers(0, 12)):
+            dd[i, f % 32] ^= np.uint8(1 << (f % 8))
+    d2 = np.concatenate([d2, dd]); o2 = np.concatenate([o2, o2[dup]]); a2 = np.concatenate([a2, a2[dup]])
+    if distractors is not None and len(distractors):
+        m = len(distractors)
+        x2 = np.concatenate([x2, rng.uniform(20, 1220, m).astype(np.float32)]); y2 = np.concatenate([y2, rng.uniform(20, 355, m).astype(np.float32)])
+        d2 = np.concatenate([d2, distractors]); o2 = np.concatenate([o2, np.zeros(m, np.int32)]); a2 = np.concatenate([a2, rng.uniform(0, 360, m).astype(np.float32)])
+    perm = rng.permutation(len(x2))
+    return dict(cam=np.array([718.856, 718.856, 607.1928, 185.2157, 386.1448, 0.5372, 0.0, 1242.0, 0.0, 375.0], np.float32),
+                xy1=np.stack([kps["x"], kps["y"]], 1).astype(np.float32), oct1=kps["octave"].astype(np.int32), ang1=kps["angle"].astype(np.float32),
+                desc1=np.ascontiguousarray(desc), xy2=np.stack([x2, y2], 1).astype(np.float32)[perm], oct2=o2[perm].astype(np.int32),
+                ang2=a2[perm].astype(np.float32), desc2=np.ascontiguousarray(d2[perm]),
+                prev_xy=np.stack([kps["x"], kps["y"]], 1).astype(np.float32), window=int(window), nnratio=float(nnratio), check_orientation=True)

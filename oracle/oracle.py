@@ -468,3 +468,27 @@ def search_by_projection_ref(case, variant="canon"):
     out = np.full(len(keep["cur_xy"]), -1, np.int32)
     n = L.orbref_search_by_projection(*args, out.ctypes.data)
     return out, n
+
+
+_INIT_ARGTYPES = [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _F, _I, _VP]
+
+
+def _init_call(fn, case):
+    c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+    prev = c["prev_xy"].astype(np.float32).copy()
+    m12 = np.full(len(c["xy1"]), -1, np.int32)
+    fn.argtypes = _INIT_ARGTYPES
+    n = fn(c["cam"].ctypes.data, len(c["xy1"]), c["xy1"].ctypes.data, c["oct1"].ctypes.data, c["ang1"].ctypes.data, c["desc1"].ctypes.data,
+           len(c["xy2"]), c["xy2"].ctypes.data, c["oct2"].ctypes.data, c["ang2"].ctypes.data, c["desc2"].ctypes.data,
+           prev.ctypes.data, int(case["window"]), float(case["nnratio"]), int(case["check_orientation"]), m12.ctypes.data)
+    return m12, prev, n
+
+
+def search_for_initialization_port(case):
+    """ORBmatcher::SearchForInitialization by the C port: (vnMatches12, vbPrevMatched after the call, nmatches)."""
+    return _init_call(Oracle.lib().orbo_search_for_initialization, case)
+
+
+def search_for_initialization_ref(case, variant="canon"):
+    """The reference's own compiled SearchForInitialization (excerpt of src/ORBmatcher.cc:780-895)."""
+    return _init_call(RefExtractor.lib(variant).orbref_search_for_initialization, case)

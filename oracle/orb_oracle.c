@@ -716,6 +716,85 @@ int orbo_search_by_projection(const float *cam, const float *Tc, const float *Tl
     return nmatches;
 }
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:780-895: octave-0
+ * keypoints of F1 search F2's grid around their previous match position; a candidate already matched at a distance <= ours is
+ * skipped, a better match steals it (the old owner loses its match); ratio test, rotation histogram, vbPrevMatched update. */
+int orbo_search_for_initialization(const float *cam, int n1, const float *xy1, const int32_t *oct1, const float *ang1, const uint8_t *desc1,
+                                   int n2, const float *xy2, const int32_t *oct2, const float *ang2, const uint8_t *desc2,
+                                   float *prev_xy, int window, float nnratio, int check_orientation, int32_t *m12)
+{
+    (void)xy1;
+    const float minX = cam[6], maxX = cam[7], minY = cam[8], maxY = cam[9];
+    const float wInv = 64.0f / (maxX - minX), hInv = 48.0f / (maxY - minY);
+    int *cell = (int *)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1));
+    int *off = (int *)calloc(64 * 48 + 1, sizeof(int)), *idx = (int *)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1));
+    for (int i = 0; i < n2; ++i) {
+        const int px = (int)roundf((xy2[2 * i] - minX) * wInv), py = (int)roundf((xy2[2 * i + 1] - minY) * hInv);
+        cell[i] = (px < 0 || px >= 64 || py < 0 || py >= 48) ? -1 : px * 48 + py;
+        if (cell[i] >= 0) off[cell[i] + 1]++;
+    }
+    for (int c = 0; c < 64 * 48; ++c) off[c + 1] += off[c];
+    {
+        int *fill = (int *)calloc(64 * 48, sizeof(int));
+        for (int i = 0; i < n2; ++i) if (cell[i] >= 0) idx[off[cell[i]] + fill[cell[i]]++] = i;
+        free(fill);
+    }
+    int *matched_dist = (int *)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1)), *m21 = (int *)malloc(sizeof(int) * (size_t)(n2 > 0 ? n2 : 1));
+    for (int i = 0; i < n2; ++i) { matched_dist[i] = INT_MAX; m21[i] = -1; }
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    int *hist_item = (int *)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1)), *hist_bin = (int *)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1));
+    int nh = 0, nmatches = 0;
+    const float r = (float)window;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int level1 = oct1[i1];
+        if (level1 > 0) continue;
+        const float x = prev_xy[2 * i1], y = prev_xy[2 * i1 + 1];
+        int nMinCellX = (int)floorf((x - minX - r) * wInv); if (nMinCellX < 0) nMinCellX = 0;
+        if (nMinCellX >= 64) continue;
+        int nMaxCellX = (int)ceilf((x - minX + r) * wInv); if (nMaxCellX > 63) nMaxCellX = 63;
+        if (nMaxCellX < 0) continue;
+        int nMinCellY = (int)floorf((y - minY - r) * hInv); if (nMinCellY < 0) nMinCellY = 0;
+        if (nMinCellY >= 48) continue;
+        int nMaxCellY = (int)ceilf((y - minY + r) * hInv); if (nMaxCellY > 47) nMaxCellY = 47;
+        if (nMaxCellY < 0) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+            for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+                for (int j = off[ix * 48 + iy]; j < off[ix * 48 + iy + 1]; ++j) {
+                    const int i2 = idx[j];
+                    if (oct2[i2] < level1 || oct2[i2] > level1) continue;          /* GetFeaturesInArea(.., level1, level1): bCheckLevels */
+                    const float distx = xy2[2 * i2] - x, disty = xy2[2 * i2 + 1] - y;
+                    if (!(fabsf(distx) < r && fabsf(disty) < r)) continue;
+                    const int dist = orbo_hamming256(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+                    if (matched_dist[i2] <= dist) continue;
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+        if (bestDist <= 50) {
+            if ((float)bestDist < (float)bestDist2 * nnratio) {
+                if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; --nmatches; }
+                m12[i1] = bestIdx2; m21[bestIdx2] = i1; matched_dist[bestIdx2] = bestDist;
+                ++nmatches;
+                if (check_orientation) { hist_item[nh] = i1; hist_bin[nh] = orbo_rotation_bin(ang1[i1], ang2[bestIdx2]); ++nh; }
+            }
+        }
+    }
+    if (check_orientation) {
+        int cnt[30] = {0}, i1 = -1, i2 = -1, i3 = -1;
+        for (int k = 0; k < nh; ++k) cnt[hist_bin[k]]++;
+        three_maxima(cnt, 30, &i1, &i2, &i3);
+        for (int b = 0; b < 30; ++b) {                                         /* bins in order, items in push order, :872-885 */
+            if (b == i1 || b == i2 || b == i3) continue;
+            for (int k = 0; k < nh; ++k)
+                if (hist_bin[k] == b && m12[hist_item[k]] >= 0) { m12[hist_item[k]] = -1; --nmatches; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; ++i1)
+        if (m12[i1] >= 0) { prev_xy[2 * i1] = xy2[2 * m12[i1]]; prev_xy[2 * i1 + 1] = xy2[2 * m12[i1] + 1]; }
+    free(cell); free(off); free(idx); free(matched_dist); free(m21); free(hist_item); free(hist_bin);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------- vocabulary
  * DBoW2 as vendored by the reference (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the tree built the way
  * loadFromTextFile builds it (:1338-1418: node ids in file order, children in file order, word ids in order of the

@@ -88,6 +88,11 @@ int orbo_search_by_projection(const float *cam, const float *Tc, const float *Tl
                               int nC, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
                               const uint8_t *cur_desc, const float *scale, int nlevels, float th, int mono, int check_orientation,
                               int32_t *cur_match);
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:780-895).  cam as above (only the image bounds are used); frame 1 / 2:
+ * mvKeysUn positions, octaves, angles, descriptors; prev_xy [n1][2] = vbPrevMatched (updated in place); m12 [n1] = vnMatches12. */
+int orbo_search_for_initialization(const float *cam, int n1, const float *xy1, const int32_t *oct1, const float *ang1, const uint8_t *desc1,
+                                   int n2, const float *xy2, const int32_t *oct2, const float *ang2, const uint8_t *desc2,
+                                   float *prev_xy, int window, float nnratio, int check_orientation, int32_t *m12);
 /* DBoW2 vocabulary tree as the reference vendors it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): built from the rows
  * of an ORBvoc text file (parent id, leaf flag, 32 descriptor bytes, weight per node, file order), descent per feature,
  * BowVector / FeatureVector assembly.  scoring: 0 L1, 1 L2, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT;

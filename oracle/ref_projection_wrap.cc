@@ -63,4 +63,25 @@ int orbref_search_by_projection(const float *cam, const float *Tcw_cur, const fl
     return n;
 }
 
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:780-895).
+// xy1 / xy2: mvKeysUn positions; prev_xy [n1][2]: vbPrevMatched, updated in place as the reference does.  Returns nmatches.
+int orbref_search_for_initialization(const float *cam, int n1, const float *xy1, const int32_t *oct1, const float *ang1, const uint8_t *desc1,
+                                     int n2, const float *xy2, const int32_t *oct2, const float *ang2, const uint8_t *desc2,
+                                     float *prev_xy, int window, float nnratio, int check_orientation, int32_t *matches12)
+{
+    ORB_SLAM2::Frame F1, F2;
+    const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, one[1] = {1.0f};
+    std::vector<float> ur1((size_t)n1, -1.0f), ur2((size_t)n2, -1.0f);
+    fill_frame(F1, cam, eye, n1, xy1, oct1, ang1, ur1.data(), desc1, one, 1);
+    fill_frame(F2, cam, eye, n2, xy2, oct2, ang2, ur2.data(), desc2, one, 1);
+    F2.AssignFeaturesToGrid();
+    std::vector<cv::Point2f> prev((size_t)n1);
+    for (int i = 0; i < n1; ++i) prev[i] = cv::Point2f(prev_xy[2 * i], prev_xy[2 * i + 1]);
+    std::vector<int> m12;
+    ORB_SLAM2::ORBmatcher matcher(nnratio, check_orientation != 0);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, window);
+    for (int i = 0; i < n1; ++i) { matches12[i] = m12[i]; prev_xy[2 * i] = prev[i].x; prev_xy[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
 } // extern "C"

@@ -3,7 +3,8 @@
 // The slices of ORB_SLAM2::Frame (include/Frame.h:43-295 of the reference), MapPoint (include/MapPoint.h) and ORBmatcher
 // (include/ORBmatcher.h:37-109) that the excerpted reference functions touch -- Frame::ComputeStereoMatches
 // (src/Frame.cc:849-1038), Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid (:601-616, 710-776),
-// ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) (src/ORBmatcher.cc:1958-2102), ComputeThreeMaxima and
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) (src/ORBmatcher.cc:1958-2102), SearchForInitialization (:780-895),
+// ComputeThreeMaxima and
 // DescriptorDistance -- so that those function bodies compile UNMODIFIED from excerpts made at build time
 // (oracle/Makefile).  Member names and types are the reference's; everything else of the classes is left out.
 #ifndef ORACLE_STEREO_SHIM_HPP
@@ -37,6 +38,7 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono, std::vector<int> &TemperalMatch);
+    int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;

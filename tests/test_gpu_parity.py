@@ -283,6 +283,22 @@ def test_search_by_projection_vs_oracle(orb, oracle_mod):
     assert n == 0 and (got == -1).all()
 
 
+def test_search_for_initialization_vs_oracle(orb, oracle_mod):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:780-895): window candidates + Hamming distances on the GPU and the
+    vMatchedDistance / vnMatches21 bookkeeping replayed on the host give the oracle's vnMatches12, vbPrevMatched and nmatches."""
+    from test_oracle_vs_ref import _initialization_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    m = orb.ORBmatcher(0.9, True, extractor=ext)
+    for case in _initialization_cases(oracle_mod):
+        for c in (case, dict(case, check_orientation=False)):
+            em, ep, en = oracle_mod.search_for_initialization_port(c)
+            gm, gp, gn = m.SearchForInitialization(c)
+            assert gn == en and np.array_equal(gm, em) and np.array_equal(gp.view(np.uint32), ep.view(np.uint32))
+    empty = dict(case, xy2=np.zeros((0, 2), np.float32), oct2=np.zeros(0, np.int32), ang2=np.zeros(0, np.float32), desc2=np.zeros((0, 32), np.uint8))
+    gm, gp, gn = m.SearchForInitialization(empty)
+    assert gn == 0 and (gm == -1).all() and np.array_equal(gp, case["prev_xy"])
+
+
 def test_vocabulary_transform_vs_oracle(orb, oracle_mod, tmp_path):
     """Frame::ComputeBoW (src/Frame.cc:778-785): ORBVocabulary::loadFromTextFile + transform on the GPU against the oracle
     port (pinned to the reference's DBoW2): words, nodes, weights per descriptor; BowVector values bit-identical."""

@@ -263,6 +263,35 @@ def _projection_cases(oracle_mod):
             ((1, 15.0, False, 0.0), (2, 7.0, True, 0.0), (3, 15.0, False, 1.2), (4, 30.0, False, -1.2), (5, 45.0, False, 0.0))]
 
 
+def _initialization_cases(oracle_mod):
+    from multimot_track_b200.synth import initialization_case, value_noise_frame
+    k, d = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)(value_noise_frame(0, 375, 1242))
+    _, d2 = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)(value_noise_frame(1, 375, 1242))
+    # (seed, windowSize, nnratio, shift): Tracking's call (window 100, ratio 0.9), a tight window, a strict ratio, off-image windows
+    return [initialization_case(s, k, d, w, r, sh, d2[:600]) for s, w, r, sh in
+            ((1, 100, 0.9, (6.0, -3.0)), (2, 10, 0.9, (3.0, 2.0)), (3, 100, 0.6, (-20.0, 9.0)), (4, 40, 0.9, (700.0, 0.0)))]
+
+
+def test_search_for_initialization_port_vs_reference(oracle_mod):
+    """ORBmatcher::SearchForInitialization: the C port against the reference's own function (src/ORBmatcher.cc:780-895 excerpted
+    unmodified, with Frame::GetFeaturesInArea): vnMatches12, vbPrevMatched after the call, nmatches; steals do happen."""
+    total = 0
+    for case in _initialization_cases(oracle_mod):
+        m12, prev, n = oracle_mod.search_for_initialization_port(case)
+        assert n == (m12 >= 0).sum()
+        taken = m12[m12 >= 0]
+        assert len(np.unique(taken)) == len(taken) and (case["oct1"][m12 >= 0] == 0).all() and (case["oct2"][taken] == 0).all()
+        assert np.array_equal(prev[m12 >= 0], case["xy2"][taken]) and np.array_equal(prev[m12 < 0], case["prev_xy"][m12 < 0])
+        total += n
+        no_ori = dict(case, check_orientation=False)
+        assert oracle_mod.search_for_initialization_port(no_ori)[2] >= n
+        if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_search_for_initialization"):
+            for c in (case, no_ori):
+                a, b = oracle_mod.search_for_initialization_port(c), oracle_mod.search_for_initialization_ref(c)
+                assert a[2] == b[2] and np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert total > 300
+
+
 def test_minicv_float_gemm_against_live_cv2(oracle_mod):
     """The projection matcher's `Rcw*x3Dw+tcw` and `-Rcw.t()*tcw` (src/ORBmatcher.cc:1968-1976, 1990-1991) go through cv::gemm;
     the port's arithmetic (float accumulation for A*B+C, double for the transposed product) is pinned to cv2 4.13 here."""
