@@ -396,7 +396,16 @@ def main():
             for _ in range(20):
                 _, _, ninit = mt.SearchForInitialization(ic)
             t_init = (time.perf_counter() - t0) / 20
-            extras = {"search_for_initialization": {"workload": "ORBmatcher::SearchForInitialization, %d x %d keypoints, window 100, ratio 0.9" % (len(kL), len(ic["xy2"])),
+            from multimot_track_b200.synth import local_points_case
+            lc = local_points_case(1, kL, dL, eL.GetScaleFactors(), 3.0, 0.8, dR[:700])
+            mt.SearchLocalPoints(lc)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                _, nloc = mt.SearchLocalPoints(lc)
+            t_loc = (time.perf_counter() - t0) / 20
+            extras = {"search_local_points": {"workload": "ORBmatcher::SearchByProjection(F, vpMapPoints, th=3), %d map points x %d features" % (len(lc["proj"]), len(lc["xy"])),
+                                              "ms_per_call": 1e3 * t_loc, "nmatches": int(nloc)},
+                      "search_for_initialization": {"workload": "ORBmatcher::SearchForInitialization, %d x %d keypoints, window 100, ratio 0.9" % (len(kL), len(ic["xy2"])),
                                                     "ms_per_call": 1e3 * t_init, "nmatches": int(ninit)},
                       "search_by_projection": {"workload": "ORBmatcher::SearchByProjection(CurrentFrame, LastFrame), %d map points x %d features, th 15" % (len(kL), len(pc["cur_xy"])),
                                                "ms_per_call": 1e3 * t_proj, "nmatches": int(nproj)},

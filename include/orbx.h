@@ -261,6 +261,23 @@ int orbx_search_for_initialization(orbx_handle *h, float min_x, float max_x, flo
                                    int n2, const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2,
                                    float *prev_matched, int window_size, float nnratio, int check_orientation, int32_t *matches12);
 
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (src/ORBmatcher.cc:418-502) with
+ * RadiusByViewingCos (:504-510), the matcher of Tracking::SearchLocalPoints (src/Tracking.cc:3464), over the frame's 64x48 grid.
+ * Local map points, per point i < n_mp: proj[i][3] = mTrackProjX, mTrackProjY, mTrackProjXR and view_cos[i] = mTrackViewCos,
+ * level[i] = mnTrackScaleLevel (as Frame::isInFrustum left them), mp_desc[i][32] = GetDescriptor(), valid[i] = mbTrackInView &&
+ * !isBad(), nobs[i] = Observations().  Frame, per feature j < n_feat: feat_xy[j][2], feat_octave (mvKeysUn), feat_uright (mvuRight,
+ * <= 0 when absent), feat_desc[j][32], feat_obs[j] = Observations() of the map point the feature already holds (< 0: none).
+ * The scale factors are the handle's.  feat_match[j] receives the index i of the map point the call assigns to feature j
+ * (F.mvpMapPoints[j] = vpMapPoints[i]), -1 where the feature is left as it was.  The window / level / right-coordinate gates and
+ * the Hamming distances run on the GPU; the claim bookkeeping, sequential in the reference (:457-459, :498), is replayed on the
+ * host.  Host pointers.  Returns nmatches (>= 0; a point with no observations can be overwritten later, so nmatches may exceed the
+ * number of assigned features, as in the reference) or a negative status. */
+int orbx_search_local_points(orbx_handle *h, float min_x, float max_x, float min_y, float max_y,
+                             int n_mp, const float *proj, const float *view_cos, const int32_t *level, const uint8_t *mp_desc,
+                             const uint8_t *valid, const int32_t *nobs,
+                             int n_feat, const float *feat_xy, const int32_t *feat_octave, const float *feat_uright,
+                             const uint8_t *feat_desc, const int32_t *feat_obs, float th, float nnratio, int32_t *feat_match);
+
 /* ---- bag-of-words vocabulary -------------------------------- */
 
 /* The DBoW2 vocabulary tree of the reference (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,

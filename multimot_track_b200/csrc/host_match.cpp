@@ -80,6 +80,37 @@ int resolve_initialization_matches(int n1, int n2, const unsigned long long *can
     return nmatches;
 }
 
+// The sequential part of ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:418-502) over the candidate lists of
+// k_local_candidates: a feature that holds an observed map point -- from before the call or assigned earlier in it -- is skipped
+// (:457-459), best / second best with their octaves (:476-489), TH_HIGH, and the ratio test only when both are on one level (:493-496).
+int resolve_local_matches(int n_mp, int n_feat, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
+                          const int32_t *feat_octave, const int32_t *feat_obs, float nnratio, int32_t *feat_match)
+{
+    std::vector<int> held((size_t)n_feat);
+    for (int j = 0; j < n_feat; ++j) { held[j] = feat_obs[j] > 0 ? feat_obs[j] : 0; feat_match[j] = -1; }
+    int nmatches = 0;
+    std::vector<unsigned long long> row;
+    for (int i = 0; i < n_mp; ++i) {
+        const int c = count[i];
+        if (c <= 0) continue;
+        row.assign(cand + offset[i], cand + offset[i] + c);
+        std::sort(row.begin(), row.end());
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int k = 0; k < c; ++k) {
+            const int j = (int)((row[k] >> 16) & 0xffffu), dist = (int)(row[k] & 0xffffu);
+            if (held[j] > 0) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = feat_octave[j]; bestIdx = j; }
+            else if (dist < bestDist2) { bestLevel2 = feat_octave[j]; bestDist2 = dist; }
+        }
+        if (bestDist <= ORBX_TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            feat_match[bestIdx] = i; held[bestIdx] = nobs[i] > 0 ? nobs[i] : 0;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
 // cand: compact lists of packed candidates (cell << 32 | feature index << 16 | distance); point i owns cand[offset[i] .. + count[i])
 int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                                const float *last_angle, const float *cur_angle, int check_orientation, int32_t *cur_match)

@@ -2014,6 +2014,48 @@ k_window_candidates(ProjSetup S, int n1, const float *__restrict__ prev_xy, cons
                 nullptr, desc2, cap, s_list[warp], lane, i, cand, count, offset, total);
 }
 
+// The window search of ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:418-502):
+// a local map point looks around (mTrackProjX, mTrackProjY) with radius RadiusByViewingCos(mTrackViewCos) [x th] x scale[predicted level]
+// on levels (predicted - 1, predicted); the right-coordinate gate uses the same radius (:463-468).  S.th carries th, S.forward bFactor.
+__global__ void __launch_bounds__(256)
+k_local_candidates(ProjSetup S, int n_mp, const float *__restrict__ proj, const float *__restrict__ view_cos, const int32_t *__restrict__ level,
+                   const uint8_t *__restrict__ mp_desc, const uint8_t *__restrict__ valid, int n_feat, const float *__restrict__ xy,
+                   const int32_t *__restrict__ octave, const float *__restrict__ uright, const uint8_t *__restrict__ desc, int cap,
+                   unsigned long long *__restrict__ cand, int *__restrict__ count, int *__restrict__ offset, int *__restrict__ total)
+{
+    __shared__ unsigned long long s_list[8][kProjCap];
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (i >= n_mp) return;
+    bool live = valid[i] != 0;
+    const int lvl = level[i];
+    float r = (double)view_cos[i] > 0.998 ? 2.5f : 4.0f;                       // RadiusByViewingCos, :504-510
+    if (S.forward) r = __fmul_rn(r, S.th);
+    const float radius = __fmul_rn(r, S.scale[lvl]);
+    const float u = proj[3 * i], v = proj[3 * i + 1];
+    int min_cx = 0, max_cx = -1, min_cy = 0, max_cy = -1;
+    if (live) {
+        min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, S.min_x), radius), S.w_inv)));
+        max_cx = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, S.min_x), radius), S.w_inv)));
+        min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
+        max_cy = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, S.min_y), radius), S.h_inv)));
+        live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
+    }
+    window_scan(S, live, u, v, radius, min_cx, max_cx, min_cy, max_cy, lvl - 1, lvl, true, proj[3 * i + 2], mp_desc + 32 * (long long)i, n_feat, xy,
+                octave, uright, desc, cap, s_list[warp], lane, i, cand, count, offset, total);
+}
+
+cudaError_t launch_local_candidates(const ProjSetup &S, int n_mp, const float *d_proj, const float *d_view_cos, const int32_t *d_level,
+                                    const uint8_t *d_mp_desc, const uint8_t *d_valid, int n_feat, const float *d_xy, const int32_t *d_octave,
+                                    const float *d_uright, const uint8_t *d_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
+                                    int *d_total, cudaStream_t st, LaunchStats *ls)
+{
+    if (n_mp <= 0) return cudaSuccess;
+    k_local_candidates<<<(n_mp + 7) / 8, 256, 0, st>>>(S, n_mp, d_proj, d_view_cos, d_level, d_mp_desc, d_valid, n_feat, d_xy, d_octave, d_uright, d_desc,
+                                                       kProjCap, d_cand, d_count, d_offset, d_total);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_window_candidates(const ProjSetup &S, int n1, const float *d_prev_xy, const int32_t *d_oct1, const uint8_t *d_desc1, int n2,
                                      const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, unsigned long long *d_cand, int *d_count,
                                      int *d_offset, int *d_total, cudaStream_t st, LaunchStats *ls)

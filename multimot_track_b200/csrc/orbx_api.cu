@@ -229,6 +229,11 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     const bool prof = h->profiling;
 #define MARK(i) do { if (prof) CU(cudaEventRecord(h->ev[i], st)); } while (0)
     MARK(1);                                     // ev[0] was recorded by the caller before the input copies
+    // measurement aid only (scripts/exp_overlap.py): leave stages out to read their marginal cost in the overlapped pipeline;
+    // the buffers keep the previous batch's contents, results are then meaningless.  1 pyramid, 2 blur, 4 FAST, 8 octree, 16 orient/desc, 32 D2H
+    const char *skip_env = std::getenv("ORBX_DEBUG_SKIP");
+    const int skip = skip_env ? std::atoi(skip_env) : 0;
+    if (!(skip & 4))
     CU(cudaMemsetAsync(h->d_cand_count, 0, (size_t)nframes * P.nlevels * sizeof(uint32_t), st));
     if (h->use_tma &&
         (h->tma_l0_base != s0.ptr || h->tma_l0_fs != s0.frame_stride || h->tma_l0_pitch != s0.pitch || h->tma_l0_frames < nframes)) {
@@ -243,28 +248,35 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
         else h->od_img_ok &= ~1u;
         h->tma_l0_base = s0.ptr; h->tma_l0_fs = s0.frame_stride; h->tma_l0_pitch = s0.pitch; h->tma_l0_frames = nframes;
     }
+    if (!(skip & 1))
     CU(launch_pyramid(h->d_params, P, s0, nframes, st, &h->stats, h->use_tma ? &h->tma : nullptr));
     MARK(2);
+    if (!(skip & 2))
     CU(launch_blur(h->d_params, P, s0, nframes, st, &h->stats, h->use_tma ? &h->blur_maps : nullptr, h->blur_tma_levels));
     MARK(3);
     {
         const unsigned all = P.nlevels >= 32 ? 0xffffffffu : (1u << P.nlevels) - 1u;
         const bool fast_tma = h->use_tma && (h->fast_ok & all) == all && std::getenv("ORBX_FAST_TMA");   // opt-in: measured slower (12 warps / SM)
+        if (!(skip & 4))
         CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_ffast_small, st, &h->stats, fast_tma ? &h->fast_maps : nullptr));
     }
     MARK(4);
+    if (!(skip & 8))
     CU(launch_octree(h->d_params, P, nframes, h->geo.max_node_cap, h->geo.max_feat, st, &h->stats));
     MARK(5);
     {
         const unsigned all = P.nlevels >= 32 ? 0xffffffffu : (1u << P.nlevels) - 1u;
         const bool od_tma = h->use_tma && (h->od_img_ok & all) == all && (h->od_blr_ok & all) == all;
+        if (!(skip & 16))
         CU(launch_orient_desc(h->d_params, P, s0, nframes, st, &h->stats, od_tma ? &h->od_maps : nullptr));
     }
     MARK(6);
     const size_t cap = (size_t)P.kp_frame_cap;
     CU(cudaMemcpyAsync(h->p_n, h->d_out_n, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!(skip & 32)) {
     CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_desc, h->d_out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, st));
+    }
     MARK(7);
 #undef MARK
     h->ev_valid = prof;
@@ -848,6 +860,65 @@ extern "C" int orbx_search_for_initialization(orbx_handle *h, float min_x, float
     for (int i = 0; i < n1; ++i)                                                                    // "Update prev matched", :888-891
         if (matches12[i] >= 0) { prev_matched[2 * i] = xy2[2 * matches12[i]]; prev_matched[2 * i + 1] = xy2[2 * matches12[i] + 1]; }
     return n;
+}
+
+extern "C" int orbx_search_local_points(orbx_handle *h, float min_x, float max_x, float min_y, float max_y,
+                                        int n_mp, const float *proj, const float *view_cos, const int32_t *level, const uint8_t *mp_desc,
+                                        const uint8_t *valid, const int32_t *nobs,
+                                        int n_feat, const float *feat_xy, const int32_t *feat_octave, const float *feat_uright,
+                                        const uint8_t *feat_desc, const int32_t *feat_obs, float th, float nnratio, int32_t *feat_match)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (n_mp < 0 || n_feat < 0 || n_feat > 65535 || !(max_x > min_x) || !(max_y > min_y) ||
+        (n_mp > 0 && (!proj || !view_cos || !level || !mp_desc || !valid || !nobs)) ||
+        (n_feat > 0 && (!feat_xy || !feat_octave || !feat_uright || !feat_desc || !feat_obs || !feat_match)))
+        return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_local_points: bad argument (at most 65535 features)");
+    for (int i = 0; i < n_mp; ++i)
+        if (valid[i] && (level[i] < 0 || level[i] >= h->tab.nlevels)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_local_points: predicted level out of range");
+    for (int j = 0; j < n_feat; ++j) feat_match[j] = -1;
+    if (n_mp == 0 || n_feat == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    ProjSetup S{};
+    S.min_x = min_x; S.max_x = max_x; S.min_y = min_y; S.max_y = max_y;
+    S.w_inv = 64.0f / (max_x - min_x); S.h_inv = 48.0f / (max_y - min_y);                           // src/Frame.cc:126-127
+    for (int l = 0; l < kMaxLevels; ++l) S.scale[l] = l < h->tab.nlevels ? h->tab.scale[l] : 1.f;
+    S.th = th; S.forward = th != 1.0;                                                               // bFactor, :422
+    // scratch: proj | view_cos | level | xy | octave | uright | count | offset | total | mp_desc | desc | valid | cand
+    auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_proj = 0, o_vc = o_proj + up((size_t)n_mp * 12), o_lvl = o_vc + up((size_t)n_mp * 4), o_xy = o_lvl + up((size_t)n_mp * 4),
+                 o_oct = o_xy + up((size_t)n_feat * 8), o_ur = o_oct + up((size_t)n_feat * 4), o_cnt = o_ur + up((size_t)n_feat * 4),
+                 o_off = o_cnt + up((size_t)n_mp * 4), o_tot = o_off + up((size_t)n_mp * 4), o_mpd = o_tot + 16, o_fd = o_mpd + up((size_t)n_mp * 32),
+                 o_val = o_fd + up((size_t)n_feat * 32), o_cand = o_val + up((size_t)n_mp), total = o_cand + (size_t)n_mp * kProjCap * 8;
+    uint8_t *d = nullptr;
+    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+    cudaStream_t st = h->stream;
+    std::vector<int> count((size_t)n_mp), offset((size_t)n_mp);
+    int ncand = 0;
+    CU(cudaMemsetAsync(d + o_tot, 0, 4, st));
+    CU(cudaMemcpyAsync(d + o_proj, proj, (size_t)n_mp * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_vc, view_cos, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_lvl, level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_xy, feat_xy, (size_t)n_feat * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_oct, feat_octave, (size_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_ur, feat_uright, (size_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_mpd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_fd, feat_desc, (size_t)n_feat * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_mp, cudaMemcpyHostToDevice, st));
+    CU(launch_local_candidates(S, n_mp, (const float *)(d + o_proj), (const float *)(d + o_vc), (const int32_t *)(d + o_lvl), d + o_mpd, d + o_val,
+                               n_feat, (const float *)(d + o_xy), (const int32_t *)(d + o_oct), (const float *)(d + o_ur), d + o_fd,
+                               (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), (int *)(d + o_off), (int *)(d + o_tot), st, &h->stats));
+    CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(offset.data(), d + o_off, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ncand, d + o_tot, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_mp; ++i)
+        if (count[i] > kProjCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_local_points: a search window holds more than 512 candidates");
+    std::vector<unsigned long long> cand((size_t)std::max(ncand, 1));
+    if (ncand > 0) {
+        CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return resolve_local_matches(n_mp, n_feat, cand.data(), count.data(), offset.data(), nobs, feat_octave, feat_obs, nnratio, feat_match);
 }
 
 // --------------------------------------------------------------- vocabulary

@@ -93,6 +93,10 @@ int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *
 int resolve_initialization_matches(int n1, int n2, const unsigned long long *cand, const int *count, const int *offset, const float *ang1,
                                    const float *ang2, float nnratio, int check_orientation, int32_t *m12);
 
+// ... and of SearchByProjection(F, vpMapPoints, th) (claims, best / second best with levels, ratio on equal levels)
+int resolve_local_matches(int n_mp, int n_feat, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
+                          const int32_t *feat_octave, const int32_t *feat_obs, float nnratio, int32_t *feat_match);
+
 // DBoW2 vocabulary tree (vocabulary.cpp): node 0 is the root, children of node i are child_ids[child_off[i] .. child_off[i+1])
 struct VocHost {
     int k = 0, L = 0, scoring = 0, weighting = 0, nnodes = 0, nwords = 0;

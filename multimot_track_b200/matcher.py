@@ -84,3 +84,19 @@ class ORBmatcher:
                                                      int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), m12.ctypes.data)
         ext._ck(rc)
         return m12, prev, rc
+
+    def SearchLocalPoints(self, case):
+        """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:418-502), the call of Tracking::SearchLocalPoints.
+        `case` (multimot_track_b200.synth.local_points_case): cam (image bounds at [6:10]), proj, view_cos, level, mp_desc, valid, nobs,
+        xy, octave, uright, desc, feat_obs, th, nnratio.  Returns (index of the newly assigned map point per feature, nmatches)."""
+        c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+        ext = self._ext
+        nf = len(c["xy"])
+        out = np.full(nf, -1, np.int32)
+        b = [float(x) for x in c["cam"][6:10]]
+        rc = ext._lib.orbx_search_local_points(ext._h, b[0], b[1], b[2], b[3], len(c["proj"]), c["proj"].ctypes.data, c["view_cos"].ctypes.data,
+                                               c["level"].ctypes.data, c["mp_desc"].ctypes.data, c["valid"].ctypes.data, c["nobs"].ctypes.data,
+                                               nf, c["xy"].ctypes.data, c["octave"].ctypes.data, c["uright"].ctypes.data, c["desc"].ctypes.data,
+                                               c["feat_obs"].ctypes.data, float(case["th"]), float(case.get("nnratio", self.mfNNratio)), out.ctypes.data)
+        ext._ck(rc)
+        return out, rc

@@ -154,3 +154,43 @@ def initialization_case(seed, kps, desc, window=100, nnratio=0.9, shift=(6.0, -3
                 desc1=np.ascontiguousarray(desc), xy2=np.stack([x2, y2], 1).astype(np.float32)[perm], oct2=o2[perm].astype(np.int32),
                 ang2=a2[perm].astype(np.float32), desc2=np.ascontiguousarray(d2[perm]),
                 prev_xy=np.stack([kps["x"], kps["y"]], 1).astype(np.float32), window=int(window), nnratio=float(nnratio), check_orientation=True)
+
+
+def local_points_case(seed, kps, desc, scale, th=3.0, nnratio=0.8, distractors=None):
+    """Input for ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:418-502, called by Tracking::SearchLocalPoints):
+    the frame's features (kps / desc of an extractor call, some with a right coordinate, some already holding a map point) and local
+    map points that project near them -- 1.4 points per feature on average so that claims collide, predicted levels at the feature's
+    octave or one above, viewing cosines on both sides of 0.998, descriptors with a few flipped bits."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    w, h, bf = 1242.0, 375.0, 386.1448
+    x = kps["x"].astype(np.float32); y = kps["y"].astype(np.float32)
+    octave = kps["octave"].astype(np.int32)
+    d = np.ascontiguousarray(desc)
+    if distractors is not None and len(distractors):
+        m = len(distractors)
+        x = np.concatenate([x, rng.uniform(20, w - 20, m).astype(np.float32)]); y = np.concatenate([y, rng.uniform(20, h - 20, m).astype(np.float32)])
+        octave = np.concatenate([octave, rng.integers(0, len(scale), m).astype(np.int32)]); d = np.concatenate([d, distractors])
+    nf = len(x)
+    depth = rng.uniform(4.0, 40.0, nf)
+    uright = np.where(rng.random(nf) < 0.6, x - bf / depth, -1.0).astype(np.float32)
+    feat_obs = np.where(rng.random(nf) < 0.15, rng.integers(0, 6, nf), -1).astype(np.int32)        # -1: no map point, 0: unobserved one
+    src = np.concatenate([rng.permutation(n), rng.choice(n, int(0.4 * n))])                         # the feature each map point comes from
+    npnt = len(src)
+    sc = np.asarray(scale, np.float32)
+    level = np.clip(octave[src] + rng.choice([0, 0, 1, 1, 2, -1], npnt), 0, len(sc) - 1).astype(np.int32)
+    spread = sc[level] * rng.choice([0.5, 2.0, 5.0], npnt)
+    proj = np.stack([x[src] + rng.uniform(-1, 1, npnt) * spread, y[src] + rng.uniform(-1, 1, npnt) * spread,
+                     np.where(uright[src] > 0, uright[src] + rng.uniform(-1, 1, npnt) * spread * 1.5, x[src] - bf / 10.0)], 1).astype(np.float32)
+    mpd = d[src].copy()
+    for i in range(npnt):
+        for f in rng.integers(0, 256, rng.integers(0, 40)):
+            mpd[i, f % 32] ^= np.uint8(1 << (f % 8))
+    view_cos = rng.choice(np.array([0.9, 0.99, 0.998, 0.9981, 0.9995, 1.0], np.float32), npnt).astype(np.float32)
+    perm = rng.permutation(nf)
+    inv = np.empty(nf, np.int64); inv[perm] = np.arange(nf)
+    return dict(cam=np.array([718.856, 718.856, 607.1928, 185.2157, bf, 0.5372, 0.0, w, 0.0, h], np.float32), proj=proj, view_cos=view_cos,
+                level=level, mp_desc=np.ascontiguousarray(mpd), valid=(rng.random(npnt) < 0.9).astype(np.uint8),
+                nobs=np.where(rng.random(npnt) < 0.3, 0, rng.integers(1, 9, npnt)).astype(np.int32),
+                xy=np.stack([x, y], 1).astype(np.float32)[perm], octave=octave[perm].astype(np.int32), uright=uright[perm],
+                desc=np.ascontiguousarray(d[perm]), feat_obs=feat_obs[perm], scale=sc, th=float(th), nnratio=float(nnratio))

@@ -492,3 +492,27 @@ def search_for_initialization_port(case):
 def search_for_initialization_ref(case, variant="canon"):
     """The reference's own compiled SearchForInitialization (excerpt of src/ORBmatcher.cc:780-895)."""
     return _init_call(RefExtractor.lib(variant).orbref_search_for_initialization, case)
+
+
+_LOCAL_ARGTYPES = [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _F, _F, _VP]
+
+
+def _local_call(fn, case):
+    c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+    out = np.full(len(c["xy"]), -1, np.int32)
+    fn.argtypes = _LOCAL_ARGTYPES
+    n = fn(c["cam"].ctypes.data, len(c["proj"]), c["proj"].ctypes.data, c["view_cos"].ctypes.data, c["level"].ctypes.data, c["mp_desc"].ctypes.data,
+           c["valid"].ctypes.data, c["nobs"].ctypes.data, len(c["xy"]), c["xy"].ctypes.data, c["octave"].ctypes.data, c["uright"].ctypes.data,
+           c["desc"].ctypes.data, c["feat_obs"].ctypes.data, c["scale"].ctypes.data, len(c["scale"]), float(case["th"]), float(case["nnratio"]),
+           out.ctypes.data)
+    return out, n
+
+
+def search_local_points_port(case):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) by the C port: (index of the newly assigned map point per feature, nmatches)."""
+    return _local_call(Oracle.lib().orbo_search_local_points, case)
+
+
+def search_local_points_ref(case, variant="canon"):
+    """The reference's own compiled function (excerpt of src/ORBmatcher.cc:418-511)."""
+    return _local_call(RefExtractor.lib(variant).orbref_search_local_points, case)

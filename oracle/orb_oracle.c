@@ -795,6 +795,79 @@ int orbo_search_for_initialization(const float *cam, int n1, const float *xy1, c
     return nmatches;
 }
 
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th), src/ORBmatcher.cc:418-502: every local map
+ * point that isInFrustum looks in a window of RadiusByViewingCos (x th) x scale[predicted level] around its projection, levels
+ * (predicted - 1, predicted); features that hold an observed map point are skipped (also those assigned earlier in this call);
+ * best / second best with their octaves, TH_HIGH, ratio only when both are on the same level. */
+int orbo_search_local_points(const float *cam, int nP, const float *proj, const float *view_cos, const int32_t *level, const uint8_t *mp_desc,
+                             const uint8_t *valid, const int32_t *nobs, int nF, const float *xy, const int32_t *octave, const float *uright,
+                             const uint8_t *desc, const int32_t *feat_obs, const float *scale, int nlevels, float th, float nnratio,
+                             int32_t *feat_match)
+{
+    (void)nlevels;
+    const float minX = cam[6], maxX = cam[7], minY = cam[8], maxY = cam[9];
+    const float wInv = 64.0f / (maxX - minX), hInv = 48.0f / (maxY - minY);
+    int *cell = (int *)malloc(sizeof(int) * (size_t)(nF > 0 ? nF : 1));
+    int *off = (int *)calloc(64 * 48 + 1, sizeof(int)), *idx = (int *)malloc(sizeof(int) * (size_t)(nF > 0 ? nF : 1));
+    for (int i = 0; i < nF; ++i) {
+        const int px = (int)roundf((xy[2 * i] - minX) * wInv), py = (int)roundf((xy[2 * i + 1] - minY) * hInv);
+        cell[i] = (px < 0 || px >= 64 || py < 0 || py >= 48) ? -1 : px * 48 + py;
+        if (cell[i] >= 0) off[cell[i] + 1]++;
+    }
+    for (int c = 0; c < 64 * 48; ++c) off[c + 1] += off[c];
+    {
+        int *fill = (int *)calloc(64 * 48, sizeof(int));
+        for (int i = 0; i < nF; ++i) if (cell[i] >= 0) idx[off[cell[i]] + fill[cell[i]]++] = i;
+        free(fill);
+    }
+    int *held_obs = (int *)malloc(sizeof(int) * (size_t)(nF > 0 ? nF : 1));
+    for (int j = 0; j < nF; ++j) { held_obs[j] = feat_obs[j] > 0 ? feat_obs[j] : 0; feat_match[j] = -1; }
+    const int bFactor = th != 1.0;
+    int nmatches = 0;
+    for (int i = 0; i < nP; ++i) {
+        if (!valid[i]) continue;
+        const int lvl = level[i];
+        float r = view_cos[i] > 0.998 ? 2.5f : 4.0f;                           /* RadiusByViewingCos, :504-510 (float vs double 0.998) */
+        if (bFactor) r *= th;
+        const float radius = r * scale[lvl];
+        const float x = proj[3 * i], y = proj[3 * i + 1];
+        const int minLevel = lvl - 1, maxLevel = lvl;
+        int nMinCellX = (int)floorf((x - minX - radius) * wInv); if (nMinCellX < 0) nMinCellX = 0;
+        if (nMinCellX >= 64) continue;
+        int nMaxCellX = (int)ceilf((x - minX + radius) * wInv); if (nMaxCellX > 63) nMaxCellX = 63;
+        if (nMaxCellX < 0) continue;
+        int nMinCellY = (int)floorf((y - minY - radius) * hInv); if (nMinCellY < 0) nMinCellY = 0;
+        if (nMinCellY >= 48) continue;
+        int nMaxCellY = (int)ceilf((y - minY + radius) * hInv); if (nMaxCellY > 47) nMaxCellY = 47;
+        if (nMaxCellY < 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+            for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+                for (int k = off[ix * 48 + iy]; k < off[ix * 48 + iy + 1]; ++k) {
+                    const int j = idx[k];
+                    if (octave[j] < minLevel) continue;                        /* bCheckLevels is always true here: maxLevel >= 0 */
+                    if (octave[j] > maxLevel) continue;
+                    const float distx = xy[2 * j] - x, disty = xy[2 * j + 1] - y;
+                    if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+                    if (held_obs[j] > 0) continue;
+                    if (uright[j] > 0) {
+                        const float er = fabsf(proj[3 * i + 2] - uright[j]);
+                        if (er > radius) continue;
+                    }
+                    const int dist = orbo_hamming256(mp_desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = octave[j]; bestIdx = j; }
+                    else if (dist < bestDist2) { bestLevel2 = octave[j]; bestDist2 = dist; }
+                }
+        if (bestDist <= 100) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            feat_match[bestIdx] = i; held_obs[bestIdx] = nobs[i] > 0 ? nobs[i] : 0;
+            ++nmatches;
+        }
+    }
+    free(cell); free(off); free(idx); free(held_obs);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------- vocabulary
  * DBoW2 as vendored by the reference (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the tree built the way
  * loadFromTextFile builds it (:1338-1418: node ids in file order, children in file order, word ids in order of the

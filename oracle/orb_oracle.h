@@ -93,6 +93,13 @@ int orbo_search_by_projection(const float *cam, const float *Tc, const float *Tl
 int orbo_search_for_initialization(const float *cam, int n1, const float *xy1, const int32_t *oct1, const float *ang1, const uint8_t *desc1,
                                    int n2, const float *xy2, const int32_t *oct2, const float *ang2, const uint8_t *desc2,
                                    float *prev_xy, int window, float nnratio, int check_orientation, int32_t *m12);
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:418-502) with
+ * RadiusByViewingCos (:504-510).  proj [nP][3] = mTrackProjX, mTrackProjY, mTrackProjXR; valid = mbTrackInView && !isBad();
+ * feat_obs[j] = Observations() of the map point feature j holds (< 0: no map point); feat_match[j] = index of the newly assigned point. */
+int orbo_search_local_points(const float *cam, int nP, const float *proj, const float *view_cos, const int32_t *level, const uint8_t *mp_desc,
+                             const uint8_t *valid, const int32_t *nobs, int nF, const float *xy, const int32_t *octave, const float *uright,
+                             const uint8_t *desc, const int32_t *feat_obs, const float *scale, int nlevels, float th, float nnratio,
+                             int32_t *feat_match);
 /* DBoW2 vocabulary tree as the reference vendors it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): built from the rows
  * of an ORBvoc text file (parent id, leaf flag, 32 descriptor bytes, weight per node, file order), descent per feature,
  * BowVector / FeatureVector assembly.  scoring: 0 L1, 1 L2, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT;

@@ -84,4 +84,40 @@ int orbref_search_for_initialization(const float *cam, int n1, const float *xy1,
     return n;
 }
 
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:418-502), the matcher of
+// Tracking::SearchLocalPoints (src/Tracking.cc:3464).  proj [nP][3] = mTrackProjX, mTrackProjY, mTrackProjXR; valid[i] = mbTrackInView
+// && !isBad(); feat_obs[j] = Observations() of the map point feature j already holds (<= 0: none / unobserved).  feat_match[j] receives
+// the index of the map point the function assigns to feature j (-1 = left as it was).  Returns nmatches.
+int orbref_search_local_points(const float *cam, int nP, const float *proj, const float *view_cos, const int32_t *level, const uint8_t *mp_desc,
+                               const uint8_t *valid, const int32_t *nobs, int nF, const float *xy_un, const int32_t *octave, const float *uright,
+                               const uint8_t *desc, const int32_t *feat_obs, const float *scale, int nlevels, float th, float nnratio,
+                               int32_t *feat_match)
+{
+    ORB_SLAM2::Frame F;
+    const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::vector<float> ang((size_t)nF, 0.f);
+    fill_frame(F, cam, eye, nF, xy_un, octave, ang.data(), uright, desc, scale, nlevels);
+    F.AssignFeaturesToGrid();
+    std::vector<ORB_SLAM2::MapPoint> pts((size_t)nP), held((size_t)nF);
+    std::vector<ORB_SLAM2::MapPoint *> vp((size_t)nP);
+    for (int i = 0; i < nP; ++i) {
+        pts[i].mDescriptor = cv::Mat(1, 32, CV_8UC1, (void *)(mp_desc + 32 * (size_t)i), 32);
+        pts[i].nObs = nobs[i];
+        pts[i].mbTrackInView = valid[i] != 0;
+        pts[i].mnTrackScaleLevel = level[i];
+        pts[i].mTrackViewCos = view_cos[i];
+        pts[i].mTrackProjX = proj[3 * i]; pts[i].mTrackProjY = proj[3 * i + 1]; pts[i].mTrackProjXR = proj[3 * i + 2];
+        vp[i] = &pts[i];
+    }
+    for (int j = 0; j < nF; ++j)
+        if (feat_obs[j] >= 0) { held[j].nObs = feat_obs[j]; F.mvpMapPoints[j] = &held[j]; }
+    ORB_SLAM2::ORBmatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(F, vp, th);
+    for (int j = 0; j < nF; ++j) {
+        ORB_SLAM2::MapPoint *p = F.mvpMapPoints[j];
+        feat_match[j] = (p && p >= &pts[0] && p < &pts[0] + nP) ? (int32_t)(p - &pts[0]) : -1;
+    }
+    return n;
+}
+
 } // extern "C"

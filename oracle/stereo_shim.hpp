@@ -4,7 +4,7 @@
 // (include/ORBmatcher.h:37-109) that the excerpted reference functions touch -- Frame::ComputeStereoMatches
 // (src/Frame.cc:849-1038), Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid (:601-616, 710-776),
 // ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) (src/ORBmatcher.cc:1958-2102), SearchForInitialization (:780-895),
-// ComputeThreeMaxima and
+// SearchByProjection(Frame&, const vector<MapPoint*>&, th) with RadiusByViewingCos (:418-511), ComputeThreeMaxima and
 // DescriptorDistance -- so that those function bodies compile UNMODIFIED from excerpts made at build time
 // (oracle/Makefile).  Member names and types are the reference's; everything else of the classes is left out.
 #ifndef ORACLE_STEREO_SHIM_HPP
@@ -29,8 +29,13 @@ public:
     cv::Mat GetWorldPos() { return mWorldPos.clone(); }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
     int Observations() { return nObs; }
+    bool isBad() { return bad; }
     cv::Mat mWorldPos, mDescriptor;      // 3x1 CV_32F, 1x32 CV_8U
     int nObs;
+    // what Frame::isInFrustum leaves for SearchByProjection(Frame&, vector<MapPoint*>&, th) (include/MapPoint.h:88-94)
+    float mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos;
+    bool mbTrackInView = false, bad = false;
+    int mnTrackScaleLevel = 0;
 };
 
 class ORBmatcher {                       // the one declaration every oracle translation unit uses
@@ -38,6 +43,8 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono, std::vector<int> &TemperalMatch);
+    int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
+    float RadiusByViewingCos(const float &viewCos);
     int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;

@@ -299,6 +299,22 @@ def test_search_for_initialization_vs_oracle(orb, oracle_mod):
     assert gn == 0 and (gm == -1).all() and np.array_equal(gp, case["prev_xy"])
 
 
+def test_search_local_points_vs_oracle(orb, oracle_mod):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:418-502): windows, gates and Hamming distances on the GPU and
+    the claim bookkeeping replayed on the host give the oracle's map point per feature and nmatches."""
+    from test_oracle_vs_ref import _local_points_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    m = orb.ORBmatcher(0.8, True, extractor=ext)
+    for case in _local_points_cases(oracle_mod):
+        exp, nexp = oracle_mod.search_local_points_port(case)
+        got, n = m.SearchLocalPoints(case)
+        assert n == nexp and np.array_equal(got, exp)
+    empty = dict(case, proj=np.zeros((0, 3), np.float32), view_cos=np.zeros(0, np.float32), level=np.zeros(0, np.int32),
+                 mp_desc=np.zeros((0, 32), np.uint8), valid=np.zeros(0, np.uint8), nobs=np.zeros(0, np.int32))
+    got, n = m.SearchLocalPoints(empty)
+    assert n == 0 and (got == -1).all()
+
+
 def test_vocabulary_transform_vs_oracle(orb, oracle_mod, tmp_path):
     """Frame::ComputeBoW (src/Frame.cc:778-785): ORBVocabulary::loadFromTextFile + transform on the GPU against the oracle
     port (pinned to the reference's DBoW2): words, nodes, weights per descriptor; BowVector values bit-identical."""

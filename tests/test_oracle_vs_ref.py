@@ -292,6 +292,28 @@ def test_search_for_initialization_port_vs_reference(oracle_mod):
     assert total > 300
 
 
+def _local_points_cases(oracle_mod):
+    from multimot_track_b200.synth import local_points_case, value_noise_frame
+    o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
+    k, d = o(value_noise_frame(0, 375, 1242))
+    _, d2 = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)(value_noise_frame(1, 375, 1242))
+    sc = o.tables()["scale"]
+    # (seed, th, nnratio): Tracking's th for RGB-D (3), monocular (1: bFactor off), after relocalisation (5); a strict ratio
+    return [local_points_case(s, k, d, sc, th, r, d2[:700]) for s, th, r in ((1, 3.0, 0.8), (2, 1.0, 0.8), (3, 5.0, 0.8), (4, 3.0, 0.6))]
+
+
+def test_search_local_points_port_vs_reference(oracle_mod):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th): the C port against the reference's own function (src/ORBmatcher.cc:418-511
+    excerpted unmodified, with Frame::GetFeaturesInArea): the map point assigned to every feature and nmatches."""
+    for case in _local_points_cases(oracle_mod):
+        a, na = oracle_mod.search_local_points_port(case)
+        assert na > 800 and na >= (a >= 0).sum() > 800
+        assert case["valid"][a[a >= 0]].all() and not (case["feat_obs"][a >= 0] > 0).any()        # valid points only, never onto an observed one
+        if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_search_local_points"):
+            b, nb = oracle_mod.search_local_points_ref(case)
+            assert nb == na and np.array_equal(a, b)
+
+
 def test_minicv_float_gemm_against_live_cv2(oracle_mod):
     """The projection matcher's `Rcw*x3Dw+tcw` and `-Rcw.t()*tcw` (src/ORBmatcher.cc:1968-1976, 1990-1991) go through cv::gemm;
     the port's arithmetic (float accumulation for A*B+C, double for the transposed product) is pinned to cv2 4.13 here."""
