@@ -403,7 +403,16 @@ def main():
             for _ in range(20):
                 _, nloc = mt.SearchLocalPoints(lc)
             t_loc = (time.perf_counter() - t0) / 20
-            extras = {"search_local_points": {"workload": "ORBmatcher::SearchByProjection(F, vpMapPoints, th=3), %d map points x %d features" % (len(lc["proj"]), len(lc["xy"])),
+            from multimot_track_b200.synth import bow_match_case
+            bc = bow_match_case(1, kL, dL, 0.7, dR[:600])
+            mt.SearchByBoW(bc)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                _, nbow = mt.SearchByBoW(bc)
+            t_bowm = (time.perf_counter() - t0) / 20
+            extras = {"search_by_bow": {"workload": "ORBmatcher::SearchByBoW(pKF, F), %d x %d features in %d / %d nodes" % (len(kL), len(bc["f_desc"]), len(bc["kf_nodes"]), len(bc["f_nodes"])),
+                                        "ms_per_call": 1e3 * t_bowm, "nmatches": int(nbow)},
+                      "search_local_points": {"workload": "ORBmatcher::SearchByProjection(F, vpMapPoints, th=3), %d map points x %d features" % (len(lc["proj"]), len(lc["xy"])),
                                               "ms_per_call": 1e3 * t_loc, "nmatches": int(nloc)},
                       "search_for_initialization": {"workload": "ORBmatcher::SearchForInitialization, %d x %d keypoints, window 100, ratio 0.9" % (len(kL), len(ic["xy2"])),
                                                     "ms_per_call": 1e3 * t_init, "nmatches": int(ninit)},

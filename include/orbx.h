@@ -278,6 +278,21 @@ int orbx_search_local_points(orbx_handle *h, float min_x, float max_x, float min
                              int n_feat, const float *feat_xy, const int32_t *feat_octave, const float *feat_uright,
                              const uint8_t *feat_desc, const int32_t *feat_obs, float th, float nnratio, int32_t *feat_match);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches, ..) (src/ORBmatcher.cc:532-663), the matcher of
+ * Tracking::TrackReferenceKeyFrame (src/Tracking.cc:2853) and Relocalization (:3651): features are compared only inside the
+ * vocabulary nodes the two DBoW2::FeatureVectors share.  Key frame, per feature i < n_kf: kf_angle (mvKeysUn), kf_desc[i][32],
+ * kf_valid[i] (GetMapPointMatches()[i] is set and not bad); frame, per feature j < n_f: f_angle (mvKeys), f_desc[j][32].  The
+ * feature vectors are flattened in map order as orbx_voc_bow returns them: node k of *_nnodes has id *_nodes[k] (ascending) and
+ * owns the feature indices *_feats[*_off[k] .. *_off[k+1]).  f_match[j] receives the key-frame feature whose map point feature j
+ * is matched to (vpMapPointMatches[j] = vpMapPointsKF[f_match[j]]), -1 for none; with check_orientation the rotation histogram
+ * pruning is applied.  All pair distances inside the shared nodes are computed on the GPU; the walk in which an already matched
+ * frame feature is skipped (:582-583) is replayed on the host.  Host pointers.  Returns nmatches or a negative status. */
+int orbx_search_by_bow(orbx_handle *h, int n_kf, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid,
+                       int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_off, const int32_t *kf_feats,
+                       int n_f, const float *f_angle, const uint8_t *f_desc,
+                       int f_nnodes, const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats,
+                       float nnratio, int check_orientation, int32_t *f_match);
+
 /* ---- bag-of-words vocabulary -------------------------------- */
 
 /* The DBoW2 vocabulary tree of the reference (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,

@@ -111,6 +111,42 @@ int resolve_local_matches(int n_mp, int n_feat, const unsigned long long *cand, 
     return nmatches;
 }
 
+// The sequential part of ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:532-663) over the distances of
+// k_bow_pair_distances: entries in the order of the merge walk (node ascending, key-frame features in node order); a frame feature
+// matched earlier is skipped (:582-583), best / second best (:589-598), TH_LOW and ratio (:601-603), rotation histogram whose
+// pruning clears and decrements unconditionally (:641-654).  entries[e] = {key-frame feature, first slot in f_feats, count, first distance}.
+int resolve_bow_matches(int n_entries, const int *entries, const uint16_t *dist, const int32_t *f_feats, int n_f, const float *kf_angle,
+                        const float *f_angle, float nnratio, int check_orientation, int32_t *f_match)
+{
+    for (int j = 0; j < n_f; ++j) f_match[j] = -1;
+    std::vector<int> hist_item, hist_bin;
+    int nmatches = 0;
+    for (int e = 0; e < n_entries; ++e) {
+        const int ik = entries[4 * e], lo = entries[4 * e + 1], cnt = entries[4 * e + 2], at = entries[4 * e + 3];
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int t = 0; t < cnt; ++t) {
+            const int jf = f_feats[lo + t];
+            if (f_match[jf] >= 0) continue;
+            const int d = dist[at + t];
+            if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = jf; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist1 <= ORBX_TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+            f_match[bestIdxF] = ik;
+            if (check_orientation) { hist_item.push_back(bestIdxF); hist_bin.push_back(rotation_bin_host(kf_angle[ik], f_angle[bestIdxF])); }
+            ++nmatches;
+        }
+    }
+    if (check_orientation) {
+        int cnt[ORBX_HISTO_LENGTH] = {0}, i1, i2, i3;
+        for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
+        three_maxima_host(cnt, i1, i2, i3);
+        for (size_t k = 0; k < hist_bin.size(); ++k)
+            if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3) { f_match[hist_item[k]] = -1; --nmatches; }
+    }
+    return nmatches;
+}
+
 // cand: compact lists of packed candidates (cell << 32 | feature index << 16 | distance); point i owns cand[offset[i] .. + count[i])
 int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                                const float *last_angle, const float *cur_angle, int check_orientation, int32_t *cur_match)

@@ -2056,6 +2056,34 @@ cudaError_t launch_local_candidates(const ProjSetup &S, int n_mp, const float *d
     return cudaGetLastError();
 }
 
+// The distances of ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:555-598): entry e = one key-frame feature with a
+// good map point in a vocabulary node both feature vectors share, (x: key-frame feature, y: first slot of the node in the frame's
+// flattened feature vector, z: number of frame features there, w: first output slot); one warp per entry, lane = frame feature.
+__global__ void __launch_bounds__(256)
+k_bow_pair_distances(int n_entries, const int4 *__restrict__ entries, const uint8_t *__restrict__ kf_desc, const uint8_t *__restrict__ f_desc,
+                     const int32_t *__restrict__ f_feats, uint16_t *__restrict__ out)
+{
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n_entries) return;
+    const int4 E = entries[e];
+    const uint4 a0 = reinterpret_cast<const uint4 *>(kf_desc)[2 * (long long)E.x], a1 = reinterpret_cast<const uint4 *>(kf_desc)[2 * (long long)E.x + 1];
+    for (int t = lane; t < E.z; t += 32) {
+        const long long j = f_feats[E.y + t];
+        const uint4 b0 = reinterpret_cast<const uint4 *>(f_desc)[2 * j], b1 = reinterpret_cast<const uint4 *>(f_desc)[2 * j + 1];
+        out[E.w + t] = (uint16_t)(__popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                  __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w));
+    }
+}
+
+cudaError_t launch_bow_pair_distances(int n_entries, const int4 *d_entries, const uint8_t *d_kf_desc, const uint8_t *d_f_desc, const int32_t *d_f_feats,
+                                      uint16_t *d_out, cudaStream_t st, LaunchStats *ls)
+{
+    if (n_entries <= 0) return cudaSuccess;
+    k_bow_pair_distances<<<(n_entries + 7) / 8, 256, 0, st>>>(n_entries, d_entries, d_kf_desc, d_f_desc, d_f_feats, d_out);
+    ls->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_window_candidates(const ProjSetup &S, int n1, const float *d_prev_xy, const int32_t *d_oct1, const uint8_t *d_desc1, int n2,
                                      const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, unsigned long long *d_cand, int *d_count,
                                      int *d_offset, int *d_total, cudaStream_t st, LaunchStats *ls)

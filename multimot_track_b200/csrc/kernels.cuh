@@ -106,6 +106,8 @@ cudaError_t launch_local_candidates(const ProjSetup &S, int n_mp, const float *d
                                     const uint8_t *d_mp_desc, const uint8_t *d_valid, int n_feat, const float *d_xy, const int32_t *d_octave,
                                     const float *d_uright, const uint8_t *d_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
                                     int *d_total, cudaStream_t st, LaunchStats *ls);
+cudaError_t launch_bow_pair_distances(int n_entries, const int4 *d_entries, const uint8_t *d_kf_desc, const uint8_t *d_f_desc, const int32_t *d_f_feats,
+                                      uint16_t *d_out, cudaStream_t st, LaunchStats *ls);
 constexpr int kProjCap = 512;        // candidates one search window may hold (d_cand needs n_last * kProjCap entries)
 cudaError_t launch_bow_descent(const uint8_t *d_feat, int n, const int32_t *d_child_off, const int32_t *d_child_ids, const uint8_t *d_node_desc,
                                const int32_t *d_word_id, int nid_level, int32_t *d_word, int32_t *d_node, int32_t *d_final, cudaStream_t st, LaunchStats *ls);

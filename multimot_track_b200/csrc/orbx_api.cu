@@ -921,6 +921,58 @@ extern "C" int orbx_search_local_points(orbx_handle *h, float min_x, float max_x
     return resolve_local_matches(n_mp, n_feat, cand.data(), count.data(), offset.data(), nobs, feat_octave, feat_obs, nnratio, feat_match);
 }
 
+extern "C" int orbx_search_by_bow(orbx_handle *h, int n_kf, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid,
+                                  int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_off, const int32_t *kf_feats,
+                                  int n_f, const float *f_angle, const uint8_t *f_desc,
+                                  int f_nnodes, const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats,
+                                  float nnratio, int check_orientation, int32_t *f_match)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (n_kf < 0 || n_f < 0 || kf_nnodes < 0 || f_nnodes < 0 || (n_kf > 0 && (!kf_angle || !kf_desc || !kf_valid)) ||
+        (kf_nnodes > 0 && (!kf_nodes || !kf_off || !kf_feats)) || (n_f > 0 && (!f_angle || !f_desc || !f_match)) ||
+        (f_nnodes > 0 && (!f_nodes || !f_off || !f_feats)))
+        return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: bad argument");
+    for (int j = 0; j < n_f; ++j) f_match[j] = -1;
+    if (n_kf == 0 || n_f == 0 || kf_nnodes == 0 || f_nnodes == 0) return 0;
+    if (kf_off[kf_nnodes] > n_kf || f_off[f_nnodes] > n_f) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: feature vector longer than the feature count");
+    for (int k = 0; k < kf_off[kf_nnodes]; ++k) if (kf_feats[k] < 0 || kf_feats[k] >= n_kf) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: key-frame feature index out of range");
+    for (int k = 0; k < f_off[f_nnodes]; ++k) if (f_feats[k] < 0 || f_feats[k] >= n_f) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: frame feature index out of range");
+    // the merge walk of :552-619 (lower_bound on sorted maps == advancing the smaller side)
+    std::vector<int> entries;
+    long long npairs = 0;
+    for (int a = 0, b = 0; a < kf_nnodes && b < f_nnodes;) {
+        if (kf_nodes[a] < f_nodes[b]) { ++a; continue; }
+        if (kf_nodes[a] > f_nodes[b]) { ++b; continue; }
+        const int cnt = f_off[b + 1] - f_off[b];
+        for (int p = kf_off[a]; p < kf_off[a + 1] && cnt > 0; ++p) {
+            const int ik = kf_feats[p];
+            if (!kf_valid[ik]) continue;
+            entries.push_back(ik); entries.push_back(f_off[b]); entries.push_back(cnt); entries.push_back((int)npairs);
+            npairs += cnt;
+        }
+        ++a; ++b;
+    }
+    const int ne = (int)(entries.size() / 4);
+    if (ne == 0) return 0;
+    if (npairs > (1ll << 30)) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_by_bow: more than 2^30 descriptor pairs");
+    CU(cudaSetDevice(h->device));
+    auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_ent = 0, o_kd = o_ent + up((size_t)ne * 16), o_fd = o_kd + up((size_t)n_kf * 32), o_ff = o_fd + up((size_t)n_f * 32),
+                 o_out = o_ff + up((size_t)f_off[f_nnodes] * 4), total = o_out + up((size_t)npairs * 2);
+    uint8_t *d = nullptr;
+    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+    cudaStream_t st = h->stream;
+    std::vector<uint16_t> dist((size_t)npairs);
+    CU(cudaMemcpyAsync(d + o_ent, entries.data(), (size_t)ne * 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_kd, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_fd, f_desc, (size_t)n_f * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_ff, f_feats, (size_t)f_off[f_nnodes] * 4, cudaMemcpyHostToDevice, st));
+    CU(launch_bow_pair_distances(ne, (const int4 *)(d + o_ent), d + o_kd, d + o_fd, (const int32_t *)(d + o_ff), (uint16_t *)(d + o_out), st, &h->stats));
+    CU(cudaMemcpyAsync(dist.data(), d + o_out, (size_t)npairs * 2, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return resolve_bow_matches(ne, entries.data(), dist.data(), f_feats, n_f, kf_angle, f_angle, nnratio, check_orientation, f_match);
+}
+
 // --------------------------------------------------------------- vocabulary
 
 struct orbx_vocabulary {

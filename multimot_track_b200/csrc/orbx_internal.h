@@ -97,6 +97,10 @@ int resolve_initialization_matches(int n1, int n2, const unsigned long long *can
 int resolve_local_matches(int n_mp, int n_feat, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                           const int32_t *feat_octave, const int32_t *feat_obs, float nnratio, int32_t *feat_match);
 
+// ... and of SearchByBoW(KeyFrame*, Frame&, ...) over the per-node pair distances
+int resolve_bow_matches(int n_entries, const int *entries, const uint16_t *dist, const int32_t *f_feats, int n_f, const float *kf_angle,
+                        const float *f_angle, float nnratio, int check_orientation, int32_t *f_match);
+
 // DBoW2 vocabulary tree (vocabulary.cpp): node 0 is the root, children of node i are child_ids[child_off[i] .. child_off[i+1])
 struct VocHost {
     int k = 0, L = 0, scoring = 0, weighting = 0, nnodes = 0, nwords = 0;

@@ -100,3 +100,20 @@ class ORBmatcher:
                                                c["feat_obs"].ctypes.data, float(case["th"]), float(case.get("nnratio", self.mfNNratio)), out.ctypes.data)
         ext._ck(rc)
         return out, rc
+
+    def SearchByBoW(self, case):
+        """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches, ..) (src/ORBmatcher.cc:532-663).  `case`
+        (multimot_track_b200.synth.bow_match_case): kf_angle, kf_desc, kf_valid, kf_nodes / kf_off / kf_feats, f_angle, f_desc,
+        f_nodes / f_off / f_feats (feature vectors flattened in map order), nnratio, check_orientation.
+        Returns (key-frame feature matched to every frame feature, nmatches)."""
+        c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+        ext = self._ext
+        nf = len(c["f_desc"])
+        out = np.full(nf, -1, np.int32)
+        rc = ext._lib.orbx_search_by_bow(ext._h, len(c["kf_desc"]), c["kf_angle"].ctypes.data, c["kf_desc"].ctypes.data, c["kf_valid"].ctypes.data,
+                                         len(c["kf_nodes"]), c["kf_nodes"].ctypes.data, c["kf_off"].ctypes.data, c["kf_feats"].ctypes.data,
+                                         nf, c["f_angle"].ctypes.data, c["f_desc"].ctypes.data, len(c["f_nodes"]), c["f_nodes"].ctypes.data,
+                                         c["f_off"].ctypes.data, c["f_feats"].ctypes.data, float(case.get("nnratio", self.mfNNratio)),
+                                         int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), out.ctypes.data)
+        ext._ck(rc)
+        return out, rc

@@ -194,3 +194,47 @@ def local_points_case(seed, kps, desc, scale, th=3.0, nnratio=0.8, distractors=N
                 nobs=np.where(rng.random(npnt) < 0.3, 0, rng.integers(1, 9, npnt)).astype(np.int32),
                 xy=np.stack([x, y], 1).astype(np.float32)[perm], octave=octave[perm].astype(np.int32), uright=uright[perm],
                 desc=np.ascontiguousarray(d[perm]), feat_obs=feat_obs[perm], scale=sc, th=float(th), nnratio=float(nnratio))
+
+
+def feature_vector(nodes):
+    """DBoW2::FeatureVector of per-feature node ids, flattened in map order: (node ids ascending, offsets, feature indices ascending
+    within a node), the layout orbx_voc_bow returns."""
+    nodes = np.asarray(nodes)
+    order = np.argsort(nodes, kind="stable")
+    ids, counts = np.unique(nodes, return_counts=True)
+    return ids.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+
+
+def _toy_nodes(desc):
+    """A stand-in for the vocabulary node of a descriptor that is stable under a few bit flips: quantised popcounts of byte groups."""
+    pc = np.unpackbits(desc, axis=1).reshape(len(desc), 4, 64).sum(2)
+    return ((pc[:, 0] // 6) * 36 + (pc[:, 1] // 6) * 6 + pc[:, 2] // 6).astype(np.int32)
+
+
+def bow_match_case(seed, kps, desc, nnratio=0.7, distractors=None, node_fn=_toy_nodes):
+    """Input for ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches, ..) (src/ORBmatcher.cc:532-663): the key frame = one extractor
+    call (85 % of its features hold a good map point); the frame = its descriptors with a few flipped bits, near-duplicates (so that
+    claims collide inside a node), shuffled, plus distractors; node ids per feature from `node_fn` (a vocabulary transform or the toy
+    quantiser above), flattened like DBoW2::FeatureVector."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    fd = desc.copy()
+    for i in range(n):
+        for f in rng.integers(0, 256, rng.integers(0, 24)):
+            fd[i, f % 32] ^= np.uint8(1 << (f % 8))
+    fa = ((kps["angle"] + rng.normal(0, 5, n)) % 360).astype(np.float32)
+    dup = rng.choice(n, n // 5, replace=False)
+    dd = fd[dup].copy()
+    for i in range(len(dup)):
+        for f in rng.integers(0, 256, rng.integers(0, 6)):
+            dd[i, f % 32] ^= np.uint8(1 << (f % 8))
+    fd = np.concatenate([fd, dd]); fa = np.concatenate([fa, ((fa[dup] + rng.normal(0, 30, len(dup))) % 360).astype(np.float32)])
+    if distractors is not None and len(distractors):
+        fd = np.concatenate([fd, distractors]); fa = np.concatenate([fa, rng.uniform(0, 360, len(distractors)).astype(np.float32)])
+    perm = rng.permutation(len(fd))
+    fd = np.ascontiguousarray(fd[perm]); fa = fa[perm].astype(np.float32)
+    kd = np.ascontiguousarray(desc)
+    kn, ko, kf = feature_vector(node_fn(kd))
+    fn_, fo, ff = feature_vector(node_fn(fd))
+    return dict(kf_angle=kps["angle"].astype(np.float32), kf_desc=kd, kf_valid=(rng.random(n) < 0.85).astype(np.uint8), kf_nodes=kn, kf_off=ko, kf_feats=kf,
+                f_angle=fa, f_desc=fd, f_nodes=fn_, f_off=fo, f_feats=ff, nnratio=float(nnratio), check_orientation=True)

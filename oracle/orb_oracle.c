@@ -868,6 +868,50 @@ int orbo_search_local_points(const float *cam, int nP, const float *proj, const 
     return nmatches;
 }
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, ...), src/ORBmatcher.cc:532-663: merge walk over the two feature vectors; in a shared
+ * node every key-frame feature with a good map point scans the frame's features of that node that are still unmatched; TH_LOW, ratio,
+ * rotation histogram whose pruning decrements unconditionally (:649-654). */
+int orbo_search_by_bow(int nK, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid, int nk_nodes, const int32_t *kf_nodes,
+                       const int32_t *kf_off, const int32_t *kf_feats, int nF, const float *f_angle, const uint8_t *f_desc, int nf_nodes,
+                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats, float nnratio, int check_orientation, int32_t *f_match)
+{
+    (void)nK;
+    for (int j = 0; j < nF; ++j) f_match[j] = -1;
+    int *hist_item = (int *)malloc(sizeof(int) * (size_t)(nF > 0 ? nF : 1)), *hist_bin = (int *)malloc(sizeof(int) * (size_t)(nF > 0 ? nF : 1));
+    int nh = 0, nmatches = 0, a = 0, b = 0;
+    while (a < nk_nodes && b < nf_nodes) {
+        if (kf_nodes[a] < f_nodes[b]) { ++a; continue; }                       /* lower_bound on a sorted map == advance */
+        if (kf_nodes[a] > f_nodes[b]) { ++b; continue; }
+        for (int p = kf_off[a]; p < kf_off[a + 1]; ++p) {
+            const int ik = kf_feats[p];
+            if (!kf_valid[ik]) continue;
+            int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+            for (int q = f_off[b]; q < f_off[b + 1]; ++q) {
+                const int jf = f_feats[q];
+                if (f_match[jf] >= 0) continue;
+                const int dist = orbo_hamming256(kf_desc + 32 * (size_t)ik, f_desc + 32 * (size_t)jf);
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = jf; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestDist1 <= 50 && (float)bestDist1 < nnratio * (float)bestDist2) {
+                f_match[bestIdxF] = ik;
+                if (check_orientation) { hist_item[nh] = bestIdxF; hist_bin[nh] = orbo_rotation_bin(kf_angle[ik], f_angle[bestIdxF]); ++nh; }
+                ++nmatches;
+            }
+        }
+        ++a; ++b;
+    }
+    if (check_orientation) {
+        int cnt[30] = {0}, i1 = -1, i2 = -1, i3 = -1;
+        for (int k = 0; k < nh; ++k) cnt[hist_bin[k]]++;
+        three_maxima(cnt, 30, &i1, &i2, &i3);
+        for (int k = 0; k < nh; ++k)
+            if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3) { f_match[hist_item[k]] = -1; --nmatches; }
+    }
+    free(hist_item); free(hist_bin);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------- vocabulary
  * DBoW2 as vendored by the reference (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the tree built the way
  * loadFromTextFile builds it (:1338-1418: node ids in file order, children in file order, word ids in order of the

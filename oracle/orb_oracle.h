@@ -100,6 +100,11 @@ int orbo_search_local_points(const float *cam, int nP, const float *proj, const 
                              const uint8_t *valid, const int32_t *nobs, int nF, const float *xy, const int32_t *octave, const float *uright,
                              const uint8_t *desc, const int32_t *feat_obs, const float *scale, int nlevels, float th, float nnratio,
                              int32_t *feat_match);
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:532-663).  Feature vectors flattened in map order (node j owns
+ * feats[off[j] .. off[j+1])); kf_valid = map point present and not bad; f_match[j] = key-frame feature matched to feature j. */
+int orbo_search_by_bow(int nK, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid, int nk_nodes, const int32_t *kf_nodes,
+                       const int32_t *kf_off, const int32_t *kf_feats, int nF, const float *f_angle, const uint8_t *f_desc, int nf_nodes,
+                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats, float nnratio, int check_orientation, int32_t *f_match);
 /* DBoW2 vocabulary tree as the reference vendors it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): built from the rows
  * of an ORBvoc text file (parent id, leaf flag, 32 descriptor bytes, weight per node, file order), descent per feature,
  * BowVector / FeatureVector assembly.  scoring: 0 L1, 1 L2, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT;

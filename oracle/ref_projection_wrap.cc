@@ -120,4 +120,37 @@ int orbref_search_local_points(const float *cam, int nP, const float *proj, cons
     return n;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches, TemperalMatch) (src/ORBmatcher.cc:532-663).  Feature vectors
+// flattened in map order: node j owns feats[off[j] .. off[j+1]).  kf_valid[i] = the key frame's feature i has a map point that is not
+// bad.  f_match[j] receives the key-frame feature whose map point feature j of F ends up with (-1 = none).  Returns nmatches.
+int orbref_search_by_bow(int nK, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid, int nk_nodes, const int32_t *kf_nodes,
+                         const int32_t *kf_off, const int32_t *kf_feats, int nF, const float *f_angle, const uint8_t *f_desc, int nf_nodes,
+                         const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats, float nnratio, int check_orientation, int32_t *f_match)
+{
+    ORB_SLAM2::KeyFrame KF;
+    ORB_SLAM2::Frame F;
+    std::vector<ORB_SLAM2::MapPoint> pts((size_t)nK);
+    KF.mvpMapPoints.assign((size_t)nK, (ORB_SLAM2::MapPoint *)0);
+    KF.mvKeysUn.resize((size_t)nK);
+    for (int i = 0; i < nK; ++i) {
+        KF.mvKeysUn[i] = cv::KeyPoint(0.f, 0.f, 31.f, kf_angle[i], 0.f, 0, -1);
+        if (kf_valid[i]) KF.mvpMapPoints[i] = &pts[i];
+    }
+    KF.mDescriptors = cv::Mat(nK, 32, CV_8UC1, (void *)kf_desc, 32);
+    for (int j = 0; j < nk_nodes; ++j)
+        for (int k = kf_off[j]; k < kf_off[j + 1]; ++k) KF.mFeatVec[(unsigned)kf_nodes[j]].push_back((unsigned)kf_feats[k]);
+    F.N = nF;
+    F.mvKeys.resize((size_t)nF);
+    for (int i = 0; i < nF; ++i) F.mvKeys[i] = cv::KeyPoint(0.f, 0.f, 31.f, f_angle[i], 0.f, 0, -1);
+    F.mDescriptors = cv::Mat(nF, 32, CV_8UC1, (void *)f_desc, 32);
+    for (int j = 0; j < nf_nodes; ++j)
+        for (int k = f_off[j]; k < f_off[j + 1]; ++k) F.mFeatVec[(unsigned)f_nodes[j]].push_back((unsigned)f_feats[k]);
+    ORB_SLAM2::ORBmatcher matcher(nnratio, check_orientation != 0);
+    std::vector<ORB_SLAM2::MapPoint *> out;
+    std::vector<int> temporal;
+    const int n = matcher.SearchByBoW(&KF, F, out, temporal);
+    for (int j = 0; j < nF; ++j) f_match[j] = out[j] ? (int32_t)(out[j] - &pts[0]) : -1;
+    return n;
+}
+
 } // extern "C"

@@ -4,7 +4,7 @@
 // (include/ORBmatcher.h:37-109) that the excerpted reference functions touch -- Frame::ComputeStereoMatches
 // (src/Frame.cc:849-1038), Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid (:601-616, 710-776),
 // ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) (src/ORBmatcher.cc:1958-2102), SearchForInitialization (:780-895),
-// SearchByProjection(Frame&, const vector<MapPoint*>&, th) with RadiusByViewingCos (:418-511), ComputeThreeMaxima and
+// SearchByProjection(Frame&, const vector<MapPoint*>&, th) with RadiusByViewingCos (:418-511), SearchByBoW(KeyFrame*, Frame&, ...) (:532-663), ComputeThreeMaxima and
 // DescriptorDistance -- so that those function bodies compile UNMODIFIED from excerpts made at build time
 // (oracle/Makefile).  Member names and types are the reference's; everything else of the classes is left out.
 #ifndef ORACLE_STEREO_SHIM_HPP
@@ -13,6 +13,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <vector>
 
 #include "minicv.hpp"
@@ -38,6 +39,22 @@ public:
     int mnTrackScaleLevel = 0;
 };
 
+}
+namespace DBoW2 {                        // Thirdparty/DBoW2/DBoW2/FeatureVector.h:24-27: node id -> indices of the local features under it
+typedef unsigned int NodeId;
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}
+namespace ORB_SLAM2 {
+
+class KeyFrame {                         // what SearchByBoW(KeyFrame*, Frame&, ...) reads of a key frame (include/KeyFrame.h)
+public:
+    std::vector<MapPoint *> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<MapPoint *> mvpMapPoints;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors;
+};
+
 class ORBmatcher {                       // the one declaration every oracle translation unit uses
 public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
@@ -45,6 +62,7 @@ public:
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono, std::vector<int> &TemperalMatch);
     int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
     float RadiusByViewingCos(const float &viewCos);
+    int SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vpMapPointMatches, std::vector<int> &TemperalMatch);
     int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;
@@ -78,6 +96,7 @@ public:
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     PyramidHolder *mpORBextractorLeft, *mpORBextractorRight;
     float mbf;
+    DBoW2::FeatureVector mFeatVec;
 };
 
 }

@@ -315,6 +315,30 @@ def test_search_local_points_vs_oracle(orb, oracle_mod):
     assert n == 0 and (got == -1).all()
 
 
+def test_search_by_bow_vs_oracle(orb, oracle_mod, tmp_path):
+    """ORBmatcher::SearchByBoW(pKF, F, ..) (src/ORBmatcher.cc:532-663): pair distances inside the shared vocabulary nodes on the GPU and
+    the skip-if-matched walk on the host give the oracle's matches; node ids once from the toy quantiser and once from the product's own
+    vocabulary transform (Frame::ComputeBoW, levelsup 4 as the reference calls it) on a synthetic tree."""
+    from test_oracle_vs_ref import _bow_match_cases, _voc_cases
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    m = orb.ORBmatcher(0.7, True, extractor=ext)
+    _, d = ext(synth(2, 375, 1242))
+    path, k, L = _voc_cases(tmp_path, d)[0]
+    voc = orb.ORBVocabulary(ext)
+    assert voc.loadFromTextFile(path)
+    node_fns = (None, lambda desc: voc.transform_each(np.ascontiguousarray(desc), max(L - 2, 0))[1])
+    for fn in node_fns:
+        for case in _bow_match_cases(oracle_mod, fn):
+            for c in (case, dict(case, check_orientation=False)):
+                exp, nexp = oracle_mod.search_by_bow_port(c)
+                got, n = m.SearchByBoW(c)
+                assert n == nexp and np.array_equal(got, exp)
+    empty = dict(case, f_angle=np.zeros(0, np.float32), f_desc=np.zeros((0, 32), np.uint8), f_nodes=np.zeros(0, np.int32),
+                 f_off=np.zeros(1, np.int32), f_feats=np.zeros(0, np.int32))
+    got, n = m.SearchByBoW(empty)
+    assert n == 0 and len(got) == 0
+
+
 def test_vocabulary_transform_vs_oracle(orb, oracle_mod, tmp_path):
     """Frame::ComputeBoW (src/Frame.cc:778-785): ORBVocabulary::loadFromTextFile + transform on the GPU against the oracle
     port (pinned to the reference's DBoW2): words, nodes, weights per descriptor; BowVector values bit-identical."""

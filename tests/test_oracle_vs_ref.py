@@ -314,6 +314,27 @@ def test_search_local_points_port_vs_reference(oracle_mod):
             assert nb == na and np.array_equal(a, b)
 
 
+def _bow_match_cases(oracle_mod, node_fn=None):
+    from multimot_track_b200.synth import bow_match_case, value_noise_frame
+    k, d = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)(value_noise_frame(0, 375, 1242))
+    _, d2 = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)(value_noise_frame(1, 375, 1242))
+    kw = {} if node_fn is None else {"node_fn": node_fn}
+    # (seed, nnratio): TrackReferenceKeyFrame (0.7), Relocalization (0.75), a loose and a strict ratio
+    return [bow_match_case(s, k, d, r, d2[:600], **kw) for s, r in ((1, 0.7), (2, 0.75), (3, 0.9), (4, 0.6))]
+
+
+def test_search_by_bow_port_vs_reference(oracle_mod):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...): the C port against the reference's own function (src/ORBmatcher.cc:532-663
+    excerpted unmodified): the key-frame feature matched to every frame feature and nmatches, with and without the rotation check."""
+    for case in _bow_match_cases(oracle_mod):
+        for c in (case, dict(case, check_orientation=False)):
+            a, na = oracle_mod.search_by_bow_port(c)
+            assert na == (a >= 0).sum() > 500 and case["kf_valid"][a[a >= 0]].all()
+            if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_search_by_bow"):
+                b, nb = oracle_mod.search_by_bow_ref(c)
+                assert nb == na and np.array_equal(a, b)
+
+
 def test_minicv_float_gemm_against_live_cv2(oracle_mod):
     """The projection matcher's `Rcw*x3Dw+tcw` and `-Rcw.t()*tcw` (src/ORBmatcher.cc:1968-1976, 1990-1991) go through cv::gemm;
     the port's arithmetic (float accumulation for A*B+C, double for the transposed product) is pinned to cv2 4.13 here."""
