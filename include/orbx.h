@@ -293,6 +293,17 @@ int orbx_search_by_bow(orbx_handle *h, int n_kf, const float *kf_angle, const ui
                        int f_nnodes, const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats,
                        float nnratio, int check_orientation, int32_t *f_match);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:897-1030), the matcher of
+ * LoopClosing::ComputeSim3 (src/LoopClosing.cc:267): as orbx_search_by_bow between two key frames.  valid1 / valid2: the feature
+ * holds a map point that is not bad; a feature of key frame 2 is used at most once (:948); the acceptance is bestDist1 < TH_LOW
+ * (strict, :973) and the ratio test.  matches12[i] receives the feature of key frame 2 whose map point feature i is matched to
+ * (vpMatches12[i] = vpMapPoints2[matches12[i]]), -1 for none.  Host pointers.  Returns nmatches or a negative status. */
+int orbx_search_by_bow_keyframes(orbx_handle *h, int n1, const float *angle1, const uint8_t *desc1, const uint8_t *valid1,
+                                 int nnodes1, const int32_t *nodes1, const int32_t *off1, const int32_t *feats1,
+                                 int n2, const float *angle2, const uint8_t *desc2, const uint8_t *valid2,
+                                 int nnodes2, const int32_t *nodes2, const int32_t *off2, const int32_t *feats2,
+                                 float nnratio, int check_orientation, int32_t *matches12);
+
 /* ---- bag-of-words vocabulary -------------------------------- */
 
 /* The DBoW2 vocabulary tree of the reference (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,

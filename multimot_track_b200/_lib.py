@@ -63,6 +63,7 @@ SIGNATURES = {
     "orbx_search_for_initialization": (_I, [_VP, _F, _F, _F, _F, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _F, _I, _VP]),
     "orbx_search_local_points": (_I, [_VP, _F, _F, _F, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _F, _F, _VP]),
     "orbx_search_by_bow": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _F, _I, _VP]),
+    "orbx_search_by_bow_keyframes": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _F, _I, _VP]),
     "orbx_search_by_projection": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _F, _I, _I, _VP]),
     "orbx_voc_load_text": (_I, [_VP, ctypes.c_char_p, ctypes.POINTER(_VP)]),
     "orbx_voc_create": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, ctypes.POINTER(_VP)]),

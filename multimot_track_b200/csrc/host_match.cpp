@@ -147,6 +147,41 @@ int resolve_bow_matches(int n_entries, const int *entries, const uint16_t *dist,
     return nmatches;
 }
 
+// The same walk for ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:897-1030): side 2 must hold a good
+// map point and be unmatched (:948-954), the threshold is strict (:973), the result is indexed by the features of key frame 1.
+int resolve_bow_matches_kf(int n_entries, const int *entries, const uint16_t *dist, const int32_t *feats2, int n1, int n2, const uint8_t *valid2,
+                           const float *ang1, const float *ang2, float nnratio, int check_orientation, int32_t *m12)
+{
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    std::vector<uint8_t> matched2((size_t)n2, 0);
+    std::vector<int> hist_item, hist_bin;
+    int nmatches = 0;
+    for (int e = 0; e < n_entries; ++e) {
+        const int i1 = entries[4 * e], lo = entries[4 * e + 1], cnt = entries[4 * e + 2], at = entries[4 * e + 3];
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int t = 0; t < cnt; ++t) {
+            const int i2 = feats2[lo + t];
+            if (matched2[i2] || !valid2[i2]) continue;
+            const int d = dist[at + t];
+            if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = i2; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist1 < ORBX_TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {
+            m12[i1] = bestIdx2; matched2[bestIdx2] = 1;
+            if (check_orientation) { hist_item.push_back(i1); hist_bin.push_back(rotation_bin_host(ang1[i1], ang2[bestIdx2])); }
+            ++nmatches;
+        }
+    }
+    if (check_orientation) {
+        int cnt[ORBX_HISTO_LENGTH] = {0}, i1, i2, i3;
+        for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
+        three_maxima_host(cnt, i1, i2, i3);
+        for (size_t k = 0; k < hist_bin.size(); ++k)
+            if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3) { m12[hist_item[k]] = -1; --nmatches; }
+    }
+    return nmatches;
+}
+
 // cand: compact lists of packed candidates (cell << 32 | feature index << 16 | distance); point i owns cand[offset[i] .. + count[i])
 int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *cand, const int *count, const int *offset, const int32_t *nobs,
                                const float *last_angle, const float *cur_angle, int check_orientation, int32_t *cur_match)

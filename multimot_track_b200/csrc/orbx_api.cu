@@ -921,6 +921,51 @@ extern "C" int orbx_search_local_points(orbx_handle *h, float min_x, float max_x
     return resolve_local_matches(n_mp, n_feat, cand.data(), count.data(), offset.data(), nobs, feat_octave, feat_obs, nnratio, feat_match);
 }
 
+// Shared by the two SearchByBoW entry points: the merge walk over the two flattened feature vectors (src/ORBmatcher.cc:552-619,
+// lower_bound on sorted maps == advancing the smaller side) and the GPU pair distances of every side-1 feature with valid1 set
+// against all side-2 features of the same node.  entries[e] = {side-1 feature, first slot in feats2, count, first distance}.
+static int bow_pair_distances(orbx_handle *h, const char *who, int n1, const uint8_t *desc1, const uint8_t *valid1, int nn1, const int32_t *nodes1,
+                              const int32_t *off1, const int32_t *feats1, int n2, const uint8_t *desc2, int nn2, const int32_t *nodes2,
+                              const int32_t *off2, const int32_t *feats2, std::vector<int> *entries, std::vector<uint16_t> *dist)
+{
+    entries->clear(); dist->clear();
+    if (off1[nn1] > n1 || off2[nn2] > n2) return fail(h, ORBX_ERR_BAD_ARG, std::string(who) + ": feature vector longer than the feature count");
+    for (int k = 0; k < off1[nn1]; ++k) if (feats1[k] < 0 || feats1[k] >= n1) return fail(h, ORBX_ERR_BAD_ARG, std::string(who) + ": feature index out of range (side 1)");
+    for (int k = 0; k < off2[nn2]; ++k) if (feats2[k] < 0 || feats2[k] >= n2) return fail(h, ORBX_ERR_BAD_ARG, std::string(who) + ": feature index out of range (side 2)");
+    long long npairs = 0;
+    for (int a = 0, b = 0; a < nn1 && b < nn2;) {
+        if (nodes1[a] < nodes2[b]) { ++a; continue; }
+        if (nodes1[a] > nodes2[b]) { ++b; continue; }
+        const int cnt = off2[b + 1] - off2[b];
+        for (int p = off1[a]; p < off1[a + 1] && cnt > 0; ++p) {
+            const int i1 = feats1[p];
+            if (!valid1[i1]) continue;
+            entries->push_back(i1); entries->push_back(off2[b]); entries->push_back(cnt); entries->push_back((int)npairs);
+            npairs += cnt;
+        }
+        ++a; ++b;
+    }
+    const int ne = (int)(entries->size() / 4);
+    if (ne == 0) return ORBX_OK;
+    if (npairs > (1ll << 30)) return fail(h, ORBX_ERR_UNSUPPORTED, std::string(who) + ": more than 2^30 descriptor pairs");
+    CU(cudaSetDevice(h->device));
+    auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_ent = 0, o_d1 = o_ent + up((size_t)ne * 16), o_d2 = o_d1 + up((size_t)n1 * 32), o_ff = o_d2 + up((size_t)n2 * 32),
+                 o_out = o_ff + up((size_t)off2[nn2] * 4), total = o_out + up((size_t)npairs * 2);
+    uint8_t *d = nullptr;
+    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+    cudaStream_t st = h->stream;
+    dist->resize((size_t)npairs);
+    CU(cudaMemcpyAsync(d + o_ent, entries->data(), (size_t)ne * 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_ff, feats2, (size_t)off2[nn2] * 4, cudaMemcpyHostToDevice, st));
+    CU(launch_bow_pair_distances(ne, (const int4 *)(d + o_ent), d + o_d1, d + o_d2, (const int32_t *)(d + o_ff), (uint16_t *)(d + o_out), st, &h->stats));
+    CU(cudaMemcpyAsync(dist->data(), d + o_out, (size_t)npairs * 2, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ORBX_OK;
+}
+
 extern "C" int orbx_search_by_bow(orbx_handle *h, int n_kf, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid,
                                   int kf_nnodes, const int32_t *kf_nodes, const int32_t *kf_off, const int32_t *kf_feats,
                                   int n_f, const float *f_angle, const uint8_t *f_desc,
@@ -934,43 +979,33 @@ extern "C" int orbx_search_by_bow(orbx_handle *h, int n_kf, const float *kf_angl
         return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: bad argument");
     for (int j = 0; j < n_f; ++j) f_match[j] = -1;
     if (n_kf == 0 || n_f == 0 || kf_nnodes == 0 || f_nnodes == 0) return 0;
-    if (kf_off[kf_nnodes] > n_kf || f_off[f_nnodes] > n_f) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: feature vector longer than the feature count");
-    for (int k = 0; k < kf_off[kf_nnodes]; ++k) if (kf_feats[k] < 0 || kf_feats[k] >= n_kf) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: key-frame feature index out of range");
-    for (int k = 0; k < f_off[f_nnodes]; ++k) if (f_feats[k] < 0 || f_feats[k] >= n_f) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow: frame feature index out of range");
-    // the merge walk of :552-619 (lower_bound on sorted maps == advancing the smaller side)
     std::vector<int> entries;
-    long long npairs = 0;
-    for (int a = 0, b = 0; a < kf_nnodes && b < f_nnodes;) {
-        if (kf_nodes[a] < f_nodes[b]) { ++a; continue; }
-        if (kf_nodes[a] > f_nodes[b]) { ++b; continue; }
-        const int cnt = f_off[b + 1] - f_off[b];
-        for (int p = kf_off[a]; p < kf_off[a + 1] && cnt > 0; ++p) {
-            const int ik = kf_feats[p];
-            if (!kf_valid[ik]) continue;
-            entries.push_back(ik); entries.push_back(f_off[b]); entries.push_back(cnt); entries.push_back((int)npairs);
-            npairs += cnt;
-        }
-        ++a; ++b;
-    }
-    const int ne = (int)(entries.size() / 4);
-    if (ne == 0) return 0;
-    if (npairs > (1ll << 30)) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_by_bow: more than 2^30 descriptor pairs");
-    CU(cudaSetDevice(h->device));
-    auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
-    const size_t o_ent = 0, o_kd = o_ent + up((size_t)ne * 16), o_fd = o_kd + up((size_t)n_kf * 32), o_ff = o_fd + up((size_t)n_f * 32),
-                 o_out = o_ff + up((size_t)f_off[f_nnodes] * 4), total = o_out + up((size_t)npairs * 2);
-    uint8_t *d = nullptr;
-    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
-    cudaStream_t st = h->stream;
-    std::vector<uint16_t> dist((size_t)npairs);
-    CU(cudaMemcpyAsync(d + o_ent, entries.data(), (size_t)ne * 16, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_kd, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_fd, f_desc, (size_t)n_f * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_ff, f_feats, (size_t)f_off[f_nnodes] * 4, cudaMemcpyHostToDevice, st));
-    CU(launch_bow_pair_distances(ne, (const int4 *)(d + o_ent), d + o_kd, d + o_fd, (const int32_t *)(d + o_ff), (uint16_t *)(d + o_out), st, &h->stats));
-    CU(cudaMemcpyAsync(dist.data(), d + o_out, (size_t)npairs * 2, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return resolve_bow_matches(ne, entries.data(), dist.data(), f_feats, n_f, kf_angle, f_angle, nnratio, check_orientation, f_match);
+    std::vector<uint16_t> dist;
+    const int rc = bow_pair_distances(h, "orbx_search_by_bow", n_kf, kf_desc, kf_valid, kf_nnodes, kf_nodes, kf_off, kf_feats, n_f, f_desc, f_nnodes,
+                                      f_nodes, f_off, f_feats, &entries, &dist);
+    if (rc != ORBX_OK) return rc;
+    return resolve_bow_matches((int)(entries.size() / 4), entries.data(), dist.data(), f_feats, n_f, kf_angle, f_angle, nnratio, check_orientation, f_match);
+}
+
+extern "C" int orbx_search_by_bow_keyframes(orbx_handle *h, int n1, const float *angle1, const uint8_t *desc1, const uint8_t *valid1,
+                                            int nnodes1, const int32_t *nodes1, const int32_t *off1, const int32_t *feats1,
+                                            int n2, const float *angle2, const uint8_t *desc2, const uint8_t *valid2,
+                                            int nnodes2, const int32_t *nodes2, const int32_t *off2, const int32_t *feats2,
+                                            float nnratio, int check_orientation, int32_t *matches12)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (n1 < 0 || n2 < 0 || nnodes1 < 0 || nnodes2 < 0 || (n1 > 0 && (!angle1 || !desc1 || !valid1 || !matches12)) ||
+        (nnodes1 > 0 && (!nodes1 || !off1 || !feats1)) || (n2 > 0 && (!angle2 || !desc2 || !valid2)) || (nnodes2 > 0 && (!nodes2 || !off2 || !feats2)))
+        return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_bow_keyframes: bad argument");
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0 || nnodes1 == 0 || nnodes2 == 0) return 0;
+    std::vector<int> entries;
+    std::vector<uint16_t> dist;
+    const int rc = bow_pair_distances(h, "orbx_search_by_bow_keyframes", n1, desc1, valid1, nnodes1, nodes1, off1, feats1, n2, desc2, nnodes2, nodes2,
+                                      off2, feats2, &entries, &dist);
+    if (rc != ORBX_OK) return rc;
+    return resolve_bow_matches_kf((int)(entries.size() / 4), entries.data(), dist.data(), feats2, n1, n2, valid2, angle1, angle2, nnratio,
+                                  check_orientation, matches12);
 }
 
 // --------------------------------------------------------------- vocabulary

@@ -101,6 +101,9 @@ int resolve_local_matches(int n_mp, int n_feat, const unsigned long long *cand, 
 int resolve_bow_matches(int n_entries, const int *entries, const uint16_t *dist, const int32_t *f_feats, int n_f, const float *kf_angle,
                         const float *f_angle, float nnratio, int check_orientation, int32_t *f_match);
 
+int resolve_bow_matches_kf(int n_entries, const int *entries, const uint16_t *dist, const int32_t *feats2, int n1, int n2, const uint8_t *valid2,
+                           const float *ang1, const float *ang2, float nnratio, int check_orientation, int32_t *m12);
+
 // DBoW2 vocabulary tree (vocabulary.cpp): node 0 is the root, children of node i are child_ids[child_off[i] .. child_off[i+1])
 struct VocHost {
     int k = 0, L = 0, scoring = 0, weighting = 0, nnodes = 0, nwords = 0;

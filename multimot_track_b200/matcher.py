@@ -117,3 +117,19 @@ class ORBmatcher:
                                          int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), out.ctypes.data)
         ext._ck(rc)
         return out, rc
+
+    def SearchByBoWKeyFrames(self, case):
+        """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (src/ORBmatcher.cc:897-1030).  `case` as for SearchByBoW with key frame 1 =
+        kf_* and key frame 2 = f_* plus f_valid.  Returns (feature of key frame 2 matched to every feature of key frame 1, nmatches)."""
+        c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+        ext = self._ext
+        n1 = len(c["kf_desc"])
+        out = np.full(n1, -1, np.int32)
+        rc = ext._lib.orbx_search_by_bow_keyframes(ext._h, n1, c["kf_angle"].ctypes.data, c["kf_desc"].ctypes.data, c["kf_valid"].ctypes.data,
+                                                   len(c["kf_nodes"]), c["kf_nodes"].ctypes.data, c["kf_off"].ctypes.data, c["kf_feats"].ctypes.data,
+                                                   len(c["f_desc"]), c["f_angle"].ctypes.data, c["f_desc"].ctypes.data, c["f_valid"].ctypes.data,
+                                                   len(c["f_nodes"]), c["f_nodes"].ctypes.data, c["f_off"].ctypes.data, c["f_feats"].ctypes.data,
+                                                   float(case.get("nnratio", self.mfNNratio)),
+                                                   int(self.mbCheckOrientation if "check_orientation" not in case else case["check_orientation"]), out.ctypes.data)
+        ext._ck(rc)
+        return out, rc

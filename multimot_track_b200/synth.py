@@ -237,4 +237,5 @@ def bow_match_case(seed, kps, desc, nnratio=0.7, distractors=None, node_fn=_toy_
     kn, ko, kf = feature_vector(node_fn(kd))
     fn_, fo, ff = feature_vector(node_fn(fd))
     return dict(kf_angle=kps["angle"].astype(np.float32), kf_desc=kd, kf_valid=(rng.random(n) < 0.85).astype(np.uint8), kf_nodes=kn, kf_off=ko, kf_feats=kf,
-                f_angle=fa, f_desc=fd, f_nodes=fn_, f_off=fo, f_feats=ff, nnratio=float(nnratio), check_orientation=True)
+                f_angle=fa, f_desc=fd, f_nodes=fn_, f_off=fo, f_feats=ff, nnratio=float(nnratio), check_orientation=True,
+                f_valid=(rng.random(len(fd)) < 0.8).astype(np.uint8))      # used when the second side is a key frame (SearchByBoW(pKF1, pKF2))

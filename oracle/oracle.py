@@ -539,3 +539,27 @@ def search_by_bow_port(case):
 def search_by_bow_ref(case, variant="canon"):
     """The reference's own compiled function (excerpt of src/ORBmatcher.cc:532-663)."""
     return _bowm_call(RefExtractor.lib(variant).orbref_search_by_bow, case)
+
+
+_BOWK_ARGTYPES = [_I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _F, _I, _VP]
+
+
+def _bowk_call(fn, case):
+    c = {k: np.ascontiguousarray(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+    out = np.full(len(c["kf_desc"]), -1, np.int32)
+    fn.argtypes = _BOWK_ARGTYPES
+    n = fn(len(c["kf_desc"]), c["kf_angle"].ctypes.data, c["kf_desc"].ctypes.data, c["kf_valid"].ctypes.data, len(c["kf_nodes"]), c["kf_nodes"].ctypes.data,
+           c["kf_off"].ctypes.data, c["kf_feats"].ctypes.data, len(c["f_desc"]), c["f_angle"].ctypes.data, c["f_desc"].ctypes.data, c["f_valid"].ctypes.data,
+           len(c["f_nodes"]), c["f_nodes"].ctypes.data, c["f_off"].ctypes.data, c["f_feats"].ctypes.data, float(case["nnratio"]),
+           int(case["check_orientation"]), out.ctypes.data)
+    return out, n
+
+
+def search_by_bow_kf_port(case):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) by the C port (key frame 1 = the case's kf_*, key frame 2 = its f_* + f_valid)."""
+    return _bowk_call(Oracle.lib().orbo_search_by_bow_kf, case)
+
+
+def search_by_bow_kf_ref(case, variant="canon"):
+    """The reference's own compiled function (excerpt of src/ORBmatcher.cc:897-1030)."""
+    return _bowk_call(RefExtractor.lib(variant).orbref_search_by_bow_kf, case)

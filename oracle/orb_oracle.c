@@ -912,6 +912,49 @@ int orbo_search_by_bow(int nK, const float *kf_angle, const uint8_t *kf_desc, co
     return nmatches;
 }
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12), src/ORBmatcher.cc:897-1030: as above between two key frames;
+ * side 2 must hold a good map point and not be matched yet (:948-954), the threshold is strict (bestDist1 < TH_LOW, :973). */
+int orbo_search_by_bow_kf(int n1, const float *ang1, const uint8_t *desc1, const uint8_t *valid1, int nn1, const int32_t *nodes1, const int32_t *off1,
+                          const int32_t *feats1, int n2, const float *ang2, const uint8_t *desc2, const uint8_t *valid2, int nn2, const int32_t *nodes2,
+                          const int32_t *off2, const int32_t *feats2, float nnratio, int check_orientation, int32_t *m12)
+{
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    unsigned char *matched2 = (unsigned char *)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+    int *hist_item = (int *)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1)), *hist_bin = (int *)malloc(sizeof(int) * (size_t)(n1 > 0 ? n1 : 1));
+    int nh = 0, nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] < nodes2[b]) { ++a; continue; }
+        if (nodes1[a] > nodes2[b]) { ++b; continue; }
+        for (int p = off1[a]; p < off1[a + 1]; ++p) {
+            const int i1 = feats1[p];
+            if (!valid1[i1]) continue;
+            int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+            for (int q = off2[b]; q < off2[b + 1]; ++q) {
+                const int i2 = feats2[q];
+                if (matched2[i2] || !valid2[i2]) continue;
+                const int dist = orbo_hamming256(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = i2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestDist1 < 50 && (float)bestDist1 < nnratio * (float)bestDist2) {
+                m12[i1] = bestIdx2; matched2[bestIdx2] = 1;
+                if (check_orientation) { hist_item[nh] = i1; hist_bin[nh] = orbo_rotation_bin(ang1[i1], ang2[bestIdx2]); ++nh; }
+                ++nmatches;
+            }
+        }
+        ++a; ++b;
+    }
+    if (check_orientation) {
+        int cnt[30] = {0}, i1 = -1, i2 = -1, i3 = -1;
+        for (int k = 0; k < nh; ++k) cnt[hist_bin[k]]++;
+        three_maxima(cnt, 30, &i1, &i2, &i3);
+        for (int k = 0; k < nh; ++k)
+            if (hist_bin[k] != i1 && hist_bin[k] != i2 && hist_bin[k] != i3) { m12[hist_item[k]] = -1; --nmatches; }
+    }
+    free(matched2); free(hist_item); free(hist_bin);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------- vocabulary
  * DBoW2 as vendored by the reference (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the tree built the way
  * loadFromTextFile builds it (:1338-1418: node ids in file order, children in file order, word ids in order of the

@@ -105,6 +105,10 @@ int orbo_search_local_points(const float *cam, int nP, const float *proj, const 
 int orbo_search_by_bow(int nK, const float *kf_angle, const uint8_t *kf_desc, const uint8_t *kf_valid, int nk_nodes, const int32_t *kf_nodes,
                        const int32_t *kf_off, const int32_t *kf_feats, int nF, const float *f_angle, const uint8_t *f_desc, int nf_nodes,
                        const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_feats, float nnratio, int check_orientation, int32_t *f_match);
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:897-1030); m12[i] = feature of key frame 2 matched to feature i. */
+int orbo_search_by_bow_kf(int n1, const float *ang1, const uint8_t *desc1, const uint8_t *valid1, int nn1, const int32_t *nodes1, const int32_t *off1,
+                          const int32_t *feats1, int n2, const float *ang2, const uint8_t *desc2, const uint8_t *valid2, int nn2, const int32_t *nodes2,
+                          const int32_t *off2, const int32_t *feats2, float nnratio, int check_orientation, int32_t *m12);
 /* DBoW2 vocabulary tree as the reference vendors it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): built from the rows
  * of an ORBvoc text file (parent id, leaf flag, 32 descriptor bytes, weight per node, file order), descent per feature,
  * BowVector / FeatureVector assembly.  scoring: 0 L1, 1 L2, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT;

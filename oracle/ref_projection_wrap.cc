@@ -153,4 +153,33 @@ int orbref_search_by_bow(int nK, const float *kf_angle, const uint8_t *kf_desc, 
     return n;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:897-1030).  valid1 / valid2: the feature has a
+// map point that is not bad.  m12[i] receives the feature of key frame 2 whose map point feature i of key frame 1 is matched to.
+int orbref_search_by_bow_kf(int n1, const float *ang1, const uint8_t *desc1, const uint8_t *valid1, int nn1, const int32_t *nodes1, const int32_t *off1,
+                            const int32_t *feats1, int n2, const float *ang2, const uint8_t *desc2, const uint8_t *valid2, int nn2, const int32_t *nodes2,
+                            const int32_t *off2, const int32_t *feats2, float nnratio, int check_orientation, int32_t *m12)
+{
+    ORB_SLAM2::KeyFrame K1, K2;
+    std::vector<ORB_SLAM2::MapPoint> p1((size_t)n1), p2((size_t)n2);
+    auto fill = [](ORB_SLAM2::KeyFrame &K, std::vector<ORB_SLAM2::MapPoint> &pts, int n, const float *ang, const uint8_t *desc, const uint8_t *valid,
+                   int nn, const int32_t *nodes, const int32_t *off, const int32_t *feats) {
+        K.mvpMapPoints.assign((size_t)n, (ORB_SLAM2::MapPoint *)0);
+        K.mvKeysUn.resize((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            K.mvKeysUn[i] = cv::KeyPoint(0.f, 0.f, 31.f, ang[i], 0.f, 0, -1);
+            if (valid[i]) K.mvpMapPoints[i] = &pts[i];
+        }
+        K.mDescriptors = cv::Mat(n, 32, CV_8UC1, (void *)desc, 32);
+        for (int j = 0; j < nn; ++j)
+            for (int k = off[j]; k < off[j + 1]; ++k) K.mFeatVec[(unsigned)nodes[j]].push_back((unsigned)feats[k]);
+    };
+    fill(K1, p1, n1, ang1, desc1, valid1, nn1, nodes1, off1, feats1);
+    fill(K2, p2, n2, ang2, desc2, valid2, nn2, nodes2, off2, feats2);
+    ORB_SLAM2::ORBmatcher matcher(nnratio, check_orientation != 0);
+    std::vector<ORB_SLAM2::MapPoint *> out;
+    const int n = matcher.SearchByBoW(&K1, &K2, out);
+    for (int i = 0; i < n1; ++i) m12[i] = out[i] ? (int32_t)(out[i] - &p2[0]) : -1;
+    return n;
+}
+
 } // extern "C"

@@ -4,7 +4,7 @@
 // (include/ORBmatcher.h:37-109) that the excerpted reference functions touch -- Frame::ComputeStereoMatches
 // (src/Frame.cc:849-1038), Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid (:601-616, 710-776),
 // ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) (src/ORBmatcher.cc:1958-2102), SearchForInitialization (:780-895),
-// SearchByProjection(Frame&, const vector<MapPoint*>&, th) with RadiusByViewingCos (:418-511), SearchByBoW(KeyFrame*, Frame&, ...) (:532-663), ComputeThreeMaxima and
+// SearchByProjection(Frame&, const vector<MapPoint*>&, th) with RadiusByViewingCos (:418-511), SearchByBoW(KeyFrame*, Frame&, ...) (:532-663), SearchByBoW(KeyFrame*, KeyFrame*, ...) (:897-1030), ComputeThreeMaxima and
 // DescriptorDistance -- so that those function bodies compile UNMODIFIED from excerpts made at build time
 // (oracle/Makefile).  Member names and types are the reference's; everything else of the classes is left out.
 #ifndef ORACLE_STEREO_SHIM_HPP
@@ -63,6 +63,7 @@ public:
     int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
     float RadiusByViewingCos(const float &viewCos);
     int SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vpMapPointMatches, std::vector<int> &TemperalMatch);
+    int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12);
     int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;

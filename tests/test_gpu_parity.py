@@ -333,6 +333,9 @@ def test_search_by_bow_vs_oracle(orb, oracle_mod, tmp_path):
                 exp, nexp = oracle_mod.search_by_bow_port(c)
                 got, n = m.SearchByBoW(c)
                 assert n == nexp and np.array_equal(got, exp)
+                exp, nexp = oracle_mod.search_by_bow_kf_port(c)                  # SearchByBoW(pKF1, pKF2, ..), :897-1030
+                got, n = m.SearchByBoWKeyFrames(c)
+                assert n == nexp and np.array_equal(got, exp)
     empty = dict(case, f_angle=np.zeros(0, np.float32), f_desc=np.zeros((0, 32), np.uint8), f_nodes=np.zeros(0, np.int32),
                  f_off=np.zeros(1, np.int32), f_feats=np.zeros(0, np.int32))
     got, n = m.SearchByBoW(empty)

@@ -335,6 +335,19 @@ def test_search_by_bow_port_vs_reference(oracle_mod):
                 assert nb == na and np.array_equal(a, b)
 
 
+def test_search_by_bow_keyframes_port_vs_reference(oracle_mod):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12): the C port against the reference's own function
+    (src/ORBmatcher.cc:897-1030 excerpted unmodified)."""
+    for case in _bow_match_cases(oracle_mod):
+        for c in (case, dict(case, check_orientation=False)):
+            a, na = oracle_mod.search_by_bow_kf_port(c)
+            taken = a[a >= 0]
+            assert na == len(taken) > 400 and len(np.unique(taken)) == len(taken) and case["f_valid"][taken].all() and case["kf_valid"][a >= 0].all()
+            if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_search_by_bow_kf"):
+                b, nb = oracle_mod.search_by_bow_kf_ref(c)
+                assert nb == na and np.array_equal(a, b)
+
+
 def test_minicv_float_gemm_against_live_cv2(oracle_mod):
     """The projection matcher's `Rcw*x3Dw+tcw` and `-Rcw.t()*tcw` (src/ORBmatcher.cc:1968-1976, 1990-1991) go through cv::gemm;
     the port's arithmetic (float accumulation for A*B+C, double for the transposed product) is pinned to cv2 4.13 here."""
