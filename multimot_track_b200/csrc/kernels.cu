@@ -704,26 +704,28 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
                 e[5] = o[sm1][3]; e[11] = o[sm1][0];
                 e[6] = a[sm2][2]; e[10] = a[sm2][0];
                 e[7] = o[sm3][2]; e[8] = a[sm3][1]; e[9] = o[sm3][1];
-                unsigned lo3[16], hi3[16];
+                // The 16 arcs of 9 in pairs: arcs 2i and 2i+1 share the 8 ring pixels 2i+1 .. 2i+8 (B), so
+                // max(min(arc 2i), min(arc 2i+1)) = min(B, max(e[2i], e[2i+9])) -- 36 packed min / max per polarity instead of 40.
+                unsigned lo2[8], hi2[8];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    lo3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-                    hi3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+                for (int i = 0; i < 8; ++i) {
+                    lo2[i] = __vmins2(e[2 * i + 1], e[(2 * i + 2) & 15]);
+                    hi2[i] = __vmaxs2(e[2 * i + 1], e[(2 * i + 2) & 15]);
                 }
-                unsigned lo9[16], hi9[16];
+                unsigned lo4[8], hi4[8];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    lo9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-                    hi9[k] = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+                for (int i = 0; i < 8; ++i) {
+                    lo4[i] = __vmins2(lo2[i], lo2[(i + 1) & 7]);
+                    hi4[i] = __vmaxs2(hi2[i], hi2[(i + 1) & 7]);
                 }
-                unsigned bm[5], dm[5];
+                unsigned bv[8], dv[8];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    bm[k] = __vimax3_s16x2(lo9[3 * k], lo9[3 * k + 1], lo9[3 * k + 2]);
-                    dm[k] = __vimin3_s16x2(hi9[3 * k], hi9[3 * k + 1], hi9[3 * k + 2]);
+                for (int i = 0; i < 8; ++i) {
+                    bv[i] = __vimin3_s16x2(lo4[i], lo4[(i + 2) & 7], __vmaxs2(e[2 * i], e[(2 * i + 9) & 15]));
+                    dv[i] = __vimax3_s16x2(hi4[i], hi4[(i + 2) & 7], __vmins2(e[2 * i], e[(2 * i + 9) & 15]));
                 }
-                const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bm[0], bm[1], bm[2]), __vimax3_s16x2(bm[3], bm[4], lo9[15]), lo9[15]);
-                const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dm[0], dm[1], dm[2]), __vimin3_s16x2(dm[3], dm[4], hi9[15]), hi9[15]);
+                const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
+                const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
                 // bright: maxmin - c - th = maxmin + (~c + 1 - th); dark: c - minmax - th = (c + 1 - th) + ~minmax
                 const unsigned tb = __viaddmax_s16x2_relu(maxmin, __vadd2(~cc, k1mth), 0u);
                 const unsigned Cv = __viaddmax_s16x2(__vadd2(cc, k1mth), ~minmax, tb) & in_mask;
