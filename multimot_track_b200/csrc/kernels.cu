@@ -610,7 +610,7 @@ struct FfCfg {
     static constexpr int PITCH = 37;                                   // tile words per row: pairs -2 .. 33, +1
     static constexpr int ROWS = CELL + 6;
     static constexpr int LIST_LANES = 32 * ((CELL + 1) / 2);           // per-lane survivor slots: a column pair keeps <= one pixel every 2nd row
-    static constexpr int LIST = LIST_LANES + (CELL + 1) / 2;           // + the second column of the lane that straddles two cells
+    static constexpr int LIST = LIST_LANES + CELL;                     // + the lane that straddles two cells (independent columns: up to one entry per row)
     static constexpr int WARP_WORDS = ROWS * PITCH + LIST;
     static constexpr int SMEM = WARPS * WARP_WORDS * 4;
 };
@@ -655,9 +655,12 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     // S' = score - th_store + 1 where the pixel is a corner at th_store (>= 1), else 0.  VIADD.16x2 / VIADDMNMX.S16x2 are
     // the native packed forms; there is no packed subtract, so differences are written as x + ~y (= x - y - 1).
     const unsigned k1mth = 0x00010001u * (unsigned)((1 - th_store) & 0xffff);
-    int nl = 0, nl2 = 0;
+    int nl = 0;
     unsigned T2 = 0, T1 = 0, U1 = 0, C1 = 0;                           // T/U/centre of rows y-2 and y-1 (0 outside the cell)
-    uint32_t *ovf = list + C::LIST_LANES;                              // second-pixel survivors of the one lane that straddles two cells
+    // a lane whose two pixels share a cell keeps at most one survivor every second row; the one lane that straddles two cells
+    // (independent columns) may have one per row and gets its own region
+    uint32_t *mylist = straddle ? list + C::LIST_LANES : list + lane;
+    const int lstride = straddle ? 1 : 32;
 
     unsigned a[7][3], o[7][4];
     const uint32_t *col = tile + lane + 2;
@@ -670,19 +673,17 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
         o[slot][2] = __funnelshift_r(w2_, w3_, 16); o[slot][3] = __funnelshift_r(w3_, w4_, 16); \
     }
     // finalize the non-max suppression of row `yy` whose centre is Cc, with max-of-3 of the rows above / below.
-    // Cc + ~m8 = Cc - m8 - 1 >= 0  <=>  centre strictly greater than all 8 neighbours (and then Cc >= 1).  Survivors go
-    // to a private list per lane (slot-major, so no ballot / prefix is needed): S' | pixel << 9 | row << 10.
+    // t = Cc + ~m8 = Cc - m8 - 1 >= 0  <=>  centre strictly greater than all 8 neighbours (and then Cc >= 1).  A row with a survivor
+    // leaves ONE entry in the lane's private list (slot-major, so no ballot / prefix is needed): S' of pixel 0 | S' of pixel 1 << 9 |
+    // row << 18, with S' = 0 for a pixel that did not survive (PRMT in sign-replicate mode turns the sign of t into the halfword mask).
 #define FF_NMS(yy, Tabove, Umid, Cc, Tbelow)                                                                     \
     {                                                                                                            \
         const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
-        const unsigned kb = ~__vadd2(~m8, (Cc)) & 0x80008000u;                                                   \
-        if (kb) {                                                                                                \
-            const unsigned yb = (unsigned)(yy) << 10;                                                            \
-            if (kb & 0x8000u) { list[nl * 32 + lane] = ((Cc) & 0xffffu) | yb; ++nl; }                            \
-            if (kb & 0x80000000u) {                                                                              \
-                const unsigned e1 = ((Cc) >> 16) | 0x200u | yb;                                                  \
-                if (straddle) { ovf[nl2] = e1; ++nl2; } else { list[nl * 32 + lane] = e1; ++nl; }                \
-            }                                                                                                    \
+        const unsigned t_ = __vadd2(~m8, (Cc));                                                                  \
+        if (~t_ & 0x80008000u) {                                                                                 \
+            const unsigned ev = (Cc) & ~__byte_perm(t_, 0u, 0xBB99);                                             \
+            mylist[nl * lstride] = (ev & 0x1ffu) | ((ev >> 7) & 0x3fe00u) | ((unsigned)(yy) << 18);              \
+            ++nl;                                                                                                \
         }                                                                                                        \
     }
 #pragma unroll
@@ -744,14 +745,16 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     __syncwarp();
     // ---- threshold choice per cell (:812-816) and emission
     const int ini = P->ini_th, mn = P->min_th;
-    const int ntot = nl + nl2, nmax = __reduce_max_sync(0xffffffffu, ntot);
+    const int nmax = __reduce_max_sync(0xffffffffu, nl);
     const int s_ini = ini - th_store + 1;                              // S' >= s_ini  <=>  score >= iniThFAST
     int strong0 = 0, strong1 = 0, weak0 = 0, weak1 = 0;
     for (int i = 0; i < nmax; ++i) {
-        if (i < ntot) {
-            const uint32_t en = i < nl ? list[i * 32 + lane] : ovf[i - nl];
-            const bool cell1 = dx0 + (int)((en >> 9) & 1u) >= wc, st = (int)(en & 0x1ffu) >= s_ini;
-            strong0 += st && !cell1; strong1 += st && cell1; weak0 += !st && !cell1; weak1 += !st && cell1;
+        if (i < nl) {
+            const uint32_t en = mylist[i * lstride];
+            const int sa = en & 0x1ffu, sb = (en >> 9) & 0x1ffu;
+            const bool a = sa >= s_ini, b = sb >= s_ini, wa = sa > 0 && !a, wb = sb > 0 && !b;
+            strong0 += (a && !c0) + (b && !c1); strong1 += (a && c0) + (b && c1);
+            weak0 += (wa && !c0) + (wb && !c1); weak1 += (wa && c0) + (wb && c1);
         }
     }
     const bool has0 = __any_sync(0xffffffffu, strong0 > 0), has1 = __any_sync(0xffffffffu, strong1 > 0);
@@ -768,11 +771,17 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     if (lane == 0) base = (int)atomicAdd(P->cand_count + frame * P->nlevels + level, (unsigned)total);
     int at = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
     const uint32_t yx0 = (uint32_t)(x0 + dx0 - kMinBorder) | (uint32_t)(y0 - kMinBorder) << 12;
-    for (int i = 0; i < ntot; ++i) {
-        const uint32_t en = i < nl ? list[i * 32 + lane] : ovf[i - nl];
-        const int px = (en >> 9) & 1u, sv = en & 0x1ffu;
-        if (sv >= (dx0 + px >= wc ? s1c : s0c)) {
-            if (at < G.cand_cap) cand[at] = yx0 + (uint32_t)px + ((en >> 10) << 12) + ((uint32_t)(sv + th_store - 1) << 24);
+    const int thr0 = c0 ? s1c : s0c, thr1 = c1 ? s1c : s0c;
+    for (int i = 0; i < nl; ++i) {
+        const uint32_t en = mylist[i * lstride];
+        const int sa = en & 0x1ffu, sb = (en >> 9) & 0x1ffu;
+        const uint32_t yx = yx0 + ((en >> 18) << 12);
+        if (sa > 0 && sa >= thr0) {
+            if (at < G.cand_cap) cand[at] = yx + ((uint32_t)(sa + th_store - 1) << 24);
+            ++at;
+        }
+        if (sb > 0 && sb >= thr1) {
+            if (at < G.cand_cap) cand[at] = yx + 1u + ((uint32_t)(sb + th_store - 1) << 24);
             ++at;
         }
     }
