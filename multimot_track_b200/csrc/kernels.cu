@@ -1012,9 +1012,9 @@ __device__ __forceinline__ void bitonic_sort_desc(u64 *v, int n_pow2)
 
 // path code of one packed candidate: initial node, then the DivideNode child index per split.
 // x and y halve independently, so the code is the OR of two host-built tables (host_tables.cpp).
-__device__ __forceinline__ uint32_t path_code(uint32_t c, const uint32_t *__restrict__ lut_x, const uint32_t *__restrict__ lut_y)
+__device__ __forceinline__ uint32_t path_code(uint32_t c, const uint32_t *lut_x, const uint32_t *lut_y)
 {
-    return __ldg(lut_x + (c & 0xfff)) | __ldg(lut_y + ((c >> 12) & 0xfff));
+    return lut_x[c & 0xfff] | lut_y[(c >> 12) & 0xfff];              // the tables are in shared memory when they fit (k_octree)
 }
 
 __device__ __forceinline__ int lower_child(const uint32_t *codes, int lo, int hi, int shift, unsigned c)
@@ -1029,12 +1029,12 @@ __device__ __forceinline__ int lower_child(const uint32_t *codes, int lo, int hi
 
 struct OctreeSmem { size_t bytes; int key_cap, skey_cap; };
 
-static OctreeSmem octree_smem(int threads, int node_cap, int max_feat, size_t budget)
+static OctreeSmem octree_smem(int threads, int node_cap, int max_feat, size_t budget, int lut_cap = 0)
 {
     OctreeSmem o;
     o.skey_cap = 1;
     while (o.skey_cap < max_feat + 3) o.skey_cap <<= 1;
-    const size_t fixed = (size_t)o.skey_cap * 8 + (size_t)node_cap * 16 + (size_t)(threads / 32) * 256 * 4;
+    const size_t fixed = (size_t)o.skey_cap * 8 + (size_t)node_cap * 16 + (size_t)(threads / 32) * 256 * 4 + (size_t)lut_cap * 4;
     long long kc = ((long long)budget - (long long)fixed) / 8;
     kc = kc < 256 ? 256 : kc;
     o.key_cap = (int)(kc & ~31LL);
@@ -1059,7 +1059,7 @@ size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
 
 template <int THREADS, int IPT>
 __global__ void __launch_bounds__(THREADS)
-k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap, int level_off)
+k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap, int level_off, int lut_cap)
 {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t oct_smem[];
@@ -1071,7 +1071,8 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)min(P->cand_count[frame * P->nlevels + level], (unsigned)G.cand_cap);
     const int N = G.n_feat, D = G.depth;
-    const uint32_t *lut_x = P->oct_lut + G.lut_off, *lut_y = lut_x + G.region_w;
+    const uint32_t *glut = P->oct_lut + G.lut_off;                  // x codes [region_w], y codes [region_h], then the cell-order tables
+    const uint32_t *lut_x = glut, *lut_y = glut + G.region_w;
 
     u64 *skey = reinterpret_cast<u64 *>(oct_smem);                 // careful-phase sort buffer
     int *nlo = reinterpret_cast<int *>(skey + skey_cap);
@@ -1080,6 +1081,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     int *eidx = ndep + node_cap;
     uint32_t *hist = reinterpret_cast<uint32_t *>(eidx + node_cap);  // [WARPS][256]
     uint32_t *bufA = hist + WARPS * 256, *bufB = bufA + key_cap;
+    uint32_t *slut = bufB + key_cap;                                // path-code tables of this level, when they fit
     if (n > key_cap) {                                              // level too dense for shared memory: L2-resident scratch
         bufA = reinterpret_cast<uint32_t *>(P->sort_scratch + ((long long)frame * P->cand_frame_elems + G.cand_off) * 2);
         bufB = bufA + G.cand_cap;
@@ -1089,9 +1091,33 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     uint32_t *kp_count = P->kp_count + frame * P->nlevels + level;
 
     if (n == 0) { if (tid == 0) *kp_count = 0; return; }
+#ifdef ORBX_OCT_TIMING
+    long long tk[8]; int ntk = 0, nsweeps = 0, ncareful = 0;
+#define OCT_TICK() do { if (tid == 0 && ntk < 8) tk[ntk++] = clock64(); } while (0)
+#else
+#define OCT_TICK() do { } while (0)
+#endif
+    OCT_TICK();
 
     // ---- LSD radix sort of the packed candidates by path code, 8 bits per pass (stable)
-    for (int i = tid; i < n; i += THREADS) bufA[i] = cand[i];
+    if (G.region_w + G.region_h <= lut_cap) {                       // every pass looks both tables up per candidate: keep them close
+        const int nl = G.region_w + G.region_h;
+        for (int base = tid; base < nl; base += 4 * THREADS) {      // four loads in flight per thread
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = base + u * THREADS < nl ? __ldg(glut + base + u * THREADS) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (base + u * THREADS < nl) slut[base + u * THREADS] = v[u];
+        }
+        lut_x = slut; lut_y = slut + G.region_w;
+    }
+    for (int base = tid; base < n; base += 8 * THREADS) {           // eight loads in flight per thread
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = base + u * THREADS < n ? __ldg(cand + base + u * THREADS) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (base + u * THREADS < n) bufA[base + u * THREADS] = v[u];
+    }
     int code_bits = 2 * D;
     for (int t = G.n_ini - 1; t > 0; t >>= 1) ++code_bits;
     const int chunk = (((n + WARPS - 1) / WARPS) + 31) & ~31;
@@ -1101,17 +1127,8 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         for (int i = tid; i < WARPS * 256; i += THREADS) hist[i] = 0;
         __syncthreads();
         uint32_t *wh = hist + warp * 256;
-        for (int base = c_lo; base < c_hi; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < c_hi;
-            const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const unsigned d = (path_code(bufA[i], lut_x, lut_y) >> shift) & 255u;
-                const unsigned peers = __match_any_sync(vm, d);
-                if ((peers & lt) == 0) wh[d] += __popc(peers);      // one leader per distinct digit
-            }
-            __syncwarp();
-        }
+        for (int i = c_lo + lane; i < c_hi; i += 32)                 // counts need no order: shared-memory atomics, loads independent
+            atomicAdd(wh + ((path_code(bufA[i], lut_x, lut_y) >> shift) & 255u), 1u);
         __syncthreads();
         {   // exclusive scan over (digit major, warp minor)
             constexpr int HPT = 256 * WARPS / THREADS;               // == 8
@@ -1125,41 +1142,59 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             for (int k = 0; k < HPT; ++k) { const int e = tid * HPT + k; hist[(e % WARPS) * 256 + e / WARPS] = (uint32_t)run; run += (int)v[k]; }
         }
         __syncthreads();
-        for (int base = c_lo; base < c_hi; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < c_hi;
-            const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            uint32_t key = 0; unsigned d = 0, peers = 0; uint32_t off = 0;
-            if (valid) {
-                key = bufA[i];
-                d = (path_code(key, lut_x, lut_y) >> shift) & 255u;
-                peers = __match_any_sync(vm, d);
-                off = wh[d];
+        // stable scatter, 32 candidates at a time in order; four groups' keys and digits are fetched ahead so that only the
+        // short offset chain through wh[] is sequential
+        for (int base = c_lo; base < c_hi; base += 128) {
+            uint32_t key[4]; unsigned dg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + 32 * u + lane;
+                key[u] = i < c_hi ? bufA[i] : 0u;
+                dg[u] = (path_code(key[u], lut_x, lut_y) >> shift) & 255u;
             }
-            __syncwarp();
-            if (valid) {
-                if ((peers & lt) == 0) wh[d] = off + __popc(peers);
-                bufB[off + __popc(peers & lt)] = key;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool valid = base + 32 * u + lane < c_hi;
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                if (vm == 0) break;                                  // warp-uniform
+                unsigned peers = 0; uint32_t off = 0;
+                if (valid) {
+                    peers = __match_any_sync(vm, dg[u]);
+                    off = wh[dg[u]];
+                }
+                __syncwarp();
+                if (valid) {
+                    if ((peers & lt) == 0) wh[dg[u]] = off + __popc(peers);
+                    bufB[off + __popc(peers & lt)] = key[u];
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         __syncthreads();
         uint32_t *t = bufA; bufA = bufB; bufB = t;
     }
+    OCT_TICK();
     uint32_t *keys = bufA, *codes = bufB;                           // sorted candidates and their path codes
     for (int i = tid; i < n; i += THREADS) codes[i] = path_code(keys[i], lut_x, lut_y);
     __syncthreads();
+    OCT_TICK();
 
-    // ---- roots, reverse list order (:553-585)
+    // ---- roots, reverse list order (:553-585): thread r finds root n_ini-1-r's range, thread 0 drops the empty ones
+    if (tid < G.n_ini && tid < node_cap) {
+        const int r = G.n_ini - 1 - tid;
+        int lo = 0, hi = n;
+        while (lo < hi) { const int m = (lo + hi) >> 1; if ((codes[m] >> (2 * D)) >= (unsigned)r) hi = m; else lo = m + 1; }
+        const int a = lo;
+        hi = n;
+        while (lo < hi) { const int m = (lo + hi) >> 1; if ((codes[m] >> (2 * D)) >= (unsigned)(r + 1)) hi = m; else lo = m + 1; }
+        reinterpret_cast<int *>(skey)[2 * tid] = a; reinterpret_cast<int *>(skey)[2 * tid + 1] = lo;
+    }
+    __syncthreads();
     if (tid == 0) {
         int na = 0;
-        for (int r = G.n_ini - 1; r >= 0; --r) {
-            int lo = 0, hi = n;
-            while (lo < hi) { const int m = (lo + hi) >> 1; if ((codes[m] >> (2 * D)) >= (unsigned)r) hi = m; else lo = m + 1; }
-            const int a = lo;
-            hi = n;
-            while (lo < hi) { const int m = (lo + hi) >> 1; if ((codes[m] >> (2 * D)) >= (unsigned)(r + 1)) hi = m; else lo = m + 1; }
-            if (lo > a) { nlo[na] = a; nhi[na] = lo; ndep[na] = 0; ++na; }
+        for (int t = 0; t < G.n_ini; ++t) {
+            const int a = reinterpret_cast<int *>(skey)[2 * t], b = reinterpret_cast<int *>(skey)[2 * t + 1];
+            if (b > a) { nlo[na] = a; nhi[na] = b; ndep[na] = 0; ++na; }
         }
         int ne = 0;
         for (int i = 0; i < na; ++i) if (nhi[i] - nlo[i] > 1) eidx[ne++] = i;
@@ -1170,7 +1205,11 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     __syncthreads();
 
     bool careful = false;
+    OCT_TICK();
     for (;;) {
+#ifdef ORBX_OCT_TIMING
+        ++nsweeps; ncareful += careful;
+#endif
         const int prev_size = size;
         // ---- visit order
         if (careful) {
@@ -1274,9 +1313,10 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         if (!careful && size + 3 * nE > N) careful = true;
     }
 
+    OCT_TICK();
     // ---- winners, list order front->back == reverse array order (:740-760): greatest response, first in the
     //      reference's candidate order (cell row, cell column, y, x).  One thread per node.
-    const uint32_t *lut_cx = lut_y + G.region_h, *lut_cy = lut_cx + G.region_w;
+    const uint32_t *lut_cx = glut + G.region_w + G.region_h, *lut_cy = lut_cx + G.region_w;   // global copies (lut_x / lut_y may be the shared ones)
     for (int j = tid; j < size; j += THREADS) {
         const int nd = size - 1 - j;
         u64 best = 0;
@@ -1291,19 +1331,30 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         stage[j] = (uint32_t)(order & 0xffffff) | (uint32_t)(best >> 40) << 24;
     }
     if (tid == 0) *kp_count = (uint32_t)size;
+#ifdef ORBX_OCT_TIMING
+    __syncthreads();
+    OCT_TICK();
+    if (tid == 0 && frame == 0)
+        printf("octree level %d n %d N %d size %d sweeps %d careful %d | sort %lld codes %lld roots %lld sweeps %lld winners %lld cycles\n", level, n, N, size,
+               nsweeps, ncareful, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4]);
+#endif
+#undef OCT_TICK
 }
 
 template <int THREADS, int IPT>
 static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int nframes, int node_cap, int max_feat, size_t budget, cudaStream_t st,
                                    int level_off = 0, int level_cnt = -1)
 {
-    const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget);
+    if (level_cnt < 0) level_cnt = hP.nlevels - level_off;
+    int lut_cap = 0;                                                 // path-code tables of the largest launched level: x codes + y codes
+    for (int l = level_off; l < level_off + level_cnt; ++l) lut_cap = std::max(lut_cap, hP.lv[l].region_w + hP.lv[l].region_h);
+    if ((size_t)lut_cap * 4 > budget / 4) lut_cap = 0;               // too large for this budget: the kernel reads them from global memory
+    const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget, lut_cap);
     {                                                                // the attribute is a per-device maximum: cheap, set every time
         cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
         if (e != cudaSuccess) return e;
     }
-    if (level_cnt < 0) level_cnt = hP.nlevels - level_off;
-    k_octree<THREADS, IPT><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off);
+    k_octree<THREADS, IPT><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap);
     return cudaGetLastError();
 }
 
