@@ -1017,14 +1017,20 @@ __device__ __forceinline__ uint32_t path_code(uint32_t c, const uint32_t *lut_x,
     return lut_x[c & 0xfff] | lut_y[(c >> 12) & 0xfff];              // the tables are in shared memory when they fit (k_octree)
 }
 
-__device__ __forceinline__ int lower_child(const uint32_t *codes, int lo, int hi, int shift, unsigned c)
+// The three child boundaries of a node at once: first indices in [lo,hi) whose 2-bit child field at `shift` is >= 1, 2, 3.  The three
+// binary searches run in lockstep over the whole range (fixed trip count), so their shared-memory loads overlap.
+__device__ __forceinline__ void lower_children(const uint32_t *codes, int lo, int hi, int shift, int *b1, int *b2, int *b3)
 {
-    // first index in [lo,hi) whose 2-bit child field at `shift` is >= c
-    while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (((codes[m] >> shift) & 3u) >= c) hi = m; else lo = m + 1;
+    int l1 = lo, h1 = hi, l2 = lo, h2 = hi, l3 = lo, h3 = hi;
+    for (int steps = 32 - __clz(hi - lo); steps > 0; --steps) {     // a range of n candidates needs at most floor(log2 n) + 1 halvings
+        const int m1 = (l1 + h1) >> 1, m2 = (l2 + h2) >> 1, m3 = (l3 + h3) >> 1;
+        const unsigned c1 = l1 < h1 ? (codes[m1] >> shift) & 3u : 0u, c2 = l2 < h2 ? (codes[m2] >> shift) & 3u : 0u,
+                       c3 = l3 < h3 ? (codes[m3] >> shift) & 3u : 0u;
+        if (l1 < h1) { if (c1 >= 1u) h1 = m1; else l1 = m1 + 1; }
+        if (l2 < h2) { if (c2 >= 2u) h2 = m2; else l2 = m2 + 1; }
+        if (l3 < h3) { if (c3 >= 3u) h3 = m3; else l3 = m3 + 1; }
     }
-    return lo;
+    *b1 = l1; *b2 = l2; *b3 = l3;
 }
 
 struct OctreeSmem { size_t bytes; int key_cap, skey_cap; };
@@ -1231,9 +1237,8 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             if (r < nE) {
                 const int p = careful ? (int)(skey[r] & 0xffffffffu) : eidx[nE - 1 - r];
                 const int lo = nlo[p], hi = nhi[p], shift = 2 * (D - 1 - ndep[p]);
-                const int b1 = lower_child(codes, lo, hi, shift, 1);
-                const int b2 = lower_child(codes, b1, hi, shift, 2);
-                const int b3 = lower_child(codes, b2, hi, shift, 3);
+                int b1, b2, b3;
+                lower_children(codes, lo, hi, shift, &b1, &b2, &b3);
                 pb[k][0] = b1; pb[k][1] = b2; pb[k][2] = b3;
                 pc[k] = (b1 > lo) + (b2 > b1) + (b3 > b2) + (hi > b3);
                 csum += pc[k];
