@@ -1098,10 +1098,12 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
 
     if (n == 0) { if (tid == 0) *kp_count = 0; return; }
 #ifdef ORBX_OCT_TIMING
-    long long tk[8]; int ntk = 0, nsweeps = 0, ncareful = 0;
+    long long tk[8], acc[5] = {0, 0, 0, 0, 0}, tl = 0; int ntk = 0, nsweeps = 0, ncareful = 0;
+#define OCT_LAP(i) do { if (tid == 0) { const long long t_ = clock64(); acc[i] += t_ - tl; tl = t_; } } while (0)
 #define OCT_TICK() do { if (tid == 0 && ntk < 8) tk[ntk++] = clock64(); } while (0)
 #else
 #define OCT_TICK() do { } while (0)
+#define OCT_LAP(i) do { } while (0)
 #endif
     OCT_TICK();
 
@@ -1215,6 +1217,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     for (;;) {
 #ifdef ORBX_OCT_TIMING
         ++nsweeps; ncareful += careful;
+        if (tid == 0) tl = clock64();
 #endif
         const int prev_size = size;
         // ---- visit order
@@ -1226,15 +1229,19 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             __syncthreads();
             bitonic_sort_desc<THREADS>(skey, sp2);
         }
+        OCT_LAP(0);
         // ---- pass 1: children of the parents this thread owns (visit ranks tid*IPT ..)
+        // visit ranks tid*ipt .. tid*ipt + ipt-1 with ipt = ceil(nE / THREADS) <= IPT: the first sweeps (a handful of parents with
+        // long ranges) spread over the threads instead of queueing IPT deep on the first few
+        const int ipt = min(IPT, max(1, (nE + THREADS - 1) / THREADS));
         int pb[IPT][3];
         int pc[IPT];
         int csum = 0;
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
-            const int r = tid * IPT + k;
+            const int r = tid * ipt + k;
             pc[k] = 0;
-            if (r < nE) {
+            if (k < ipt && r < nE) {
                 const int p = careful ? (int)(skey[r] & 0xffffffffu) : eidx[nE - 1 - r];
                 const int lo = nlo[p], hi = nhi[p], shift = 2 * (D - 1 - ndep[p]);
                 int b1, b2, b3;
@@ -1244,6 +1251,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
                 csum += pc[k];
             }
         }
+        OCT_LAP(1);
         int total_c;
         const int incl = block_scan_incl<THREADS>(csum, warp_sums, &total_c);
         // ---- cutoff m (careful phase: smallest m with size + sum_{i<m}(c_i - 1) >= N)
@@ -1253,8 +1261,8 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             int run = incl - csum;                                  // children of all earlier ranks
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
-                const int r = tid * IPT + k;
-                if (r < nE) {
+                const int r = tid * ipt + k;
+                if (k < ipt && r < nE) {
                     const int before = size + run - r;              // size + sum_{i<r}(c_i-1)
                     run += pc[k];
                     const int after = size + run - (r + 1);
@@ -1264,13 +1272,14 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             __syncthreads();
         }
         const int m = s_m, added = s_added;
+        OCT_LAP(2);
         // ---- pass 2: append children in visit order, retire the parents
         {
             int off = incl - csum;
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
-                const int r = tid * IPT + k;
-                if (r < nE && r < m) {
+                const int r = tid * ipt + k;
+                if (k < ipt && r < nE && r < m) {
                     const int p = careful ? (int)(skey[r] & 0xffffffffu) : eidx[nE - 1 - r];
                     const int lo = nlo[p], hi = nhi[p], dep = ndep[p] + 1;
                     const int b[5] = {lo, pb[k][0], pb[k][1], pb[k][2], hi};
@@ -1286,15 +1295,17 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         __syncthreads();
         const int n_pre = size + added;
         size = size - m + added;
+        OCT_LAP(3);
         // ---- stable compaction of the array + new expandable list
         {
+            const int ipt2 = min(IPT, max(1, (n_pre + THREADS - 1) / THREADS));
             int rl[IPT], rh[IPT], rd[IPT];
             int alive = 0, multi = 0;
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
-                const int i = tid * IPT + k;
+                const int i = tid * ipt2 + k;
                 rd[k] = -1;
-                if (i < n_pre) {
+                if (k < ipt2 && i < n_pre) {
                     rl[k] = nlo[i]; rh[k] = nhi[i]; rd[k] = ndep[i];
                     if (rd[k] >= 0) { ++alive; multi += (rh[k] - rl[k] > 1); }
                 }
@@ -1313,6 +1324,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             nE = tot >> 16;
             __syncthreads();
         }
+        OCT_LAP(4);
         // ---- termination (:667-737)
         if (size >= N || size == prev_size) break;
         if (!careful && size + 3 * nE > N) careful = true;
@@ -1340,10 +1352,11 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     __syncthreads();
     OCT_TICK();
     if (tid == 0 && frame == 0)
-        printf("octree level %d n %d N %d size %d sweeps %d careful %d | sort %lld codes %lld roots %lld sweeps %lld winners %lld cycles\n", level, n, N, size,
-               nsweeps, ncareful, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4]);
+        printf("octree level %d n %d N %d size %d sweeps %d careful %d | sort %lld codes %lld roots %lld sweeps %lld (order %lld pass1 %lld scan %lld pass2 %lld compact %lld) winners %lld cycles\n", level, n, N, size,
+               nsweeps, ncareful, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], acc[0], acc[1], acc[2], acc[3], acc[4], tk[5] - tk[4]);
 #endif
 #undef OCT_TICK
+#undef OCT_LAP
 }
 
 template <int THREADS, int IPT>
