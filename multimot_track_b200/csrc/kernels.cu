@@ -1135,8 +1135,14 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         for (int i = tid; i < WARPS * 256; i += THREADS) hist[i] = 0;
         __syncthreads();
         uint32_t *wh = hist + warp * 256;
-        for (int i = c_lo + lane; i < c_hi; i += 32)                 // counts need no order: shared-memory atomics, loads independent
-            atomicAdd(wh + ((path_code(bufA[i], lut_x, lut_y) >> shift) & 255u), 1u);
+        for (int base = c_lo + lane; base < c_hi; base += 256) {     // counts need no order: shared-memory atomics, eight loads in flight
+            uint32_t k8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) k8[u] = base + 32 * u < c_hi ? bufA[base + 32 * u] : 0u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (base + 32 * u < c_hi) atomicAdd(wh + ((path_code(k8[u], lut_x, lut_y) >> shift) & 255u), 1u);
+        }
         __syncthreads();
         {   // exclusive scan over (digit major, warp minor)
             constexpr int HPT = 256 * WARPS / THREADS;               // == 8
@@ -1334,18 +1340,37 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     // ---- winners, list order front->back == reverse array order (:740-760): greatest response, first in the
     //      reference's candidate order (cell row, cell column, y, x).  One thread per node.
     const uint32_t *lut_cx = glut + G.region_w + G.region_h, *lut_cy = lut_cx + G.region_w;   // global copies (lut_x / lut_y may be the shared ones)
-    for (int j = tid; j < size; j += THREADS) {
-        const int nd = size - 1 - j;
-        u64 best = 0;
-        for (int i = nlo[nd]; i < nhi[nd]; ++i) {
-            const uint32_t c = keys[i];
-            const uint32_t x = c & 0xfff, y = (c >> 12) & 0xfff;
-            const u64 order = (u64)(__ldg(lut_cy + y) + __ldg(lut_cx + x)) << 24 | (c & 0xffffffu);
-            const u64 v = (u64)(c >> 24) << 40 | (~order & 0xffffffffffull);
-            best = v > best ? v : best;
+    if (n >= 16 * size) {
+        // many candidates per node (large images): a warp per node, lanes stride over its candidates
+        for (int j = warp; j < size; j += WARPS) {
+            const int nd = size - 1 - j;
+            u64 best = 0;
+            for (int i = nlo[nd] + lane; i < nhi[nd]; i += 32) {
+                const uint32_t c = keys[i];
+                const uint32_t x = c & 0xfff, y = (c >> 12) & 0xfff;
+                const u64 order = (u64)(__ldg(lut_cy + y) + __ldg(lut_cx + x)) << 24 | (c & 0xffffffu);
+                const u64 v = (u64)(c >> 24) << 40 | (~order & 0xffffffffffull);
+                best = v > best ? v : best;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+            const u64 order = ~best & 0xffffffffffull;
+            if (lane == 0) stage[j] = (uint32_t)(order & 0xffffff) | (uint32_t)(best >> 40) << 24;
         }
-        const u64 order = ~best & 0xffffffffffull;
-        stage[j] = (uint32_t)(order & 0xffffff) | (uint32_t)(best >> 40) << 24;
+    } else {
+        for (int j = tid; j < size; j += THREADS) {
+            const int nd = size - 1 - j;
+            u64 best = 0;
+            for (int i = nlo[nd]; i < nhi[nd]; ++i) {
+                const uint32_t c = keys[i];
+                const uint32_t x = c & 0xfff, y = (c >> 12) & 0xfff;
+                const u64 order = (u64)(__ldg(lut_cy + y) + __ldg(lut_cx + x)) << 24 | (c & 0xffffffu);
+                const u64 v = (u64)(c >> 24) << 40 | (~order & 0xffffffffffull);
+                best = v > best ? v : best;
+            }
+            const u64 order = ~best & 0xffffffffffull;
+            stage[j] = (uint32_t)(order & 0xffffff) | (uint32_t)(best >> 40) << 24;
+        }
     }
     if (tid == 0) *kp_count = (uint32_t)size;
 #ifdef ORBX_OCT_TIMING
