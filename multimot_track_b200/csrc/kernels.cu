@@ -157,6 +157,20 @@ struct ResizeArgs {                  // everything the kernel needs, resolved on
     int ntx, nty, nchunks;           // tiles per row / column; a CTA owns column tx and the tile rows chunk, chunk + nchunks, ...
 };
 
+// a = two 16-bit weights, b = pixel bytes: a.lo * b.byte0 + a.hi * b.byte1 (lo) or a.lo * b.byte2 + a.hi * b.byte3 (hi)
+__device__ __forceinline__ unsigned dp2a_lo_uu(unsigned a, unsigned b)
+{
+    unsigned d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0u));
+    return d;
+}
+__device__ __forceinline__ unsigned dp2a_hi_uu(unsigned a, unsigned b)
+{
+    unsigned d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0u));
+    return d;
+}
+
 __global__ void __launch_bounds__(256)
 k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
 {
@@ -184,14 +198,24 @@ k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
     };
     int ty = chunk;
     if (tid == 0 && ty < A.nty) issue(ty, 0);
-    // the four destination columns of this thread: source offsets inside the box and 11-bit weights (fixed for the CTA)
-    int o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0}, c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+    // the four destination columns of this thread (fixed for the CTA): their <= 8 source bytes start at byte `wb` (word aligned)
+    // + `sh` / 8 of the box row; sel01 / sel23 pick (S[s0], S[s1]) of two columns each out of that window, wk = a0 | a1 << 16 are
+    // the 11-bit weights of one column, so that H = S[s0]*a0 + S[s1]*a1 is one two-way dot product (IDP.2A)
+    int wb = 0, sh = 0;
+    unsigned sel01 = 0, sel23 = 0, wk[4] = {0, 0, 0, 0};
     if (col_ok) {
+        int i0[4], i1[4];
+        int first = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                                  // tables are padded to a multiple of 4 entries
             const ResizeTab e = A.xt[x4 + k];
-            o0[k] = e.s0 - sx_lo; o1[k] = e.s1 - sx_lo; c0[k] = e.c0; c1[k] = e.c1;
+            if (k == 0) first = e.s0 - sx_lo;
+            i0[k] = e.s0 - sx_lo - first; i1[k] = e.s1 - sx_lo - first;   // 0 .. 7 (<= 2x down-scaling)
+            wk[k] = (unsigned)e.c0 | (unsigned)e.c1 << 16;
         }
+        wb = first & ~3; sh = (first & 3) * 8;
+        sel01 = (unsigned)(i0[0] | i1[0] << 4 | i0[1] << 8 | i1[1] << 12);
+        sel23 = (unsigned)(i0[2] | i1[2] << 4 | i0[3] << 8 | i1[3] << 12);
     }
     uint8_t *dcol = A.dst + (long long)frame * A.frame_stride + x4;
     unsigned phase = 0;
@@ -207,14 +231,18 @@ k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
         phase ^= 1u << b;
         // ---- horizontal pass: source rows of the window -> Hs[r][x] = (S[s0]*a0 + S[s1]*a1) >> 4
         if (col_ok) {
-            const uint8_t *row = rs_smem + b * A.box_bytes + g * A.box_w;
+            const uint8_t *row = rs_smem + b * A.box_bytes + g * A.box_w + wb;
             int *hrow = Hs + g * kRzTW + 4 * q;
             for (int r = g; r < nrows; r += 8, row += 8 * A.box_w, hrow += 8 * kRzTW) {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(row);
+                const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+                const uint32_t p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
                 int4 h;
-                h.x = (row[o0[0]] * c0[0] + row[o1[0]] * c1[0]) >> 4;
-                h.y = (row[o0[1]] * c0[1] + row[o1[1]] * c1[1]) >> 4;
-                h.z = (row[o0[2]] * c0[2] + row[o1[2]] * c1[2]) >> 4;
-                h.w = (row[o0[3]] * c0[3] + row[o1[3]] * c1[3]) >> 4;
+                h.x = (int)(dp2a_lo_uu(wk[0], p01) >> 4);
+                h.y = (int)(dp2a_hi_uu(wk[1], p01) >> 4);
+                h.z = (int)(dp2a_lo_uu(wk[2], p23) >> 4);
+                h.w = (int)(dp2a_hi_uu(wk[3], p23) >> 4);
                 *reinterpret_cast<int4 *>(hrow) = h;
             }
         }
