@@ -157,17 +157,23 @@ struct ResizeArgs {                  // everything the kernel needs, resolved on
     int ntx, nty, nchunks;           // tiles per row / column; a CTA owns column tx and the tile rows chunk, chunk + nchunks, ...
 };
 
-// a = two 16-bit weights, b = pixel bytes: a.lo * b.byte0 + a.hi * b.byte1 (lo) or a.lo * b.byte2 + a.hi * b.byte3 (hi)
-__device__ __forceinline__ unsigned dp2a_lo_uu(unsigned a, unsigned b)
+// a = two 16-bit values, b = four bytes: c + a.lo * b.byte0 + a.hi * b.byte1 (lo) or c + a.lo * b.byte2 + a.hi * b.byte3 (hi)
+__device__ __forceinline__ unsigned dp2a_lo_uu(unsigned a, unsigned b, unsigned c = 0u)
 {
     unsigned d;
-    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0u));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-__device__ __forceinline__ unsigned dp2a_hi_uu(unsigned a, unsigned b)
+__device__ __forceinline__ unsigned dp2a_hi_uu(unsigned a, unsigned b, unsigned c = 0u)
 {
     unsigned d;
-    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0u));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned dp4a_uu(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 
@@ -476,7 +482,7 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
     constexpr int TW = kBlurTileW, TH = kBlurTileH, RWD = kBlurRawWords, PB = kBlurBoxW;
     struct __align__(128) RawBuf { uint32_t w[TH + 6][RWD]; };        // TMA destinations must be 128-byte aligned
     __shared__ RawBuf sraw[2];
-    __shared__ uint2 shv[TH + 6][TW / 4];
+    __shared__ uint4 shv[(TH + 6) / 2][TW / 4];                      // H of two tile rows interleaved: H(x, 2p) | H(x, 2p+1) << 16
     __shared__ __align__(8) uint64_t mbar[2];
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -554,42 +560,47 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
             }
         }
         __syncthreads();
-        // ---- horizontal pass, 4 pixels (two 16x2 pairs) per item
-        for (int i = tid; i < (TH + 6) * (TW / 4); i += 256) {
-            const int r = i / (TW / 4), q = i - r * (TW / 4);
-            const uint32_t w0 = raw[r][q + 3], w1 = raw[r][q + 4], w2 = raw[r][q + 5];   // pixels x-4..x-1 | x..x+3 | x+4..x+7
-            const uint32_t p0 = __byte_perm(w0, 0, 0x4140), p1 = __byte_perm(w0, 0, 0x4342), p2 = __byte_perm(w1, 0, 0x4140);
-            const uint32_t p3 = __byte_perm(w1, 0, 0x4342), p4 = __byte_perm(w2, 0, 0x4140), p5 = __byte_perm(w2, 0, 0x4342);
-            const uint32_t a0 = __funnelshift_r(p0, p1, 16), a1 = p1, a2 = __funnelshift_r(p1, p2, 16), a3 = p2;
-            const uint32_t a4 = __funnelshift_r(p2, p3, 16), a5 = p3, a6 = __funnelshift_r(p3, p4, 16), a7 = p4;
-            const uint32_t a8 = __funnelshift_r(p4, p5, 16);                   // a_k = pixels (x-3+k, x-2+k)
-            // seven multiply-adds each (IMAD runs on the FMA pipe, which has twice the integer-ALU throughput)
-            const uint32_t o01 = mad7(a0, a1, a2, a3, a4, a5, a6, 0u), o23 = mad7(a2, a3, a4, a5, a6, a7, a8, 0u);
-            shv[r][q] = make_uint2(o01, o23);
+        // ---- horizontal pass: item = (pair of tile rows, pixel quad).  H(x) = sum_i k[i] * p[x+i-3] as two four-way dot
+        //      products (IDP.4A) on the byte windows x-3..x and x+1..x+4 (funnel shifts of the three aligned words around the quad);
+        //      the two rows leave interleaved, H(x, r) | H(x, r+1) << 16, which is the operand form the vertical pass wants
+        constexpr unsigned kWA = 18u | 34u << 8 | 48u << 16 | 56u << 24, kWB = 48u | 34u << 8 | 18u << 16;
+        for (int i = tid; i < (TH + 6) / 2 * (TW / 4); i += 256) {
+            const int pr = i / (TW / 4), q = i - pr * (TW / 4);
+            uint32_t hrow[2][4];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint32_t *rw = &raw[2 * pr + rr][q + 3];
+                const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];              // pixels x-4..x-1 | x..x+3 | x+4..x+7
+                hrow[rr][0] = dp4a_uu(__funnelshift_r(w1, w2, 8), kWB, dp4a_uu(__funnelshift_r(w0, w1, 8), kWA, 0u));
+                hrow[rr][1] = dp4a_uu(__funnelshift_r(w1, w2, 16), kWB, dp4a_uu(__funnelshift_r(w0, w1, 16), kWA, 0u));
+                hrow[rr][2] = dp4a_uu(__funnelshift_r(w1, w2, 24), kWB, dp4a_uu(__funnelshift_r(w0, w1, 24), kWA, 0u));
+                hrow[rr][3] = dp4a_uu(w2, kWB, dp4a_uu(w1, kWA, 0u));
+            }
+            shv[pr][q] = make_uint4(__byte_perm(hrow[0][0], hrow[1][0], 0x5410), __byte_perm(hrow[0][1], hrow[1][1], 0x5410),
+                                    __byte_perm(hrow[0][2], hrow[1][2], 0x5410), __byte_perm(hrow[0][3], hrow[1][3], 0x5410));
         }
         __syncthreads();
-        // ---- vertical pass: thread = (pixel quad, 8-row segment)
+        // ---- vertical pass: thread = (pixel quad, 8-row segment).  V(y) = sum_j k[j] * H(y+j) + 32768 over the row pairs as four
+        //      two-way dot products (IDP.2A): even rows pair the taps (0,1)(2,3)(4,5)(6,-), odd rows (-,0)(1,2)(3,4)(5,6)
         const int q = tid & 31, seg = tid >> 5;
         const int gx = tx0 + 4 * q, gy0 = ty0 + seg * 8;
         if (gx < G.w && gy0 < G.h) {
+            uint4 pv[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) pv[j] = shv[seg * 4 + j][q];
             uint32_t out[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) out[r] = 0;
+            for (int m = 0; m < 4; ++m) {
+                const uint32_t *p0 = &pv[m].x, *p1 = &pv[m + 1].x, *p2 = &pv[m + 2].x, *p3 = &pv[m + 3].x;
+                uint32_t ve[4], vo[4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t lo[14], hi[14];
-#pragma unroll
-                for (int j = 0; j < 14; ++j) {
-                    const uint2 t = shv[seg * 8 + j][q];
-                    const uint32_t w = half ? t.y : t.x;
-                    lo[j] = w & 0xffffu; hi[j] = w >> 16;
+                for (int c = 0; c < 4; ++c) {
+                    ve[c] = dp2a_lo_uu(p3[c], 18u, dp2a_lo_uu(p2[c], 48u | 34u << 8, dp2a_lo_uu(p1[c], 48u | 56u << 8, dp2a_lo_uu(p0[c], 18u | 34u << 8, 32768u))));
+                    vo[c] = dp2a_lo_uu(p3[c], 34u | 18u << 8, dp2a_lo_uu(p2[c], 56u | 48u << 8, dp2a_lo_uu(p1[c], 34u | 48u << 8, dp2a_lo_uu(p0[c], 18u << 8, 32768u))));
                 }
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint32_t v0 = mad7(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5], lo[r + 6], 32768u);
-                    const uint32_t v1 = mad7(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5], hi[r + 6], 32768u);
-                    out[r] |= ((v0 >> 16) | (v1 >> 16) << 8) << (16 * half);
-                }
+                // byte 2 of each sum is the rounded result (sums < 2^24)
+                out[2 * m] = __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
+                out[2 * m + 1] = __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
             }
             uint8_t *dst = P->blur + (long long)frame * P->pyr_frame_bytes + G.img_off + gx;
 #pragma unroll
