@@ -181,6 +181,7 @@ def main():
     torch.cuda.set_device(local)
     numa_cpus = bind_to_gpu_numa_node(torch, local) if world > 1 and not os.environ.get("ORBX_NO_NUMA_BIND") else None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.warmup < 3:
         args.warmup = 3

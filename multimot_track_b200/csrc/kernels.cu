@@ -977,8 +977,11 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
         const dim3 grid((n_small + C::WARPS - 1) / C::WARPS, nframes);
         // 4 CTAs / SM (104 registers) and a 12-deep staging unroll measured best; 5 CTAs at 96 registers, shallower unrolls,
         // persistent CTAs and the TMA variant above were all slower
-        cudaFuncSetAttribute(k_fast_fused<44, 4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        k_fast_fused<44, 4, 12><<<grid, C::WARPS * 32, C::SMEM, st>>>(dP, s0, 0, n_small);
+        // experiment knob: extra dynamic shared memory per CTA caps the FAST CTAs per SM and leaves registers / shared memory to the
+        // other handles' kernels (k_blur, k_resize_sep fit beside three of them).  Measured slower: 16 KB (3 CTAs / SM) 0.311 vs 0.291 ms.
+        static const int pad = std::getenv("ORBX_FAST_PAD_KB") ? std::atoi(std::getenv("ORBX_FAST_PAD_KB")) * 1024 : 0;
+        cudaFuncSetAttribute(k_fast_fused<44, 4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad);
+        k_fast_fused<44, 4, 12><<<grid, C::WARPS * 32, C::SMEM + pad, st>>>(dP, s0, 0, n_small);
         ls->launches++;
     }
     if (hP.n_ffast_work > n_small) {
