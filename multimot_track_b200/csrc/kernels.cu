@@ -685,10 +685,16 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     const int dx0 = 2 * lane, dx1 = dx0 + 1;
     const bool in0 = dx0 < span, in1 = dx1 < span;
     const int c0 = dx0 >= wc, c1 = dx1 >= wc;                          // cell (0/1) of my pixels
-    const unsigned in_mask = (in0 ? 0xffffu : 0u) | (in1 ? 0xffff0000u : 0u);
-    // Lv = (left neighbour of px0, px0 as left neighbour of px1); Rv = (px1 as right neighbour of px0, right neighbour of px1)
-    const unsigned mL = ((dx0 > 0 && (dx0 - 1 >= wc) == c0) ? 0xffffu : 0u) | ((c0 == c1) ? 0xffff0000u : 0u);
-    const unsigned mR = ((in1 && c0 == c1) ? 0xffffu : 0u) | ((dx1 + 1 < span && (dx1 + 1 >= wc) == c1) ? 0xffff0000u : 0u);
+    // pixels outside the job keep whatever score their ring gives (they are never anybody's neighbour, see below) and are
+    // dropped where survivors are recorded
+    const unsigned in_mask = (in0 ? 0xffffu : 0u) | (in1 ? 0xffff0000u : 0u), in_sign = in_mask & 0x80008000u;
+    // Lv = (left neighbour of px0, px0 as left neighbour of px1); Rv = (px1 as right neighbour of px0, right neighbour of px1),
+    // each half zero when that neighbour is in another cell or outside the job.  Scores S' are <= 255, so the high byte of
+    // every half is zero and ONE byte permute both moves the halves and masks them (a masked half selects high bytes only).
+    const bool mL0 = dx0 > 0 && (dx0 - 1 >= wc) == c0, mL1 = c0 == c1;
+    const bool mR0 = in1 && c0 == c1, mR1 = dx1 + 1 < span && (dx1 + 1 >= wc) == c1;
+    const unsigned selL = (mL0 ? 0x76u : 0x77u) | (mL1 ? 0x1000u : 0x1100u);       // __byte_perm(Cv, Pl, selL) = (Pl.hi | 0, Cv.lo | 0)
+    const unsigned selR = (mR0 ? 0x32u : 0x33u) | (mR1 ? 0x5400u : 0x5500u);       // __byte_perm(Cv, Pr, selR) = (Cv.hi | 0, Pr.lo | 0)
     const bool straddle = in1 && c0 != c1;                             // my two pixels belong to different cells: independent columns
     const int th_store = min(P->min_th, P->ini_th);
     // S' = score - th_store + 1 where the pixel is a corner at th_store (>= 1), else 0.  VIADD.16x2 / VIADDMNMX.S16x2 are
@@ -719,8 +725,8 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     {                                                                                                            \
         const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
         const unsigned t_ = __vadd2(~m8, (Cc));                                                                  \
-        if (~t_ & 0x80008000u) {                                                                                 \
-            const unsigned ev = (Cc) & ~__byte_perm(t_, 0u, 0xBB99);                                             \
+        if (~t_ & in_sign) {                                                                                     \
+            const unsigned ev = (Cc) & ~__byte_perm(t_, 0u, 0xBB99) & in_mask;                                   \
             mylist[nl * lstride] = (ev & 0x1ffu) | ((ev >> 7) & 0x3fe00u) | ((unsigned)(yy) << 18);              \
             ++nl;                                                                                                \
         }                                                                                                        \
@@ -768,10 +774,10 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
                 const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
                 // bright: maxmin - c - th = maxmin + (~c + 1 - th); dark: c - minmax - th = (c + 1 - th) + ~minmax
                 const unsigned tb = __viaddmax_s16x2_relu(maxmin, __vadd2(~cc, k1mth), 0u);
-                const unsigned Cv = __viaddmax_s16x2(__vadd2(cc, k1mth), ~minmax, tb) & in_mask;
+                const unsigned Cv = __viaddmax_s16x2(__vadd2(cc, k1mth), ~minmax, tb);
                 // neighbours in the same row, masked to the pixels' own cells
                 const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
-                const unsigned Lv = __funnelshift_r(Pl, Cv, 16) & mL, Rv = __funnelshift_r(Cv, Pr, 16) & mR;
+                const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
                 const unsigned T0 = __vimax3_s16x2(Lv, Cv, Rv), U0 = __vmaxs2(Lv, Rv);
                 if (y > 0) FF_NMS(y - 1, T2, U1, C1, T0)
                 T2 = T1; T1 = T0; U1 = U0; C1 = Cv;
