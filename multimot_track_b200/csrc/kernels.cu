@@ -772,9 +772,8 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
                 }
                 const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
                 const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
-                // bright: maxmin - c - th = maxmin + (~c + 1 - th); dark: c - minmax - th = (c + 1 - th) + ~minmax
-                const unsigned tb = __viaddmax_s16x2_relu(maxmin, __vadd2(~cc, k1mth), 0u);
-                const unsigned Cv = __viaddmax_s16x2(__vadd2(cc, k1mth), ~minmax, tb);
+                // bright - 1 = maxmin + ~c, dark - 1 = c + ~minmax; S' = max(bright, dark) - th, clamped at 0
+                const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, ~minmax, __vadd2(maxmin, ~cc)), k1mth, 0u);
                 // neighbours in the same row, masked to the pixels' own cells
                 const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
                 const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
