@@ -675,6 +675,14 @@ __device__ __forceinline__ FfJob ff_job(const DevParams *__restrict__ P, int wid
 }
 
 // Scores, cell-local non-max suppression, threshold choice and emission of one job whose 16-bit tile is staged.
+// ~x as x * -1 + -1: an IMAD, i.e. FMA-pipe work, in a kernel that is bound by the integer ALU pipe (LOP3 would go there)
+__device__ __forceinline__ unsigned not_fma(unsigned x)
+{
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, 0xffffffff, 0xffffffff;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 template <int CELL>
 __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, const FfJob &J, uint32_t *tile, uint32_t *list, int lane)
 {
@@ -724,7 +732,7 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
 #define FF_NMS(yy, Tabove, Umid, Cc, Tbelow)                                                                     \
     {                                                                                                            \
         const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
-        const unsigned t_ = __vadd2(~m8, (Cc));                                                                  \
+        const unsigned t_ = __vadd2(not_fma(m8), (Cc));                                                                  \
         if (~t_ & in_sign) {                                                                                     \
             const unsigned ev = (Cc) & ~__byte_perm(t_, 0u, 0xBB99) & in_mask;                                   \
             mylist[nl * lstride] = (ev & 0x1ffu) | ((ev >> 7) & 0x3fe00u) | ((unsigned)(yy) << 18);              \
@@ -773,7 +781,7 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
                 const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
                 const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
                 // bright - 1 = maxmin + ~c, dark - 1 = c + ~minmax; S' = max(bright, dark) - th, clamped at 0
-                const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, ~minmax, __vadd2(maxmin, ~cc)), k1mth, 0u);
+                const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, not_fma(minmax), __vadd2(maxmin, not_fma(cc))), k1mth, 0u);
                 // neighbours in the same row, masked to the pixels' own cells
                 const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
                 const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
