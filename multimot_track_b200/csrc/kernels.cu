@@ -683,6 +683,19 @@ __device__ __forceinline__ unsigned not_fma(unsigned x)
     return r;
 }
 
+__device__ __forceinline__ unsigned lds_u16(unsigned addr)          // kept apart from the word loads of the same row on purpose
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned mad_fma(unsigned a, unsigned b, unsigned c)
+{
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 template <int CELL>
 __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, const FfJob &J, uint32_t *tile, uint32_t *list, int lane)
 {
@@ -717,13 +730,18 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
 
     unsigned a[7][3], o[7][4];
     const uint32_t *col = tile + lane + 2;
+    const unsigned col_s = smem_u32(col);
+    // the odd-offset pairs (w_k.hi, w_k+1.lo) as hi16(w_k) + w_k+1 * 65536: a 16-bit shared-memory load and an IMAD (FMA pipe)
+    // instead of a funnel shift (ALU pipe, the one this kernel is bound by)
 #define FF_LOAD(slot, r)                                                                        \
     {                                                                                           \
         const uint32_t *q = col + (r) * C::PITCH;                                               \
-        const unsigned w0_ = q[-2], w1_ = q[-1], w2_ = q[0], w3_ = q[1], w4_ = q[2];            \
+        const unsigned qa = col_s + (r) * (C::PITCH * 4);                                       \
+        const unsigned w1_ = q[-1], w2_ = q[0], w3_ = q[1], w4_ = q[2];                         \
+        const unsigned h0_ = lds_u16(qa - 6), h1_ = lds_u16(qa - 2), h2_ = lds_u16(qa + 2), h3_ = lds_u16(qa + 6); \
         a[slot][0] = w1_; a[slot][1] = w2_; a[slot][2] = w3_;                                   \
-        o[slot][0] = __funnelshift_r(w0_, w1_, 16); o[slot][1] = __funnelshift_r(w1_, w2_, 16); \
-        o[slot][2] = __funnelshift_r(w2_, w3_, 16); o[slot][3] = __funnelshift_r(w3_, w4_, 16); \
+        o[slot][0] = mad_fma(w1_, 65536u, h0_); o[slot][1] = mad_fma(w2_, 65536u, h1_);         \
+        o[slot][2] = mad_fma(w3_, 65536u, h2_); o[slot][3] = mad_fma(w4_, 65536u, h3_);         \
     }
     // finalize the non-max suppression of row `yy` whose centre is Cc, with max-of-3 of the rows above / below.
     // t = Cc + ~m8 = Cc - m8 - 1 >= 0  <=>  centre strictly greater than all 8 neighbours (and then Cc >= 1).  A row with a survivor
