@@ -179,7 +179,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
-    numa_cpus = bind_to_gpu_numa_node(torch, local) if world > 1 and not os.environ.get("ORBX_NO_NUMA_BIND") else None
+    # the pinned host buffers (first touch) and the submitting thread go to the CPUs next to the GPU; the CPU baseline later
+    # gets the process's original affinity back
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_cpus = bind_to_gpu_numa_node(torch, local) if not os.environ.get("ORBX_NO_NUMA_BIND") else None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -433,6 +436,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.oracle import Oracle, RefExtractor
+        if affinity0 is not None:
+            os.sched_setaffinity(0, affinity0)                          # all host cores for the reference
         cores = os.cpu_count() or 1
         chunk = np.ascontiguousarray(pool[:max(1, min(POOL_DISTINCT, cores))])
         if RefExtractor.available("asis"):
