@@ -112,6 +112,19 @@ def test_other_shapes_and_parameters(orb, oracle_mod, shape, params):
     check_frame(ext, o, synth(40, *shape), "shape%s" % (shape,))
 
 
+@pytest.mark.parametrize("shape,params", [((241, 323), (400, 1.7, 3, 20, 7)), ((613, 401), (800, 1.85, 3, 20, 7)),
+                                          ((377, 1241), (1200, 2.0, 3, 20, 7)), ((301, 1023), (900, 1.1, 10, 30, 2))])
+def test_scale_factors_and_odd_sizes(orb, oracle_mod, shape, params):
+    """Odd widths / heights (partial resize, blur and FAST tiles on every side) and scale factors up to 2: 1.7 and 1.85 are the widest
+    source windows the separable TMA resize takes (its byte-permute selectors span 8 source bytes per four columns), 2.0 goes to the
+    plain kernel; thresholds 30 / 2 make almost every pixel a survivor candidate of the per-lane lists."""
+    ext = orb.ORBextractor(*params)
+    o = oracle_mod.Oracle(*params)
+    check_frame(ext, o, synth(41, *shape), "scale%s" % (params[1],))
+    from multimot_track_b200.synth import uniform_noise_frame
+    check_frame(ext, o, uniform_noise_frame(6, *shape), "noise%s" % (shape,))
+
+
 def test_edge_inputs(orb, oracle_mod):
     ext = orb.ORBextractor(1000, 1.2, 8, 20, 7)
     o = oracle_mod.Oracle(1000, 1.2, 8, 20, 7)
