@@ -1750,6 +1750,9 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevPara
     __syncthreads();
     const int n = s_prefix[L];
     if (blockIdx.x == 0 && threadIdx.x == 0) P->out_n[frame] = n;
+    uint32_t rmask[8];                                               // this lane's (= patch row's) circular mask, fixed for the kernel
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rmask[k] = smask[k * 32 + lane];
     const int step = gridDim.x * kOdWarps;
     int j = blockIdx.x * kOdWarps + warp;
     if (j >= n) return;
@@ -1838,15 +1841,15 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevPara
             int rowsum = 0, mu = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t v = __funnelshift_r(w[k], w[k + 1], sh) & smask[k * 32 + lane];
+                const uint32_t v = __funnelshift_r(w[k], w[k + 1], sh) & rmask[k];
                 constexpr int kOnes = 0x01010101;
                 const int u0 = 4 * k - 15;
                 const int wu = (u0 & 0xff) | ((u0 + 1) & 0xff) << 8 | ((u0 + 2) & 0xff) << 16 | ((u0 + 3) & 0xff) << 24;
                 rowsum = dp4a_us(v, kOnes, rowsum);
                 mu = dp4a_us(v, wu, mu);
             }
-            m10 = warp_sum(mu);
-            m01 = warp_sum((lane - 15) * rowsum);
+            m10 = __reduce_add_sync(0xffffffffu, mu);                 // REDUX.SUM: one instruction per moment
+            m01 = __reduce_add_sync(0xffffffffu, (lane - 15) * rowsum);
         }
         const float angle = fast_atan2_deg((float)m01, (float)m10);
         // ---- steered rBRIEF (:108-147)
