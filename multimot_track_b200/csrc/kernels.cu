@@ -1753,6 +1753,9 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevPara
     uint32_t rmask[8];                                               // this lane's (= patch row's) circular mask, fixed for the kernel
 #pragma unroll
     for (int k = 0; k < 8; ++k) rmask[k] = smask[k * 32 + lane];
+    float4 rpat[8];                                                  // and its eight rBRIEF sample pairs (byte `lane` of the descriptor)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rpat[k] = spatf[k * 32 + lane];
     const int step = gridDim.x * kOdWarps;
     int j = blockIdx.x * kOdWarps + warp;
     if (j >= n) return;
@@ -1865,7 +1868,7 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevPara
         unsigned byte = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float4 pt = spatf[k * 32 + lane];
+            const float4 pt = rpat[k];
             const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, bs), __fmul_rn(pt.y, a)), kMagic));
             const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, bs)), kMagic));
             const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, bs), __fmul_rn(pt.w, a)), kMagic));
