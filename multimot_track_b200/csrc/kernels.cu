@@ -1836,21 +1836,29 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevPara
         int m10, m01;
         {
             const int xoff = cx - 15 - ((cx - 15) & ~15);
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(icp + (lane < 31 ? lane : 0) * kOdIcW + (xoff & ~3));
+            // the whole 48-byte box row as three 128-bit loads; the patch starts at word xoff / 4 of it (uniform over the warp)
+            const uint4 *row = reinterpret_cast<const uint4 *>(icp + (lane < 31 ? lane : 0) * kOdIcW);
+            const uint4 q0 = row[0], q1 = row[1], q2 = row[2];
+            const uint32_t rw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
             const int sh = (xoff & 3) * 8;
-            uint32_t w[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) w[k] = row[k];
             int rowsum = 0, mu = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t v = __funnelshift_r(w[k], w[k + 1], sh) & rmask[k];
-                constexpr int kOnes = 0x01010101;
-                const int u0 = 4 * k - 15;
-                const int wu = (u0 & 0xff) | ((u0 + 1) & 0xff) << 8 | ((u0 + 2) & 0xff) << 16 | ((u0 + 3) & 0xff) << 24;
-                rowsum = dp4a_us(v, kOnes, rowsum);
-                mu = dp4a_us(v, wu, mu);
+#define OD_MOMENTS(WO)                                                                                       \
+            _Pragma("unroll")                                                                                \
+            for (int k = 0; k < 8; ++k) {                                                                    \
+                const uint32_t v = __funnelshift_r(rw[WO + k], rw[WO + k + 1], sh) & rmask[k];               \
+                constexpr int kOnes = 0x01010101;                                                            \
+                const int u0 = 4 * k - 15;                                                                   \
+                const int wu = (u0 & 0xff) | ((u0 + 1) & 0xff) << 8 | ((u0 + 2) & 0xff) << 16 | ((u0 + 3) & 0xff) << 24; \
+                rowsum = dp4a_us(v, kOnes, rowsum);                                                          \
+                mu = dp4a_us(v, wu, mu);                                                                     \
             }
+            switch (xoff >> 2) {
+            case 0: OD_MOMENTS(0) break;
+            case 1: OD_MOMENTS(1) break;
+            case 2: OD_MOMENTS(2) break;
+            default: OD_MOMENTS(3) break;
+            }
+#undef OD_MOMENTS
             m10 = __reduce_add_sync(0xffffffffu, mu);                 // REDUX.SUM: one instruction per moment
             m01 = __reduce_add_sync(0xffffffffu, (lane - 15) * rowsum);
         }
