@@ -1986,8 +1986,14 @@ k_match_partial(const uint32_t *__restrict__ A, int nA, const uint32_t *__restri
         __syncthreads();
         for (int j = 0; j < cnt; ++j) {
             const uint4 lo = sB[2 * j], hi = sB[2 * j + 1];
-            const int d = __popc(a[0] ^ lo.x) + __popc(a[1] ^ lo.y) + __popc(a[2] ^ lo.z) + __popc(a[3] ^ lo.w) +
-                          __popc(a[4] ^ hi.x) + __popc(a[5] ^ hi.y) + __popc(a[6] ^ hi.z) + __popc(a[7] ^ hi.w);
+            // POPC is the slow instruction (16 lanes / clk / SM): three carry-save adders (two LOP3 each) fold the eight XOR words
+            // into two "ones" words and three "twos" words, five POPC instead of eight
+            const uint32_t x0 = a[0] ^ lo.x, x1 = a[1] ^ lo.y, x2 = a[2] ^ lo.z, x3 = a[3] ^ lo.w;
+            const uint32_t x4 = a[4] ^ hi.x, x5 = a[5] ^ hi.y, x6 = a[6] ^ hi.z, x7 = a[7] ^ hi.w;
+            const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
+            const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
+            const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
+            const int d = __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
             match_update(d, t0 + j, b1, bi, b2);
         }
     }
