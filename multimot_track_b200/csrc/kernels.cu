@@ -564,8 +564,11 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
         //      products (IDP.4A) on the byte windows x-3..x and x+1..x+4 (funnel shifts of the three aligned words around the quad);
         //      the two rows leave interleaved, H(x, r) | H(x, r+1) << 16, which is the operand form the vertical pass wants
         constexpr unsigned kWA = 18u | 34u << 8 | 48u << 16 | 56u << 24, kWB = 48u | 34u << 8 | 18u << 16;
-        for (int i = tid; i < (TH + 6) / 2 * (TW / 4); i += 256) {
+        // edge tiles: only the row pairs / quads the vertical pass of the pixels inside the image will read
+        const int pr_end = min((TH + 6) / 2, (min(TH, G.h - ty0) + 7) >> 1), q_end = min(TW / 4, (G.w - tx0 + 3) >> 2);
+        for (int i = tid; i < pr_end * (TW / 4); i += 256) {
             const int pr = i / (TW / 4), q = i - pr * (TW / 4);
+            if (q >= q_end) continue;
             uint32_t hrow[2][4];
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
@@ -991,6 +994,15 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
 {
     if (hP.n_ffast_work == 0) return cudaSuccess;
     if (maps) {
+        int max_cell = 0;
+        for (int l = 0; l < hP.nlevels; ++l) max_cell = std::max(max_cell, std::max(hP.lv[l].h_cell, hP.lv[l].w_cell));
+        if (max_cell <= 40 && n_small == hP.n_ffast_work) {
+            // cells of at most 40 rows: raw box + 16-bit tile + lists take 13.75 KB per warp, so four CTAs (16 warps) stay resident
+            cudaError_t e = launch_fast_tma<40>(dP, *maps, 0, n_small, nframes, st);
+            if (e != cudaSuccess) return e;
+            ls->launches++;
+            return cudaSuccess;
+        }
         if (n_small > 0) {
             cudaError_t e = launch_fast_tma<44>(dP, *maps, 0, n_small, nframes, st);
             if (e != cudaSuccess) return e;
