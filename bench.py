@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--handles", type=int, default=6)
     args = ap.parse_args()
     H, W, nfeat, nlev, batch, desc = WORKLOADS[args.workload]
+    if os.environ.get("ORBX_BENCH_BATCH"):                            # experiment knob: another batch size for the named shape
+        batch = int(os.environ["ORBX_BENCH_BATCH"])
+        desc = desc.rsplit(",", 1)[0] + ", batch %d per GPU" % batch
 
     if args.impl == "reference":
         return run_reference(args, H, W, nfeat, nlev, batch, desc)
