@@ -84,6 +84,28 @@ def test_port_matches_live_reference(oracle_mod):
                 assert np.array_equal(o.level_padded(l), ref.pyramid_level(l, True))
 
 
+@pytest.mark.parametrize("shape,params", [((241, 323), (400, 1.7, 3, 20, 7)), ((613, 401), (800, 1.85, 3, 20, 7)),
+                                          ((377, 1241), (1200, 2.0, 3, 20, 7)), ((301, 1023), (900, 1.1, 10, 30, 2)),
+                                          ((230, 231), (300, 1.2, 8, 20, 7)), ((300, 700), (500, 1.5, 4, 25, 10))])
+def test_port_matches_live_reference_scale_factors(oracle_mod, shape, params):
+    """The shapes / scale factors / thresholds of the GPU parity tests (tests/test_gpu_parity.py::test_scale_factors_and_odd_sizes,
+    test_other_shapes_and_parameters): the port equals the reference's own ORBextractor.cc there too, on value noise and on dense
+    uniform noise (keypoints incl. angle bits, descriptors, every pyramid level with and without the border)."""
+    if not oracle_mod.RefExtractor.available("canon"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from multimot_track_b200.synth import uniform_noise_frame, value_noise_frame
+    ref = oracle_mod.RefExtractor(*params, "canon")
+    o = oracle_mod.Oracle(*params)
+    for img in (value_noise_frame(41, *shape), uniform_noise_frame(6, *shape)):
+        rk, rd = ref(img)
+        ok, od = o(img)
+        assert len(ok) > 50 and kps_equal_exact(ok, rk) and np.array_equal(ok["angle"].view(np.uint32), rk["angle"].view(np.uint32))
+        assert np.array_equal(od, rd)
+        for l in range(params[2]):
+            assert np.array_equal(o.level_image(l), ref.pyramid_level(l))
+            assert np.array_equal(o.level_padded(l), ref.pyramid_level(l, True))
+
+
 def test_hamming_and_matcher_rule(oracle_mod):
     rng = np.random.default_rng(3)
     A = rng.integers(0, 256, (40, 32), dtype=np.uint8)
