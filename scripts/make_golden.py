@@ -3,7 +3,7 @@
 container, where /root/reference and cv2 4.13.0 exist; the GPU box has neither the
 reference tree nor needs cv2 for these).
 
-  kitti_gray_00000{0,1}.png   grey KITTI sample frames, converted exactly like the
+  kitti_gray_00000{0..4}.png   grey KITTI sample frames, converted exactly like the
                               reference driver (imread UNCHANGED + RGB2GRAY on the stored
                               BGR bytes: Examples/RGB-D/rgbd_tum.cc:122, src/Tracking.cc:459-465)
   golden_kitti.npz            outputs of the REFERENCE's own ORBextractor.cc (canonical
@@ -41,7 +41,7 @@ def crc(a):
 # ---- KITTI frames through the reference's compiled extractor
 g = {}
 grays = []
-for i in (0, 1):
+for i in range(5):
     img = cv2.imread("%s/kitti_sample/image/%06d.png" % (REF, i), cv2.IMREAD_UNCHANGED)
     gray = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
     cv2.imwrite(os.path.join(OUT, "kitti_gray_%06d.png" % i), gray, [cv2.IMWRITE_PNG_COMPRESSION, 9])
@@ -67,6 +67,15 @@ for i in (0, 1):
         g["ncand_" + tag] = np.array([len(o.level_candidates(l)) for l in range(8)], np.int32)
         g["mincells_" + tag] = np.array([o.level_min_cells(l)[0] for l in range(8)], np.int32)
         g["blur_crc_" + tag] = np.array([crc(o.level_blurred(l)) for l in range(8)], np.uint32)
+# Config 1's consecutive-frame matching: frame i against frame i+1 with the reference's scan (src/ORBmatcher.cc:574-605),
+# distances by the reference's own compiled DescriptorDistance on a sample of pairs, TH_LOW / TH_HIGH, ratio 0.9
+for i in range(4):
+    dA, dB = g["desc_f%d_n4000" % i], g["desc_f%d_n4000" % (i + 1)]
+    for th in (50, 100):
+        idx, d1, d2, acc = Oracle.match(dA, dB, th, 0.9)
+        for j in range(0, len(dA), 97):                    # spot-check the port's distances against the reference's function
+            assert RefExtractor.descriptor_distance(dA[j], dB[idx[j]]) == d1[j]
+        g["match_f%d_th%d" % (i, th)] = np.stack([idx, d1, d2, acc.astype(np.int32)], 1).astype(np.int16)
 t = RefExtractor(2000, 1.2, 8, 20, 7).tables()
 for k, v in t.items():
     g["tables2000_" + k] = v

@@ -55,7 +55,7 @@ def test_kitti_golden_reference(orb, golden_kitti, kitti_frames):
     bad_total = bits_total = 0
     for nfeat in (4000, 2000):
         ext = orb.ORBextractor(nfeat, 1.2, 8, 20, 7)
-        for f in (0, 1):
+        for f in range(5):
             tag = "f%d_n%d" % (f, nfeat)
             kps, desc = ext(kitti_frames[f])
             ref_k, ref_d = golden_kitti["kps_" + tag], golden_kitti["desc_" + tag]
@@ -74,7 +74,7 @@ def test_kitti_golden_reference(orb, golden_kitti, kitti_frames):
 def test_kitti_stages_vs_oracle(orb, oracle_mod, kitti_frames):
     ext = orb.ORBextractor(4000, 1.2, 8, 20, 7)
     o = oracle_mod.Oracle(4000, 1.2, 8, 20, 7)
-    for f in (0, 1):
+    for f in range(5):
         check_frame(ext, o, kitti_frames[f], "kitti%d" % f)
 
 

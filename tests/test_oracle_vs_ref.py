@@ -9,7 +9,7 @@ import pytest
 from conftest import crc32, desc_bit_mismatch, kps_equal_exact
 
 
-@pytest.mark.parametrize("frame", [0, 1])
+@pytest.mark.parametrize("frame", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("nfeat", [2000, 4000])
 def test_port_matches_reference_golden(oracle_mod, golden_kitti, kitti_frames, frame, nfeat):
     tag = "f%d_n%d" % (frame, nfeat)
