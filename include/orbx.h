@@ -20,6 +20,9 @@
  * There is no CPU fallback: every compute entry point needs a CUDA device
  * (sm_100a) and returns ORBX_ERR_CUDA when none is usable.
  *
+ * Devices: every entry point runs on its handle's device and restores the calling
+ * thread's current CUDA device before it returns.
+ *
  * Threading: a handle owns one CUDA stream and all of its scratch memory.  One
  * handle must not be used from two threads at once; different handles may run
  * concurrently (the reference's stereo Frame constructor runs two extractor
@@ -152,7 +155,11 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int nframes
 /* Same, with the frames already resident in device memory (frame f starts at
  * d_frames + f*frame_stride_bytes).  Split into an asynchronous submit on the
  * handle's stream and a collect that waits for it, so a caller can keep several
- * handles in flight (results of batch i copy back while batch i+1 computes). */
+ * handles in flight (results of batch i copy back while batch i+1 computes).
+ * Lifetime of d_frames: when the pointer, stride_bytes and frame_stride_bytes are all multiples of 16 the frames are
+ * read IN PLACE as pyramid level 0 -- by this submit and by later orbx_get_pyramid_level(level 0) / orbx_stereo_match
+ * calls on the handle -- so they must stay unchanged until the next submit on this handle.  Otherwise (or with
+ * ORBX_OPT_COPY_INPUT set) they are copied into the handle's own level-0 slots and may be reused after the collect. */
 int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int nframes, int width, int height,
                        int stride_bytes, size_t frame_stride_bytes);
 int orbx_submit_host(orbx_handle *h, const uint8_t *const *frames, int nframes, int width, int height,
@@ -177,6 +184,10 @@ int orbx_get_level_size(const orbx_handle *h, int level, int *width, int *height
  * BORDER_REFLECT_101 frame of src/ORBextractor.cc:1126-1132, which
  * Frame::ComputeStereoMatches may read around a keypoint (src/Frame.cc:960-977). */
 int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride, int with_border);
+
+/* Levels 0 .. nlevels-1 of frame `frame` at once, level l into dst[l] with row stride dst_stride[l] (same meaning of
+ * with_border): one synchronisation for the whole pyramid -- what the adapter fills mvImagePyramid with. */
+int orbx_get_pyramid_levels(orbx_handle *h, int frame, int nlevels, uint8_t *const *dst, const int *dst_stride, int with_border);
 
 /* The 7x7 sigma=2 blurred level the descriptors were sampled from (:1089-1090). */
 int orbx_get_blurred_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride);
@@ -240,7 +251,8 @@ typedef struct orbx_projection_setup {
  * (CurrentFrame.mvpMapPoints[j]), -1 for none; with check_orientation the rotation histogram pruning is applied.
  * The projections, window tests and Hamming distances run on the GPU; the greedy claim bookkeeping, sequential in the
  * reference (:2028-2030, :2053), is replayed on the host over the candidate lists.  Host pointers.
- * Returns nmatches (>= 0) or a negative status (ORBX_ERR_UNSUPPORTED when one window holds more than 512 candidates). */
+ * Returns nmatches (>= 0) or a negative status.  A window may hold any number of candidates (up to 512 are staged in shared
+ * memory; a fuller window makes the call run a second time with a global staging area sized from the counts). */
 int orbx_search_by_projection(orbx_handle *h, const orbx_projection_setup *setup,
                               int n_last, const float *world_pos, const uint8_t *mp_desc, const uint8_t *valid, const int32_t *nobs,
                               const int32_t *last_octave, const float *last_angle,
@@ -254,8 +266,7 @@ int orbx_search_by_projection(orbx_handle *h, const orbx_projection_setup *setup
  * window centres and updated in place for the matched keypoints as the reference does (:888-891); nnratio = mfNNratio,
  * check_orientation = mbCheckOrientation.  matches12[i] receives vnMatches12.  The window / level gates and the Hamming
  * distances run on the GPU; the order-dependent vMatchedDistance / vnMatches21 bookkeeping (:819, :838-846) is replayed on the
- * host over the candidate lists.  Host pointers.  Returns nmatches (>= 0) or a negative status (ORBX_ERR_UNSUPPORTED when one
- * window holds more than 512 candidates). */
+ * host over the candidate lists.  Host pointers.  Returns nmatches (>= 0) or a negative status. */
 int orbx_search_for_initialization(orbx_handle *h, float min_x, float max_x, float min_y, float max_y,
                                    int n1, const int32_t *octave1, const float *angle1, const uint8_t *desc1,
                                    int n2, const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2,
@@ -369,6 +380,62 @@ int orbx_stereo_match(orbx_handle *left, orbx_handle *right, int frame_left, int
 int orbx_set_profiling(orbx_handle *h, int on);
 int orbx_get_stage_ms(orbx_handle *h, float *ms, int cap);
 const char *orbx_stage_name(int stage);
+
+/* ---- frame-sharded multi-GPU dispatcher ------------------------------ */
+
+/* Frames are independent inside ORBextractor::operator() -- the reference itself runs two extractor instances on two threads
+ * for a stereo pair (src/Frame.cc:96-99) -- so a batch or sequence shards frame-parallel across the GPUs of a box with no
+ * exchange between them.  A pool owns, per device, one worker thread and `depth` extractor handles: a submit only queues the
+ * shards, the worker threads issue the copies and launches (the caller's thread never sits in the CUDA launch path), `depth`
+ * submits overlap on every GPU, and the results land in pinned host memory per shard. */
+typedef struct orbx_pool orbx_pool;
+
+typedef struct {
+    orbx_config    extractor;   /* constructor arguments and sizing hints of every handle; max_batch = frames per device per
+                                   submit; device_id is ignored                                                            */
+    int32_t        ndevices;    /* entries of devices[]; 0 = one worker on the calling thread's current device             */
+    const int32_t *devices;     /* CUDA ordinals, one worker each (an ordinal may repeat: several workers on one GPU)       */
+    int32_t        depth;       /* submits in flight per device = handles per worker; 0 = 6                                 */
+} orbx_pool_config;
+
+/* One shard of a collected submit: nframes frames starting at frame first_frame of the submit; frame f of the shard has
+ * n[f] keypoints at kps + f*cap_per_frame and descriptors at desc + f*cap_per_frame*32 (pinned host memory of the pool). */
+typedef struct {
+    const orbx_keypoint *kps;
+    const uint8_t       *desc;
+    const int32_t       *n;
+    int32_t nframes, first_frame, cap_per_frame, device;
+} orbx_shard_result;
+
+int orbx_pool_create(const orbx_pool_config *cfg, orbx_pool **out);
+void orbx_pool_destroy(orbx_pool *p);
+const char *orbx_pool_last_error(const orbx_pool *p);      /* p may be NULL: last orbx_pool_create failure of the thread */
+int orbx_pool_devices(const orbx_pool *p);                  /* number of shards per submit                                 */
+int orbx_pool_depth(const orbx_pool *p);
+/* Handle `slot` (0 .. depth-1) of shard `shard`, e.g. for orbx_get_tables or stage read-back between submits. */
+orbx_handle *orbx_pool_handle(orbx_pool *p, int shard, int slot);
+/* The split every submit uses: shard g of G owns the contiguous frames [g*F/G, (g+1)*F/G). */
+void orbx_pool_shard_range(int nframes, int nshards, int shard, int *first, int *count);
+
+/* Host frames (as orbx_extract_batch takes them), split into contiguous blocks over the devices.  Returns a ticket >= 0
+ * without waiting for the GPUs, or a negative status (ORBX_ERR_STATE when `depth` tickets are uncollected).  The frame
+ * buffers must stay valid until the ticket is collected. */
+long long orbx_pool_submit_host(orbx_pool *p, const uint8_t *const *frames, int nframes, int width, int height, int stride_bytes);
+/* Device-resident shards (per-GPU replicas of a frame pool): shard g = nframes[g] frames at d_frames[g] on device g's GPU,
+ * laid out as orbx_submit_device takes them (same lifetime rule). */
+long long orbx_pool_submit_device(orbx_pool *p, const uint8_t *const *d_frames, const int32_t *nframes, int width, int height,
+                                  int stride_bytes, size_t frame_stride_bytes);
+/* Waits for every shard of the ticket and fills shards[orbx_pool_devices()] (may be NULL).  The views stay valid until the
+ * submit that returns ticket + depth.  Tickets may be collected in any order. */
+int orbx_pool_collect(orbx_pool *p, long long ticket, orbx_shard_result *shards);
+
+/* ---- options --------------------------------------------------------------- */
+
+/* Runtime options of a handle; set between batches (ORBX_ERR_STATE while a submit is pending). */
+#define ORBX_OPT_TMA_STAGING 1   /* 1 (default): tiles / patches arrive by cp.async.bulk.tensor; 0: plain staging loads (same results) */
+#define ORBX_OPT_FAST_TMA    2   /* 1: persistent TMA variant of the FAST kernel; default 0 (slower in the pipelined loop)           */
+#define ORBX_OPT_COPY_INPUT  3   /* 1: orbx_submit_device always copies the frames into the handle's level-0 slots; default 0        */
+int orbx_set_option(orbx_handle *h, int option, int value);
 
 /* ---- misc ---------------------------------------------------------------- */
 

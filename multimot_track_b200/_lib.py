@@ -35,6 +35,15 @@ class OrbxPlan(ctypes.Structure):
                [("umax", ctypes.c_int32 * 16)]
 
 
+class OrbxPoolConfig(ctypes.Structure):
+    _fields_ = [("extractor", OrbxConfig), ("ndevices", ctypes.c_int32), ("devices", ctypes.POINTER(ctypes.c_int32)), ("depth", ctypes.c_int32)]
+
+
+class OrbxShardResult(ctypes.Structure):
+    _fields_ = [("kps", ctypes.c_void_p), ("desc", ctypes.c_void_p), ("n", ctypes.c_void_p), ("nframes", ctypes.c_int32),
+                ("first_frame", ctypes.c_int32), ("cap_per_frame", ctypes.c_int32), ("device", ctypes.c_int32)]
+
+
 # every symbol include/orbx.h declares: (restype, argtypes)
 _VP, _I, _F, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 SIGNATURES = {
@@ -53,6 +62,7 @@ SIGNATURES = {
     "orbx_collect_view": (_I, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_I)]),
     "orbx_get_level_size": (_I, [_VP, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "orbx_get_pyramid_level": (_I, [_VP, _I, _I, _VP, _I, _I]),
+    "orbx_get_pyramid_levels": (_I, [_VP, _I, _I, _VP, _VP, _I]),
     "orbx_get_blurred_level": (_I, [_VP, _I, _I, _VP, _I]),
     "orbx_get_candidates": (_I, [_VP, _I, _I, _VP, _I, ctypes.POINTER(_I)]),
     "orbx_hamming256": (_I, [_VP, _VP]),
@@ -73,6 +83,17 @@ SIGNATURES = {
     "orbx_voc_bow": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "orbx_distinctive_descriptors": (_I, [_VP, _VP, _VP, _I, _VP, _VP]),
     "orbx_stereo_match": (_I, [_VP, _VP, _I, _I, _F, _VP, _VP, _VP, _I, _VP]),
+    "orbx_set_option": (_I, [_VP, _I, _I]),
+    "orbx_pool_create": (_I, [ctypes.POINTER(OrbxPoolConfig), ctypes.POINTER(_VP)]),
+    "orbx_pool_destroy": (None, [_VP]),
+    "orbx_pool_last_error": (ctypes.c_char_p, [_VP]),
+    "orbx_pool_devices": (_I, [_VP]),
+    "orbx_pool_depth": (_I, [_VP]),
+    "orbx_pool_handle": (_VP, [_VP, _I, _I]),
+    "orbx_pool_shard_range": (None, [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    "orbx_pool_submit_host": (ctypes.c_longlong, [_VP, _VP, _I, _I, _I, _I]),
+    "orbx_pool_submit_device": (ctypes.c_longlong, [_VP, _VP, _VP, _I, _I, _I, _SZ]),
+    "orbx_pool_collect": (_I, [_VP, ctypes.c_longlong, _VP]),
     "orbx_set_profiling": (_I, [_VP, _I]),
     "orbx_get_stage_ms": (_I, [_VP, _VP, _I]),
     "orbx_stage_name": (ctypes.c_char_p, [_I]),

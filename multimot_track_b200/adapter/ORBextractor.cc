@@ -9,6 +9,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "orbx.h"
 
@@ -69,13 +70,23 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
     }
 
     if (mbExportPyramid) {
+        // mvImagePyramid (src/ORBextractor.cc:1111-1136): every level a view into a (w+38)x(h+38) parent with the reflect-101 frame.
+        // All parents live side by side in ONE refcounted matrix and arrive with one synchronisation (orbx_get_pyramid_levels);
+        // the views keep that matrix alive the way the reference's per-level temporaries are kept alive by their views.
+        std::vector<int> lw(nlevels), lh(nlevels), xoff(nlevels), strides(nlevels);
+        int total_w = 0, max_h = 0;
         for (int level = 0; level < nlevels; ++level) {
-            int w = 0, h = 0;
-            check(mpHandle, orbx_get_level_size(mpHandle, level, &w, &h), "orbx_get_level_size");
-            cv::Mat temp(h + 2 * EDGE_THRESHOLD, w + 2 * EDGE_THRESHOLD, CV_8UC1);
-            check(mpHandle, orbx_get_pyramid_level(mpHandle, 0, level, temp.data, (int)temp.step, 1), "orbx_get_pyramid_level");
-            mvImagePyramid[level] = temp(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, w, h));
+            check(mpHandle, orbx_get_level_size(mpHandle, level, &lw[level], &lh[level]), "orbx_get_level_size");
+            xoff[level] = total_w;
+            total_w += lw[level] + 2 * EDGE_THRESHOLD;
+            if (lh[level] + 2 * EDGE_THRESHOLD > max_h) max_h = lh[level] + 2 * EDGE_THRESHOLD;
         }
+        cv::Mat store(max_h, total_w, CV_8UC1);
+        std::vector<uint8_t *> dst(nlevels);
+        for (int level = 0; level < nlevels; ++level) { dst[level] = store.data + xoff[level]; strides[level] = (int)store.step; }
+        check(mpHandle, orbx_get_pyramid_levels(mpHandle, 0, nlevels, dst.data(), strides.data(), 1), "orbx_get_pyramid_levels");
+        for (int level = 0; level < nlevels; ++level)
+            mvImagePyramid[level] = store(cv::Rect(xoff[level] + EDGE_THRESHOLD, EDGE_THRESHOLD, lw[level], lh[level]));
     }
 }
 

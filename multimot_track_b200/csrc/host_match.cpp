@@ -19,6 +19,9 @@ int rotation_bin_host(float a, float b)                              // :2060-20
     const float factor = 1.0f / ORBX_HISTO_LENGTH;
     float rot = a - b;
     if (rot < 0.0) rot += 360.0f;
+    // the reference asserts bin in [0, HISTO_LENGTH) (:618 and the other matchers); angles outside [0, 360) or NaN go to the overflow
+    // bin HISTO_LENGTH, which ComputeThreeMaxima never selects, so such a match is pruned instead of indexing out of bounds
+    if (!(rot >= 0.0f && rot < 915.0f)) return ORBX_HISTO_LENGTH;
     int bin = (int)roundf(rot * factor);
     if (bin == ORBX_HISTO_LENGTH) bin = 0;
     return bin;
@@ -71,7 +74,7 @@ int resolve_initialization_matches(int n1, int n2, const unsigned long long *can
         }
     }
     if (check_orientation) {
-        int cnt[ORBX_HISTO_LENGTH] = {0}, i1, i2, i3;
+        int cnt[ORBX_HISTO_LENGTH + 1] = {0}, i1, i2, i3;
         for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
         three_maxima_host(cnt, i1, i2, i3);
         for (size_t k = 0; k < hist_bin.size(); ++k)
@@ -138,7 +141,7 @@ int resolve_bow_matches(int n_entries, const int *entries, const uint16_t *dist,
         }
     }
     if (check_orientation) {
-        int cnt[ORBX_HISTO_LENGTH] = {0}, i1, i2, i3;
+        int cnt[ORBX_HISTO_LENGTH + 1] = {0}, i1, i2, i3;
         for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
         three_maxima_host(cnt, i1, i2, i3);
         for (size_t k = 0; k < hist_bin.size(); ++k)
@@ -173,7 +176,7 @@ int resolve_bow_matches_kf(int n_entries, const int *entries, const uint16_t *di
         }
     }
     if (check_orientation) {
-        int cnt[ORBX_HISTO_LENGTH] = {0}, i1, i2, i3;
+        int cnt[ORBX_HISTO_LENGTH + 1] = {0}, i1, i2, i3;
         for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
         three_maxima_host(cnt, i1, i2, i3);
         for (size_t k = 0; k < hist_bin.size(); ++k)
@@ -208,7 +211,7 @@ int resolve_projection_matches(int n_last, int n_cur, const unsigned long long *
         }
     }
     if (check_orientation) {
-        int cnt[ORBX_HISTO_LENGTH] = {0};
+        int cnt[ORBX_HISTO_LENGTH + 1] = {0};
         for (size_t k = 0; k < hist_bin.size(); ++k) cnt[hist_bin[k]]++;
         int i1, i2, i3;
         three_maxima_host(cnt, i1, i2, i3);

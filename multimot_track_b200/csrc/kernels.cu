@@ -12,6 +12,7 @@
 // Integer stages are bit-exact restatements of the OpenCV fixed-point arithmetic;
 // float stages use explicit round-to-nearest intrinsics so nothing is contracted
 // into an FMA.
+#include <type_traits>
 #include "kernels.cuh"
 
 #include <cstdio>
@@ -21,6 +22,19 @@
 namespace orbx {
 
 constexpr int kMaxOptInSmem = 224 * 1024;     // dynamic shared memory opt-in cap (227 KB per CTA on sm_100, minus room for static)
+
+// Experiment knobs (scripts/exp_*.py) exist only in the -DORBX_DEBUG_KNOBS build (`make dbg` -> liborbx_dbg.so); the release
+// library never reads the environment.
+static inline int debug_knob(const char *name, int dflt)
+{
+#ifdef ORBX_DEBUG_KNOBS
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
 
 // ------------------------------------------------------------------ helpers
 
@@ -762,56 +776,66 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) FF_LOAD(r, r)
-    for (int g = 0; g < nrows; g += 7) {
+    // one row of scores + the NMS of the row above; U = row index mod 7 (a compile-time constant: the 7-row window rotates through
+    // fixed register slots).  Whole groups of seven rows run without per-row guards, the last partial group with them.
+    auto ff_row = [&](auto U, const int y) {
+        constexpr int u = decltype(U)::value;
+        FF_LOAD((u + 6) % 7, y + 6)
+        const int sc = (u + 3) % 7, sp3 = (u + 6) % 7, sp2 = (u + 5) % 7, sp1 = (u + 4) % 7;
+        const int sm1 = (u + 2) % 7, sm2 = (u + 1) % 7, sm3 = u % 7;
+        const unsigned cc = a[sc][1];
+        unsigned e[16];
+        e[0] = a[sp3][1]; e[1] = o[sp3][2]; e[15] = o[sp3][1];
+        e[2] = a[sp2][2]; e[14] = a[sp2][0];
+        e[3] = o[sp1][3]; e[13] = o[sp1][0];
+        e[4] = o[sc][3];  e[12] = o[sc][0];
+        e[5] = o[sm1][3]; e[11] = o[sm1][0];
+        e[6] = a[sm2][2]; e[10] = a[sm2][0];
+        e[7] = o[sm3][2]; e[8] = a[sm3][1]; e[9] = o[sm3][1];
+        // The 16 arcs of 9 in pairs: arcs 2i and 2i+1 share the 8 ring pixels 2i+1 .. 2i+8 (B), so
+        // max(min(arc 2i), min(arc 2i+1)) = min(B, max(e[2i], e[2i+9])) -- 36 packed min / max per polarity instead of 40.
+        unsigned lo2[8], hi2[8];
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            const int y = g + u;
-            if (y < nrows) {
-                FF_LOAD((u + 6) % 7, y + 6)
-                const int sc = (u + 3) % 7, sp3 = (u + 6) % 7, sp2 = (u + 5) % 7, sp1 = (u + 4) % 7;
-                const int sm1 = (u + 2) % 7, sm2 = (u + 1) % 7, sm3 = u % 7;
-                const unsigned cc = a[sc][1];
-                unsigned e[16];
-                e[0] = a[sp3][1]; e[1] = o[sp3][2]; e[15] = o[sp3][1];
-                e[2] = a[sp2][2]; e[14] = a[sp2][0];
-                e[3] = o[sp1][3]; e[13] = o[sp1][0];
-                e[4] = o[sc][3];  e[12] = o[sc][0];
-                e[5] = o[sm1][3]; e[11] = o[sm1][0];
-                e[6] = a[sm2][2]; e[10] = a[sm2][0];
-                e[7] = o[sm3][2]; e[8] = a[sm3][1]; e[9] = o[sm3][1];
-                // The 16 arcs of 9 in pairs: arcs 2i and 2i+1 share the 8 ring pixels 2i+1 .. 2i+8 (B), so
-                // max(min(arc 2i), min(arc 2i+1)) = min(B, max(e[2i], e[2i+9])) -- 36 packed min / max per polarity instead of 40.
-                unsigned lo2[8], hi2[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    lo2[i] = __vmins2(e[2 * i + 1], e[(2 * i + 2) & 15]);
-                    hi2[i] = __vmaxs2(e[2 * i + 1], e[(2 * i + 2) & 15]);
-                }
-                unsigned lo4[8], hi4[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    lo4[i] = __vmins2(lo2[i], lo2[(i + 1) & 7]);
-                    hi4[i] = __vmaxs2(hi2[i], hi2[(i + 1) & 7]);
-                }
-                unsigned bv[8], dv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    bv[i] = __vimin3_s16x2(lo4[i], lo4[(i + 2) & 7], __vmaxs2(e[2 * i], e[(2 * i + 9) & 15]));
-                    dv[i] = __vimax3_s16x2(hi4[i], hi4[(i + 2) & 7], __vmins2(e[2 * i], e[(2 * i + 9) & 15]));
-                }
-                const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
-                const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
-                // bright - 1 = maxmin + ~c, dark - 1 = c + ~minmax; S' = max(bright, dark) - th, clamped at 0
-                const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, not_fma(minmax), __vadd2(maxmin, not_fma(cc))), k1mth, 0u);
-                // neighbours in the same row, masked to the pixels' own cells
-                const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
-                const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
-                const unsigned T0 = __vimax3_s16x2(Lv, Cv, Rv), U0 = __vmaxs2(Lv, Rv);
-                if (y > 0) FF_NMS(y - 1, T2, U1, C1, T0)
-                T2 = T1; T1 = T0; U1 = U0; C1 = Cv;
-            }
+        for (int i = 0; i < 8; ++i) {
+            lo2[i] = __vmins2(e[2 * i + 1], e[(2 * i + 2) & 15]);
+            hi2[i] = __vmaxs2(e[2 * i + 1], e[(2 * i + 2) & 15]);
         }
+        unsigned lo4[8], hi4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            lo4[i] = __vmins2(lo2[i], lo2[(i + 1) & 7]);
+            hi4[i] = __vmaxs2(hi2[i], hi2[(i + 1) & 7]);
+        }
+        unsigned bv[8], dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            bv[i] = __vimin3_s16x2(lo4[i], lo4[(i + 2) & 7], __vmaxs2(e[2 * i], e[(2 * i + 9) & 15]));
+            dv[i] = __vimax3_s16x2(hi4[i], hi4[(i + 2) & 7], __vmins2(e[2 * i], e[(2 * i + 9) & 15]));
+        }
+        const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
+        const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
+        // bright - 1 = maxmin + ~c, dark - 1 = c + ~minmax; S' = max(bright, dark) - th, clamped at 0
+        const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, not_fma(minmax), __vadd2(maxmin, not_fma(cc))), k1mth, 0u);
+        // neighbours in the same row, masked to the pixels' own cells
+        const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
+        const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
+        const unsigned T0 = __vimax3_s16x2(Lv, Cv, Rv), U0 = __vmaxs2(Lv, Rv);
+        if (y > 0) FF_NMS(y - 1, T2, U1, C1, T0)
+        T2 = T1; T1 = T0; U1 = U0; C1 = Cv;
+    };
+    int g = 0;
+    for (; g + 7 <= nrows; g += 7) {
+        ff_row(std::integral_constant<int, 0>{}, g);     ff_row(std::integral_constant<int, 1>{}, g + 1);
+        ff_row(std::integral_constant<int, 2>{}, g + 2); ff_row(std::integral_constant<int, 3>{}, g + 3);
+        ff_row(std::integral_constant<int, 4>{}, g + 4); ff_row(std::integral_constant<int, 5>{}, g + 5);
+        ff_row(std::integral_constant<int, 6>{}, g + 6);
     }
+    if (g < nrows) ff_row(std::integral_constant<int, 0>{}, g);
+    if (g + 1 < nrows) ff_row(std::integral_constant<int, 1>{}, g + 1);
+    if (g + 2 < nrows) ff_row(std::integral_constant<int, 2>{}, g + 2);
+    if (g + 3 < nrows) ff_row(std::integral_constant<int, 3>{}, g + 3);
+    if (g + 4 < nrows) ff_row(std::integral_constant<int, 4>{}, g + 4);
+    if (g + 5 < nrows) ff_row(std::integral_constant<int, 5>{}, g + 5);
     FF_NMS(nrows - 1, T2, U1, C1, 0u)
 #undef FF_LOAD
 #undef FF_NMS
@@ -1022,7 +1046,7 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
         // persistent CTAs and the TMA variant above were all slower
         // experiment knob: extra dynamic shared memory per CTA caps the FAST CTAs per SM and leaves registers / shared memory to the
         // other handles' kernels (k_blur, k_resize_sep fit beside three of them).  Measured slower: 16 KB (3 CTAs / SM) 0.311 vs 0.291 ms.
-        static const int pad = std::getenv("ORBX_FAST_PAD_KB") ? std::atoi(std::getenv("ORBX_FAST_PAD_KB")) * 1024 : 0;
+        static const int pad = debug_knob("ORBX_FAST_PAD_KB", 0) * 1024;
         cudaFuncSetAttribute(k_fast_fused<44, 4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad);
         k_fast_fused<44, 4, 12><<<grid, C::WARPS * 32, C::SMEM + pad, st>>>(dP, s0, 0, n_small);
         ls->launches++;
@@ -1136,7 +1160,7 @@ static OctreeSmem octree_smem(int threads, int node_cap, int max_feat, size_t bu
 // shared-memory budget of the 256-thread octree CTA (experiment knob ORBX_OCT_BUDGET_KB)
 static size_t oct_small_budget()
 {
-    static const size_t b = std::getenv("ORBX_OCT_BUDGET_KB") ? (size_t)std::atoi(std::getenv("ORBX_OCT_BUDGET_KB")) * 1024 : 100 * 1024;
+    static const size_t b = (size_t)debug_knob("ORBX_OCT_BUDGET_KB", 100) * 1024;
     return b;
 }
 
@@ -1497,7 +1521,7 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
         int split = 0;                                                // first level whose image has < 40 % of level 0's pixels
         const long long p0 = (long long)hP.lv[0].w * hP.lv[0].h;
         while (split < hP.nlevels && (long long)hP.lv[split].w * hP.lv[split].h * 5 >= p0 * 2) ++split;
-        static const bool no_split = std::getenv("ORBX_OCT_NOSPLIT") != nullptr;
+        static const bool no_split = debug_knob("ORBX_OCT_NOSPLIT", 0) != 0;
         if (nframes >= 8 && split > 0 && split < hP.nlevels && !no_split) {
             ls->launches++;
             cudaError_t e = launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget() / 2 + 4096, st, split, hP.nlevels - split);
@@ -1934,7 +1958,7 @@ cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0
         const int max_useful = (hP.kp_frame_cap + kOdWarps - 1) / kOdWarps;
         if (per_frame > max_useful) per_frame = max_useful;
         if (per_frame < 1) per_frame = 1;
-        static const int mode = std::getenv("ORBX_OD_MODE") ? std::atoi(std::getenv("ORBX_OD_MODE")) : 1;   // 0 = LDGSTS chunks (measured slower), 1 = TMA boxes
+        static const int mode = debug_knob("ORBX_OD_MODE", 1);   // 0 = LDGSTS chunks (measured slower), 1 = TMA boxes
         if (mode == 1) k_orient_desc_tma<true><<<dim3(per_frame, nframes), kOdWarps * 32, kOdSmemBytes, st>>>(dP, *maps, s0);
         else k_orient_desc_tma<false><<<dim3(per_frame, nframes), kOdWarps * 32, kOdSmemBytes, st>>>(dP, *maps, s0);
         return cudaGetLastError();
@@ -2044,6 +2068,9 @@ __device__ __forceinline__ int rotation_bin(float a, float b)
 {
     float rot = __fsub_rn(a, b);
     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    // the reference asserts bin in [0, HISTO_LENGTH) (:618); angles outside [0, 360) or NaN (uninitialised keypoints) land in the
+    // overflow bin HISTO_LENGTH, which ComputeThreeMaxima never sees, so such a match is pruned instead of indexing out of bounds
+    if (!(rot >= 0.0f && rot < 915.0f)) return ORBX_HISTO_LENGTH;
     int bin = (int)roundf(__fmul_rn(rot, 1.0f / ORBX_HISTO_LENGTH));
     return bin == ORBX_HISTO_LENGTH ? 0 : bin;
 }
@@ -2159,7 +2186,7 @@ __global__ void __launch_bounds__(256)
 k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_pos, const uint8_t *__restrict__ mp_desc,
                      const uint8_t *__restrict__ valid, const int32_t *__restrict__ last_octave, int n_cur,
                      const float *__restrict__ cur_xy, const int32_t *__restrict__ cur_octave, const float *__restrict__ cur_uright,
-                     const uint8_t *__restrict__ cur_desc, int cap, unsigned long long *__restrict__ cand, int *__restrict__ count,
+                     const uint8_t *__restrict__ cur_desc, int cap, unsigned long long *__restrict__ gstage, unsigned long long *__restrict__ cand, int *__restrict__ count,
                      int *__restrict__ offset, int *__restrict__ total)
 {
     __shared__ unsigned long long s_list[8][kProjCap];               // per-warp staging; the lists leave compacted (one atomicAdd per point)
@@ -2196,14 +2223,14 @@ k_project_candidates(ProjSetup S, int n_last, const float *__restrict__ world_po
         live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
     }
     window_scan(S, live, u, v, radius, min_cx, max_cx, min_cy, max_cy, min_level, max_level, true, __fsub_rn(u, __fmul_rn(S.bf, invzc)),
-                mp_desc + 32 * (long long)i, n_cur, cur_xy, cur_octave, cur_uright, cur_desc, cap, s_list[warp], lane, i, cand, count, offset, total);
+                mp_desc + 32 * (long long)i, n_cur, cur_xy, cur_octave, cur_uright, cur_desc, cap, gstage ? gstage + (size_t)i * cap : s_list[warp], lane, i, cand, count, offset, total);
 }
 
 // The window search of ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:797): octave-0 keypoints of F1 look around
 // vbPrevMatched[i1] in F2's grid, levels (level1, level1), radius = windowSize, no stereo gate.
 __global__ void __launch_bounds__(256)
 k_window_candidates(ProjSetup S, int n1, const float *__restrict__ prev_xy, const int32_t *__restrict__ oct1, const uint8_t *__restrict__ desc1,
-                    int n2, const float *__restrict__ xy2, const int32_t *__restrict__ oct2, const uint8_t *__restrict__ desc2, int cap,
+                    int n2, const float *__restrict__ xy2, const int32_t *__restrict__ oct2, const uint8_t *__restrict__ desc2, int cap, unsigned long long *__restrict__ gstage,
                     unsigned long long *__restrict__ cand, int *__restrict__ count, int *__restrict__ offset, int *__restrict__ total)
 {
     __shared__ unsigned long long s_list[8][kProjCap];
@@ -2221,7 +2248,7 @@ k_window_candidates(ProjSetup S, int n1, const float *__restrict__ prev_xy, cons
         live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
     }
     window_scan(S, live, u, v, radius, min_cx, max_cx, min_cy, max_cy, level1, level1, false, 0.f, desc1 + 32 * (long long)i, n2, xy2, oct2,
-                nullptr, desc2, cap, s_list[warp], lane, i, cand, count, offset, total);
+                nullptr, desc2, cap, gstage ? gstage + (size_t)i * cap : s_list[warp], lane, i, cand, count, offset, total);
 }
 
 // The window search of ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:418-502):
@@ -2230,14 +2257,15 @@ k_window_candidates(ProjSetup S, int n1, const float *__restrict__ prev_xy, cons
 __global__ void __launch_bounds__(256)
 k_local_candidates(ProjSetup S, int n_mp, const float *__restrict__ proj, const float *__restrict__ view_cos, const int32_t *__restrict__ level,
                    const uint8_t *__restrict__ mp_desc, const uint8_t *__restrict__ valid, int n_feat, const float *__restrict__ xy,
-                   const int32_t *__restrict__ octave, const float *__restrict__ uright, const uint8_t *__restrict__ desc, int cap,
+                   const int32_t *__restrict__ octave, const float *__restrict__ uright, const uint8_t *__restrict__ desc, int cap, unsigned long long *__restrict__ gstage,
                    unsigned long long *__restrict__ cand, int *__restrict__ count, int *__restrict__ offset, int *__restrict__ total)
 {
     __shared__ unsigned long long s_list[8][kProjCap];
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (i >= n_mp) return;
     bool live = valid[i] != 0;
-    const int lvl = level[i];
+    // mnTrackScaleLevel is uninitialised for points outside the frustum (valid == 0): only a live point's level indexes the scale table
+    const int lvl = live ? min(max(level[i], 0), kMaxLevels - 1) : 0;
     float r = (double)view_cos[i] > 0.998 ? 2.5f : 4.0f;                       // RadiusByViewingCos, :504-510
     if (S.forward) r = __fmul_rn(r, S.th);
     const float radius = __fmul_rn(r, S.scale[lvl]);
@@ -2251,17 +2279,17 @@ k_local_candidates(ProjSetup S, int n_mp, const float *__restrict__ proj, const 
         live = min_cx < 64 && max_cx >= 0 && min_cy < 48 && max_cy >= 0;
     }
     window_scan(S, live, u, v, radius, min_cx, max_cx, min_cy, max_cy, lvl - 1, lvl, true, proj[3 * i + 2], mp_desc + 32 * (long long)i, n_feat, xy,
-                octave, uright, desc, cap, s_list[warp], lane, i, cand, count, offset, total);
+                octave, uright, desc, cap, gstage ? gstage + (size_t)i * cap : s_list[warp], lane, i, cand, count, offset, total);
 }
 
 cudaError_t launch_local_candidates(const ProjSetup &S, int n_mp, const float *d_proj, const float *d_view_cos, const int32_t *d_level,
                                     const uint8_t *d_mp_desc, const uint8_t *d_valid, int n_feat, const float *d_xy, const int32_t *d_octave,
-                                    const float *d_uright, const uint8_t *d_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
+                                    const float *d_uright, const uint8_t *d_desc, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_count, int *d_offset,
                                     int *d_total, cudaStream_t st, LaunchStats *ls)
 {
     if (n_mp <= 0) return cudaSuccess;
     k_local_candidates<<<(n_mp + 7) / 8, 256, 0, st>>>(S, n_mp, d_proj, d_view_cos, d_level, d_mp_desc, d_valid, n_feat, d_xy, d_octave, d_uright, d_desc,
-                                                       kProjCap, d_cand, d_count, d_offset, d_total);
+                                                       cap, d_stage, d_cand, d_count, d_offset, d_total);
     ls->launches++;
     return cudaGetLastError();
 }
@@ -2295,23 +2323,23 @@ cudaError_t launch_bow_pair_distances(int n_entries, const int4 *d_entries, cons
 }
 
 cudaError_t launch_window_candidates(const ProjSetup &S, int n1, const float *d_prev_xy, const int32_t *d_oct1, const uint8_t *d_desc1, int n2,
-                                     const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, unsigned long long *d_cand, int *d_count,
+                                     const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_count,
                                      int *d_offset, int *d_total, cudaStream_t st, LaunchStats *ls)
 {
     if (n1 <= 0) return cudaSuccess;
-    k_window_candidates<<<(n1 + 7) / 8, 256, 0, st>>>(S, n1, d_prev_xy, d_oct1, d_desc1, n2, d_xy2, d_oct2, d_desc2, kProjCap, d_cand, d_count, d_offset, d_total);
+    k_window_candidates<<<(n1 + 7) / 8, 256, 0, st>>>(S, n1, d_prev_xy, d_oct1, d_desc1, n2, d_xy2, d_oct2, d_desc2, cap, d_stage, d_cand, d_count, d_offset, d_total);
     ls->launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_project_candidates(const ProjSetup &S, int n_last, const float *d_world, const uint8_t *d_mp_desc, const uint8_t *d_valid,
                                       const int32_t *d_last_octave, int n_cur, const float *d_cur_xy, const int32_t *d_cur_octave,
-                                      const float *d_cur_uright, const uint8_t *d_cur_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
+                                      const float *d_cur_uright, const uint8_t *d_cur_desc, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_count, int *d_offset,
                                       int *d_total, cudaStream_t st, LaunchStats *ls)
 {
     if (n_last <= 0) return cudaSuccess;
     k_project_candidates<<<(n_last + 7) / 8, 256, 0, st>>>(S, n_last, d_world, d_mp_desc, d_valid, d_last_octave, n_cur, d_cur_xy, d_cur_octave,
-                                                          d_cur_uright, d_cur_desc, kProjCap, d_cand, d_count, d_offset, d_total);
+                                                          d_cur_uright, d_cur_desc, cap, d_stage, d_cand, d_count, d_offset, d_total);
     ls->launches++;
     return cudaGetLastError();
 }

@@ -97,18 +97,18 @@ struct ProjSetup {                   // camera, current pose and window paramete
 };
 cudaError_t launch_project_candidates(const ProjSetup &S, int n_last, const float *d_world, const uint8_t *d_mp_desc, const uint8_t *d_valid,
                                       const int32_t *d_last_octave, int n_cur, const float *d_cur_xy, const int32_t *d_cur_octave,
-                                      const float *d_cur_uright, const uint8_t *d_cur_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
+                                      const float *d_cur_uright, const uint8_t *d_cur_desc, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_count, int *d_offset,
                                       int *d_total, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_window_candidates(const ProjSetup &S, int n1, const float *d_prev_xy, const int32_t *d_oct1, const uint8_t *d_desc1, int n2,
-                                     const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, unsigned long long *d_cand, int *d_count,
+                                     const float *d_xy2, const int32_t *d_oct2, const uint8_t *d_desc2, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_count,
                                      int *d_offset, int *d_total, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_local_candidates(const ProjSetup &S, int n_mp, const float *d_proj, const float *d_view_cos, const int32_t *d_level,
                                     const uint8_t *d_mp_desc, const uint8_t *d_valid, int n_feat, const float *d_xy, const int32_t *d_octave,
-                                    const float *d_uright, const uint8_t *d_desc, unsigned long long *d_cand, int *d_count, int *d_offset,
+                                    const float *d_uright, const uint8_t *d_desc, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_count, int *d_offset,
                                     int *d_total, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_bow_pair_distances(int n_entries, const int4 *d_entries, const uint8_t *d_kf_desc, const uint8_t *d_f_desc, const int32_t *d_f_feats,
                                       uint16_t *d_out, cudaStream_t st, LaunchStats *ls);
-constexpr int kProjCap = 512;        // candidates one search window may hold (d_cand needs n_last * kProjCap entries)
+constexpr int kProjCap = 512;        // candidates one search window stages in shared memory; a fuller window makes the call rerun with a global staging area sized from the counts
 cudaError_t launch_bow_descent(const uint8_t *d_feat, int n, const int32_t *d_child_off, const int32_t *d_child_ids, const uint8_t *d_node_desc,
                                const int32_t *d_word_id, int nid_level, int32_t *d_word, int32_t *d_node, int32_t *d_final, cudaStream_t st, LaunchStats *ls);
 constexpr int kDistinctiveMaxObs = 1024;      // observations of one map point that fit the CTA's shared memory

@@ -57,6 +57,7 @@ struct orbx_handle {
     TmaMaps tma;                        // pyramid source descriptors (levels >= 2 from our buffer, level 1 from the batch's level 0)
     const void *tma_l0_base = nullptr; long long tma_l0_fs = 0; int tma_l0_pitch = 0, tma_l0_frames = 0;
     bool use_tma = true;
+    bool opt_tma = true, opt_fast_tma = false, opt_copy_input = false;   // orbx_set_option
     FastMaps fast_maps; unsigned fast_ok = 0;               // FAST raw boxes (bit l = level l encoded)
     OdMaps od_maps; unsigned od_img_ok = 0, od_blr_ok = 0;  // orientation / descriptor patch boxes (bit l = level l encoded)
     BlurMaps blur_maps; unsigned blur_tma_levels = 0;       // blur source boxes: bit l set = maps.m[l] valid (level 0 per batch source)
@@ -84,6 +85,26 @@ int fail(orbx_handle *h, int code, const std::string &msg) { if (h) h->err = msg
     } while (0)
 
 template <typename T> void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+// Entry points run on the handle's device and restore the caller's current device on the way out (multi-GPU callers keep
+// their own device selection).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = err == cudaSuccess; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define ON_DEVICE(hh)                                                                                    \
+    DeviceGuard device_guard_((hh)->device);                                                             \
+    if (device_guard_.err != cudaSuccess)                                                                \
+        return fail(h, ORBX_ERR_CUDA, std::string("cudaSetDevice failed: ") + cudaGetErrorString(device_guard_.err))
 
 // Grow-only device scratch of a handle (the calls that use it are synchronous, so one buffer is enough).
 int get_scratch(orbx_handle *h, size_t bytes, void **out)
@@ -151,7 +172,7 @@ int ensure_batch(orbx_handle *h, int nframes)
     CU(cudaMemsetAsync(h->d_blur, 0, F * g.pyr_frame_bytes, h->stream));
     h->batch_cap = nframes;
     // TMA descriptors of the pyramid levels that live in our own buffer (source of level l is level l-1 >= 1)
-    h->use_tma = std::getenv("ORBX_NO_TMA") == nullptr;
+    h->use_tma = h->opt_tma;
     for (int l = 0; l < kMaxLevels; ++l) h->tma.ok[l] = false;
     h->tma_l0_base = nullptr;
     for (int l = 2; l < g.nlevels && h->use_tma; ++l) {
@@ -200,13 +221,13 @@ int ensure_geometry(orbx_handle *h, int width, int height, int nframes)
     CU(cudaMalloc(&h->d_xtab, std::max<size_t>(g.xtab.size(), 4) * sizeof(ResizeTab)));
     CU(cudaMalloc(&h->d_ytab, std::max<size_t>(g.ytab.size(), 4) * sizeof(ResizeTab)));
     CU(cudaMalloc(&h->d_blur_work, std::max<size_t>(g.blur_work.size(), 1) * sizeof(uint32_t)));
-    if (!g.xtab.empty()) CU(cudaMemcpy(h->d_xtab, g.xtab.data(), g.xtab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
-    if (!g.ytab.empty()) CU(cudaMemcpy(h->d_ytab, g.ytab.data(), g.ytab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    if (!g.xtab.empty()) CU(cudaMemcpyAsync(h->d_xtab, h->geo.xtab.data(), g.xtab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, h->stream));
+    if (!g.ytab.empty()) CU(cudaMemcpyAsync(h->d_ytab, h->geo.ytab.data(), g.ytab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMalloc(&h->d_ffast_work, std::max<size_t>(g.ffast_work.size(), 1) * sizeof(uint32_t)));
-    if (!g.ffast_work.empty()) CU(cudaMemcpy(h->d_ffast_work, g.ffast_work.data(), g.ffast_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!g.ffast_work.empty()) CU(cudaMemcpyAsync(h->d_ffast_work, h->geo.ffast_work.data(), g.ffast_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMalloc(&h->d_oct_lut, std::max<size_t>(g.oct_lut.size(), 1) * sizeof(uint32_t)));
-    if (!g.oct_lut.empty()) CU(cudaMemcpy(h->d_oct_lut, g.oct_lut.data(), g.oct_lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (!g.blur_work.empty()) CU(cudaMemcpy(h->d_blur_work, g.blur_work.data(), g.blur_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!g.oct_lut.empty()) CU(cudaMemcpyAsync(h->d_oct_lut, h->geo.oct_lut.data(), g.oct_lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    if (!g.blur_work.empty()) CU(cudaMemcpyAsync(h->d_blur_work, h->geo.blur_work.data(), g.blur_work.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
 
     DevParams &P = h->hp;
     std::memset(&P, 0, sizeof(P));
@@ -215,6 +236,7 @@ int ensure_geometry(orbx_handle *h, int width, int height, int nframes)
     for (int l = 0; l < g.nlevels; ++l) { P.lv[l] = g.lv[l]; P.xtab_off[l] = g.xtab_off[l]; P.ytab_off[l] = g.ytab_off[l]; }
     for (int i = 0; i < 16; ++i) P.umax[i] = h->tab.umax[i];
     P.n_blur_work = (int)g.blur_work.size(); P.n_ffast_work = (int)g.ffast_work.size();
+    CU(cudaStreamSynchronize(h->stream));      // the table uploads above (sources live in h->geo) are complete before any kernel can read them
     h->geo_valid = true;
     return ensure_batch(h, std::max(nframes, keep_cap));
 }
@@ -231,8 +253,12 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     MARK(1);                                     // ev[0] was recorded by the caller before the input copies
     // measurement aid only (scripts/exp_overlap.py): leave stages out to read their marginal cost in the overlapped pipeline;
     // the buffers keep the previous batch's contents, results are then meaningless.  1 pyramid, 2 blur, 4 FAST, 8 octree, 16 orient/desc, 32 D2H
+#ifdef ORBX_DEBUG_KNOBS
     const char *skip_env = std::getenv("ORBX_DEBUG_SKIP");
     const int skip = skip_env ? std::atoi(skip_env) : 0;
+#else
+    constexpr int skip = 0;                      // the release library has no such knob: every stage always runs
+#endif
     if (!(skip & 4))
     CU(cudaMemsetAsync(h->d_cand_count, 0, (size_t)nframes * P.nlevels * sizeof(uint32_t), st));
     if (h->use_tma &&
@@ -256,7 +282,7 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     MARK(3);
     {
         const unsigned all = P.nlevels >= 32 ? 0xffffffffu : (1u << P.nlevels) - 1u;
-        const bool fast_tma = h->use_tma && (h->fast_ok & all) == all && std::getenv("ORBX_FAST_TMA");   // opt-in: measured slower (12 warps / SM)
+        const bool fast_tma = h->use_tma && (h->fast_ok & all) == all && h->opt_fast_tma;   // opt-in (ORBX_OPT_FAST_TMA): measured slower in the pipelined loop
         if (!(skip & 4))
         CU(launch_fast(h->d_params, P, s0, nframes, h->geo.n_ffast_small, st, &h->stats, fast_tma ? &h->fast_maps : nullptr));
     }
@@ -314,12 +340,14 @@ extern "C" int orbx_create(const orbx_config *cfg, orbx_handle **out)
     h->device = dev;
     build_tables(cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th_fast, cfg->min_th_fast, &h->tab);
     int rc = ORBX_OK;
+    DeviceGuard device_guard_(dev);
     auto init = [&]() -> int {
-        CU(cudaSetDevice(dev));
+        if (device_guard_.err != cudaSuccess) return fail(h, ORBX_ERR_CUDA, std::string("cudaSetDevice failed: ") + cudaGetErrorString(device_guard_.err));
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&h->d_params, sizeof(DevParams)));
         CU(cudaMalloc(&h->d_pattern, sizeof(kPatternHost)));
-        CU(cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
         if (cfg->max_width > 0 && cfg->max_height > 0)
             return ensure_geometry(h, cfg->max_width, cfg->max_height, std::max(cfg->max_batch, 1));
         return ORBX_OK;
@@ -333,7 +361,7 @@ extern "C" int orbx_create(const orbx_config *cfg, orbx_handle **out)
 extern "C" void orbx_destroy(orbx_handle *h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard device_guard_(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_batch_buffers(h);
     free_geo_tables(h);
@@ -407,13 +435,13 @@ extern "C" int orbx_submit_device(orbx_handle *h, const uint8_t *d_frames, int n
     int rc = check_shape(h, nframes, width, height, stride_bytes);
     if (rc != ORBX_OK) return rc;
     if (frame_stride_bytes < (size_t)stride_bytes * (size_t)(height - 1) + (size_t)width) return fail(h, ORBX_ERR_BAD_ARG, "frame_stride_bytes too small");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (h->pending) return fail(h, ORBX_ERR_STATE, "a batch is already pending on this handle: call orbx_collect first");
     rc = ensure_geometry(h, width, height, nframes);
     if (rc != ORBX_OK) return rc;
     if (h->profiling) CU(cudaEventRecord(h->ev[0], h->stream));
     Src0 s0;
-    if (aligned16(d_frames, stride_bytes, (long long)frame_stride_bytes)) {
+    if (!h->opt_copy_input && aligned16(d_frames, stride_bytes, (long long)frame_stride_bytes)) {
         s0.ptr = d_frames; s0.pitch = stride_bytes; s0.frame_stride = (long long)frame_stride_bytes;   // used in place
     } else {
         const LevelGeom &L0 = h->geo.lv[0];
@@ -434,7 +462,7 @@ static int submit_host_frames(orbx_handle *h, const uint8_t *const *frames, int 
     int rc = check_shape(h, nframes, width, height, stride_bytes / channels);
     if (rc != ORBX_OK) return rc;
     for (int f = 0; f < nframes; ++f) if (!frames[f]) return fail(h, ORBX_ERR_BAD_ARG, "NULL frame pointer");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (h->pending) return fail(h, ORBX_ERR_STATE, "a batch is already pending on this handle: call orbx_collect first");
     rc = ensure_geometry(h, width, height, nframes);
     if (rc != ORBX_OK) return rc;
@@ -489,7 +517,7 @@ extern "C" int orbx_collect_view(orbx_handle *h, const orbx_keypoint **kps, cons
 {
     if (!h) return ORBX_ERR_BAD_ARG;
     if (!h->pending) return fail(h, ORBX_ERR_STATE, "orbx_collect without a pending submit");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(cudaStreamSynchronize(h->stream));
     h->pending = false;
     if (kps) *kps = h->p_kps;
@@ -558,7 +586,7 @@ extern "C" int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, uint
     int rc = stage_ready(h, frame, level);
     if (rc != ORBX_OK) return rc;
     if (!dst) return fail(h, ORBX_ERR_BAD_ARG, "NULL dst");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const LevelGeom &L = h->geo.lv[level];
     const uint8_t *src; int pitch;
     if (level == 0) { src = h->last_src0.ptr + (size_t)frame * h->last_src0.frame_stride; pitch = h->last_src0.pitch; }
@@ -578,13 +606,47 @@ extern "C" int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, uint
     return ORBX_OK;
 }
 
+// All levels of one frame with a single synchronisation (mvImagePyramid for the stereo path: the adapter used to pay a pad kernel,
+// a copy and a synchronize per level).
+extern "C" int orbx_get_pyramid_levels(orbx_handle *h, int frame, int nlevels, uint8_t *const *dst, const int *dst_stride, int with_border)
+{
+    int rc = stage_ready(h, frame, 0);
+    if (rc != ORBX_OK) return rc;
+    if (!dst || !dst_stride || nlevels < 1 || nlevels > h->geo.nlevels) return fail(h, ORBX_ERR_BAD_ARG, "orbx_get_pyramid_levels: bad argument");
+    ON_DEVICE(h);
+    const int b = with_border ? kEdge : 0;
+    size_t need = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const LevelGeom &L = h->geo.lv[l];
+        if (!dst[l] || dst_stride[l] < L.w + 2 * b) return fail(h, ORBX_ERR_BAD_ARG, "orbx_get_pyramid_levels: NULL level pointer or stride too small");
+        need += (size_t)(L.w + 2 * b) * (L.h + 2 * b);
+    }
+    if (with_border && need > h->pad_bytes) { CU(cudaStreamSynchronize(h->stream)); dfree(h->d_pad); CU(cudaMalloc(&h->d_pad, need)); h->pad_bytes = need; }
+    size_t off = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const LevelGeom &L = h->geo.lv[l];
+        const uint8_t *src; int pitch;
+        if (l == 0) { src = h->last_src0.ptr + (size_t)frame * h->last_src0.frame_stride; pitch = h->last_src0.pitch; }
+        else { src = h->d_pyr + (size_t)frame * h->geo.pyr_frame_bytes + L.img_off; pitch = L.pitch; }
+        const int W = L.w + 2 * b, H = L.h + 2 * b;
+        if (with_border) {
+            CU(launch_pad_level(src, L.w, L.h, pitch, h->d_pad + off, W, h->stream, &h->stats));
+            CU(cudaMemcpy2DAsync(dst[l], dst_stride[l], h->d_pad + off, W, W, H, cudaMemcpyDeviceToHost, h->stream));
+        } else
+            CU(cudaMemcpy2DAsync(dst[l], dst_stride[l], src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+        off += (size_t)W * H;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
 extern "C" int orbx_get_blurred_level(orbx_handle *h, int frame, int level, uint8_t *dst, int dst_stride)
 {
     int rc = stage_ready(h, frame, level);
     if (rc != ORBX_OK) return rc;
     const LevelGeom &L = h->geo.lv[level];
     if (!dst || dst_stride < L.w) return fail(h, ORBX_ERR_BAD_ARG, "bad dst / dst_stride");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(cudaMemcpy2DAsync(dst, dst_stride, h->d_blur + (size_t)frame * h->geo.pyr_frame_bytes + L.img_off, L.pitch, L.w, L.h,
                          cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -596,7 +658,7 @@ extern "C" int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t
     int rc = stage_ready(h, frame, level);
     if (rc != ORBX_OK) return rc;
     if (!n) return fail(h, ORBX_ERR_BAD_ARG, "NULL n");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const LevelGeom &L = h->geo.lv[level];
     uint32_t cnt = 0;
     CU(cudaMemcpyAsync(&cnt, h->d_cand_count + (size_t)frame * h->geo.nlevels + level, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -644,7 +706,7 @@ extern "C" int orbx_match_device(orbx_handle *h, const uint8_t *dA, int nA, cons
     if (nA < 0 || nB < 0 || (nA > 0 && (!dA || !d_idx || !d_d1 || !d_d2)) || (nB > 0 && !dB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_match_device: bad argument");
     if (((uintptr_t)dA | (uintptr_t)dB) % 16) return fail(h, ORBX_ERR_BAD_ARG, "descriptor arrays must be 16-byte aligned");
     if (nA == 0) return ORBX_OK;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int nchunks = match_chunks(nA, nB);
     int rc = ensure_partial(h, nA, nchunks);
     if (rc != ORBX_OK) return rc;
@@ -659,7 +721,7 @@ extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const ui
     if (!h) return ORBX_ERR_BAD_ARG;
     if (nA < 0 || nB < 0 || (nA > 0 && (!descA || !idx || !d1 || !d2)) || (nB > 0 && !descB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_match: bad argument");
     if (nA == 0) return 0;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if ((size_t)nA > h->m_capA) { dfree(h->m_A); CU(cudaMalloc(&h->m_A, (size_t)nA * 32)); h->m_capA = nA; }
     if ((size_t)std::max(nB, 1) > h->m_capB) { dfree(h->m_B); CU(cudaMalloc(&h->m_B, (size_t)std::max(nB, 1) * 32)); h->m_capB = std::max(nB, 1); }
     if ((size_t)nA > h->m_cap_out) {
@@ -692,7 +754,7 @@ extern "C" int orbx_rotation_filter_device(orbx_handle *h, int nA, const int32_t
 {
     if (!h) return ORBX_ERR_BAD_ARG;
     if (nA < 0 || (nA > 0 && (!d_idx || !d_accept || !d_angleA || !d_angleB))) return fail(h, ORBX_ERR_BAD_ARG, "orbx_rotation_filter_device: bad argument");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(launch_rotation_filter(nA, d_idx, d_accept, d_angleA, d_angleB, d_hist, d_top3, d_kept, h->stream, &h->stats));
     return ORBX_OK;
 }
@@ -704,7 +766,7 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     if (nA < 0 || nB < 0 || (nA > 0 && (!idx || !accept || !angleA)) || (nB > 0 && !angleB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_rotation_filter: bad argument");
     for (int i = 0; i < nA; ++i)
         if (accept[i] && (idx[i] < 0 || idx[i] >= nB)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_rotation_filter: accepted match with idx outside [0, nB)");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     cudaStream_t st = h->stream;
     // one scratch block: idx | angleA | angleB | hist[30] top3[3] kept[1] | accept
     const size_t words = (size_t)nA * 2 + (size_t)nB + 34;
@@ -733,6 +795,50 @@ extern "C" int orbx_rotation_filter(orbx_handle *h, int nA, const int32_t *idx, 
     return res[33];
 }
 
+
+// ------------------------------------------------- windowed candidate search
+// The three windowed matchers share this: `enqueue(d, cap, stage, cand, cnt, off, tot)` copies the call's inputs into the first
+// `in_bytes` of the scratch block d and launches its candidate kernel for n queries.  First run: the kernels stage a window's
+// candidates in shared memory (kProjCap per window).  The reference has no such limit, so when a window holds more (wide th * 2
+// retries, windowSize 100 on dense frames) the call runs once more with a global staging area of max(count) entries per query.
+template <typename Enqueue>
+static int run_window_search(orbx_handle *h, int n, size_t in_bytes, Enqueue enqueue, std::vector<int> *count, std::vector<int> *offset,
+                             std::vector<unsigned long long> *cand)
+{
+    cudaStream_t st = h->stream;
+    count->assign((size_t)n, 0); offset->assign((size_t)n, 0);
+    int cap = kProjCap;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const size_t in_al = (in_bytes + 255) / 256 * 256, meta = ((size_t)n * 8 + 16 + 255) / 256 * 256;
+        const size_t cand_bytes = (size_t)n * cap * 8, stage_bytes = attempt ? cand_bytes : 0;
+        uint8_t *d = nullptr;
+        { const int rcs = get_scratch(h, in_al + meta + cand_bytes + stage_bytes, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+        int *d_cnt = (int *)(d + in_al), *d_off = d_cnt + n, *d_tot = d_off + n;
+        unsigned long long *d_cand = (unsigned long long *)(d + in_al + meta), *d_stage = attempt ? d_cand + (size_t)n * cap : nullptr;
+        int ncand = 0;
+        CU(cudaMemsetAsync(d_tot, 0, 4, st));
+        { const int rcl = enqueue(d, cap, d_stage, d_cand, d_cnt, d_off, d_tot); if (rcl != ORBX_OK) return rcl; }
+        CU(cudaMemcpyAsync(count->data(), d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(offset->data(), d_off, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&ncand, d_tot, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        int most = 0;
+        for (int i = 0; i < n; ++i) most = std::max(most, (*count)[i]);
+        if (most > cap) {
+            if (attempt) return fail(h, ORBX_ERR_CUDA, "windowed search: candidate count changed between two runs");
+            cap = (most + 63) / 64 * 64;
+            continue;
+        }
+        cand->assign((size_t)std::max(ncand, 1), 0ull);
+        if (ncand > 0) {
+            CU(cudaMemcpyAsync(cand->data(), d_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return ORBX_OK;
+    }
+    return ORBX_OK;
+}
+
 // ------------------------------------------------------- projection matcher
 
 extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_setup *cam,
@@ -750,7 +856,7 @@ extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_s
         if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= h->tab.nlevels)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_by_projection: octave out of range");
     for (int j = 0; j < n_cur; ++j) cur_match[j] = -1;
     if (n_last == 0 || n_cur == 0) return 0;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     ProjSetup S;
     S.fx = cam->fx; S.fy = cam->fy; S.cx = cam->cx; S.cy = cam->cy; S.bf = cam->bf; S.b = cam->b;
     S.min_x = cam->min_x; S.max_x = cam->max_x; S.min_y = cam->min_y; S.max_y = cam->max_y;
@@ -771,41 +877,29 @@ extern "C" int orbx_search_by_projection(orbx_handle *h, const orbx_projection_s
         tlc2 = s + Tl[4 * 2 + 3];
         S.forward = tlc2 > cam->b && !mono; S.backward = -tlc2 > cam->b && !mono;
     }
-    // scratch: world | last_octave | cur_xy | cur_octave | cur_uright | count | offset | total | mp_desc | cur_desc | valid | cand
-    const size_t a4 = 16;
-    auto up = [&](size_t v) { return (v + a4 - 1) / a4 * a4; };
+    // scratch inputs: world | last_octave | cur_xy | cur_octave | cur_uright | mp_desc | cur_desc | valid
+    auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_world = 0, o_loct = o_world + up((size_t)n_last * 12), o_xy = o_loct + up((size_t)n_last * 4), o_coct = o_xy + up((size_t)n_cur * 8),
-                 o_ur = o_coct + up((size_t)n_cur * 4), o_cnt = o_ur + up((size_t)n_cur * 4), o_off = o_cnt + up((size_t)n_last * 4),
-                 o_tot = o_off + up((size_t)n_last * 4), o_mpd = o_tot + 16, o_cd = o_mpd + up((size_t)n_last * 32),
-                 o_val = o_cd + up((size_t)n_cur * 32), o_cand = o_val + up((size_t)n_last), total = o_cand + (size_t)n_last * kProjCap * 8;
-    uint8_t *d = nullptr;
-    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+                 o_ur = o_coct + up((size_t)n_cur * 4), o_mpd = o_ur + up((size_t)n_cur * 4), o_cd = o_mpd + up((size_t)n_last * 32),
+                 o_val = o_cd + up((size_t)n_cur * 32), in_bytes = o_val + up((size_t)n_last);
     cudaStream_t st = h->stream;
-    std::vector<int> count((size_t)n_last), offset((size_t)n_last);
-    int ncand = 0;
-    CU(cudaMemsetAsync(d + o_tot, 0, 4, st));
-    CU(cudaMemcpyAsync(d + o_world, world_pos, (size_t)n_last * 12, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_loct, last_octave, (size_t)n_last * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_xy, cur_xy, (size_t)n_cur * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_coct, cur_octave, (size_t)n_cur * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_ur, cur_uright, (size_t)n_cur * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_mpd, mp_desc, (size_t)n_last * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_cd, cur_desc, (size_t)n_cur * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_last, cudaMemcpyHostToDevice, st));
-    CU(launch_project_candidates(S, n_last, (const float *)(d + o_world), d + o_mpd, d + o_val, (const int32_t *)(d + o_loct), n_cur,
-                                 (const float *)(d + o_xy), (const int32_t *)(d + o_coct), (const float *)(d + o_ur), d + o_cd,
-                                 (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), (int *)(d + o_off), (int *)(d + o_tot), st, &h->stats));
-    CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n_last * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(offset.data(), d + o_off, (size_t)n_last * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&ncand, d + o_tot, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < n_last; ++i)
-        if (count[i] > kProjCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_by_projection: a search window holds more than 512 candidates");
-    std::vector<unsigned long long> cand((size_t)std::max(ncand, 1));
-    if (ncand > 0) {
-        CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
+    std::vector<int> count, offset;
+    std::vector<unsigned long long> cand;
+    auto enqueue = [&](uint8_t *d, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_cnt, int *d_off, int *d_tot) -> int {
+        CU(cudaMemcpyAsync(d + o_world, world_pos, (size_t)n_last * 12, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_loct, last_octave, (size_t)n_last * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_xy, cur_xy, (size_t)n_cur * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_coct, cur_octave, (size_t)n_cur * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_ur, cur_uright, (size_t)n_cur * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_mpd, mp_desc, (size_t)n_last * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_cd, cur_desc, (size_t)n_cur * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_last, cudaMemcpyHostToDevice, st));
+        CU(launch_project_candidates(S, n_last, (const float *)(d + o_world), d + o_mpd, d + o_val, (const int32_t *)(d + o_loct), n_cur,
+                                     (const float *)(d + o_xy), (const int32_t *)(d + o_coct), (const float *)(d + o_ur), d + o_cd,
+                                     cap, d_stage, d_cand, d_cnt, d_off, d_tot, st, &h->stats));
+        return ORBX_OK;
+    };
+    { const int rcw = run_window_search(h, n_last, in_bytes, enqueue, &count, &offset, &cand); if (rcw != ORBX_OK) return rcw; }
     return resolve_projection_matches(n_last, n_cur, cand.data(), count.data(), offset.data(), nobs, last_angle, cur_angle, check_orientation, cur_match);
 }
 
@@ -820,42 +914,30 @@ extern "C" int orbx_search_for_initialization(orbx_handle *h, float min_x, float
         return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_for_initialization: bad argument (at most 65535 features in the second frame)");
     for (int i = 0; i < n1; ++i) matches12[i] = -1;
     if (n1 == 0 || n2 == 0) return 0;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     ProjSetup S{};
     S.min_x = min_x; S.max_x = max_x; S.min_y = min_y; S.max_y = max_y;
     S.w_inv = 64.0f / (max_x - min_x); S.h_inv = 48.0f / (max_y - min_y);                           // src/Frame.cc:126-127
     S.th = (float)window_size;                                                                      // const float &r of GetFeaturesInArea
-    // scratch: prev | oct1 | xy2 | oct2 | count | offset | total | desc1 | desc2 | cand
+    // scratch inputs: prev | oct1 | xy2 | oct2 | desc1 | desc2
     auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_prev = 0, o_o1 = o_prev + up((size_t)n1 * 8), o_xy = o_o1 + up((size_t)n1 * 4), o_o2 = o_xy + up((size_t)n2 * 8),
-                 o_cnt = o_o2 + up((size_t)n2 * 4), o_off = o_cnt + up((size_t)n1 * 4), o_tot = o_off + up((size_t)n1 * 4), o_d1 = o_tot + 16,
-                 o_d2 = o_d1 + up((size_t)n1 * 32), o_cand = o_d2 + up((size_t)n2 * 32), total = o_cand + (size_t)n1 * kProjCap * 8;
-    uint8_t *d = nullptr;
-    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+                 o_d1 = o_o2 + up((size_t)n2 * 4), o_d2 = o_d1 + up((size_t)n1 * 32), in_bytes = o_d2 + up((size_t)n2 * 32);
     cudaStream_t st = h->stream;
-    std::vector<int> count((size_t)n1), offset((size_t)n1);
-    int ncand = 0;
-    CU(cudaMemsetAsync(d + o_tot, 0, 4, st));
-    CU(cudaMemcpyAsync(d + o_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_o1, octave1, (size_t)n1 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_xy, xy2, (size_t)n2 * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_o2, octave2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
-    CU(launch_window_candidates(S, n1, (const float *)(d + o_prev), (const int32_t *)(d + o_o1), d + o_d1, n2, (const float *)(d + o_xy),
-                                (const int32_t *)(d + o_o2), d + o_d2, (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), (int *)(d + o_off),
-                                (int *)(d + o_tot), st, &h->stats));
-    CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(offset.data(), d + o_off, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&ncand, d + o_tot, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < n1; ++i)
-        if (count[i] > kProjCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_for_initialization: a search window holds more than 512 candidates");
-    std::vector<unsigned long long> cand((size_t)std::max(ncand, 1));
-    if (ncand > 0) {
-        CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
+    std::vector<int> count, offset;
+    std::vector<unsigned long long> cand;
+    auto enqueue = [&](uint8_t *d, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_cnt, int *d_off, int *d_tot) -> int {
+        CU(cudaMemcpyAsync(d + o_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_o1, octave1, (size_t)n1 * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_xy, xy2, (size_t)n2 * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_o2, octave2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_d1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_d2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+        CU(launch_window_candidates(S, n1, (const float *)(d + o_prev), (const int32_t *)(d + o_o1), d + o_d1, n2, (const float *)(d + o_xy),
+                                    (const int32_t *)(d + o_o2), d + o_d2, cap, d_stage, d_cand, d_cnt, d_off, d_tot, st, &h->stats));
+        return ORBX_OK;
+    };
+    { const int rcw = run_window_search(h, n1, in_bytes, enqueue, &count, &offset, &cand); if (rcw != ORBX_OK) return rcw; }
     const int n = resolve_initialization_matches(n1, n2, cand.data(), count.data(), offset.data(), angle1, angle2, nnratio, check_orientation, matches12);
     for (int i = 0; i < n1; ++i)                                                                    // "Update prev matched", :888-891
         if (matches12[i] >= 0) { prev_matched[2 * i] = xy2[2 * matches12[i]]; prev_matched[2 * i + 1] = xy2[2 * matches12[i] + 1]; }
@@ -877,47 +959,36 @@ extern "C" int orbx_search_local_points(orbx_handle *h, float min_x, float max_x
         if (valid[i] && (level[i] < 0 || level[i] >= h->tab.nlevels)) return fail(h, ORBX_ERR_BAD_ARG, "orbx_search_local_points: predicted level out of range");
     for (int j = 0; j < n_feat; ++j) feat_match[j] = -1;
     if (n_mp == 0 || n_feat == 0) return 0;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     ProjSetup S{};
     S.min_x = min_x; S.max_x = max_x; S.min_y = min_y; S.max_y = max_y;
     S.w_inv = 64.0f / (max_x - min_x); S.h_inv = 48.0f / (max_y - min_y);                           // src/Frame.cc:126-127
     for (int l = 0; l < kMaxLevels; ++l) S.scale[l] = l < h->tab.nlevels ? h->tab.scale[l] : 1.f;
     S.th = th; S.forward = th != 1.0;                                                               // bFactor, :422
-    // scratch: proj | view_cos | level | xy | octave | uright | count | offset | total | mp_desc | desc | valid | cand
+    // scratch inputs: proj | view_cos | level | xy | octave | uright | mp_desc | desc | valid
     auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_proj = 0, o_vc = o_proj + up((size_t)n_mp * 12), o_lvl = o_vc + up((size_t)n_mp * 4), o_xy = o_lvl + up((size_t)n_mp * 4),
-                 o_oct = o_xy + up((size_t)n_feat * 8), o_ur = o_oct + up((size_t)n_feat * 4), o_cnt = o_ur + up((size_t)n_feat * 4),
-                 o_off = o_cnt + up((size_t)n_mp * 4), o_tot = o_off + up((size_t)n_mp * 4), o_mpd = o_tot + 16, o_fd = o_mpd + up((size_t)n_mp * 32),
-                 o_val = o_fd + up((size_t)n_feat * 32), o_cand = o_val + up((size_t)n_mp), total = o_cand + (size_t)n_mp * kProjCap * 8;
-    uint8_t *d = nullptr;
-    { const int rcs = get_scratch(h, total, (void **)&d); if (rcs != ORBX_OK) return rcs; }
+                 o_oct = o_xy + up((size_t)n_feat * 8), o_ur = o_oct + up((size_t)n_feat * 4), o_mpd = o_ur + up((size_t)n_feat * 4),
+                 o_fd = o_mpd + up((size_t)n_mp * 32), o_val = o_fd + up((size_t)n_feat * 32), in_bytes = o_val + up((size_t)n_mp);
     cudaStream_t st = h->stream;
-    std::vector<int> count((size_t)n_mp), offset((size_t)n_mp);
-    int ncand = 0;
-    CU(cudaMemsetAsync(d + o_tot, 0, 4, st));
-    CU(cudaMemcpyAsync(d + o_proj, proj, (size_t)n_mp * 12, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_vc, view_cos, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_lvl, level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_xy, feat_xy, (size_t)n_feat * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_oct, feat_octave, (size_t)n_feat * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_ur, feat_uright, (size_t)n_feat * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_mpd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_fd, feat_desc, (size_t)n_feat * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_mp, cudaMemcpyHostToDevice, st));
-    CU(launch_local_candidates(S, n_mp, (const float *)(d + o_proj), (const float *)(d + o_vc), (const int32_t *)(d + o_lvl), d + o_mpd, d + o_val,
-                               n_feat, (const float *)(d + o_xy), (const int32_t *)(d + o_oct), (const float *)(d + o_ur), d + o_fd,
-                               (unsigned long long *)(d + o_cand), (int *)(d + o_cnt), (int *)(d + o_off), (int *)(d + o_tot), st, &h->stats));
-    CU(cudaMemcpyAsync(count.data(), d + o_cnt, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(offset.data(), d + o_off, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&ncand, d + o_tot, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < n_mp; ++i)
-        if (count[i] > kProjCap) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_search_local_points: a search window holds more than 512 candidates");
-    std::vector<unsigned long long> cand((size_t)std::max(ncand, 1));
-    if (ncand > 0) {
-        CU(cudaMemcpyAsync(cand.data(), d + o_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
+    std::vector<int> count, offset;
+    std::vector<unsigned long long> cand;
+    auto enqueue = [&](uint8_t *d, int cap, unsigned long long *d_stage, unsigned long long *d_cand, int *d_cnt, int *d_off, int *d_tot) -> int {
+        CU(cudaMemcpyAsync(d + o_proj, proj, (size_t)n_mp * 12, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_vc, view_cos, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_lvl, level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_xy, feat_xy, (size_t)n_feat * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_oct, feat_octave, (size_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_ur, feat_uright, (size_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_mpd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_fd, feat_desc, (size_t)n_feat * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d + o_val, valid, (size_t)n_mp, cudaMemcpyHostToDevice, st));
+        CU(launch_local_candidates(S, n_mp, (const float *)(d + o_proj), (const float *)(d + o_vc), (const int32_t *)(d + o_lvl), d + o_mpd, d + o_val,
+                                   n_feat, (const float *)(d + o_xy), (const int32_t *)(d + o_oct), (const float *)(d + o_ur), d + o_fd,
+                                   cap, d_stage, d_cand, d_cnt, d_off, d_tot, st, &h->stats));
+        return ORBX_OK;
+    };
+    { const int rcw = run_window_search(h, n_mp, in_bytes, enqueue, &count, &offset, &cand); if (rcw != ORBX_OK) return rcw; }
     return resolve_local_matches(n_mp, n_feat, cand.data(), count.data(), offset.data(), nobs, feat_octave, feat_obs, nnratio, feat_match);
 }
 
@@ -948,7 +1019,7 @@ static int bow_pair_distances(orbx_handle *h, const char *who, int n1, const uin
     const int ne = (int)(entries->size() / 4);
     if (ne == 0) return ORBX_OK;
     if (npairs > (1ll << 30)) return fail(h, ORBX_ERR_UNSUPPORTED, std::string(who) + ": more than 2^30 descriptor pairs");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     auto up = [&](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_ent = 0, o_d1 = o_ent + up((size_t)ne * 16), o_d2 = o_d1 + up((size_t)n1 * 32), o_ff = o_d2 + up((size_t)n2 * 32),
                  o_out = o_ff + up((size_t)off2[nn2] * 4), total = o_out + up((size_t)npairs * 2);
@@ -1021,22 +1092,23 @@ static int voc_upload(orbx_handle *h, orbx_vocabulary *v)
 {
     const VocHost &H = v->host;
     v->device = h->device;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(cudaMalloc(&v->d_child_off, H.child_off.size() * 4));
     CU(cudaMalloc(&v->d_child_ids, std::max<size_t>(H.child_ids.size(), 1) * 4));
     CU(cudaMalloc(&v->d_word_id, H.word_id.size() * 4));
     CU(cudaMalloc(&v->d_desc, H.desc.size()));
-    CU(cudaMemcpy(v->d_child_off, H.child_off.data(), H.child_off.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(v->d_child_ids, H.child_ids.data(), H.child_ids.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(v->d_word_id, H.word_id.data(), H.word_id.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(v->d_desc, H.desc.data(), H.desc.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(v->d_child_off, H.child_off.data(), H.child_off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(v->d_child_ids, H.child_ids.data(), H.child_ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(v->d_word_id, H.word_id.data(), H.word_id.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(v->d_desc, H.desc.data(), H.desc.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }
 
 extern "C" void orbx_voc_destroy(orbx_vocabulary *v)
 {
     if (!v) return;
-    cudaSetDevice(v->device);
+    DeviceGuard device_guard_(v->device);
     dfree(v->d_child_off); dfree(v->d_child_ids); dfree(v->d_word_id); dfree(v->d_desc);
     delete v;
 }
@@ -1091,7 +1163,7 @@ extern "C" int orbx_voc_transform(orbx_handle *h, const orbx_vocabulary *v, cons
     if (!v || n < 0 || (n > 0 && (!desc || !word || !node || !weight))) return fail(h, ORBX_ERR_BAD_ARG, "orbx_voc_transform: bad argument");
     if (v->device != h->device) return fail(h, ORBX_ERR_BAD_ARG, "orbx_voc_transform: the vocabulary lives on another device");
     if (n == 0) return ORBX_OK;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     cudaStream_t st = h->stream;
     uint8_t *d = nullptr;
     const size_t feat_bytes = ((size_t)n * 32 + 255) / 256 * 256;
@@ -1138,7 +1210,7 @@ extern "C" int orbx_distinctive_descriptors(orbx_handle *h, const uint8_t *desc,
     if (max_obs > kDistinctiveMaxObs) return fail(h, ORBX_ERR_UNSUPPORTED, "orbx_distinctive_descriptors: more than 1024 observations of one map point");
     const int total = offsets[npoints];
     if (total > 0 && !desc) return fail(h, ORBX_ERR_BAD_ARG, "orbx_distinctive_descriptors: NULL desc");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     cudaStream_t st = h->stream;
     uint8_t *d = nullptr;
     const size_t desc_bytes = ((size_t)std::max(total, 1) * 32 + 255) / 256 * 256, off_bytes = ((size_t)(npoints + 1) * 4 + 255) / 256 * 256;
@@ -1172,7 +1244,7 @@ extern "C" int orbx_stereo_match(orbx_handle *L, orbx_handle *R, int frame_left,
     if (L->geo.width != R->geo.width || L->geo.height != R->geo.height || L->tab.nlevels != R->tab.nlevels ||
         L->tab.scale_factor_f != R->tab.scale_factor_f)
         return fail(L, ORBX_ERR_BAD_ARG, "orbx_stereo_match: the two extractors differ in image size / levels / scale factor");
-    CU(cudaSetDevice(L->device));
+    ON_DEVICE(L);
     const int capL = L->geo.kp_frame_cap;
     // scratch: u_right | depth | desc_index | sad (capL each) | kept
     uint32_t *d = nullptr;
@@ -1205,6 +1277,28 @@ extern "C" int orbx_stereo_match(orbx_handle *L, orbx_handle *R, int frame_left,
     return kept < 0 ? 0 : kept;
 }
 
+// ------------------------------------------------------------------ options
+
+extern "C" int orbx_set_option(orbx_handle *h, int option, int value)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (h->pending) return fail(h, ORBX_ERR_STATE, "orbx_set_option: a batch is pending on this handle");
+    ON_DEVICE(h);
+    switch (option) {
+    case ORBX_OPT_TMA_STAGING:
+        if (h->opt_tma != (value != 0)) {
+            CU(cudaStreamSynchronize(h->stream));
+            h->opt_tma = value != 0;
+            const int keep = h->batch_cap;
+            if (h->geo_valid && keep > 0) { free_batch_buffers(h); h->have_batch = false; return ensure_batch(h, keep); }   // re-encodes / drops the tensor maps
+        }
+        return ORBX_OK;
+    case ORBX_OPT_FAST_TMA: h->opt_fast_tma = value != 0; return ORBX_OK;
+    case ORBX_OPT_COPY_INPUT: h->opt_copy_input = value != 0; return ORBX_OK;
+    default: return fail(h, ORBX_ERR_BAD_ARG, "orbx_set_option: unknown option");
+    }
+}
+
 // ---------------------------------------------------------------- profiling
 
 static const char *kStageNames[ORBX_NUM_STAGES] = {"input", "pyramid", "blur", "fast", "octree", "orient_desc", "d2h"};
@@ -1214,7 +1308,7 @@ extern "C" const char *orbx_stage_name(int stage) { return stage >= 0 && stage <
 extern "C" int orbx_set_profiling(orbx_handle *h, int on)
 {
     if (!h) return ORBX_ERR_BAD_ARG;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (on && !h->ev[0])
         for (int i = 0; i <= ORBX_NUM_STAGES; ++i) CU(cudaEventCreate(&h->ev[i]));
     h->profiling = on != 0;
@@ -1226,7 +1320,7 @@ extern "C" int orbx_get_stage_ms(orbx_handle *h, float *ms, int cap)
 {
     if (!h || !ms) return ORBX_ERR_BAD_ARG;
     if (!h->ev_valid || h->pending) return fail(h, ORBX_ERR_STATE, "no profiled batch has completed (enable profiling, submit, collect)");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     for (int i = 0; i < ORBX_NUM_STAGES && i < cap; ++i) CU(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
     return ORBX_NUM_STAGES;
 }
@@ -1236,7 +1330,7 @@ extern "C" int orbx_get_stage_ms(orbx_handle *h, float *ms, int cap)
 extern "C" int orbx_sync(orbx_handle *h)
 {
     if (!h) return ORBX_ERR_BAD_ARG;
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }

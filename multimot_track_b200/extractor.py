@@ -166,6 +166,11 @@ class ORBextractor:
         n = np.frombuffer(nb, dtype=np.int32)
         return kps, desc, n
 
+    OPT_TMA_STAGING, OPT_FAST_TMA, OPT_COPY_INPUT = 1, 2, 3        # ORBX_OPT_* of include/orbx.h
+
+    def set_option(self, option, value):
+        self._ck(self._lib.orbx_set_option(self._h, int(option), int(value)))
+
     def set_profiling(self, on=True):
         self._ck(self._lib.orbx_set_profiling(self._h, int(bool(on))))
 

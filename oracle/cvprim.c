@@ -64,23 +64,33 @@ void cvp_resize_linear_u8(const uint8_t *src, int sw, int sh, int sstride,
         ialpha[2 * dx + 1] = sat_s16_from_float(fx * 2048.f);
     }
 
+    int have[2] = {-1, -1};                 /* source row held by rows[0] / rows[1] (cv::resize keeps them between rows too) */
     for (int dy = 0; dy < dh; ++dy) {
         float fy = (float)((dy + 0.5) * scale_y - 0.5);
         int sy = cvp_floor_d(fy);
         fy -= sy;
         const int16_t b0 = sat_s16_from_float((1.f - fy) * 2048.f);
         const int16_t b1 = sat_s16_from_float(fy * 2048.f);
-        const int sy0 = clampi(sy, 0, sh - 1), sy1 = clampi(sy + 1, 0, sh - 1);
-        const uint8_t *S0 = src + (size_t)sy0 * sstride, *S1 = src + (size_t)sy1 * sstride;
-        for (int dx = 0; dx < dw; ++dx) {
-            const int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
-            const int a0 = ialpha[2 * dx], a1 = ialpha[2 * dx + 1];
-            rows[0][dx] = S0[sx] * a0 + S0[sx1] * a1;
-            rows[1][dx] = S1[sx] * a0 + S1[sx1] * a1;
+        const int want[2] = {clampi(sy, 0, sh - 1), clampi(sy + 1, 0, sh - 1)};
+        if (have[1] == want[0] && have[0] != want[0]) {        /* the lower row of the previous pair is the upper row now */
+            int32_t *t = rows[0]; rows[0] = rows[1]; rows[1] = t;
+            have[0] = have[1]; have[1] = -1;
+        }
+        for (int k = 0; k < 2; ++k) {
+            if (have[k] == want[k]) continue;
+            if (k == 1 && want[1] == want[0]) { memcpy(rows[1], rows[0], sizeof(int32_t) * (size_t)dw); have[1] = want[1]; continue; }
+            const uint8_t *S = src + (size_t)want[k] * sstride;
+            int32_t *r = rows[k];
+            for (int dx = 0; dx < dw; ++dx) {
+                const int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+                r[dx] = S[sx] * ialpha[2 * dx] + S[sx1] * ialpha[2 * dx + 1];
+            }
+            have[k] = want[k];
         }
         uint8_t *D = dst + (size_t)dy * dstride;
+        const int32_t *r0 = rows[0], *r1 = rows[1];
         for (int dx = 0; dx < dw; ++dx) {
-            int v = (((b0 * (rows[0][dx] >> 4)) >> 16) + ((b1 * (rows[1][dx] >> 4)) >> 16) + 2) >> 2;
+            int v = (((b0 * (r0[dx] >> 4)) >> 16) + ((b1 * (r1[dx] >> 4)) >> 16) + 2) >> 2;
             D[dx] = (uint8_t)clampi(v, 0, 255);
         }
     }
@@ -110,7 +120,9 @@ void cvp_border_reflect101_u8(const uint8_t *src, int w, int h, int sstride,
     for (int y = 0; y < h; ++y) {
         memcpy(row, src + (size_t)y * sstride, (size_t)w);
         uint8_t *d = dst + (size_t)(y + top) * dstride;
-        for (int x = 0; x < W; ++x) d[x] = row[reflect101(x - left, w)];
+        for (int x = 0; x < left; ++x) d[x] = row[reflect101(x - left, w)];
+        memcpy(d + left, row, (size_t)w);
+        for (int x = left + w; x < W; ++x) d[x] = row[reflect101(x - left, w)];
     }
     free(row);
     for (int y = 0; y < H; ++y) {
@@ -122,8 +134,36 @@ void cvp_border_reflect101_u8(const uint8_t *src, int w, int h, int sstride,
 
 /* -------------------------------------------------------------------- blur */
 
+/* Same arithmetic laid out for the vectoriser: the row is extended by its reflect-101 margins once, then both passes are plain
+ * loops over contiguous data (what OpenCV's SIMD path does; the scalar form below stays as the cross-check). */
 void cvp_gaussian7x7_s2_u8(const uint8_t *src, int w, int h, int sstride,
                            uint8_t *dst, int dstride)
+{
+    uint16_t *H = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)w * (size_t)h);
+    uint8_t *pad = (uint8_t *)malloc((size_t)w + 6);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *s = src + (size_t)y * sstride;
+        for (int i = 0; i < 3; ++i) { pad[i] = s[reflect101(i - 3, w)]; pad[w + 3 + i] = s[reflect101(w + i, w)]; }
+        memcpy(pad + 3, s, (size_t)w);
+        uint16_t *hr = H + (size_t)y * w;
+        for (int x = 0; x < w; ++x)
+            hr[x] = (uint16_t)(18u * (pad[x] + pad[x + 6]) + 34u * (pad[x + 1] + pad[x + 5]) + 48u * (pad[x + 2] + pad[x + 4]) + 56u * pad[x + 3]);
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t *r0 = H + (size_t)reflect101(y - 3, h) * w, *r1 = H + (size_t)reflect101(y - 2, h) * w, *r2 = H + (size_t)reflect101(y - 1, h) * w,
+                       *r3 = H + (size_t)y * w, *r4 = H + (size_t)reflect101(y + 1, h) * w, *r5 = H + (size_t)reflect101(y + 2, h) * w,
+                       *r6 = H + (size_t)reflect101(y + 3, h) * w;
+        uint8_t *d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x) {
+            const uint32_t acc = 18u * ((uint32_t)r0[x] + r6[x]) + 34u * ((uint32_t)r1[x] + r5[x]) + 48u * ((uint32_t)r2[x] + r4[x]) + 56u * (uint32_t)r3[x];
+            d[x] = (uint8_t)((acc + 32768u) >> 16);
+        }
+    }
+    free(pad); free(H);
+}
+
+void cvp_gaussian7x7_s2_u8_scalar(const uint8_t *src, int w, int h, int sstride,
+                                  uint8_t *dst, int dstride)
 {
     static const uint32_t k[7] = {18, 34, 48, 56, 48, 34, 18};
     uint16_t *H = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)w * (size_t)h);
@@ -183,8 +223,8 @@ static inline int has9(unsigned m)         /* 9 contiguous set bits in a 16-bit 
     return (m & 0xffffu) != 0;
 }
 
-int cvp_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold,
-                 int nms, cvp_corner *out, int cap)
+int cvp_fast9_16_scalar(const uint8_t *img, int w, int h, int stride, int threshold,
+                        int nms, cvp_corner *out, int cap)
 {
     if (w < 7 || h < 7) return 0;
     int off[16];
@@ -233,6 +273,84 @@ int cvp_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold,
     free(S);
     return n;
 }
+
+#if defined(__AVX2__)
+#include <immintrin.h>
+/* 32 pixels at a time on unsigned bytes.  With sat(a - b) = max(a - b, 0):  B_k = sat(r_k - c), D_k = sat(c - r_k),
+ * bright = max over the sixteen 9-arcs of min(B over the arc), dark likewise on D, and max(bright, dark) = max(A, 0) for the
+ * A of cornerScore<16> -- exact wherever the score can reach a threshold >= 1.  The arcs are taken in pairs 2i, 2i+1 that share
+ * the eight ring pixels 2i+1 .. 2i+8: max(min arc 2i, min arc 2i+1) = min(those eight, max(r_2i, r_2i+9)).  Every pixel is
+ * scored (no pre-test: on these lanes the full score costs about as much as OpenCV's compass test does per pixel). */
+static inline __m256i fast_arcs_u8(const __m256i *e)
+{
+    __m256i l2[8], l4[8], best = _mm256_setzero_si256();
+    for (int i = 0; i < 8; ++i) l2[i] = _mm256_min_epu8(e[2 * i + 1], e[(2 * i + 2) & 15]);
+    for (int i = 0; i < 8; ++i) l4[i] = _mm256_min_epu8(l2[i], l2[(i + 1) & 7]);
+    for (int i = 0; i < 8; ++i) {
+        const __m256i eight = _mm256_min_epu8(l4[i], l4[(i + 2) & 7]);
+        best = _mm256_max_epu8(best, _mm256_min_epu8(eight, _mm256_max_epu8(e[2 * i], e[(2 * i + 9) & 15])));
+    }
+    return best;
+}
+
+int cvp_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold,
+                 int nms, cvp_corner *out, int cap)
+{
+    if (w < 7 || h < 7) return 0;
+    if (threshold < 1 || threshold > 254) return cvp_fast9_16_scalar(img, w, h, stride, threshold, nms, out, cap);
+    /* padded copy: 32-byte loads may run past the row end, and the score rows need zeroed margins */
+    const int ts = (w + 32 + 31) & ~31;
+    uint8_t *T = (uint8_t *)calloc((size_t)ts * (size_t)(h + 1), 1), *S = (uint8_t *)calloc((size_t)ts * (size_t)(h + 1), 1);
+    for (int y = 0; y < h; ++y) memcpy(T + (size_t)y * ts, img + (size_t)y * stride, (size_t)w);
+    int off[16];
+    for (int k = 0; k < 16; ++k) off[k] = RING_DY[k] * ts + RING_DX[k];
+    const __m256i vt = _mm256_set1_epi8((char)threshold), one = _mm256_set1_epi8(1);
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t *row = T + (size_t)y * ts;
+        uint8_t *srow = S + (size_t)y * ts;
+        for (int x = 3; x < w - 3; x += 32) {
+            const __m256i c = _mm256_loadu_si256((const __m256i *)(row + x));
+            __m256i b[16], d[16];
+            for (int k = 0; k < 16; ++k) {
+                const __m256i r = _mm256_loadu_si256((const __m256i *)(row + x + off[k]));
+                b[k] = _mm256_subs_epu8(r, c);
+                d[k] = _mm256_subs_epu8(c, r);
+            }
+            const __m256i a = _mm256_max_epu8(fast_arcs_u8(b), fast_arcs_u8(d));     /* max(A, 0) */
+            /* score = A - 1; corner at t <=> A - 1 >= t <=> A > t; S holds the score of corners, 0 elsewhere (as cv::FAST) */
+            const __m256i is_corner = _mm256_cmpeq_epi8(_mm256_subs_epu8(a, vt), _mm256_setzero_si256());       /* 0xff where NOT a corner */
+            const __m256i sc = _mm256_andnot_si256(is_corner, _mm256_sub_epi8(a, one));
+            _mm256_storeu_si256((__m256i *)(srow + x), sc);
+        }
+        for (int x = w - 3; x < ts; ++x) srow[x] = 0;                 /* the last chunk spilled past the scored columns */
+    }
+    int n = 0;
+    const int t = threshold;
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t *s0 = S + (size_t)(y - 1) * ts, *s1 = S + (size_t)y * ts, *s2 = S + (size_t)(y + 1) * ts;
+        for (int x = 3; x < w - 3; ++x) {
+            const int sc = s1[x];
+            if (sc < t) continue;
+            if (nms) {
+                if (!(sc > s1[x - 1] && sc > s1[x + 1] &&
+                      sc > s0[x - 1] && sc > s0[x] && sc > s0[x + 1] &&
+                      sc > s2[x - 1] && sc > s2[x] && sc > s2[x + 1]))
+                    continue;
+            }
+            if (n < cap) { out[n].x = x; out[n].y = y; out[n].score = sc; }
+            ++n;
+        }
+    }
+    free(T); free(S);
+    return n;
+}
+#else
+int cvp_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold,
+                 int nms, cvp_corner *out, int cap)
+{
+    return cvp_fast9_16_scalar(img, w, h, stride, threshold, nms, out, cap);
+}
+#endif
 
 /* --------------------------------------------------------------- fastAtan2 */
 

@@ -1,7 +1,7 @@
 /*
  * oracle/cvprim.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Scalar C restatements of the OpenCV primitives that the reference's ORB
+ * C restatements of the OpenCV primitives that the reference's ORB
  * front end calls (src/ORBextractor.cc:103,809-815,1090,1116,1124-1132 in the
  * reference tree).  OpenCV itself is not vendored by the reference and its
  * C++ library is absent from this image, so the arithmetic is restated from
@@ -42,6 +42,10 @@ void cvp_border_reflect101_u8(const uint8_t *src, int w, int h, int sstride,
 void cvp_gaussian7x7_s2_u8(const uint8_t *src, int w, int h, int sstride,
                            uint8_t *dst, int dstride);
 
+/* The plain scalar form of the same blur (cross-check of the vectorised one). */
+void cvp_gaussian7x7_s2_u8_scalar(const uint8_t *src, int w, int h, int sstride,
+                                  uint8_t *dst, int dstride);
+
 typedef struct { int x, y, score; } cvp_corner;
 
 /* FAST-9/16 corner score of one pixel (OpenCV cornerScore<16>: the largest
@@ -54,6 +58,11 @@ int cvp_fast_score(const uint8_t *p, int stride);
  * (may exceed cap; only the first cap are written). */
 int cvp_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold,
                  int nms, cvp_corner *out, int cap);
+
+/* The scalar form (compass pre-test, 16-bit ring masks, cornerScore per corner), as cv::FAST's generic path; the function above
+ * scores 32 pixels at a time with AVX2 byte min / max when the build has it.  Identical outputs (tests/test_oracle_cvprim.py). */
+int cvp_fast9_16_scalar(const uint8_t *img, int w, int h, int stride, int threshold,
+                        int nms, cvp_corner *out, int cap);
 
 /* cv::fastAtan2(y, x): degrees in [0, 360), 7th-order polynomial, fp32. */
 float cvp_fast_atan2(float y, float x);

@@ -4,7 +4,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-import multimot_track_b200 as orb
+import multimot_track_b200 as orb          # run with ORBX_LIBRARY=multimot_track_b200/liborbx_dbg.so (make -C multimot_track_b200/csrc dbg): the release library has no ORBX_DEBUG_SKIP
 from bench import make_pool, POOL_DISTINCT
 
 H, W, batch = 375, 1242, 32

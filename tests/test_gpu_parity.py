@@ -458,19 +458,33 @@ def test_cpp_adapter_drop_in(orb, oracle_mod, tmp_path):
 
 
 def test_tma_and_plain_staging_agree(orb, oracle_mod):
-    """The pyramid's TMA-staged kernel (cp.async.bulk.tensor) and its plain shared-memory staging fallback
-    (forced with ORBX_NO_TMA) both reproduce the oracle bit for bit."""
-    import os
+    """The TMA-staged kernels (cp.async.bulk.tensor) and their plain staging fallbacks (ORBX_OPT_TMA_STAGING = 0), the persistent TMA
+    variant of the FAST kernel (ORBX_OPT_FAST_TMA) and the copied-input path (ORBX_OPT_COPY_INPUT) all reproduce the oracle bit for bit."""
+    import torch
     img = synth(11, 375, 1242)
     o = oracle_mod.Oracle(2000, 1.2, 8, 20, 7)
-    o(img)
-    for no_tma in (False, True):
-        if no_tma:
-            os.environ["ORBX_NO_TMA"] = "1"
-        try:
-            ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
-            ext(img)
-            for l in range(8):
-                assert np.array_equal(ext.pyramid_level(l), o.level_image(l)), (no_tma, l)
-        finally:
-            os.environ.pop("ORBX_NO_TMA", None)
+    ext = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    check_frame(ext, o, img, "tma")
+    ext.set_option(ext.OPT_FAST_TMA, 1)
+    check_frame(ext, o, img, "fast-tma")
+    ext.set_option(ext.OPT_FAST_TMA, 0)
+    ext.set_option(ext.OPT_TMA_STAGING, 0)
+    check_frame(ext, o, img, "plain")
+    ext.set_option(ext.OPT_TMA_STAGING, 1)
+    check_frame(ext, o, img, "tma again")
+    with pytest.raises(orb.OrbxError):
+        ext.set_option(99, 1)
+    # device-resident, aligned frames: in place by default, copied with ORBX_OPT_COPY_INPUT (then the caller's buffer may be
+    # overwritten after the collect without changing what level 0 reads back)
+    okps, odesc = o(img)
+    buf = torch.zeros((1, 375, 1280), dtype=torch.uint8, device="cuda")
+    buf[0, :, :1242] = torch.from_numpy(img).cuda()
+    torch.cuda.synchronize()
+    for copy in (0, 1):
+        ext.set_option(ext.OPT_COPY_INPUT, copy)
+        ext.submit_device(buf.data_ptr(), 1, 1242, 375, 1280, 375 * 1280)
+        kps, desc, n = ext.collect_view()
+        assert kps_equal_exact(kps[0, :n[0]], okps) and np.array_equal(desc[0, :n[0]], odesc)
+    buf.zero_()
+    torch.cuda.synchronize()
+    assert np.array_equal(ext.pyramid_level(0), img)

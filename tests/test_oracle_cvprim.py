@@ -111,3 +111,31 @@ def test_gray_conversion_against_live_cv2(L):
         codes = {(3, 1): cv2.COLOR_RGB2GRAY, (3, 0): cv2.COLOR_BGR2GRAY, (4, 1): cv2.COLOR_RGBA2GRAY, (4, 0): cv2.COLOR_BGRA2GRAY}
         for rgb in (1, 0):
             assert np.array_equal(_gray(L, img, rgb), cv2.cvtColor(img, codes[(c, rgb)]))
+
+
+def test_vectorised_primitives_equal_their_scalar_forms(L):
+    """The AVX2 / vectoriser-friendly forms of FAST and the blur (the ones the reference-compiled CPU baseline runs on) against the
+    plain scalar restatements, on sizes around the 32-pixel chunk and the cell sizes the reference calls cv::FAST with (36 .. 38)."""
+    rng = np.random.default_rng(11)
+    from multimot_track_b200.synth import value_noise_frame
+    for (h, w) in ((7, 7), (8, 9), (36, 36), (36, 37), (38, 38), (37, 39), (20, 70), (41, 67), (64, 99), (90, 131)):
+        for kind in range(3):
+            if kind == 0:
+                img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            elif kind == 1:
+                img = value_noise_frame(h + w, max(h, 24), max(w, 24))[:h, :w].copy()
+            else:
+                img = (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)            # saturating differences
+            big = np.zeros((h, w + 13), np.uint8); big[:, :w] = img
+            view = big[:, :w]                                                        # stride != width
+            for th in (1, 7, 20, 100, 254):
+                for nms in (1, 0):
+                    buf = (Corner * img.size)(); buf2 = (Corner * img.size)()
+                    n = L.cvp_fast9_16(ctypes.c_void_p(view.ctypes.data), w, h, view.strides[0], th, nms, buf, img.size)
+                    n2 = L.cvp_fast9_16_scalar(ctypes.c_void_p(view.ctypes.data), w, h, view.strides[0], th, nms, buf2, img.size)
+                    assert n == n2, (h, w, kind, th, nms)
+                    assert all((buf[i].x, buf[i].y, buf[i].s) == (buf2[i].x, buf2[i].y, buf2[i].s) for i in range(n)), (h, w, kind, th, nms)
+            a = np.zeros_like(img); b = np.zeros_like(img)
+            L.cvp_gaussian7x7_s2_u8(ctypes.c_void_p(view.ctypes.data), w, h, view.strides[0], ctypes.c_void_p(a.ctypes.data), a.strides[0])
+            L.cvp_gaussian7x7_s2_u8_scalar(ctypes.c_void_p(view.ctypes.data), w, h, view.strides[0], ctypes.c_void_p(b.ctypes.data), b.strides[0])
+            assert np.array_equal(a, b), (h, w, kind)

@@ -399,3 +399,26 @@ def test_search_by_projection_port_vs_reference(oracle_mod):
         if oracle_mod.RefExtractor.available("canon") and hasattr(oracle_mod.RefExtractor.lib("canon"), "orbref_search_by_projection"):
             b, nb = oracle_mod.search_by_projection_ref(case)
             assert nb == na and np.array_equal(a, b)
+
+
+def test_cv2_restatement_cross_check(oracle_mod, kitti_frames, golden_kitti):
+    """the independent Python restatement on the real cv2 4.13 primitives (oracle/cv2_restatement.py; also the
+    second CPU baseline of bench.py) against the C port and the reference-derived goldens: every stage and all outputs identical."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle.cv2_restatement import Cv2Extractor
+    from multimot_track_b200.synth import value_noise_frame
+    for img, params, gold in ((kitti_frames[2], (4000, 1.2, 8, 20, 7), "f2_n4000"), (value_noise_frame(3, 375, 1242), (2000, 1.2, 8, 20, 7), None),
+                              (value_noise_frame(5, 300, 500), (700, 1.3, 5, 15, 5), None)):
+        e = Cv2Extractor(*params)
+        k, d = e(img)
+        o = oracle_mod.Oracle(*params)
+        ok, od = o(img)
+        for l in range(params[2]):
+            assert np.array_equal(e.pyramid[l], o.level_image(l)) and np.array_equal(e.padded[l], o.level_padded(l)), l
+            assert np.array_equal(e.candidates[l], o.level_candidates(l)), l
+            if e.blurred[l] is not None:
+                assert np.array_equal(e.blurred[l], o.level_blurred(l)), l
+        assert kps_equal_exact(k, ok) and np.array_equal(k["angle"].view(np.uint32), ok["angle"].view(np.uint32))
+        assert desc_bit_mismatch(d, od)[0] == 0
+        if gold:
+            assert kps_equal_exact(k, golden_kitti["kps_" + gold]) and np.array_equal(d, golden_kitti["desc_" + gold])
