@@ -43,6 +43,7 @@ WORKLOADS = {
     "k2": (1080, 1920, 5000, 8, 64, "synthetic 1920x1080 u8, 8 levels x1.2, 5000 features, batch 64 per GPU"),
     "k4": (2160, 3840, 10000, 12, 8, "synthetic 3840x2160 u8, 12 levels x1.2, 10000 features, batch 8 per GPU"),
 }
+LANES = {"k1": 1, "k2": 1, "k4": 1}        # dispatcher workers per GPU (sub-batches per batch), measured per workload
 POOL_DISTINCT = 64
 METRIC = "orb_extract_describe_frames_per_s"
 
@@ -188,6 +189,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the matcher / next-row timings (profiling runs)")
     ap.add_argument("--handles", type=int, default=6, help="batches in flight per GPU (depth of the native dispatcher)")
     ap.add_argument("--batch", type=int, default=0, help="experiment: another batch size for the named shape")
+    ap.add_argument("--full-records", action="store_true", help="device-resident loop with 28-byte cv::KeyPoint records instead of the 12-byte compact ones")
+    ap.add_argument("--lanes", type=int, default=0, help="dispatcher workers per GPU: a batch is split into that many contiguous sub-batches, each with its own "
+                                                          "worker thread, handles and streams (0 = the workload's default)")
     args = ap.parse_args()
     t_start = time.time()
     H, W, nfeat, nlev, batch, desc = WORKLOADS[args.workload]
@@ -240,7 +244,12 @@ def main():
     depth = max(1, args.handles)
     # the native frame-sharded dispatcher with this rank's GPU as its only device: one C++ worker thread issues the copies and
     # launches, `depth` handles (streams) keep consecutive batches in flight; Python only queues tickets and collects views
-    xpool = orb.ExtractorPool(*params, devices=[local], depth=depth, max_width=W, max_height=H, max_batch=batch)
+    lanes = args.lanes if args.lanes > 0 else LANES[args.workload]
+    lanes = max(1, min(lanes, batch))
+    sub = [shard_bounds(batch, g, lanes) for g in range(lanes)]      # contiguous sub-batches of this rank's block, one per worker
+    xpool = orb.ExtractorPool(*params, devices=[local] * lanes, depth=depth, max_width=W, max_height=H, max_batch=max(hi - lo for lo, hi in sub))
+    OPT_COMPACT = orb.ORBextractor.OPT_COMPACT_KEYPOINTS
+    compact = not args.full_records
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,21 +266,28 @@ def main():
 
     def submit_dev(step):
         b = frames_of_step(step) % nbatches
-        return xpool.submit_device([dpool[b * batch].data_ptr()], [batch], W, H, pitch, H * pitch)
+        return xpool.submit_device([dpool[b * batch + lo].data_ptr() for lo, hi in sub], [hi - lo for lo, hi in sub], W, H, pitch, H * pitch)
 
     def submit_host(step):
         b = (frames_of_step(step) * batch) % POOL_DISTINCT
         return xpool.submit_host([hnp[(b + j) % POOL_DISTINCT] for j in range(batch)])
+
+    def prime():
+        """Setup, not measurement: every handle of the dispatcher sees one batch through each entry point, so lazy first-use work
+        (kernel module loads, tensor-map encodes, pinned staging) is not charged to whichever step first lands on a cold handle."""
+        for submit in (submit_dev, submit_host):
+            for t in [submit(s) for s in range(depth)]:
+                xpool.collect(t)
 
     def run(submit, steps, first_step=0):
         """Pipelined loop: at most `depth` tickets outstanding; the oldest is collected before the next submit."""
         tickets, kp_total = [], 0
         for s in range(first_step, first_step + steps):
             if len(tickets) == depth:
-                kp_total += int(xpool.collect(tickets.pop(0))[0][3].sum())
+                kp_total += sum(int(sh[3].sum()) for sh in xpool.collect(tickets.pop(0)))
             tickets.append(submit(s))
         for t in tickets:
-            kp_total += int(xpool.collect(t)[0][3].sum())
+            kp_total += sum(int(sh[3].sum()) for sh in xpool.collect(t))
         return kp_total
 
     def timed(submit, steps, warmup):
@@ -304,11 +320,17 @@ def main():
         sampler.start()
         time.sleep(0.25)
     note = (lambda m: print("[bench %.1fs] %s" % (time.time() - t_start, m), file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
-    note("pool of %d frames resident, dispatcher up" % nslots)
+    prime()
+    xpool.set_option(OPT_COMPACT, int(compact))
+    prime()
+    note("pool of %d frames resident, dispatcher up and primed" % nslots)
+    # device-resident loop: the results land in pinned host memory as descriptors + 12-byte compact keypoint records (lossless:
+    # orbx_expand_keypoints rebuilds the cv::KeyPoint exactly; the self-check below does that for every record it compares)
     ms_dev, kp_dev, launches, (t0, t1) = timed(submit_dev, args.steps, args.warmup)
     note("device-resident loop done: %.4f ms/step" % (ms_dev / args.steps))
     clocks = sampler.stop(t0, t1) if sampler else None
-    # ---- e2e: host buffers through the plugin entry point
+    # ---- e2e: host buffers through the plugin entry point, results as full 28-byte cv::KeyPoint records + descriptors
+    xpool.set_option(OPT_COMPACT, 0)
     ms_e2e, kp_e2e, _, _ = timed(submit_host, args.steps, args.warmup)
     note("host-buffer loop done: %.4f ms/step" % (ms_e2e / args.steps))
 
@@ -340,10 +362,14 @@ def main():
                     ref[i] = (k, d)
         bad_frames = bad_bits = bits = 0
         max_angle = 0.0
-        for submit, idx in ((submit_dev, idx_dev), (submit_host, idx_host)):
-            _, kps, descs, n = xpool.collect(submit(check_step))[0]
+        for submit, idx, cmp in ((submit_dev, idx_dev, compact), (submit_host, idx_host, False)):
+            xpool.set_option(OPT_COMPACT, int(cmp))
+            shards = xpool.collect(submit(check_step))
             for f, i in enumerate(idx):
-                k, d = kps[f, :n[f]], descs[f, :n[f]]
+                first, kps, descs, n = [sh for sh in shards if sh[0] <= f < sh[0] + len(sh[3])][0]
+                k, d = kps[f - first, :n[f - first]], descs[f - first, :n[f - first]]
+                if cmp:
+                    k = xpool.expand_keypoints(k)
                 rk, rd = ref[i]
                 same = len(k) == len(rk) and all(np.array_equal(k[c], rk[c]) for c in ("x", "y", "size", "response", "octave", "class_id"))
                 if same:
@@ -483,11 +509,14 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": desc, "nfeatures": nfeat, "nlevels": nlev, "scale_factor": 1.2, "ini_th_fast": 20, "min_th_fast": 7,
                            "batch_per_gpu": batch, "global_batch": batch * world, "sharding": "frame-parallel, no collective", "cpu_bind": cpu_bind,
-                           "dispatcher": "orbx_pool (native worker thread per GPU), %d batches in flight" % depth,
+                           "dispatcher": "orbx_pool: %d native worker thread(s) per GPU, each batch split into %d contiguous sub-batch(es), %d batches in flight" % (lanes, lanes, depth),
                            "l2": "inputs larger than L2: %d frame slots = %.0f MB in HBM, walked cyclically" % (nslots, nslots * H * pitch / 2 ** 20),
-                           "input_row_pitch": pitch, "keypoints_per_step": kp_dev / max(1, args.steps)},
+                           "input_row_pitch": pitch, "keypoints_per_step": kp_dev / max(1, args.steps),
+                           "result_records": ("orbx_keypoint_compact (12 B, lossless) + descriptor (32 B) per keypoint, %d B D2H per step" % (batch * (cap * 44 + 4))) if compact
+                                             else "cv::KeyPoint (28 B) + descriptor (32 B) per keypoint, %d B D2H per step" % (batch * (cap * 60 + 4))},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": batch * H * W, "d2h_bytes_per_step": batch * (cap * 60 + 4),
+                        "records": "cv::KeyPoint (28 B) + descriptor (32 B) per keypoint",
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "parity_checked": bool(parity and parity["checked"]), "parity": parity,
                 "roofline": roofline, "cpu_baseline": cpu, "matcher": matcher, "next_rows": extras}

@@ -81,6 +81,17 @@ typedef struct {
     int32_t class_id;
 } orbx_keypoint;
 
+/* The same keypoint without its redundant fields, 12 bytes (ORBX_OPT_COMPACT_KEYPOINTS): integer pixel position IN ITS OWN
+ * PYRAMID LEVEL, octave, FAST response (an integer <= 255) and the angle.  Lossless: orbx_expand_keypoints rebuilds the
+ * cv::KeyPoint exactly (pt = position * mvScaleFactor[octave] in float, size from the octave, class_id = -1).  A batch's
+ * keypoints shrink from 28 to 12 bytes on their way to the host (results are 44 instead of 60 bytes per keypoint). */
+typedef struct {
+    uint16_t x, y;
+    uint8_t  octave, response;
+    uint16_t reserved;
+    float    angle;
+} orbx_keypoint_compact;
+
 /* ---- lifetime ---------------------------------------------------------- */
 
 /* Replaces `new ORBextractor(nFeatures, fScaleFactor, nLevels, fIniThFAST, fMinThFAST)`
@@ -172,6 +183,13 @@ int orbx_collect(orbx_handle *h, orbx_keypoint *kps, uint8_t *desc, int cap_per_
  * they stay valid until the next submit on this handle.  Any pointer may be NULL. */
 int orbx_collect_view(orbx_handle *h, const orbx_keypoint **kps, const uint8_t **desc, const int **n_out,
                       int *cap_per_frame);
+
+/* With ORBX_OPT_COMPACT_KEYPOINTS set the device-to-host copy carries orbx_keypoint_compact records: orbx_collect still fills
+ * cv::KeyPoint-layout arrays (expanded on the host), orbx_collect_view is replaced by this call (frame f at ckps + f*cap). */
+int orbx_collect_view_compact(orbx_handle *h, const orbx_keypoint_compact **ckps, const uint8_t **desc, const int **n_out,
+                              int *cap_per_frame);
+/* Rebuilds n cv::KeyPoint records from compact ones with the handle's constructor tables (exact: one float multiply each). */
+int orbx_expand_keypoints(const orbx_handle *h, const orbx_keypoint_compact *in, int n, orbx_keypoint *out);
 
 /* ---- mvImagePyramid and stage read-back -------------------------------- */
 
@@ -396,15 +414,17 @@ typedef struct {
     int32_t        ndevices;    /* entries of devices[]; 0 = one worker on the calling thread's current device             */
     const int32_t *devices;     /* CUDA ordinals, one worker each (an ordinal may repeat: several workers on one GPU)       */
     int32_t        depth;       /* submits in flight per device = handles per worker; 0 = 6                                 */
+    int32_t        compact_keypoints;  /* ORBX_OPT_COMPACT_KEYPOINTS on every handle: shards carry ckps instead of kps       */
 } orbx_pool_config;
 
 /* One shard of a collected submit: nframes frames starting at frame first_frame of the submit; frame f of the shard has
  * n[f] keypoints at kps + f*cap_per_frame and descriptors at desc + f*cap_per_frame*32 (pinned host memory of the pool). */
 typedef struct {
-    const orbx_keypoint *kps;
+    const orbx_keypoint *kps;                 /* NULL when the pool delivers compact records */
     const uint8_t       *desc;
     const int32_t       *n;
     int32_t nframes, first_frame, cap_per_frame, device;
+    const orbx_keypoint_compact *ckps;        /* frame f at ckps + f*cap_per_frame; NULL unless compact_keypoints */
 } orbx_shard_result;
 
 int orbx_pool_create(const orbx_pool_config *cfg, orbx_pool **out);
@@ -412,6 +432,8 @@ void orbx_pool_destroy(orbx_pool *p);
 const char *orbx_pool_last_error(const orbx_pool *p);      /* p may be NULL: last orbx_pool_create failure of the thread */
 int orbx_pool_devices(const orbx_pool *p);                  /* number of shards per submit                                 */
 int orbx_pool_depth(const orbx_pool *p);
+/* ORBX_OPT_* on every handle of the pool; only while no ticket is outstanding (ORBX_ERR_STATE otherwise). */
+int orbx_pool_set_option(orbx_pool *p, int option, int value);
 /* Handle `slot` (0 .. depth-1) of shard `shard`, e.g. for orbx_get_tables or stage read-back between submits. */
 orbx_handle *orbx_pool_handle(orbx_pool *p, int shard, int slot);
 /* The split every submit uses: shard g of G owns the contiguous frames [g*F/G, (g+1)*F/G). */
@@ -435,6 +457,7 @@ int orbx_pool_collect(orbx_pool *p, long long ticket, orbx_shard_result *shards)
 #define ORBX_OPT_TMA_STAGING 1   /* 1 (default): tiles / patches arrive by cp.async.bulk.tensor; 0: plain staging loads (same results) */
 #define ORBX_OPT_FAST_TMA    2   /* 1: persistent TMA variant of the FAST kernel; default 0 (slower in the pipelined loop)           */
 #define ORBX_OPT_COPY_INPUT  3   /* 1: orbx_submit_device always copies the frames into the handle's level-0 slots; default 0        */
+#define ORBX_OPT_COMPACT_KEYPOINTS 4 /* 1: keypoints travel to the host as 12-byte orbx_keypoint_compact records; default 0            */
 int orbx_set_option(orbx_handle *h, int option, int value);
 
 /* ---- misc ---------------------------------------------------------------- */

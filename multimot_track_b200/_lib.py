@@ -36,12 +36,13 @@ class OrbxPlan(ctypes.Structure):
 
 
 class OrbxPoolConfig(ctypes.Structure):
-    _fields_ = [("extractor", OrbxConfig), ("ndevices", ctypes.c_int32), ("devices", ctypes.POINTER(ctypes.c_int32)), ("depth", ctypes.c_int32)]
+    _fields_ = [("extractor", OrbxConfig), ("ndevices", ctypes.c_int32), ("devices", ctypes.POINTER(ctypes.c_int32)), ("depth", ctypes.c_int32),
+                ("compact_keypoints", ctypes.c_int32)]
 
 
 class OrbxShardResult(ctypes.Structure):
     _fields_ = [("kps", ctypes.c_void_p), ("desc", ctypes.c_void_p), ("n", ctypes.c_void_p), ("nframes", ctypes.c_int32),
-                ("first_frame", ctypes.c_int32), ("cap_per_frame", ctypes.c_int32), ("device", ctypes.c_int32)]
+                ("first_frame", ctypes.c_int32), ("cap_per_frame", ctypes.c_int32), ("device", ctypes.c_int32), ("ckps", ctypes.c_void_p)]
 
 
 # every symbol include/orbx.h declares: (restype, argtypes)
@@ -59,6 +60,9 @@ SIGNATURES = {
     "orbx_submit_device": (_I, [_VP, _VP, _I, _I, _I, _I, _SZ]),
     "orbx_submit_host": (_I, [_VP, _VP, _I, _I, _I, _I]),
     "orbx_collect": (_I, [_VP, _VP, _VP, _I, _VP]),
+    "orbx_collect_view_compact": (_I, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_I)]),
+    "orbx_expand_keypoints": (_I, [_VP, _VP, _I, _VP]),
+    "orbx_pool_set_option": (_I, [_VP, _I, _I]),
     "orbx_collect_view": (_I, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.POINTER(_I)]),
     "orbx_get_level_size": (_I, [_VP, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "orbx_get_pyramid_level": (_I, [_VP, _I, _I, _VP, _I, _I]),

@@ -1717,6 +1717,8 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(const DevParams *
             }
             reinterpret_cast<float *>(P->out_kps + row)[lane] = f;
         }
+        if (P->out_ckps && lane < 3)                                   // orbx_keypoint_compact: x | y << 16, octave | response << 8, angle
+            P->out_ckps[3 * row + lane] = lane == 0 ? (uint32_t)cx | (uint32_t)cy << 16 : (lane == 1 ? (uint32_t)level | (c >> 24) << 8 : __float_as_uint(angle));
     }
 }
 
@@ -1938,6 +1940,8 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc_tma(const DevPara
             f = lane == 5 ? __int_as_float(level) : f;
             f = lane == 6 ? __int_as_float(-1) : f;
             if (lane < 7) reinterpret_cast<float *>(P->out_kps + orow)[lane] = f;
+            if (P->out_ckps && lane < 3)                               // orbx_keypoint_compact: x | y << 16, octave | response << 8, angle
+                P->out_ckps[3 * orow + lane] = lane == 0 ? (uint32_t)cx | (uint32_t)cy << 16 : (lane == 1 ? (uint32_t)level | (c >> 24) << 8 : __float_as_uint(angle));
         }
         if (!v1) break;
         c0 = c1; lv0 = lv1; c1 = c2; lv1 = lv2; v1 = v2; j += step;

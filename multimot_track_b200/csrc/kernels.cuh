@@ -28,6 +28,7 @@ struct DevParams {
     uint32_t *kp_count;           // [F][nlevels]
     unsigned long long *sort_scratch;   // [F][cand_frame_elems]  octree keys when a level does not fit shared memory
     orbx_keypoint *out_kps;       // [F][kp_frame_cap]
+    uint32_t *out_ckps;           // [F][kp_frame_cap][3]   compact 12-byte records beside the full ones (ORBX_OPT_COMPACT_KEYPOINTS), else NULL
     uint8_t *out_desc;            // [F][kp_frame_cap][32]
     int *out_n;                   // [F]
     const ResizeTab *xtab, *ytab;

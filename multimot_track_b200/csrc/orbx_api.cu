@@ -37,6 +37,8 @@ struct orbx_handle {
     uint32_t *d_cand = nullptr, *d_cand_count = nullptr, *d_kp_stage = nullptr, *d_kp_count = nullptr;
     unsigned long long *d_sort = nullptr;
     orbx_keypoint *d_out_kps = nullptr;
+    uint32_t *d_out_ckps = nullptr;     // compact records beside the full ones (opt_compact)
+    orbx_keypoint_compact *p_ckps = nullptr;
     uint8_t *d_out_desc = nullptr;
     int *d_out_n = nullptr;
     uint8_t *d_pad = nullptr; size_t pad_bytes = 0;
@@ -57,7 +59,7 @@ struct orbx_handle {
     TmaMaps tma;                        // pyramid source descriptors (levels >= 2 from our buffer, level 1 from the batch's level 0)
     const void *tma_l0_base = nullptr; long long tma_l0_fs = 0; int tma_l0_pitch = 0, tma_l0_frames = 0;
     bool use_tma = true;
-    bool opt_tma = true, opt_fast_tma = false, opt_copy_input = false;   // orbx_set_option
+    bool opt_tma = true, opt_fast_tma = false, opt_copy_input = false, opt_compact = false;   // orbx_set_option
     FastMaps fast_maps; unsigned fast_ok = 0;               // FAST raw boxes (bit l = level l encoded)
     OdMaps od_maps; unsigned od_img_ok = 0, od_blr_ok = 0;  // orientation / descriptor patch boxes (bit l = level l encoded)
     BlurMaps blur_maps; unsigned blur_tma_levels = 0;       // blur source boxes: bit l set = maps.m[l] valid (level 0 per batch source)
@@ -127,7 +129,8 @@ void free_batch_buffers(orbx_handle *h)
 {
     dfree(h->d_pyr); dfree(h->d_blur); dfree(h->d_cand); dfree(h->d_cand_count); dfree(h->d_kp_stage);
     dfree(h->d_kp_count); dfree(h->d_sort); dfree(h->d_out_kps); dfree(h->d_out_desc); dfree(h->d_out_n);
-    hfree(h->p_kps); hfree(h->p_desc); hfree(h->p_n);
+    dfree(h->d_out_ckps);
+    hfree(h->p_kps); hfree(h->p_desc); hfree(h->p_n); hfree(h->p_ckps);
     h->batch_cap = 0;
 }
 
@@ -138,7 +141,7 @@ int upload_params(orbx_handle *h)
     DevParams &P = h->hp;
     P.pyr = h->d_pyr; P.blur = h->d_blur; P.cand = h->d_cand; P.cand_count = h->d_cand_count;
     P.kp_stage = h->d_kp_stage; P.kp_count = h->d_kp_count; P.sort_scratch = h->d_sort;
-    P.out_kps = h->d_out_kps; P.out_desc = h->d_out_desc; P.out_n = h->d_out_n;
+    P.out_kps = h->d_out_kps; P.out_desc = h->d_out_desc; P.out_n = h->d_out_n; P.out_ckps = h->d_out_ckps;
     P.xtab = h->d_xtab; P.ytab = h->d_ytab; P.blur_work = h->d_blur_work; P.ffast_work = h->d_ffast_work; P.oct_lut = h->d_oct_lut;
     P.pattern = h->d_pattern;
     CU(cudaMemcpyAsync(h->d_params, &P, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
@@ -166,6 +169,15 @@ int ensure_batch(orbx_handle *h, int nframes)
     CU(cudaMallocHost(&h->p_kps, F * g.kp_frame_cap * sizeof(orbx_keypoint)));
     CU(cudaMallocHost(&h->p_desc, F * g.kp_frame_cap * 32));
     CU(cudaMallocHost(&h->p_n, F * sizeof(int)));
+    if (h->opt_compact) {
+        CU(cudaMalloc(&h->d_out_ckps, F * g.kp_frame_cap * sizeof(orbx_keypoint_compact)));
+        CU(cudaMallocHost(&h->p_ckps, F * g.kp_frame_cap * sizeof(orbx_keypoint_compact)));
+    }
+    {   // landing area of the host-frame entry points (tightly packed grey frames; grows on demand for padded / colour input), so that
+        // the first orbx_submit_host on a pre-sized handle does not allocate -- and synchronise the device -- inside a caller's pipeline
+        const size_t want = F * (size_t)g.width * (size_t)g.height;
+        if (want > h->in_bytes) { dfree(h->d_in); CU(cudaMalloc(&h->d_in, want)); h->in_bytes = want; }
+    }
     // rows beyond a level's width are padding that kernels may write but never read as data;
     // clear once so read-back of padded rows is deterministic
     CU(cudaMemsetAsync(h->d_pyr, 0, F * g.pyr_frame_bytes, h->stream));
@@ -300,7 +312,8 @@ int enqueue_pipeline(orbx_handle *h, Src0 s0, int nframes)
     const size_t cap = (size_t)P.kp_frame_cap;
     CU(cudaMemcpyAsync(h->p_n, h->d_out_n, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!(skip & 32)) {
-    CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
+    if (h->opt_compact) CU(cudaMemcpyAsync(h->p_ckps, h->d_out_ckps, (size_t)nframes * cap * sizeof(orbx_keypoint_compact), cudaMemcpyDeviceToHost, st));
+    else CU(cudaMemcpyAsync(h->p_kps, h->d_out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->p_desc, h->d_out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, st));
     }
     MARK(7);
@@ -513,10 +526,47 @@ extern "C" int orbx_extract_color(orbx_handle *h, const uint8_t *image, int widt
     return orbx_collect(h, kps, desc, cap, n_out);
 }
 
+static void expand_keypoints(const orbx_handle *h, const orbx_keypoint_compact *in, int n, orbx_keypoint *out)
+{
+    const int L = h->tab.nlevels;
+    for (int i = 0; i < n; ++i) {
+        const orbx_keypoint_compact c = in[i];
+        const int o = c.octave < L ? c.octave : L - 1;
+        orbx_keypoint k;
+        k.x = (float)c.x * h->tab.scale[o]; k.y = (float)c.y * h->tab.scale[o];        // pt *= mvScaleFactor[level] (src/ORBextractor.cc:1098-1104); scale[0] == 1
+        k.size = (float)(int)(31.0f * h->tab.scale[o]);                                  // PATCH_SIZE * mvScaleFactor[level] into the int scaledPatchSize (:841-846)
+        k.angle = c.angle; k.response = (float)c.response; k.octave = c.octave; k.class_id = -1;
+        out[i] = k;
+    }
+}
+
+extern "C" int orbx_expand_keypoints(const orbx_handle *h, const orbx_keypoint_compact *in, int n, orbx_keypoint *out)
+{
+    if (!h || n < 0 || (n > 0 && (!in || !out))) return ORBX_ERR_BAD_ARG;
+    expand_keypoints(h, in, n, out);
+    return ORBX_OK;
+}
+
+extern "C" int orbx_collect_view_compact(orbx_handle *h, const orbx_keypoint_compact **ckps, const uint8_t **desc, const int **n_out, int *cap_per_frame)
+{
+    if (!h) return ORBX_ERR_BAD_ARG;
+    if (!h->pending) return fail(h, ORBX_ERR_STATE, "orbx_collect without a pending submit");
+    if (!h->opt_compact) return fail(h, ORBX_ERR_STATE, "orbx_collect_view_compact: ORBX_OPT_COMPACT_KEYPOINTS is off on this handle");
+    ON_DEVICE(h);
+    CU(cudaStreamSynchronize(h->stream));
+    h->pending = false;
+    if (ckps) *ckps = h->p_ckps;
+    if (desc) *desc = h->p_desc;
+    if (n_out) *n_out = h->p_n;
+    if (cap_per_frame) *cap_per_frame = h->geo.kp_frame_cap;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_collect_view(orbx_handle *h, const orbx_keypoint **kps, const uint8_t **desc, const int **n_out, int *cap_per_frame)
 {
     if (!h) return ORBX_ERR_BAD_ARG;
     if (!h->pending) return fail(h, ORBX_ERR_STATE, "orbx_collect without a pending submit");
+    if (h->opt_compact && kps) return fail(h, ORBX_ERR_STATE, "orbx_collect_view: the handle delivers compact keypoints (use orbx_collect_view_compact or orbx_collect)");
     ON_DEVICE(h);
     CU(cudaStreamSynchronize(h->stream));
     h->pending = false;
@@ -539,7 +589,8 @@ extern "C" int orbx_collect(orbx_handle *h, orbx_keypoint *kps, uint8_t *desc, i
         const int n = h->p_n[f];
         n_out[f] = n;
         if (n > cap_per_frame) { status = fail(h, ORBX_ERR_CAPACITY, "cap_per_frame smaller than the keypoint count (see orbx_max_keypoints)"); continue; }
-        std::memcpy(kps + (size_t)f * cap_per_frame, h->p_kps + f * cap, (size_t)n * sizeof(orbx_keypoint));
+        if (h->opt_compact) expand_keypoints(h, h->p_ckps + f * cap, n, kps + (size_t)f * cap_per_frame);
+        else std::memcpy(kps + (size_t)f * cap_per_frame, h->p_kps + f * cap, (size_t)n * sizeof(orbx_keypoint));
         std::memcpy(desc + (size_t)f * cap_per_frame * 32, h->p_desc + f * cap * 32, (size_t)n * 32);
     }
     return status;
@@ -1295,6 +1346,14 @@ extern "C" int orbx_set_option(orbx_handle *h, int option, int value)
         return ORBX_OK;
     case ORBX_OPT_FAST_TMA: h->opt_fast_tma = value != 0; return ORBX_OK;
     case ORBX_OPT_COPY_INPUT: h->opt_copy_input = value != 0; return ORBX_OK;
+    case ORBX_OPT_COMPACT_KEYPOINTS:
+        if (h->opt_compact != (value != 0)) {
+            CU(cudaStreamSynchronize(h->stream));
+            h->opt_compact = value != 0;
+            const int keep = h->batch_cap;
+            if (h->geo_valid && keep > 0) { free_batch_buffers(h); h->have_batch = false; return ensure_batch(h, keep); }
+        }
+        return ORBX_OK;
     default: return fail(h, ORBX_ERR_BAD_ARG, "orbx_set_option: unknown option");
     }
 }

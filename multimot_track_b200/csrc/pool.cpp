@@ -50,6 +50,7 @@ struct Worker {
 struct orbx_pool {
     std::vector<Worker> workers;
     int depth = 6;
+    bool compact = false;
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
     bool stop = false;
@@ -132,6 +133,7 @@ extern "C" int orbx_pool_create(const orbx_pool_config *cfg, orbx_pool **out)
     orbx_pool *p = new (std::nothrow) orbx_pool();
     if (!p) return pfail(nullptr, ORBX_ERR_OOM, "host allocation failed");
     p->depth = cfg->depth > 0 ? cfg->depth : 6;
+    p->compact = cfg->compact_keypoints != 0;
     p->collected.assign((size_t)p->depth, 1);
     const int G = cfg->ndevices > 0 ? cfg->ndevices : 1;
     p->workers.resize((size_t)G);
@@ -143,7 +145,8 @@ extern "C" int orbx_pool_create(const orbx_pool_config *cfg, orbx_pool **out)
         for (int k = 0; k < p->depth; ++k) {
             orbx_config c = cfg->extractor;
             c.device_id = w.device;
-            const int rc = orbx_create(&c, &w.ring[(size_t)k].h);
+            int rc = orbx_create(&c, &w.ring[(size_t)k].h);
+            if (rc == ORBX_OK && cfg->compact_keypoints) rc = orbx_set_option(w.ring[(size_t)k].h, ORBX_OPT_COMPACT_KEYPOINTS, 1);
             if (rc != ORBX_OK) {
                 const std::string msg = std::string("orbx_pool_create: device ") + std::to_string(w.device) + ": " + orbx_last_error(nullptr);
                 orbx_pool_destroy(p);
@@ -180,6 +183,22 @@ extern "C" orbx_handle *orbx_pool_handle(orbx_pool *p, int shard, int slot)
 {
     if (!p || shard < 0 || shard >= (int)p->workers.size() || slot < 0 || slot >= p->depth) return nullptr;
     return p->workers[(size_t)shard].ring[(size_t)slot].h;
+}
+
+extern "C" int orbx_pool_set_option(orbx_pool *p, int option, int value)
+{
+    if (!p) return ORBX_ERR_BAD_ARG;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (p->released != p->next_ticket) return pfail(p, ORBX_ERR_STATE, "orbx_pool_set_option: collect every outstanding ticket first");
+    }
+    for (Worker &w : p->workers)
+        for (Slot &s : w.ring) {
+            const int rc = orbx_set_option(s.h, option, value);
+            if (rc != ORBX_OK) return pfail(p, rc, orbx_last_error(s.h));
+        }
+    if (option == ORBX_OPT_COMPACT_KEYPOINTS) p->compact = value != 0;
+    return ORBX_OK;
 }
 
 extern "C" void orbx_pool_shard_range(int nframes, int nshards, int shard, int *first, int *count)
@@ -250,7 +269,8 @@ extern "C" int orbx_pool_collect(orbx_pool *p, long long ticket, orbx_shard_resu
         else if (s.nframes > 0) {
             const int *n = nullptr;
             int cap = 0;
-            rc = orbx_collect_view(s.h, &r.kps, &r.desc, &n, &cap);       // waits for the shard's stream; views into pinned memory
+            rc = p->compact ? orbx_collect_view_compact(s.h, &r.ckps, &r.desc, &n, &cap)      // waits for the shard's stream; views into pinned memory
+                            : orbx_collect_view(s.h, &r.kps, &r.desc, &n, &cap);
             r.n = n; r.cap_per_frame = cap;
             if (rc != ORBX_OK) pfail(p, rc, "shard " + std::to_string(g) + ": " + orbx_last_error(s.h));
         }

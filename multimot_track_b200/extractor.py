@@ -16,6 +16,10 @@ KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle"
                            ("octave", "<i4"), ("class_id", "<i4")])
 
 
+# orbx_keypoint_compact (12 bytes): position in the keypoint's own pyramid level, octave, FAST response, angle
+COMPACT_KEYPOINT_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("octave", "u1"), ("response", "u1"), ("reserved", "<u2"), ("angle", "<f4")])
+
+
 class _PyramidView:
     """`mvImagePyramid`: level images of the last processed frame, fetched from the GPU on access."""
 
@@ -166,7 +170,25 @@ class ORBextractor:
         n = np.frombuffer(nb, dtype=np.int32)
         return kps, desc, n
 
-    OPT_TMA_STAGING, OPT_FAST_TMA, OPT_COPY_INPUT = 1, 2, 3        # ORBX_OPT_* of include/orbx.h
+    OPT_TMA_STAGING, OPT_FAST_TMA, OPT_COPY_INPUT, OPT_COMPACT_KEYPOINTS = 1, 2, 3, 4        # ORBX_OPT_* of include/orbx.h
+
+    def collect_view_compact(self):
+        """As collect_view with ORBX_OPT_COMPACT_KEYPOINTS set: kps [F,cap] of COMPACT_KEYPOINT_DTYPE."""
+        pk, pd, pn, cap = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+        self._ck(self._lib.orbx_collect_view_compact(self._h, ctypes.byref(pk), ctypes.byref(pd), ctypes.byref(pn), ctypes.byref(cap)))
+        F, c = self._last_batch, cap.value
+        kb = (ctypes.c_uint8 * (F * c * 12)).from_address(pk.value)
+        db = (ctypes.c_uint8 * (F * c * 32)).from_address(pd.value)
+        nb = (ctypes.c_int32 * F).from_address(pn.value)
+        return (np.frombuffer(kb, dtype=COMPACT_KEYPOINT_DTYPE).reshape(F, c), np.frombuffer(db, dtype=np.uint8).reshape(F, c, 32),
+                np.frombuffer(nb, dtype=np.int32))
+
+    def expand_keypoints(self, ckps):
+        """orbx_expand_keypoints: compact records -> cv::KeyPoint records (exact)."""
+        c = np.ascontiguousarray(ckps, COMPACT_KEYPOINT_DTYPE)
+        out = np.zeros(len(c), KEYPOINT_DTYPE)
+        self._ck(self._lib.orbx_expand_keypoints(self._h, c.ctypes.data, len(c), out.ctypes.data))
+        return out
 
     def set_option(self, option, value):
         self._ck(self._lib.orbx_set_option(self._h, int(option), int(value)))

@@ -6,17 +6,18 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .extractor import KEYPOINT_DTYPE
+from .extractor import COMPACT_KEYPOINT_DTYPE, KEYPOINT_DTYPE
 from .sharding import shard_bounds
 
 
 class ExtractorPool:
-    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, devices=None, depth=6, max_width=0, max_height=0, max_batch=0):
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, devices=None, depth=6, max_width=0, max_height=0, max_batch=0,
+                 compact_keypoints=False):
         self._lib = _lib.load_library()
         self._devs = (ctypes.c_int32 * len(devices))(*devices) if devices else None
         cfg = _lib.OrbxPoolConfig(_lib.OrbxConfig(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST),
                                                   int(max_width), int(max_height), int(max_batch), -1),
-                                  len(devices) if devices else 0, self._devs, int(depth))
+                                  len(devices) if devices else 0, self._devs, int(depth), int(bool(compact_keypoints)))
         p = ctypes.c_void_p()
         rc = self._lib.orbx_pool_create(ctypes.byref(cfg), ctypes.byref(p))
         if rc != 0:
@@ -41,6 +42,16 @@ class ExtractorPool:
         if rc < 0:
             raise _lib.OrbxError(int(rc), (self._lib.orbx_pool_last_error(self._p) or b"").decode())
         return rc
+
+    def set_option(self, option, value):
+        """ORBX_OPT_* on every handle (no ticket may be outstanding)."""
+        self._ck(self._lib.orbx_pool_set_option(self._p, int(option), int(value)))
+
+    def expand_keypoints(self, ckps):
+        c = np.ascontiguousarray(ckps, COMPACT_KEYPOINT_DTYPE)
+        out = np.zeros(len(c), KEYPOINT_DTYPE)
+        self._lib.orbx_expand_keypoints(self.handle_ptr(0, 0), c.ctypes.data, len(c), out.ctypes.data)
+        return out
 
     def shard_range(self, nframes, shard):
         first, count = ctypes.c_int(), ctypes.c_int()
@@ -76,7 +87,8 @@ class ExtractorPool:
 
     def collect(self, ticket):
         """Waits for the ticket; returns a list of shards: (first_frame, kps [F,cap], desc [F,cap,32], n [F]) as views of the
-        pool's pinned buffers (valid until the submit that returns ticket + depth)."""
+        pool's pinned buffers (valid until the submit that returns ticket + depth); kps are COMPACT_KEYPOINT_DTYPE records when the
+        pool delivers compact keypoints (expand_keypoints rebuilds cv::KeyPoint records)."""
         res = (_lib.OrbxShardResult * self.nshards)()
         self._ck(self._lib.orbx_pool_collect(self._p, int(ticket), res))
         self._keep.pop(ticket, None)
@@ -86,9 +98,13 @@ class ExtractorPool:
             if F == 0:
                 out.append((r.first_frame, np.zeros((0, 0), KEYPOINT_DTYPE), np.zeros((0, 0, 32), np.uint8), np.zeros(0, np.int32)))
                 continue
-            kb = (ctypes.c_uint8 * (F * c * 28)).from_address(r.kps)
+            if r.ckps:
+                kb = (ctypes.c_uint8 * (F * c * 12)).from_address(r.ckps)
+                kps = np.frombuffer(kb, dtype=COMPACT_KEYPOINT_DTYPE).reshape(F, c)
+            else:
+                kb = (ctypes.c_uint8 * (F * c * 28)).from_address(r.kps)
+                kps = np.frombuffer(kb, dtype=KEYPOINT_DTYPE).reshape(F, c)
             db = (ctypes.c_uint8 * (F * c * 32)).from_address(r.desc)
             nb = (ctypes.c_int32 * F).from_address(r.n)
-            out.append((r.first_frame, np.frombuffer(kb, dtype=KEYPOINT_DTYPE).reshape(F, c), np.frombuffer(db, dtype=np.uint8).reshape(F, c, 32),
-                        np.frombuffer(nb, dtype=np.int32)))
+            out.append((r.first_frame, kps, np.frombuffer(db, dtype=np.uint8).reshape(F, c, 32), np.frombuffer(nb, dtype=np.int32)))
         return out

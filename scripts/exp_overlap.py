@@ -7,10 +7,12 @@ import torch
 import multimot_track_b200 as orb          # run with ORBX_LIBRARY=multimot_track_b200/liborbx_dbg.so (make -C multimot_track_b200/csrc dbg): the release library has no ORBX_DEBUG_SKIP
 from bench import make_pool, POOL_DISTINCT
 
-H, W, batch = 375, 1242, 32
+from bench import WORKLOADS
+WL = os.environ.get("EXP_WORKLOAD", "k1")
+H, W, NFEAT, NLEV, batch, _ = WORKLOADS[WL]
 pool = make_pool(H, W)
 pitch = (W + 63) // 64 * 64
-reps = 6
+reps = 6 if WL == "k1" else 1
 nslots = POOL_DISTINCT * reps
 dpool = torch.zeros((nslots, H, pitch), dtype=torch.uint8, device="cuda")
 src = torch.from_numpy(pool).cuda()
@@ -18,7 +20,7 @@ for r in range(reps):
     dpool[r * POOL_DISTINCT:(r + 1) * POOL_DISTINCT, :, :W] = src
 nb = nslots // batch
 NH = int(os.environ.get("EXP_MAX_HANDLES", "12"))
-handles = [orb.ORBextractor(2000, 1.2, 8, 20, 7, device_id=0, max_width=W, max_height=H, max_batch=batch) for _ in range(NH)]
+handles = [orb.ORBextractor(NFEAT, 1.2, NLEV, 20, 7, device_id=0, max_width=W, max_height=H, max_batch=batch) for _ in range(NH)]
 
 
 def run(nh, steps, first=0):
@@ -34,7 +36,7 @@ def run(nh, steps, first=0):
             handles[i].collect_view()
 
 
-def timed(nh, steps=200):
+def timed(nh, steps=200 if WL == "k1" else 60):
     run(nh, 20)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

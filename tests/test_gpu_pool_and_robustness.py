@@ -165,3 +165,61 @@ def test_rotation_histogram_with_invalid_angles(orb, oracle_mod):
     ok = ~bad
     ka2, oh2, ot2 = oracle_mod.Oracle.rotation_filter(idx[ok], acc[ok], a[ok], b)     # the valid matches alone
     assert np.array_equal(hist2, oh2) and np.array_equal(acc2[ok], ka2)
+
+
+def test_compact_keypoints_are_lossless(orb, oracle_mod):
+    """ORBX_OPT_COMPACT_KEYPOINTS: 12-byte records on the way to the host; orbx_expand_keypoints and orbx_collect rebuild the
+    28-byte cv::KeyPoint exactly (all seven fields bit-identical to the full-record path and to the oracle), descriptors unchanged;
+    the device-resident consumers (stereo association) keep working; the pool delivers the same."""
+    params = (2000, 1.2, 8, 20, 7)
+    frames = [synth(s, 375, 1242) for s in range(5)]
+    o = oracle_mod.Oracle(*params)
+    ref = [tuple(a.copy() for a in o(f)) for f in frames]
+    ext = orb.ORBextractor(*params)
+    full = ext.extract_batch(frames)
+    ext.set_option(ext.OPT_COMPACT_KEYPOINTS, 1)
+    comp = ext.extract_batch(frames)                                 # orbx_collect expands on the host
+    for f in range(5):
+        assert np.array_equal(full[f][0], comp[f][0]) and np.array_equal(full[f][1], comp[f][1])
+        assert kps_equal_exact(comp[f][0], ref[f][0]) and np.array_equal(comp[f][0]["angle"], ref[f][0]["angle"])
+    ext.submit_host(frames)
+    with pytest.raises(orb.OrbxError):
+        ext.collect_view()                                           # full-record views are not available in compact mode
+    ck, cd, n = ext.collect_view_compact()
+    assert ck.dtype.itemsize == 12
+    for f in range(5):
+        k = ext.expand_keypoints(ck[f, :n[f]])
+        assert np.array_equal(k, full[f][0]) and np.array_equal(cd[f, :n[f]], full[f][1])
+        assert (ck[f, :n[f]]["octave"] == full[f][0]["octave"]).all() and (ck[f, :n[f]]["response"] == full[f][0]["response"]).all()
+    # other scale factor / level count: the expansion uses the handle's own tables
+    p2 = (900, 1.37, 5, 15, 5)
+    e2 = orb.ORBextractor(*p2)
+    img = synth(9, 480, 640)
+    a = e2(img)
+    e2.set_option(e2.OPT_COMPACT_KEYPOINTS, 1)
+    b = e2(img)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # stereo association still reads the full records that stay on the device
+    L, R = __import__("multimot_track_b200.synth", fromlist=["stereo_pair"]).stereo_pair(3, 375, 1242)
+    eL, eR = orb.ORBextractor(*params), orb.ORBextractor(*params)
+    eL(L); eR(R)
+    base = eL.stereo_match(eR, 386.1448)
+    eL.set_option(eL.OPT_COMPACT_KEYPOINTS, 1); eR.set_option(eR.OPT_COMPACT_KEYPOINTS, 1)
+    eL(L); eR(R)
+    again = eL.stereo_match(eR, 386.1448)
+    assert base[3] == again[3] and all(np.array_equal(x, y) for x, y in zip(base[:3], again[:3]))
+    # pool: compact at creation, switched off and on again between tickets
+    pool = orb.ExtractorPool(*params, devices=[0, 0], depth=2, max_width=1242, max_height=375, max_batch=4, compact_keypoints=True)
+    for mode in (1, 0, 1):
+        pool.set_option(orb.ORBextractor.OPT_COMPACT_KEYPOINTS, mode)
+        shards = pool.collect(pool.submit_host(frames))
+        for first, kps, desc, n in shards:
+            assert kps.dtype.itemsize == (12 if mode else 28)
+            for f in range(len(n)):
+                k = pool.expand_keypoints(kps[f, :n[f]]) if mode else kps[f, :n[f]]
+                assert np.array_equal(k, full[first + f][0]) and np.array_equal(desc[f, :n[f]], full[first + f][1])
+    t = pool.submit_host(frames)
+    with pytest.raises(orb.OrbxError):
+        pool.set_option(orb.ORBextractor.OPT_COMPACT_KEYPOINTS, 0)   # a ticket is outstanding
+    pool.collect(t)
+    pool.close()
