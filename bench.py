@@ -60,13 +60,14 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, cpus=None):
+        self.rows, self.proc, self.gpu, self.cpus = [], None, gpu_index, cpus
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                         preexec_fn=(lambda: os.sched_setaffinity(0, self.cpus)) if self.cpus else None)   # not on the bench's own CPUs
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--workload", default="k1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the matcher / next-row timings (profiling runs)")
+    ap.add_argument("--cpu-bind", default="none", choices=["auto", "none"], help="multi-rank runs: pin each rank to its own slice of the GPU's CPUs")
     ap.add_argument("--handles", type=int, default=6, help="batches in flight per GPU (depth of the native dispatcher)")
     ap.add_argument("--batch", type=int, default=0, help="experiment: another batch size for the named shape")
     ap.add_argument("--full-records", action="store_true", help="device-resident loop with 28-byte cv::KeyPoint records instead of the 12-byte compact ones")
@@ -216,7 +218,7 @@ def main():
     # the pinned host buffers (first touch), the submitting thread and the dispatcher's worker thread go to CPUs next to the GPU;
     # the CPU baseline later gets the process's original affinity back
     affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
-    cpu_bind = bind_to_gpu_cpus(torch, local, world_local) if (world > 1 and affinity0 is not None) else None
+    cpu_bind = bind_to_gpu_cpus(torch, local, world_local) if (world > 1 and affinity0 is not None and args.cpu_bind == "auto") else None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -304,18 +306,20 @@ def main():
         t1 = time.time()
         ms = ev0.elapsed_time(ev1)
         nl = xpool.launch_count() - l0
+        per_rank = [ms]
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)                  # the job is as slow as its slowest rank
-            ms = float(t.item())
+            g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(g, torch.tensor([ms], dtype=torch.float64, device="cuda"))
+            per_rank = [float(x.item()) for x in g]
+            ms = max(per_rank)                                        # the job is as slow as its slowest rank
             c = torch.tensor([nl], dtype=torch.int64, device="cuda")  # our kernels launched by all ranks inside the timed region
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             nl = int(c.item())
-        return ms, kp, nl, (t0, t1)
+        return ms, kp, nl, (t0, t1, per_rank)
 
     # ---- value: device-resident inputs
     # clocks / throttle reasons: rank 0 samples its own GPU (one nvidia-smi poller per job is enough)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, (affinity0 - os.sched_getaffinity(0)) or None if affinity0 is not None else None) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
@@ -326,12 +330,12 @@ def main():
     note("pool of %d frames resident, dispatcher up and primed" % nslots)
     # device-resident loop: the results land in pinned host memory as descriptors + 12-byte compact keypoint records (lossless:
     # orbx_expand_keypoints rebuilds the cv::KeyPoint exactly; the self-check below does that for every record it compares)
-    ms_dev, kp_dev, launches, (t0, t1) = timed(submit_dev, args.steps, args.warmup)
+    ms_dev, kp_dev, launches, (t0, t1, per_rank_dev) = timed(submit_dev, args.steps, args.warmup)
     note("device-resident loop done: %.4f ms/step" % (ms_dev / args.steps))
     clocks = sampler.stop(t0, t1) if sampler else None
     # ---- e2e: host buffers through the plugin entry point, results as full 28-byte cv::KeyPoint records + descriptors
     xpool.set_option(OPT_COMPACT, 0)
-    ms_e2e, kp_e2e, _, _ = timed(submit_host, args.steps, args.warmup)
+    ms_e2e, kp_e2e, _, (_, _, per_rank_e2e) = timed(submit_host, args.steps, args.warmup)
     note("host-buffer loop done: %.4f ms/step" % (ms_e2e / args.steps))
 
     value = job_throughput([batch * args.steps] * world, [ms_dev * 1e-3] * world)
@@ -505,7 +509,7 @@ def main():
     note("cpu baselines done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_dev / args.steps, "ms_per_step_per_rank": [round(v / args.steps, 4) for v in per_rank_dev], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": desc, "nfeatures": nfeat, "nlevels": nlev, "scale_factor": 1.2, "ini_th_fast": 20, "min_th_fast": 7,
                            "batch_per_gpu": batch, "global_batch": batch * world, "sharding": "frame-parallel, no collective", "cpu_bind": cpu_bind,
@@ -517,7 +521,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": batch * H * W, "d2h_bytes_per_step": batch * (cap * 60 + 4),
                         "records": "cv::KeyPoint (28 B) + descriptor (32 B) per keypoint",
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "ms_per_step_per_rank": [round(v / args.steps, 4) for v in per_rank_e2e]},
                 "gpu_launches": launches, "parity_checked": bool(parity and parity["checked"]), "parity": parity,
                 "roofline": roofline, "cpu_baseline": cpu, "matcher": matcher, "next_rows": extras}
         print(json.dumps(line))

@@ -1998,16 +1998,27 @@ cudaError_t launch_pad_level(const uint8_t *src, int w, int h, int pitch, uint8_
 constexpr int kMatchThreads = 128;
 constexpr int kMatchTile = 128;
 
-__device__ __forceinline__ void match_update(int d, int j, int &b1, int &bi, int &b2)
+// One thread = one query row; the chunk's B rows pass through shared memory.  Per pair: 8 XOR, three carry-save adders (two LOP3
+// each) that fold the eight XOR words into two "ones" and three "twos" words, five POPC (the slow instruction: 16 lanes / clk / SM)
+// instead of eight, and the update rule of :589-598 on packed keys  d << 22 | j  (j = index inside the chunk): the smallest key is
+// the least distance at its lowest index, the second smallest key carries the second smallest distance of the multiset, so the rule
+// is  b2 = min(b2, max(b1, key)); b1 = min(b1, key)  -- three min / max, no compare / select chain.  The weighted sum of the five
+// counts and the key are built with IMADs (FMA pipe), leaving the integer ALU pipe to the LOP3s.
+constexpr int kMatchKeyShift = 22;                                   // d <= 256 -> keys < 2^31; chunks hold fewer than 2^22 rows
+__device__ __forceinline__ unsigned imad_u(unsigned a, unsigned b, unsigned c)
 {
-    if (d < b1) { b2 = b1; b1 = d; bi = j; }
-    else if (d < b2) b2 = d;
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 __global__ void __launch_bounds__(kMatchThreads)
-k_match_partial(const uint32_t *__restrict__ A, int nA, const uint32_t *__restrict__ B, int nB, int chunk, int4 *__restrict__ partial)
+k_match_partial(const uint32_t *__restrict__ A, int nA, const uint32_t *__restrict__ B, int nB, int chunk, int4 *partial,
+                unsigned *__restrict__ arrive, int th, float ratio, int32_t *__restrict__ idx, int32_t *__restrict__ d1o, int32_t *__restrict__ d2o,
+                uint8_t *__restrict__ accept, int *__restrict__ naccept)
 {
     __shared__ uint4 sB[kMatchTile * 2];
+    __shared__ unsigned s_ticket;
     const int i = blockIdx.x * kMatchThreads + threadIdx.x;
     const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, nB);
     uint32_t a[8];
@@ -2018,43 +2029,54 @@ k_match_partial(const uint32_t *__restrict__ A, int nA, const uint32_t *__restri
 #pragma unroll
         for (int k = 0; k < 8; ++k) a[k] = 0;
     }
-    int b1 = 256, b2 = 256, bi = -1;
+    constexpr unsigned kNone = 256u << kMatchKeyShift | ((1u << kMatchKeyShift) - 1u);      // above every real key
+    unsigned b1 = kNone, b2 = kNone;
     for (int t0 = j0; t0 < j1; t0 += kMatchTile) {
         const int cnt = min(kMatchTile, j1 - t0);
         __syncthreads();
         for (int k = threadIdx.x; k < cnt * 2; k += kMatchThreads) sB[k] = reinterpret_cast<const uint4 *>(B)[2 * (long long)t0 + k];
         __syncthreads();
+        unsigned jrel = (unsigned)(t0 - j0);
+#pragma unroll 4
         for (int j = 0; j < cnt; ++j) {
             const uint4 lo = sB[2 * j], hi = sB[2 * j + 1];
-            // POPC is the slow instruction (16 lanes / clk / SM): three carry-save adders (two LOP3 each) fold the eight XOR words
-            // into two "ones" words and three "twos" words, five POPC instead of eight
             const uint32_t x0 = a[0] ^ lo.x, x1 = a[1] ^ lo.y, x2 = a[2] ^ lo.z, x3 = a[3] ^ lo.w;
             const uint32_t x4 = a[4] ^ hi.x, x5 = a[5] ^ hi.y, x6 = a[6] ^ hi.z, x7 = a[7] ^ hi.w;
             const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
             const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
             const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
-            const int d = __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
-            match_update(d, t0 + j, b1, bi, b2);
+            const unsigned twos = __popc(c0) + __popc(c1) + __popc(c2);                     // one IADD3
+            const unsigned d = imad_u(twos, 2u, __popc(s2)) + __popc(x7);
+            const unsigned key = imad_u(d, 1u << kMatchKeyShift, jrel);
+            jrel = imad_u(jrel, 1u, 1u);
+            b2 = min(b2, max(b1, key));
+            b1 = min(b1, key);
         }
     }
-    if (i < nA) partial[(long long)blockIdx.y * nA + i] = make_int4(b1, bi, b2, 0);
-}
-
-__global__ void k_match_merge(const int4 *__restrict__ partial, int nA, int nchunks, int th, float ratio,
-                              int32_t *__restrict__ idx, int32_t *__restrict__ d1, int32_t *__restrict__ d2,
-                              uint8_t *__restrict__ accept, int *__restrict__ naccept)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nA) {
+        const int d1 = (int)(b1 >> kMatchKeyShift), d2 = (int)(b2 >> kMatchKeyShift);
+        const bool any = b1 != kNone;
+        partial[(long long)blockIdx.y * nA + i] = make_int4(any ? d1 : 256, any ? j0 + (int)(b1 & ((1u << kMatchKeyShift) - 1u)) : -1, b2 != kNone ? d2 : 256, 0);
+    }
+    // ---- the last chunk's CTA of this row block to arrive merges the row block's partial results (chunks in ascending index
+    //      order, so "lowest index attaining the minimum" survives) and applies the threshold and the ratio test (:601-603)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(arrive + blockIdx.x, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.y - 1) return;
+    if (threadIdx.x == 0) arrive[blockIdx.x] = 0;                    // ready for the next call on this stream
+    __threadfence();
     bool ok = false;
     if (i < nA) {
-        int b1 = 256, b2 = 256, bi = -1;
-        for (int c = 0; c < nchunks; ++c) {              // chunks in ascending index order
-            const int4 p = partial[(long long)c * nA + i];
-            if (p.x < b1) { b2 = min(b1, p.z); b1 = p.x; bi = p.y; }
-            else b2 = min(b2, p.x);
+        int m1 = 256, m2 = 256, mi = -1;
+        for (int c = 0; c < (int)gridDim.y; ++c) {
+            const int4 p = __ldcg(partial + (long long)c * nA + i);   // written by other CTAs: read through L2
+            if (p.x < m1) { m2 = min(m1, p.z); m1 = p.x; mi = p.y; }
+            else m2 = min(m2, p.x);
         }
-        idx[i] = bi; d1[i] = b1; d2[i] = b2;
-        ok = bi >= 0 && b1 <= th && (float)b1 < __fmul_rn(ratio, (float)b2);
+        idx[i] = mi; d1o[i] = m1; d2o[i] = m2;
+        ok = mi >= 0 && m1 <= th && (float)m1 < __fmul_rn(ratio, (float)m2);
         if (accept) accept[i] = ok;
     }
     if (naccept) {
@@ -2631,7 +2653,9 @@ int match_chunks(int nA, int nB)
 {
     if (nB <= 0) return 1;
     const int row_blocks = (nA + kMatchThreads - 1) / kMatchThreads;
-    int want = (148 * 4 + row_blocks - 1) / (row_blocks > 0 ? row_blocks : 1);     // ~4 CTAs per SM in flight
+    // enough CTAs that the 148 SMs end together: at least ~16 CTAs per SM overall (5000 x 5000: 40 row blocks x 40 chunks of one
+    // 128-row tile; with 15 chunks of three tiles the 600 CTAs left some SMs with 5 CTAs and others with 4)
+    int want = (148 * 16 + row_blocks - 1) / (row_blocks > 0 ? row_blocks : 1);
     const int max_chunks = (nB + kMatchTile - 1) / kMatchTile;
     if (want < 1) want = 1;
     if (want > max_chunks) want = max_chunks;
@@ -2640,15 +2664,14 @@ int match_chunks(int nA, int nB)
 
 cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB, int th, float ratio,
                          int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept, int *d_naccept,
-                         int4 *d_partial, int nchunks, cudaStream_t st, LaunchStats *ls)
+                         int4 *d_partial, unsigned *d_arrive, int nchunks, cudaStream_t st, LaunchStats *ls)
 {
     if (nA <= 0) return cudaSuccess;
     int chunk = nB > 0 ? (nB + nchunks - 1) / nchunks : 1;
     chunk = (chunk + kMatchTile - 1) / kMatchTile * kMatchTile;
     dim3 grid((nA + kMatchThreads - 1) / kMatchThreads, nchunks);
-    k_match_partial<<<grid, kMatchThreads, 0, st>>>(dA, nA, dB, nB, chunk, d_partial);
-    k_match_merge<<<(nA + 127) / 128, 128, 0, st>>>(d_partial, nA, nchunks, th, ratio, d_idx, d_d1, d_d2, d_accept, d_naccept);
-    ls->launches += 2;
+    k_match_partial<<<grid, kMatchThreads, 0, st>>>(dA, nA, dB, nB, chunk, d_partial, d_arrive, th, ratio, d_idx, d_d1, d_d2, d_accept, d_naccept);
+    ls->launches += 1;
     return cudaGetLastError();
 }
 

@@ -86,7 +86,8 @@ cudaError_t launch_orient_desc(const DevParams *dP, const DevParams &hP, Src0 s0
 cudaError_t launch_pad_level(const uint8_t *src, int w, int h, int pitch, uint8_t *dst, int dst_pitch, cudaStream_t st, LaunchStats *ls);
 cudaError_t launch_match(const uint32_t *dA, int nA, const uint32_t *dB, int nB, int th, float ratio,
                          int32_t *d_idx, int32_t *d_d1, int32_t *d_d2, uint8_t *d_accept, int *d_naccept,
-                         int4 *d_partial, int nchunks, cudaStream_t st, LaunchStats *ls);
+                         int4 *d_partial, unsigned *d_arrive, int nchunks, cudaStream_t st, LaunchStats *ls);   // d_arrive: one zeroed counter per 128 query rows
+constexpr int kMatchRowsPerBlock = 128;
 cudaError_t launch_rotation_filter(int nA, const int32_t *d_idx, uint8_t *d_accept, const float *d_angleA, const float *d_angleB,
                                    int32_t *d_hist, int32_t *d_top3, int *d_kept, cudaStream_t st, LaunchStats *ls);
 struct ProjSetup {                   // camera, current pose and window parameters of SearchByProjection, by value

@@ -56,6 +56,7 @@ struct orbx_handle {
     uint32_t *m_A = nullptr, *m_B = nullptr; size_t m_capA = 0, m_capB = 0;
     int32_t *m_out = nullptr; uint8_t *m_acc = nullptr; int *m_nacc = nullptr; size_t m_cap_out = 0;
     int4 *m_partial = nullptr; size_t m_cap_partial = 0;
+    unsigned *m_arrive = nullptr; size_t m_cap_arrive = 0;         // arrival counters of the matcher's fused merge (zero between calls)
     TmaMaps tma;                        // pyramid source descriptors (levels >= 2 from our buffer, level 1 from the batch's level 0)
     const void *tma_l0_base = nullptr; long long tma_l0_fs = 0; int tma_l0_pitch = 0, tma_l0_frames = 0;
     bool use_tma = true;
@@ -379,7 +380,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     free_batch_buffers(h);
     free_geo_tables(h);
     dfree(h->d_params); dfree(h->d_pattern); dfree(h->d_pad); dfree(h->d_in); dfree(h->d_scratch);
-    dfree(h->m_A); dfree(h->m_B); dfree(h->m_out); dfree(h->m_acc); dfree(h->m_nacc); dfree(h->m_partial);
+    dfree(h->m_A); dfree(h->m_B); dfree(h->m_out); dfree(h->m_acc); dfree(h->m_nacc); dfree(h->m_partial); dfree(h->m_arrive);
     for (int i = 0; i <= ORBX_NUM_STAGES; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -747,6 +748,14 @@ static int ensure_partial(orbx_handle *h, int nA, int nchunks)
     const size_t need = (size_t)nA * nchunks;
     if (need > h->m_cap_partial) { dfree(h->m_partial); CU(cudaMalloc(&h->m_partial, need * sizeof(int4))); h->m_cap_partial = need; }
     if (!h->m_nacc) CU(cudaMalloc(&h->m_nacc, sizeof(int)));
+    const size_t blocks = ((size_t)nA + kMatchRowsPerBlock - 1) / kMatchRowsPerBlock;
+    if (blocks > h->m_cap_arrive) {
+        CU(cudaStreamSynchronize(h->stream));
+        dfree(h->m_arrive);
+        CU(cudaMalloc(&h->m_arrive, blocks * sizeof(unsigned)));
+        CU(cudaMemsetAsync(h->m_arrive, 0, blocks * sizeof(unsigned), h->stream));
+        h->m_cap_arrive = blocks;
+    }
     return ORBX_OK;
 }
 
@@ -762,7 +771,7 @@ extern "C" int orbx_match_device(orbx_handle *h, const uint8_t *dA, int nA, cons
     int rc = ensure_partial(h, nA, nchunks);
     if (rc != ORBX_OK) return rc;
     CU(launch_match((const uint32_t *)dA, nA, (const uint32_t *)dB, nB, th, ratio, d_idx, d_d1, d_d2, d_accept, nullptr,
-                    h->m_partial, nchunks, h->stream, &h->stats));
+                    h->m_partial, h->m_arrive, nchunks, h->stream, &h->stats));
     return ORBX_OK;
 }
 
@@ -789,7 +798,7 @@ extern "C" int orbx_match(orbx_handle *h, const uint8_t *descA, int nA, const ui
     if (nB > 0) CU(cudaMemcpyAsync(h->m_B, descB, (size_t)nB * 32, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->m_nacc, 0, sizeof(int), st));
     CU(launch_match(h->m_A, nA, h->m_B, nB, th, ratio, h->m_out, h->m_out + nA, h->m_out + 2 * (size_t)nA, h->m_acc, h->m_nacc,
-                    h->m_partial, nchunks, st, &h->stats));
+                    h->m_partial, h->m_arrive, nchunks, st, &h->stats));
     int nacc = 0;
     CU(cudaMemcpyAsync(idx, h->m_out, (size_t)nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(d1, h->m_out + nA, (size_t)nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
