@@ -481,10 +481,10 @@ __device__ __forceinline__ uint32_t mad7(uint32_t p0, uint32_t p1, uint32_t p2, 
 
 struct BlurItem { int level, tx0, ty0, frame; };
 
-__device__ __forceinline__ BlurItem blur_item(const DevParams *__restrict__ P, int item)
+// item = frame * n_blur_work + widx; the persistent loop advances (frame, widx) incrementally (no division per tile)
+__device__ __forceinline__ BlurItem blur_item(const DevParams *__restrict__ P, int frame, int widx)
 {
-    const int nw = P->n_blur_work, frame = item / nw;
-    const uint32_t wk = P->blur_work[item - frame * nw];
+    const uint32_t wk = P->blur_work[widx];
     BlurItem it;
     it.level = wk >> 24; it.ty0 = ((wk >> 12) & 0xfff) * kBlurTileH; it.tx0 = (wk & 0xfff) * kBlurTileW; it.frame = frame;
     return it;
@@ -506,8 +506,10 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
     }
     __syncthreads();
     // thread 0: start the box of `item` into buffer b (no-op for a level without a tensor map)
-    auto issue = [&](int item, int b) {
-        const BlurItem it = blur_item(P, item);
+    const int nw = P->n_blur_work, gstep = (int)gridDim.x;
+    auto advance = [&](int &frame, int &widx) { widx += gstep; while (widx >= nw) { widx -= nw; ++frame; } };
+    auto issue = [&](int frame, int widx, int b) {
+        const BlurItem it = blur_item(P, frame, widx);
         if (!((tma_levels >> it.level) & 1u)) return;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads/writes of this buffer come first
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar[b])), "r"((TH + 6) * PB) : "memory");
@@ -516,12 +518,16 @@ k_blur(const DevParams *__restrict__ P, Src0 s0, const __grid_constant__ BlurMap
                         "r"(it.tx0 - 16), "r"(it.ty0 - 3), "r"(it.frame) : "memory");
     };
     int item = blockIdx.x;
-    if (tid == 0 && item < total_items) issue(item, 0);
+    int cur_frame = item / nw, cur_widx = item - cur_frame * nw;     // the only division: once per CTA
+    if (tid == 0 && item < total_items) issue(cur_frame, cur_widx, 0);
     unsigned phase = 0;                                              // bit b = parity the next wait on buffer b uses
-    for (int n = 0; item < total_items; item += gridDim.x, ++n) {
+    for (int n = 0; item < total_items; item += gstep, ++n) {
         const int b = n & 1;
-        if (tid == 0 && item + (int)gridDim.x < total_items) issue(item + gridDim.x, b ^ 1);
-        const BlurItem it = blur_item(P, item);
+        int nxt_frame = cur_frame, nxt_widx = cur_widx;
+        advance(nxt_frame, nxt_widx);
+        if (tid == 0 && item + gstep < total_items) issue(nxt_frame, nxt_widx, b ^ 1);
+        const BlurItem it = blur_item(P, cur_frame, cur_widx);
+        cur_frame = nxt_frame; cur_widx = nxt_widx;
         const int level = it.level, tx0 = it.tx0, ty0 = it.ty0, frame = it.frame;
         const LevelGeom &G = P->lv[level];
         uint32_t (*raw)[RWD] = sraw[b].w;
@@ -713,7 +719,11 @@ __device__ __forceinline__ unsigned mad_fma(unsigned a, unsigned b, unsigned c)
     return r;
 }
 
-template <int CELL>
+// BOUND_ONLY (experiment builds, ORBX_FAST_BOUND=1): the exact score is replaced by its cheap upper bound from the eight opposing
+// ring pairs, U = max(min(A, B) - c, c - max(A, B)) - 1 with A = min_k max(r_k, r_k+8), B = max_k min(r_k, r_k+8) (every 9-arc holds one
+// pixel of every opposing pair and both pixels of one).  Results are then NOT the reference's; the variant exists to time the floor of
+// any "pre-test first, exact score for the survivors" scheme: this is the work such a scheme still does for EVERY pixel.
+template <int CELL, bool BOUND_ONLY = false>
 __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, const FfJob &J, uint32_t *tile, uint32_t *list, int lane)
 {
     using C = FfCfg<CELL>;
@@ -792,6 +802,15 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
         e[5] = o[sm1][3]; e[11] = o[sm1][0];
         e[6] = a[sm2][2]; e[10] = a[sm2][0];
         e[7] = o[sm3][2]; e[8] = a[sm3][1]; e[9] = o[sm3][1];
+        unsigned maxmin, minmax;
+        if (BOUND_ONLY) {
+            unsigned M[8], m[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { M[i] = __vmaxs2(e[i], e[i + 8]); m[i] = __vmins2(e[i], e[i + 8]); }
+            const unsigned A = __vimin3_s16x2(__vimin3_s16x2(M[0], M[1], M[2]), __vimin3_s16x2(M[3], M[4], M[5]), __vmins2(M[6], M[7]));
+            const unsigned B = __vimax3_s16x2(__vimax3_s16x2(m[0], m[1], m[2]), __vimax3_s16x2(m[3], m[4], m[5]), __vmaxs2(m[6], m[7]));
+            maxmin = __vmins2(A, B); minmax = __vmaxs2(A, B);
+        } else {
         // The 16 arcs of 9 in pairs: arcs 2i and 2i+1 share the 8 ring pixels 2i+1 .. 2i+8 (B), so
         // max(min(arc 2i), min(arc 2i+1)) = min(B, max(e[2i], e[2i+9])) -- 36 packed min / max per polarity instead of 40.
         unsigned lo2[8], hi2[8];
@@ -812,8 +831,9 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
             bv[i] = __vimin3_s16x2(lo4[i], lo4[(i + 2) & 7], __vmaxs2(e[2 * i], e[(2 * i + 9) & 15]));
             dv[i] = __vimax3_s16x2(hi4[i], hi4[(i + 2) & 7], __vmins2(e[2 * i], e[(2 * i + 9) & 15]));
         }
-        const unsigned maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
-        const unsigned minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
+        maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
+        minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
+        }
         // bright - 1 = maxmin + ~c, dark - 1 = c + ~minmax; S' = max(bright, dark) - th, clamped at 0
         const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, not_fma(minmax), __vadd2(maxmin, not_fma(cc))), k1mth, 0u);
         // neighbours in the same row, masked to the pixels' own cells
@@ -918,7 +938,7 @@ __device__ __forceinline__ void ff_stage(const uint8_t *src, int sp, int x_org, 
     }
 }
 
-template <int CELL, int MINB = 4, int UNR = 4>
+template <int CELL, int MINB = 4, int UNR = 4, bool BOUND_ONLY = false>
 __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, MINB) k_fast_fused(const DevParams *__restrict__ P, Src0 s0, int work_off, int work_end)
 {
     using C = FfCfg<CELL>;
@@ -933,7 +953,7 @@ __global__ void __launch_bounds__(FfCfg<CELL>::WARPS * 32, MINB) k_fast_fused(co
     const uint8_t *img = level_ptr(P, s0, frame, J.level, &sp);
     ff_stage<CELL, false, UNR>(img, sp, 0, 0, P->lv[J.level].h - 1, (sp >> 2) - 1, J, tile, lane);
     __syncwarp();
-    ff_process<CELL>(P, J, tile, list, lane);
+    ff_process<CELL, BOUND_ONLY>(P, J, tile, list, lane);
 }
 
 // ---- persistent TMA variant: every warp walks (job, frame) items; the raw pixel box of the NEXT item (96 bytes x
@@ -1047,8 +1067,16 @@ cudaError_t launch_fast(const DevParams *dP, const DevParams &hP, Src0 s0, int n
         // experiment knob: extra dynamic shared memory per CTA caps the FAST CTAs per SM and leaves registers / shared memory to the
         // other handles' kernels (k_blur, k_resize_sep fit beside three of them).  Measured slower: 16 KB (3 CTAs / SM) 0.311 vs 0.291 ms.
         static const int pad = debug_knob("ORBX_FAST_PAD_KB", 0) * 1024;
+#ifdef ORBX_DEBUG_KNOBS
+        if (debug_knob("ORBX_FAST_BOUND", 0)) {                        // timing experiment only: results are not the reference's
+            cudaFuncSetAttribute(k_fast_fused<44, 4, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad);
+            k_fast_fused<44, 4, 12, true><<<grid, C::WARPS * 32, C::SMEM + pad, st>>>(dP, s0, 0, n_small);
+        } else
+#endif
+        {
         cudaFuncSetAttribute(k_fast_fused<44, 4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + pad);
         k_fast_fused<44, 4, 12><<<grid, C::WARPS * 32, C::SMEM + pad, st>>>(dP, s0, 0, n_small);
+        }
         ls->launches++;
     }
     if (hP.n_ffast_work > n_small) {
@@ -1530,7 +1558,11 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
         }
         return launch_octree_t<256, 4>(dP, hP, nframes, max_node_cap, max_feat, oct_small_budget(), st);
     }
-    if (max_node_cap <= 4096) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
+    // Large images (3840x2160: ~10^5 candidates on level 0, far beyond shared memory) sort through the L2-resident scratch and are
+    // bound by the CTA's own throughput; with one CTA per (frame, level) there are fewer CTAs than SMs, so each gets a whole SM:
+    // 1024 threads instead of 512 (debug knob ORBX_OCT_THREADS to compare)
+    const int big = debug_knob("ORBX_OCT_THREADS", hP.lv[0].cand_cap > 1000000 ? 1024 : 512);
+    if (max_node_cap <= 4096 && big != 1024) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
     return launch_octree_t<1024, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
 }
 

@@ -23,7 +23,8 @@ BASE_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "data", "config", "e2e")
 
 
-@pytest.mark.parametrize("name", ["r1_bench_k1.json", "r1_bench_k2.json", "r1_bench_k4.json", "r1_bench_k1_8gpu.json"])
+@pytest.mark.parametrize("name", ["r1_bench_k1.json", "r1_bench_k2.json", "r1_bench_k4.json", "r1_bench_k1_8gpu.json",
+                                  "r2_bench_k1.json", "r2_bench_k1_20steps.json", "r2_bench_k2.json", "r2_bench_k4.json", "r2_bench_k1_8gpu.json"])
 def test_our_arm_line(name):
     d = _line(name)
     for k in BASE_KEYS + ("clocks", "gpu_launches", "roofline"):
@@ -47,10 +48,20 @@ def test_our_arm_line(name):
         for k in ("value", "unit", "cores", "kind", "sample"):
             assert k in c, k
         assert c["kind"] in ("reference", "port")
+    if name.startswith("r2_"):
+        assert d["parity_checked"] is True and d["parity"]["frames_with_keypoint_mismatch"] == 0 and d["parity"]["descriptor_bits_differing"] == 0
+        if d["n_gpus"] == 1 and d.get("cpu_baseline"):
+            legs = d["cpu_baseline"]["legs"]                       # both CPU legs, the faster one named
+            assert {"reference", "cv2"} <= set(legs) and d["cpu_baseline"]["value"] == max(v["value"] for v in legs.values() if "value" in v)
+        if d.get("matcher") and "error" not in d["matcher"]:
+            m = d["matcher"]
+            assert m["equals_cpu_scan"] is True and m["accepted_th_high"] >= m["accepted_th_low"] > 0 and 0 < m["frac_of_popc_peak"] < 1
+            assert m["cpu_baseline"]["ms_per_call"] > m["ms_per_call"]
 
 
-def test_reference_arm_line():
-    d = _line("r1_bench_reference_arm.json")
+@pytest.mark.parametrize("name", ["r1_bench_reference_arm.json", "r2_bench_reference_arm.json"])
+def test_reference_arm_line(name):
+    d = _line(name)
     for k in BASE_KEYS + ("impl", "cpu_baseline"):
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "orb_extract_describe_frames_per_s"
