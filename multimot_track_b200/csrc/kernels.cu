@@ -13,6 +13,7 @@
 // float stages use explicit round-to-nearest intrinsics so nothing is contracted
 // into an FMA.
 #include <type_traits>
+#include <cooperative_groups.h>
 #include "kernels.cuh"
 
 #include <cstdio>
@@ -1200,16 +1201,27 @@ size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
     return o.bytes;
 }
 
-template <int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS)
-k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap, int level_off, int lut_cap)
+// CLUSTER > 1 (levels of very large images, ~10^5 candidates): a thread-block cluster of CLUSTER CTAs shares one (frame, level).
+// The radix sort -- two thirds of such a level's time in a single CTA -- and the path-code pass are split over the cluster's CTAs
+// (every CTA owns a contiguous slice of the keys per pass; the per-warp digit counts are exchanged through the L2-resident
+// scratch and ordered by cluster barriers, so the sort stays the same stable LSD sort); CTA 0 then builds the tree alone.
+// MODE 0: the whole thing in one launch.  MODE 1: sort + path codes only (the clustered launch of 4K-class images).  MODE 2: the tree
+// on keys / codes a MODE 1 launch left sorted in the scratch -- a plain launch with a small shared-memory footprint, so that the
+// octree of one batch shares the SMs with the other batches' kernels instead of pinning idle cluster CTAs on them.
+template <int THREADS, int IPT, int CLUSTER = 1, int MODE = 0>
+__global__ void __launch_bounds__(THREADS, (CLUSTER > 1 || MODE == 2) ? 2 : 1)
+k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap, int level_off, int lut_cap, int nframes_lm)
 {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t oct_smem[];
     __shared__ int warp_sums[32];
     __shared__ int s_m, s_added;
 
-    const int level = blockIdx.x + level_off, frame = blockIdx.y;
+    const int crank = CLUSTER > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+    // plain launches: grid (level, frame).  Clustered launches: a 1-D grid of clusters in level-major order (all frames' level 0
+    // first, the longest-running ones), so that the clusters that wait for a free slot are the short ones
+    const int cid = CLUSTER > 1 ? (int)blockIdx.x / CLUSTER : 0;
+    const int level = (CLUSTER > 1 ? cid / nframes_lm : (int)blockIdx.x) + level_off, frame = CLUSTER > 1 ? cid % nframes_lm : (int)blockIdx.y;
     const LevelGeom &G = P->lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)min(P->cand_count[frame * P->nlevels + level], (unsigned)G.cand_cap);
@@ -1225,15 +1237,17 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
     uint32_t *hist = reinterpret_cast<uint32_t *>(eidx + node_cap);  // [WARPS][256]
     uint32_t *bufA = hist + WARPS * 256, *bufB = bufA + key_cap;
     uint32_t *slut = bufB + key_cap;                                // path-code tables of this level, when they fit
-    if (n > key_cap) {                                              // level too dense for shared memory: L2-resident scratch
+    uint32_t *ghist = nullptr;                                      // CLUSTER > 1: per-warp digit counts of every CTA of the cluster
+    if (n > key_cap || CLUSTER > 1 || MODE == 2) {                  // level too dense for shared memory: L2-resident scratch
         bufA = reinterpret_cast<uint32_t *>(P->sort_scratch + ((long long)frame * P->cand_frame_elems + G.cand_off) * 2);
         bufB = bufA + G.cand_cap;
+        ghist = bufB + G.cand_cap;                                  // the slot holds 16 bytes per candidate: 8 * cand_cap bytes are free
     }
     const uint32_t *cand = P->cand + (long long)frame * P->cand_frame_elems + G.cand_off;
     uint32_t *stage = P->kp_stage + (long long)frame * P->kp_frame_cap + G.kp_off;
     uint32_t *kp_count = P->kp_count + frame * P->nlevels + level;
 
-    if (n == 0) { if (tid == 0) *kp_count = 0; return; }
+    if (n == 0) { if (tid == 0 && crank == 0) *kp_count = 0; return; }       // uniform over the cluster: nobody waits at a barrier
 #ifdef ORBX_OCT_TIMING
     long long tk[8], acc[5] = {0, 0, 0, 0, 0}, tl = 0; int ntk = 0, nsweeps = 0, ncareful = 0;
 #define OCT_LAP(i) do { if (tid == 0) { const long long t_ = clock64(); acc[i] += t_ - tl; tl = t_; } } while (0)
@@ -1244,6 +1258,11 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
 #endif
     OCT_TICK();
 
+    int code_bits = 2 * D;
+    for (int t = G.n_ini - 1; t > 0; t >>= 1) ++code_bits;
+    if (MODE == 2) {                                                // sorted by a MODE 1 launch: an odd number of passes leaves the keys in the second buffer
+        if (((code_bits + 7) / 8) & 1) { uint32_t *t = bufA; bufA = bufB; bufB = t; }
+    } else {
     // ---- LSD radix sort of the packed candidates by path code, 8 bits per pass (stable)
     if (G.region_w + G.region_h <= lut_cap) {                       // every pass looks both tables up per candidate: keep them close
         const int nl = G.region_w + G.region_h;
@@ -1256,17 +1275,18 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
         }
         lut_x = slut; lut_y = slut + G.region_w;
     }
-    for (int base = tid; base < n; base += 8 * THREADS) {           // eight loads in flight per thread
+    constexpr int CW = WARPS * CLUSTER;                             // warps that share the sort; global warp gw owns the gw-th slice of every pass
+    const int gw = crank * WARPS + warp;
+    for (int base = crank * THREADS + tid; base < n; base += 8 * THREADS * CLUSTER) {           // eight loads in flight per thread
         uint32_t v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = base + u * THREADS < n ? __ldg(cand + base + u * THREADS) : 0u;
+        for (int u = 0; u < 8; ++u) v[u] = base + u * THREADS * CLUSTER < n ? __ldg(cand + base + u * THREADS * CLUSTER) : 0u;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) if (base + u * THREADS < n) bufA[base + u * THREADS] = v[u];
+        for (int u = 0; u < 8; ++u) if (base + u * THREADS * CLUSTER < n) bufA[base + u * THREADS * CLUSTER] = v[u];
     }
-    int code_bits = 2 * D;
-    for (int t = G.n_ini - 1; t > 0; t >>= 1) ++code_bits;
-    const int chunk = (((n + WARPS - 1) / WARPS) + 31) & ~31;
-    const int c_lo = min(warp * chunk, n), c_hi = min(c_lo + chunk, n);
+    if (CLUSTER > 1) { __threadfence(); cooperative_groups::this_cluster().sync(); }
+    const int chunk = (((n + CW - 1) / CW) + 31) & ~31;
+    const int c_lo = min(gw * chunk, n), c_hi = min(c_lo + chunk, n);
     const unsigned lt = lanemask_lt();
     for (int shift = 0; shift < code_bits; shift += 8) {
         for (int i = tid; i < WARPS * 256; i += THREADS) hist[i] = 0;
@@ -1281,6 +1301,26 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
                 if (base + 32 * u < c_hi) atomicAdd(wh + ((path_code(k8[u], lut_x, lut_y) >> shift) & 255u), 1u);
         }
         __syncthreads();
+        if (CLUSTER > 1) {
+            // every CTA publishes its warps' counts, then derives the start of each of ITS warps' runs: digit major, then global warp
+            for (int i = tid; i < WARPS * 256; i += THREADS) ghist[crank * WARPS * 256 + i] = hist[i];
+            __threadfence();
+            cooperative_groups::this_cluster().sync();
+            int total_d = 0, before_cta = 0;
+            if (tid < 256) {
+                for (int g2 = 0; g2 < CW; ++g2) {
+                    const int c = (int)__ldcg(ghist + g2 * 256 + tid);
+                    if (g2 == crank * WARPS) before_cta = total_d;
+                    total_d += c;
+                }
+            }
+            int tot;
+            const int digit_base = block_scan_incl<THREADS>(tid < 256 ? total_d : 0, warp_sums, &tot) - total_d;
+            if (tid < 256) {
+                int run = digit_base + before_cta;
+                for (int w2 = 0; w2 < WARPS; ++w2) { const int c = (int)hist[w2 * 256 + tid]; hist[w2 * 256 + tid] = (uint32_t)run; run += c; }
+            }
+        } else
         {   // exclusive scan over (digit major, warp minor)
             constexpr int HPT = 256 * WARPS / THREADS;               // == 8
             uint32_t v[HPT];
@@ -1322,12 +1362,20 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
             }
         }
         __syncthreads();
+        if (CLUSTER > 1) { __threadfence(); cooperative_groups::this_cluster().sync(); }
         uint32_t *t = bufA; bufA = bufB; bufB = t;
     }
     OCT_TICK();
-    uint32_t *keys = bufA, *codes = bufB;                           // sorted candidates and their path codes
-    for (int i = tid; i < n; i += THREADS) codes[i] = path_code(keys[i], lut_x, lut_y);
+    for (int i = crank * THREADS + tid; i < n; i += THREADS * CLUSTER) bufB[i] = path_code(bufA[i], lut_x, lut_y);
     __syncthreads();
+    if (CLUSTER > 1) {
+        __threadfence();
+        cooperative_groups::this_cluster().sync();
+        if (crank != 0) return;                                     // the tree is built by CTA 0 of the cluster
+    }
+    }
+    if (MODE == 1) return;                                          // keys (bufA) and codes (bufB) stay in the scratch for the MODE 2 launch
+    uint32_t *keys = bufA, *codes = bufB;                           // sorted candidates and their path codes
     OCT_TICK();
 
     // ---- roots, reverse list order (:553-585): thread r finds root n_ini-1-r's range, thread 0 drops the empty ones
@@ -1521,20 +1569,32 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
 #undef OCT_LAP
 }
 
-template <int THREADS, int IPT>
+template <int THREADS, int IPT, int CLUSTER = 1, int MODE = 0>
 static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int nframes, int node_cap, int max_feat, size_t budget, cudaStream_t st,
                                    int level_off = 0, int level_cnt = -1)
 {
     if (level_cnt < 0) level_cnt = hP.nlevels - level_off;
+    if (level_cnt <= 0) return cudaSuccess;
     int lut_cap = 0;                                                 // path-code tables of the largest launched level: x codes + y codes
     for (int l = level_off; l < level_off + level_cnt; ++l) lut_cap = std::max(lut_cap, hP.lv[l].region_w + hP.lv[l].region_h);
-    if ((size_t)lut_cap * 4 > budget / 4) lut_cap = 0;               // too large for this budget: the kernel reads them from global memory
+    if ((size_t)lut_cap * 4 > budget / 4 || CLUSTER > 1 || MODE == 2) lut_cap = 0;   // too large for this budget (or a launch that keeps
+                                                                     // several CTAs per SM): the kernel reads them from global memory (L1-resident)
+    if (MODE == 1) { node_cap = 0; max_feat = -3; }                  // sort only: no node arrays, no careful-phase buffer, just the digit counters
     const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget, lut_cap);
     {                                                                // the attribute is a per-device maximum: cheap, set every time
-        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT, CLUSTER, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
         if (e != cudaSuccess) return e;
     }
-    k_octree<THREADS, IPT><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap);
+    if (CLUSTER > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(level_cnt * nframes * CLUSTER); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = o.bytes; cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = CLUSTER; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_octree<THREADS, IPT, CLUSTER, MODE>, dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap, nframes);
+    }
+    k_octree<THREADS, IPT, CLUSTER, MODE><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap, nframes);
     return cudaGetLastError();
 }
 
@@ -1561,6 +1621,16 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
     // Large images (3840x2160: ~10^5 candidates on level 0, far beyond shared memory) sort through the L2-resident scratch and are
     // bound by the CTA's own throughput; with one CTA per (frame, level) there are fewer CTAs than SMs, so each gets a whole SM:
     // 1024 threads instead of 512 (debug knob ORBX_OCT_THREADS to compare)
+    // 4K-class images (3840x2160: ~10^5 candidates on level 0, far beyond shared memory): the levels whose candidates cannot fit
+    // a CTA's shared memory are sorted by a cluster of four CTAs each (k_octree<.., 4>), launched first; the small levels follow
+    // as single CTAs.  ORBX_OCT_CLUSTER=0 (debug-knob build) keeps everything on single 1024-thread CTAs for comparison.
+    if (max_node_cap <= 4096 && hP.lv[0].cand_cap > 1000000 && debug_knob("ORBX_OCT_CLUSTER", 1)) {
+        // a clustered sort launch for all levels (level-major grid: the long sorts start first), then the tree launch on the sorted scratch
+        cudaError_t e = launch_octree_t<512, 8, 4, 1>(dP, hP, nframes, max_node_cap, max_feat, 0, st, 0, hP.nlevels);
+        if (e != cudaSuccess) return e;
+        ls->launches++;
+        return launch_octree_t<512, 8, 1, 2>(dP, hP, nframes, max_node_cap, max_feat, 0, st, 0, hP.nlevels);
+    }
     const int big = debug_knob("ORBX_OCT_THREADS", hP.lv[0].cand_cap > 1000000 ? 1024 : 512);
     if (max_node_cap <= 4096 && big != 1024) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
     return launch_octree_t<1024, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
