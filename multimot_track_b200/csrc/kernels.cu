@@ -1624,7 +1624,11 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
     // 4K-class images (3840x2160: ~10^5 candidates on level 0, far beyond shared memory): the levels whose candidates cannot fit
     // a CTA's shared memory are sorted by a cluster of four CTAs each (k_octree<.., 4>), launched first; the small levels follow
     // as single CTAs.  ORBX_OCT_CLUSTER=0 (debug-knob build) keeps everything on single 1024-thread CTAs for comparison.
-    if (max_node_cap <= 4096 && hP.lv[0].cand_cap > 1000000 && debug_knob("ORBX_OCT_CLUSTER", 1)) {
+    int min_cap = hP.lv[0].cand_cap;
+    for (int l = 1; l < hP.nlevels; ++l) min_cap = std::min(min_cap, hP.lv[l].cand_cap);
+    // (the cluster's digit counts, 4 CTAs x 16 warps x 256 counters, live in the free half of a level's 16-byte-per-candidate scratch slot:
+    // every level must have room for them, else the single-CTA path below takes the whole image)
+    if (max_node_cap <= 4096 && hP.lv[0].cand_cap > 1000000 && (size_t)min_cap * 8 >= (size_t)4 * 16 * 256 * 4 && debug_knob("ORBX_OCT_CLUSTER", 1)) {
         // a clustered sort launch for all levels (level-major grid: the long sorts start first), then the tree launch on the sorted scratch
         cudaError_t e = launch_octree_t<512, 8, 4, 1>(dP, hP, nframes, max_node_cap, max_feat, 0, st, 0, hP.nlevels);
         if (e != cudaSuccess) return e;

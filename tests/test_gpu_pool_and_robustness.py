@@ -223,3 +223,18 @@ def test_compact_keypoints_are_lossless(orb, oracle_mod):
         pool.set_option(orb.ORBextractor.OPT_COMPACT_KEYPOINTS, 0)   # a ticket is outstanding
     pool.collect(t)
     pool.close()
+
+
+@pytest.mark.parametrize("params", [(6000, 1.2, 12, 20, 7), (3000, 2.0, 5, 20, 7)])
+def test_4k_octree_cluster_and_fallback(orb, oracle_mod, params):
+    """3840x2160: with 12 levels x1.2 every level's octree sort runs on a cluster of four CTAs (sort launch + tree launch); with a
+    steep pyramid the small top level has no room for the cluster's counters in its scratch slot and the whole image takes the
+    single-CTA path.  Both equal the oracle, as a single frame and inside a batch of three."""
+    frames = [synth(s, 2160, 3840) for s in (21, 22, 23)]
+    o = oracle_mod.Oracle(*params)
+    ref = [tuple(a.copy() for a in o(f)) for f in frames]
+    ext = orb.ORBextractor(*params)
+    k, d = ext(frames[0])
+    assert kps_equal_exact(k, ref[0][0]) and np.array_equal(k["angle"], ref[0][0]["angle"]) and np.array_equal(d, ref[0][1])
+    for (k, d), (rk, rd) in zip(ext.extract_batch(frames), ref):
+        assert kps_equal_exact(k, rk) and np.array_equal(d, rd)
