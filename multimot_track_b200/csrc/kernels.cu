@@ -14,6 +14,9 @@
 // into an FMA.
 #include <type_traits>
 #include <cooperative_groups.h>
+#ifndef RZ_SEP_TH
+#define RZ_SEP_TH 32
+#endif
 #include "kernels.cuh"
 
 #include <cstdio>
@@ -90,6 +93,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
 // is fetched once per tile.
 
 constexpr int kRzTW = 128, kRzTH = 32, kRzSrcWords = 68, kRzSrcRows = 68;
+constexpr int kRzSepTH = RZ_SEP_TH;              // tile height of the TMA / separable kernel (rows per thread: kRzSepTH / 8)
 
 // Rows [y0, y_end) x columns [x0, x0+128) of `level` from a staged source window: sb points at source pixel
 // (sx_lo, sy_lo), row pitch `spitch` bytes.  256 threads as 32x8, 4 pixels x 4 rows per thread.
@@ -210,7 +214,7 @@ k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
     }
     __syncthreads();
     auto issue = [&](int ty, int b) {                               // thread 0
-        const int sy_lo = A.yt[ty * kRzTH].s0;
+        const int sy_lo = A.yt[ty * kRzSepTH].s0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar[b])), "r"(A.box_w * A.box_h) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -243,11 +247,11 @@ k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
     for (int n = 0; ty < A.nty; ty += A.nchunks, ++n) {
         const int b = n & 1;
         if (tid == 0 && ty + A.nchunks < A.nty) issue(ty + A.nchunks, b ^ 1);
-        const int y0 = ty * kRzTH, y_end = min(y0 + kRzTH, A.h);
+        const int y0 = ty * kRzSepTH, y_end = min(y0 + kRzSepTH, A.h);
         const int sy_lo = A.yt[y0].s0, nrows = A.yt[y_end - 1].s1 - sy_lo + 1;
-        ResizeTab ey[4];
+        ResizeTab ey[kRzSepTH / 8];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) ey[rr] = A.yt[min(y0 + g + 8 * rr, y_end - 1)];
+        for (int rr = 0; rr < kRzSepTH / 8; ++rr) ey[rr] = A.yt[min(y0 + g + 8 * rr, y_end - 1)];
         mbar_wait_parity(&mbar[b], (phase >> b) & 1u);
         phase ^= 1u << b;
         // ---- horizontal pass: source rows of the window -> Hs[r][x] = (S[s0]*a0 + S[s1]*a1) >> 4
@@ -271,7 +275,7 @@ k_resize_sep(const __grid_constant__ CUtensorMap tmap, const ResizeArgs A)
         // ---- vertical pass: out = (((b0*H0) >> 16) + ((b1*H1) >> 16) + 2) >> 2; no clamp needed (see resize_rows)
         if (col_ok) {
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
+            for (int rr = 0; rr < kRzSepTH / 8; ++rr) {
                 const int y = y0 + g + 8 * rr;
                 if (y < y_end) {
                     const ResizeTab e = ey[rr];
@@ -292,7 +296,7 @@ void resize_box(const LevelGeom &src, const LevelGeom &dst, int *box_w, int *box
 {
     // footprint of a 128x32 destination tile: ceil(128*ratio)+2 source columns, +15 for the 16-byte aligned origin
     const int fw = (int)(((long long)kRzTW * src.w + dst.w - 1) / dst.w) + 2 + 15 + 1;
-    const int fh = (int)(((long long)kRzTH * src.h + dst.h - 1) / dst.h) + 3;
+    const int fh = (int)(((long long)kRzSepTH * src.h + dst.h - 1) / dst.h) + 3;
     const int bw = (fw + 15) & ~15;
     if (bw > 256 || fh > 256) { *box_w = 0; *box_h = 0; return; }
     *box_w = bw; *box_h = fh;
@@ -427,7 +431,7 @@ cudaError_t launch_pyramid(const DevParams *dP, const DevParams &hP, Src0 s0, in
                 }
                 int per_sm = (int)((227 * 1024) / (smem + 1024));
                 per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
-                const int ntx = grid.x, nty = grid.y;
+                const int ntx = grid.x, nty = (D.h + kRzSepTH - 1) / kRzSepTH;
                 const int cap = std::max(1, 148 * per_sm / nframes / ntx);   // resident CTAs available to one tile column of one frame
                 const int iters = (nty + cap - 1) / cap;
                 ResizeArgs A;

@@ -117,3 +117,35 @@ def test_adapter_compiles_against_reference_surface():
            "-I", os.path.join(ROOT, "include"), "-I", src, os.path.join(src, "ORBextractor.cc"), os.path.join(src, "ORBmatcher_core.cc"),
            os.path.join(src, "adapter_check.cc")]
     subprocess.check_call(cmd)
+
+
+def test_pool_entry_points_without_gpu(lib):
+    """The dispatcher's host-only pieces: the frame split every submit uses equals multimot_track_b200.sharding (the split
+    bench.py's ranks use), creation fails loudly without a device, NULL handling, struct sizes the C header promises."""
+    import ctypes
+    from multimot_track_b200 import _lib
+    from multimot_track_b200.sharding import seam_pairs, shard_bounds
+    for F in (1, 5, 13, 32, 64, 100000):
+        for G in (1, 2, 3, 4, 8):
+            covered = 0
+            for g in range(G):
+                first, count = ctypes.c_int(), ctypes.c_int()
+                lib.orbx_pool_shard_range(F, G, g, ctypes.byref(first), ctypes.byref(count))
+                assert (first.value, first.value + count.value) == shard_bounds(F, g, G)
+                assert first.value == covered
+                covered += count.value
+            assert covered == F
+            assert all(b == a + 1 for a, b in seam_pairs(F, G))
+    assert ctypes.sizeof(_lib.OrbxShardResult) == 48 and ctypes.sizeof(_lib.OrbxPoolConfig) == 56 and ctypes.sizeof(_lib.OrbxConfig) == 36  # sizeof() of the C structs of include/orbx.h
+    assert lib.orbx_pool_devices(None) == -1 and lib.orbx_pool_depth(None) == -1 and lib.orbx_pool_handle(None, 0, 0) is None
+    assert lib.orbx_pool_collect(None, 0, None) == -1 and lib.orbx_pool_set_option(None, 1, 1) == -1
+    assert lib.orbx_expand_keypoints(None, None, 0, None) == -1
+    import torch
+    if not torch.cuda.is_available():
+        cfg = _lib.OrbxPoolConfig(_lib.OrbxConfig(1000, 1.2, 8, 20, 7, 0, 0, 0, -1), 0, None, 2, 0)
+        p = ctypes.c_void_p()
+        assert lib.orbx_pool_create(ctypes.byref(cfg), ctypes.byref(p)) == -3 and not p.value
+        assert b"no usable CUDA device" in lib.orbx_pool_last_error(None)
+    bad = _lib.OrbxPoolConfig(_lib.OrbxConfig(1000, 1.2, 8, 20, 7, 0, 0, 0, -1), -1, None, 2, 0)
+    p = ctypes.c_void_p()
+    assert lib.orbx_pool_create(ctypes.byref(bad), ctypes.byref(p)) == -1

@@ -20,7 +20,10 @@ def _worker(rank, world, port, nframes, q):
     bounds = [None] * world
     dist.all_gather_object(bounds, (lo, hi))
     t = torch.tensor([1.0 + rank], dtype=torch.float64)           # pretend device time of this rank
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    g = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(g, t)                                          # bench.py: per-rank times, the job takes the slowest rank's
+    assert [float(x.item()) for x in g] == [1.0 + r for r in range(world)]
+    t = torch.tensor([max(float(x.item()) for x in g)], dtype=torch.float64)
     n = torch.tensor([hi - lo], dtype=torch.int64)
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
     dist.barrier()
