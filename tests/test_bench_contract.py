@@ -24,7 +24,8 @@ BASE_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 @pytest.mark.parametrize("name", ["r1_bench_k1.json", "r1_bench_k2.json", "r1_bench_k4.json", "r1_bench_k1_8gpu.json",
-                                  "r2_bench_k1.json", "r2_bench_k1_20steps.json", "r2_bench_k2.json", "r2_bench_k4.json", "r2_bench_k1_8gpu.json"])
+                                  "r2_bench_k1.json", "r2_bench_k1_20steps.json", "r2_bench_k2.json", "r2_bench_k4.json", "r2_bench_k1_8gpu.json",
+                                  "r2_bench_k1_2gpu.json", "r2_bench_k1_4gpu_20steps.json", "r2_bench_k4_2gpu.json", "r2_bench_k4_4gpu.json", "r2_bench_k4_8gpu.json"])
 def test_our_arm_line(name):
     d = _line(name)
     for k in BASE_KEYS + ("clocks", "gpu_launches", "roofline"):
