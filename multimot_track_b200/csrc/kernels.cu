@@ -1212,8 +1212,8 @@ size_t octree_smem_bytes(int max_node_cap, int max_feat, int *key_cap)
 // MODE 0: the whole thing in one launch.  MODE 1: sort + path codes only (the clustered launch of 4K-class images).  MODE 2: the tree
 // on keys / codes a MODE 1 launch left sorted in the scratch -- a plain launch with a small shared-memory footprint, so that the
 // octree of one batch shares the SMs with the other batches' kernels instead of pinning idle cluster CTAs on them.
-template <int THREADS, int IPT, int CLUSTER = 1, int MODE = 0>
-__global__ void __launch_bounds__(THREADS, (CLUSTER > 1 || MODE == 2) ? 2 : 1)
+template <int THREADS, int IPT, int CLUSTER = 1, int MODE = 0, int MINB = ((CLUSTER > 1 || MODE == 2) ? 2 : 1)>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_cap, int level_off, int lut_cap, int nframes_lm)
 {
     constexpr int WARPS = THREADS / 32;
@@ -1573,7 +1573,7 @@ k_octree(const DevParams *__restrict__ P, int node_cap, int skey_cap, int key_ca
 #undef OCT_LAP
 }
 
-template <int THREADS, int IPT, int CLUSTER = 1, int MODE = 0>
+template <int THREADS, int IPT, int CLUSTER = 1, int MODE = 0, int MINB = ((CLUSTER > 1 || MODE == 2) ? 2 : 1)>
 static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int nframes, int node_cap, int max_feat, size_t budget, cudaStream_t st,
                                    int level_off = 0, int level_cnt = -1)
 {
@@ -1586,7 +1586,7 @@ static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int
     if (MODE == 1) { node_cap = 0; max_feat = -3; }                  // sort only: no node arrays, no careful-phase buffer, just the digit counters
     const OctreeSmem o = octree_smem(THREADS, node_cap, max_feat, budget, lut_cap);
     {                                                                // the attribute is a per-device maximum: cheap, set every time
-        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT, CLUSTER, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_octree<THREADS, IPT, CLUSTER, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptInSmem);
         if (e != cudaSuccess) return e;
     }
     if (CLUSTER > 1) {
@@ -1596,9 +1596,9 @@ static cudaError_t launch_octree_t(const DevParams *dP, const DevParams &hP, int
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = CLUSTER; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k_octree<THREADS, IPT, CLUSTER, MODE>, dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap, nframes);
+        return cudaLaunchKernelEx(&cfg, k_octree<THREADS, IPT, CLUSTER, MODE, MINB>, dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap, nframes);
     }
-    k_octree<THREADS, IPT, CLUSTER, MODE><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap, nframes);
+    k_octree<THREADS, IPT, CLUSTER, MODE, MINB><<<dim3(level_cnt, nframes), THREADS, o.bytes, st>>>(dP, node_cap, o.skey_cap, o.key_cap, level_off, lut_cap, nframes);
     return cudaGetLastError();
 }
 
@@ -1640,7 +1640,14 @@ cudaError_t launch_octree(const DevParams *dP, const DevParams &hP, int nframes,
         return launch_octree_t<512, 8, 1, 2>(dP, hP, nframes, max_node_cap, max_feat, 0, st, 0, hP.nlevels);
     }
     const int big = debug_knob("ORBX_OCT_THREADS", hP.lv[0].cand_cap > 1000000 ? 1024 : 512);
-    if (max_node_cap <= 4096 && big != 1024) return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
+    if (max_node_cap <= 4096 && big != 1024) {
+        // 1920x1080-class images: 512 CTAs per 64-frame batch.  Two CTAs per SM (64 registers, ~105 KB of shared memory: the keys of the
+        // big levels then sort through the L2 scratch, which costs the sort nothing -- it is bound by its own scatter chain, not by
+        // where the keys live) instead of one with everything in 200 KB: fewer waves, and room for the other batches' kernels
+        if (debug_knob("ORBX_OCT_TWO_PER_SM", 1) && nframes * hP.nlevels > 148)
+            return launch_octree_t<512, 8, 1, 0, 2>(dP, hP, nframes, max_node_cap, max_feat, 105 * 1024, st);
+        return launch_octree_t<512, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
+    }
     return launch_octree_t<1024, 8>(dP, hP, nframes, max_node_cap, max_feat, 200 * 1024, st);
 }
 
