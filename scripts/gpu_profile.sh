@@ -13,7 +13,7 @@ timeout 600 python bench.py --workload k4 --steps 300 --no-cpu-baseline --no-ext
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_${tag}.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_launches_${tag}.log 2>&1; echo launches_exit=$?
 for wl in k1 k2 k4; do
-  case $wl in k1) SC="-s 24 -c 12";; k2) SC="-s 22 -c 11";; k4) SC="-s 30 -c 15";; esac
+  case $wl in k1) SC="-s 24 -c 12";; k2) SC="-s 22 -c 11";; k4) SC="-s 32 -c 16";; esac
   timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_fast_fused|k_blur|k_orient_desc|k_octree|k_resize" $SC -f \
       -o $O/prof_${tag}_${wl} python scripts/run_workload.py $wl 4 > $O/ncu_full_${tag}_${wl}.log 2>&1; echo full_${wl}_exit=$?
   ncu -i $O/prof_${tag}_${wl}.ncu-rep --page raw --csv > $O/ncu_raw_${tag}_${wl}.csv 2>/dev/null
