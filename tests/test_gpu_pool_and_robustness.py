@@ -228,8 +228,8 @@ def test_compact_keypoints_are_lossless(orb, oracle_mod):
 @pytest.mark.parametrize("params", [(6000, 1.2, 12, 20, 7), (3000, 2.0, 5, 20, 7)])
 def test_4k_octree_cluster_and_fallback(orb, oracle_mod, params):
     """3840x2160: with 12 levels x1.2 every level's octree sort runs on a cluster of four CTAs (sort launch + tree launch); with a
-    steep pyramid the small top level has no room for the cluster's counters in its scratch slot and the whole image takes the
-    single-CTA path.  Both equal the oracle, as a single frame and inside a batch of three."""
+    steep pyramid (x2.0, 5 levels) the small top level has no room for the cluster's counters in its scratch slot and the whole
+    image takes the single-CTA path.  Both equal the oracle, as a single frame and inside a batch of three."""
     frames = [synth(s, 2160, 3840) for s in (21, 22, 23)]
     o = oracle_mod.Oracle(*params)
     ref = [tuple(a.copy() for a in o(f)) for f in frames]
