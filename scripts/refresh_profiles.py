@@ -53,7 +53,7 @@ want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd"), ("dram
         ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma%"), ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("smsp__inst_executed.sum", "inst"), ("launch__registers_per_thread", "regs"),
-        ("launch__grid_size", "grid"), ("launch__block_size", "block")]
+        ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("lts__t_sector_hit_rate.pct", "l2hit%")]
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
 frames = {"k1": "batch of 32 frames, 1242x375, 2000 features", "k2": "batch of 64 frames, 1920x1080, 5000 features",
           "k4": "batch of 8 frames, 3840x2160, 12 levels, 10000 features", "matcher": "5000 x 5000 descriptors"}
@@ -68,7 +68,7 @@ for wl in ("k1", "k2", "k4", "matcher"):
     h, units = rr[0], rr[1]
     kk = h.index("Kernel Name")
     lines += ["", "# %s: %s -- one capture per launch of one batch (`ncu --set full --clock-control none`), DRAM GB/s = (read + write) / duration" % (wl, frames[wl]),
-              "%-30s %8s %9s %9s %6s %6s %6s %6s %7s %6s %10s %5s %7s" % ("kernel", "us", "dram MB", "DRAM GB/s", "dram%", "alu%", "fma%", "xu%", "issue%", "occ%", "warp-inst", "regs", "grid")]
+              "%-30s %8s %9s %9s %6s %6s %6s %6s %6s %7s %6s %10s %5s %7s" % ("kernel", "us", "dram MB", "DRAM GB/s", "dram%", "l2hit%", "alu%", "fma%", "xu%", "issue%", "occ%", "warp-inst", "regs", "grid")]
     tw = {}
     total_us = 0.0
     for r in rr[2:]:
@@ -83,8 +83,8 @@ for wl in ("k1", "k2", "k4", "matcher"):
                     v[short] = 0.0
         mb = (v.get("rd", 0) + v.get("wr", 0)) / 1e6
         total_us += v.get("us", 0)
-        lines.append("%-30s %8.1f %9.2f %9.0f %6.1f %6.1f %6.1f %6.1f %7.1f %6.1f %10.0f %5.0f %7.0f" % (
-            name[:30], v.get("us", 0), mb, mb * 1e6 / max(v.get("us", 1) * 1e-6, 1e-12) / 1e9, v.get("dram%", 0), v.get("alu%", 0), v.get("fma%", 0), v.get("xu%", 0),
+        lines.append("%-30s %8.1f %9.2f %9.0f %6.1f %6.1f %6.1f %6.1f %6.1f %7.1f %6.1f %10.0f %5.0f %7.0f" % (
+            name[:30], v.get("us", 0), mb, mb * 1e6 / max(v.get("us", 1) * 1e-6, 1e-12) / 1e9, v.get("dram%", 0), v.get("l2hit%", 0), v.get("alu%", 0), v.get("fma%", 0), v.get("xu%", 0),
             v.get("issue%", 0), v.get("occ%", 0), v.get("inst", 0), v.get("regs", 0), v.get("grid", 0)))
         base = name.split("<")[0]
         tw[base] = tw.get(base, 0) + int(v.get("rd", 0) + v.get("wr", 0))
@@ -95,7 +95,7 @@ for wl in ("k1", "k2", "k4", "matcher"):
         shutil.copy(hot, os.path.join(P, "%s_ncu_hot_lines_%s.txt" % (tag, wl)))
 open(os.path.join(P, "%s_kernel_table.txt" % tag), "w").write(
     "# per-kernel summary of the round-2 `ncu --set full` captures (scripts/gpu_profile.sh); peak copy bandwidth on this pod 6545 GB/s (MEASURED_PEAKS.json);\n"
-    "# alu% = integer ALU pipe, fma% = FMA pipe (IMAD, IDP), xu% = XU pipe (POPC), all as % of peak while the SM was active" + "\n".join(lines) + "\n")
+    "# l2hit% = lts__t_sector_hit_rate; alu% = integer ALU pipe, fma% = FMA pipe (IMAD, IDP), xu% = XU pipe (POPC), all as % of peak while the SM was active" + "\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
 print(open(os.path.join(P, "%s_kernel_table.txt" % tag)).read())
 print(open(os.path.join(P, "%s_launch_shares.txt" % tag)).read())
