@@ -68,3 +68,18 @@ def test_reference_arm_line(name):
     assert d["impl"] == "reference" and d["metric"] == "orb_extract_describe_frames_per_s"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_algorithmic_bytes_formula_matches_survey():
+    """B_alg = 5P + P0 - P_last + 16C + 96K + min(749K, P) + min(512K, P); K1 exact: 10.59 MB per frame."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from bench import algorithmic_bytes
+    k1 = [(1242, 375), (1035, 312), (862, 260), (719, 217), (599, 181), (499, 151), (416, 126), (347, 105)]
+    C, K = 18410, 2008
+    P = sum(w * h for w, h in k1)
+    assert P == 1441432
+    st = algorithmic_bytes(k1, C, K)
+    expect = 5 * P + k1[0][0] * k1[0][1] - k1[-1][0] * k1[-1][1] + 16 * C + 96 * K + min(749 * K, P) + min(512 * K, P)
+    assert st["total"] == expect and abs(st["total"] / 1e6 - 10.59) < 0.01
+    assert st["pyramid"] + st["fast"] + st["octree"] + st["orient_desc"] + st["blur"] == st["total"]
