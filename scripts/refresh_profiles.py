@@ -56,11 +56,12 @@ want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd"), ("dram
         ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("lts__t_sector_hit_rate.pct", "l2hit%")]
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
 frames = {"k1": "batch of 32 frames, 1242x375, 2000 features", "k2": "batch of 64 frames, 1920x1080, 5000 features",
-          "k4": "batch of 8 frames, 3840x2160, 12 levels, 10000 features", "matcher": "5000 x 5000 descriptors"}
+          "k4": "batch of 8 frames, 3840x2160, 12 levels, 10000 features", "matcher": "5000 x 5000 descriptors",
+          "next": "the SURVEY 8f kernels on K1-sized inputs (scripts/run_next_rows.py; first capture of every kernel)"}
 traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) from `ncu --set full --clock-control none` captures of "
                        "scripts/run_workload.py <workload> (one batch; k_resize_sep is the SUM over the level launches); table: profiles/%s_kernel_table.txt" % tag}
 lines = []
-for wl in ("k1", "k2", "k4", "matcher"):
+for wl in ("k1", "k2", "k4", "matcher", "next"):
     path = os.path.join(G, "ncu_raw_%s_%s.csv" % (tag, wl))
     if not os.path.exists(path):
         continue
@@ -71,8 +72,13 @@ for wl in ("k1", "k2", "k4", "matcher"):
               "%-30s %8s %9s %9s %6s %6s %6s %6s %6s %7s %6s %10s %5s %7s" % ("kernel", "us", "dram MB", "DRAM GB/s", "dram%", "l2hit%", "alu%", "fma%", "xu%", "issue%", "occ%", "warp-inst", "regs", "grid")]
     tw = {}
     total_us = 0.0
+    seen_next = set()
     for r in rr[2:]:
         name = r[kk].split("(")[0].replace("void ", "")
+        if wl == "next":
+            if name in seen_next:
+                continue
+            seen_next.add(name)
         v = {}
         for m, short in want:
             if m in h:
