@@ -7,7 +7,7 @@
 //   IC_Angle + rBRIEF           :77-147, :472-479, :1034-1041         k_orient_desc
 //   7x7 sigma=2 blur            :1089-1090                            k_blur
 //   border (mvImagePyramid)     :1126-1132                            k_pad_reflect101
-//   Hamming best/second-best    src/ORBmatcher.cc:574-605,2279-2295   k_match_partial / k_match_merge
+//   Hamming best/second-best    src/ORBmatcher.cc:574-605,2279-2295   k_match_partial (merge fused: last-arriving CTA)
 //
 // Integer stages are bit-exact restatements of the OpenCV fixed-point arithmetic;
 // float stages use explicit round-to-nearest intrinsics so nothing is contracted
