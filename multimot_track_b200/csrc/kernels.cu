@@ -705,13 +705,9 @@ __device__ __forceinline__ FfJob ff_job(const DevParams *__restrict__ P, int wid
 }
 
 // Scores, cell-local non-max suppression, threshold choice and emission of one job whose 16-bit tile is staged.
-// ~x as x * -1 + -1: an IMAD, i.e. FMA-pipe work, in a kernel that is bound by the integer ALU pipe (LOP3 would go there)
-__device__ __forceinline__ unsigned not_fma(unsigned x)
-{
-    unsigned r;
-    asm("mad.lo.u32 %0, %1, 0xffffffff, 0xffffffff;" : "=r"(r) : "r"(x));
-    return r;
-}
+// ~x as x * -1 + -1, and ~x - k in one go as x * -1 + (-1 - k): an IMAD, i.e. FMA-pipe work, in a kernel that is bound by the
+// integer ALU pipe.  The multiplier has to be a register ptxas cannot see through (it folds a literal -1 into an IADD3, ALU pipe
+// again): ff_process derives it from a kernel-parameter field.
 
 __device__ __forceinline__ unsigned lds_u16(unsigned addr)          // kept apart from the word loads of the same row on purpose
 {
@@ -754,7 +750,9 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     const int th_store = min(P->min_th, P->ini_th);
     // S' = score - th_store + 1 where the pixel is a corner at th_store (>= 1), else 0.  VIADD.16x2 / VIADDMNMX.S16x2 are
     // the native packed forms; there is no packed subtract, so differences are written as x + ~y (= x - y - 1).
-    const unsigned k1mth = 0x00010001u * (unsigned)((1 - th_store) & 0xffff);
+    // (x half by half) -x - th = ~x - (th - 1): no borrow between the halves for x <= 255, th <= 255, so one 32-bit IMAD does both
+    const unsigned m1 = (unsigned)(P->nlevels >> 31) - 1u;             // 0xffffffff, opaque to the compiler
+    const unsigned kv = 0xffffffffu - 0x00010001u * (unsigned)(th_store - 1);
     int nl = 0;
     unsigned T2 = 0, T1 = 0, U1 = 0, C1 = 0;                           // T/U/centre of rows y-2 and y-1 (0 outside the cell)
     // a lane whose two pixels share a cell keeps at most one survivor every second row; the one lane that straddles two cells
@@ -784,7 +782,7 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
 #define FF_NMS(yy, Tabove, Umid, Cc, Tbelow)                                                                     \
     {                                                                                                            \
         const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
-        const unsigned t_ = __vadd2(not_fma(m8), (Cc));                                                                  \
+        const unsigned t_ = __vadd2(mad_fma(m8, m1, m1), (Cc));                                                                \
         if (~t_ & in_sign) {                                                                                     \
             const unsigned ev = (Cc) & ~__byte_perm(t_, 0u, 0xBB99) & in_mask;                                   \
             mylist[nl * lstride] = (ev & 0x1ffu) | ((ev >> 7) & 0x3fe00u) | ((unsigned)(yy) << 18);              \
@@ -818,31 +816,33 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
             const unsigned B = __vimax3_s16x2(__vimax3_s16x2(m[0], m[1], m[2]), __vimax3_s16x2(m[3], m[4], m[5]), __vmaxs2(m[6], m[7]));
             maxmin = __vmins2(A, B); minmax = __vmaxs2(A, B);
         } else {
-        // The 16 arcs of 9 in pairs: arcs 2i and 2i+1 share the 8 ring pixels 2i+1 .. 2i+8 (B), so
-        // max(min(arc 2i), min(arc 2i+1)) = min(B, max(e[2i], e[2i+9])) -- 36 packed min / max per polarity instead of 40.
-        unsigned lo2[8], hi2[8];
+        // The 16 arcs of 9 in pairs: arcs 2j and 2j+1 share the 8 ring pixels 2j+1 .. 2j+8 (W_j), so
+        // max(min(arc 2j), min(arc 2j+1)) = min(W_j, max(e[2j], e[2j+9])).  W_j is four consecutive pair minima lo2[j .. j+3]; the windows
+        // of the pairs 2i and 2i+1 share the middle three (ring pixels 4i+3 .. 4i+8), taken once per i as a three-input min:
+        // 8 + 8 + 4 + 8 + 4 = 32 packed min / max per polarity.
+        unsigned lo2[8], hi2[8], mx[8], mn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             lo2[i] = __vmins2(e[2 * i + 1], e[(2 * i + 2) & 15]);
             hi2[i] = __vmaxs2(e[2 * i + 1], e[(2 * i + 2) & 15]);
-        }
-        unsigned lo4[8], hi4[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            lo4[i] = __vmins2(lo2[i], lo2[(i + 1) & 7]);
-            hi4[i] = __vmaxs2(hi2[i], hi2[(i + 1) & 7]);
+            mx[i] = __vmaxs2(e[2 * i], e[(2 * i + 9) & 15]);
+            mn[i] = __vmins2(e[2 * i], e[(2 * i + 9) & 15]);
         }
         unsigned bv[8], dv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            bv[i] = __vimin3_s16x2(lo4[i], lo4[(i + 2) & 7], __vmaxs2(e[2 * i], e[(2 * i + 9) & 15]));
-            dv[i] = __vimax3_s16x2(hi4[i], hi4[(i + 2) & 7], __vmins2(e[2 * i], e[(2 * i + 9) & 15]));
+        for (int i = 0; i < 4; ++i) {
+            const unsigned cmin = __vimin3_s16x2(lo2[2 * i + 1], lo2[(2 * i + 2) & 7], lo2[(2 * i + 3) & 7]);
+            const unsigned cmax = __vimax3_s16x2(hi2[2 * i + 1], hi2[(2 * i + 2) & 7], hi2[(2 * i + 3) & 7]);
+            bv[2 * i] = __vimin3_s16x2(cmin, lo2[2 * i], mx[2 * i]);
+            bv[2 * i + 1] = __vimin3_s16x2(cmin, lo2[(2 * i + 4) & 7], mx[2 * i + 1]);
+            dv[2 * i] = __vimax3_s16x2(cmax, hi2[2 * i], mn[2 * i]);
+            dv[2 * i + 1] = __vimax3_s16x2(cmax, hi2[(2 * i + 4) & 7], mn[2 * i + 1]);
         }
         maxmin = __vimax3_s16x2(__vimax3_s16x2(bv[0], bv[1], bv[2]), __vimax3_s16x2(bv[3], bv[4], bv[5]), __vmaxs2(bv[6], bv[7]));
         minmax = __vimin3_s16x2(__vimin3_s16x2(dv[0], dv[1], dv[2]), __vimin3_s16x2(dv[3], dv[4], dv[5]), __vmins2(dv[6], dv[7]));
         }
-        // bright - 1 = maxmin + ~c, dark - 1 = c + ~minmax; S' = max(bright, dark) - th, clamped at 0
-        const unsigned Cv = __viaddmax_s16x2_relu(__viaddmax_s16x2(cc, not_fma(minmax), __vadd2(maxmin, not_fma(cc))), k1mth, 0u);
+        // S' = max(bright, dark) - th clamped at 0, bright = maxmin - c, dark = c - minmax: (-c - th) and (-minmax - th) by IMAD
+        const unsigned Cv = __viaddmax_s16x2_relu(cc, mad_fma(minmax, m1, kv), __vadd2(maxmin, mad_fma(cc, m1, kv)));
         // neighbours in the same row, masked to the pixels' own cells
         const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
         const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
