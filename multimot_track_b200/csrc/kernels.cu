@@ -715,6 +715,30 @@ __device__ __forceinline__ unsigned lds_u16(unsigned addr)          // kept apar
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
+// d = a & ~b and nz = (d != 0) as ONE LOP3 with a predicate output (written as two C operations the compiler emits two LOP3s)
+__device__ __forceinline__ void and_not_p(unsigned &d, unsigned &nz, unsigned a, unsigned b)
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, 0, 0;\n\tlop3.or.b32 %0|p, %2, %3, 0, 0x30, q;\n\tselp.u32 %1, 1, 0, p;\n\t}"
+        : "=r"(d), "=r"(nz) : "r"(a), "r"(b));
+}
+// prmt in its generic PTX mode: bit 3 of a selector nibble replicates the sign of the chosen byte.  (__byte_perm documents three
+// bits per nibble only, and the compiler does drop the fourth from a selector it cannot see as a constant.)
+__device__ __forceinline__ unsigned prmt_generic(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned mad_fma(unsigned a, unsigned b, unsigned c)
 {
     unsigned r;
@@ -738,7 +762,7 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     const int c0 = dx0 >= wc, c1 = dx1 >= wc;                          // cell (0/1) of my pixels
     // pixels outside the job keep whatever score their ring gives (they are never anybody's neighbour, see below) and are
     // dropped where survivors are recorded
-    const unsigned in_mask = (in0 ? 0xffffu : 0u) | (in1 ? 0xffff0000u : 0u), in_sign = in_mask & 0x80008000u;
+    const unsigned sel_nm = (in0 ? 0x99u : 0xCCu) | (in1 ? 0xBB00u : 0xCC00u);     // sign of t per halfword, or "not a survivor" outside the job
     // Lv = (left neighbour of px0, px0 as left neighbour of px1); Rv = (px1 as right neighbour of px0, right neighbour of px1),
     // each half zero when that neighbour is in another cell or outside the job.  Scores S' are <= 255, so the high byte of
     // every half is zero and ONE byte permute both moves the halves and masks them (a masked half selects high bytes only).
@@ -753,12 +777,13 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     // (x half by half) -x - th = ~x - (th - 1): no borrow between the halves for x <= 255, th <= 255, so one 32-bit IMAD does both
     const unsigned m1 = (unsigned)(P->nlevels >> 31) - 1u;             // 0xffffffff, opaque to the compiler
     const unsigned kv = 0xffffffffu - 0x00010001u * (unsigned)(th_store - 1);
-    int nl = 0;
     unsigned T2 = 0, T1 = 0, U1 = 0, C1 = 0;                           // T/U/centre of rows y-2 and y-1 (0 outside the cell)
     // a lane whose two pixels share a cell keeps at most one survivor every second row; the one lane that straddles two cells
     // (independent columns) may have one per row and gets its own region
-    uint32_t *mylist = straddle ? list + C::LIST_LANES : list + lane;
+    uint32_t *const mylist = straddle ? list + C::LIST_LANES : list + lane;
     const int lstride = straddle ? 1 : 32;
+    const unsigned lp0 = smem_u32(mylist), lstride4 = 4u * lstride;
+    unsigned lp = lp0;                                                 // 32-bit shared-memory address of the lane's next free slot
 
     unsigned a[7][3], o[7][4];
     const uint32_t *col = tile + lane + 2;
@@ -776,25 +801,29 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
         o[slot][2] = mad_fma(w3_, 65536u, h2_); o[slot][3] = mad_fma(w4_, 65536u, h3_);         \
     }
     // finalize the non-max suppression of row `yy` whose centre is Cc, with max-of-3 of the rows above / below.
-    // t = Cc + ~m8 = Cc - m8 - 1 >= 0  <=>  centre strictly greater than all 8 neighbours (and then Cc >= 1).  A row with a survivor
-    // leaves ONE entry in the lane's private list (slot-major, so no ballot / prefix is needed): S' of pixel 0 | S' of pixel 1 << 9 |
-    // row << 18, with S' = 0 for a pixel that did not survive (PRMT in sign-replicate mode turns the sign of t into the halfword mask).
-#define FF_NMS(yy, Tabove, Umid, Cc, Tbelow)                                                                     \
+    // t = Cc + ~m8 = Cc - m8 - 1 >= 0  <=>  centre strictly greater than all 8 neighbours (and then Cc >= 1).  PRMT in sign-replicate
+    // mode turns the sign of t into a halfword mask, and takes the mask of a pixel outside the job from a constant instead (sel_nm).
+    // A row with a survivor leaves ONE entry in the lane's private list (slot-major, so no ballot / prefix is needed):
+    // S' of pixel 0 | row << 9 | S' of pixel 1 << 16, S' = 0 for a pixel that did not survive.  Nearly every warp row has a survivor in
+    // some lane, so the append is written to compile to predicated instructions, not a divergent branch.
+#define FF_NMS(yy9, Tabove, Umid, Cc, Tbelow)                                                                    \
     {                                                                                                            \
         const unsigned m8 = __vimax3_s16x2(Tabove, Umid, Tbelow);                                                \
-        const unsigned t_ = __vadd2(mad_fma(m8, m1, m1), (Cc));                                                                \
-        if (~t_ & in_sign) {                                                                                     \
-            const unsigned ev = (Cc) & ~__byte_perm(t_, 0u, 0xBB99) & in_mask;                                   \
-            mylist[nl * lstride] = (ev & 0x1ffu) | ((ev >> 7) & 0x3fe00u) | ((unsigned)(yy) << 18);              \
-            ++nl;                                                                                                \
+        const unsigned t_ = __vadd2(mad_fma(m8, m1, m1), (Cc));                                                  \
+        unsigned ev, any_;                                                                                       \
+        and_not_p(ev, any_, (Cc), prmt_generic(t_, 0x80808080u, sel_nm));                                        \
+        if (any_) {                                                                                              \
+            sts_u32(lp, ev + (yy9));                                                                             \
+            lp += lstride4;                                                                                      \
         }                                                                                                        \
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) FF_LOAD(r, r)
     // one row of scores + the NMS of the row above; U = row index mod 7 (a compile-time constant: the 7-row window rotates through
     // fixed register slots).  Whole groups of seven rows run without per-row guards, the last partial group with them.
-    auto ff_row = [&](auto U, const int y) {
+    auto ff_row = [&](auto U, const int g, const unsigned g9) {        // row g + u of the job; g is a multiple of 7, g9 = g << 9
         constexpr int u = decltype(U)::value;
+        const int y = g + u;
         FF_LOAD((u + 6) % 7, y + 6)
         const int sc = (u + 3) % 7, sp3 = (u + 6) % 7, sp2 = (u + 5) % 7, sp1 = (u + 4) % 7;
         const int sm1 = (u + 2) % 7, sm2 = (u + 1) % 7, sm3 = u % 7;
@@ -847,40 +876,41 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
         const unsigned Pl = __shfl_up_sync(0xffffffffu, Cv, 1), Pr = __shfl_down_sync(0xffffffffu, Cv, 1);
         const unsigned Lv = __byte_perm(Cv, Pl, selL), Rv = __byte_perm(Cv, Pr, selR);
         const unsigned T0 = __vimax3_s16x2(Lv, Cv, Rv), U0 = __vmaxs2(Lv, Rv);
-        if (y > 0) FF_NMS(y - 1, T2, U1, C1, T0)
+        if (u > 0 || g > 0) FF_NMS(g9 + (unsigned)((u - 1) * 512), T2, U1, C1, T0)
         T2 = T1; T1 = T0; U1 = U0; C1 = Cv;
     };
     int g = 0;
-    for (; g + 7 <= nrows; g += 7) {
-        ff_row(std::integral_constant<int, 0>{}, g);     ff_row(std::integral_constant<int, 1>{}, g + 1);
-        ff_row(std::integral_constant<int, 2>{}, g + 2); ff_row(std::integral_constant<int, 3>{}, g + 3);
-        ff_row(std::integral_constant<int, 4>{}, g + 4); ff_row(std::integral_constant<int, 5>{}, g + 5);
-        ff_row(std::integral_constant<int, 6>{}, g + 6);
+    unsigned g9 = 0;
+    for (; g + 7 <= nrows; g += 7, g9 += 7u << 9) {
+        ff_row(std::integral_constant<int, 0>{}, g, g9); ff_row(std::integral_constant<int, 1>{}, g, g9);
+        ff_row(std::integral_constant<int, 2>{}, g, g9); ff_row(std::integral_constant<int, 3>{}, g, g9);
+        ff_row(std::integral_constant<int, 4>{}, g, g9); ff_row(std::integral_constant<int, 5>{}, g, g9);
+        ff_row(std::integral_constant<int, 6>{}, g, g9);
     }
-    if (g < nrows) ff_row(std::integral_constant<int, 0>{}, g);
-    if (g + 1 < nrows) ff_row(std::integral_constant<int, 1>{}, g + 1);
-    if (g + 2 < nrows) ff_row(std::integral_constant<int, 2>{}, g + 2);
-    if (g + 3 < nrows) ff_row(std::integral_constant<int, 3>{}, g + 3);
-    if (g + 4 < nrows) ff_row(std::integral_constant<int, 4>{}, g + 4);
-    if (g + 5 < nrows) ff_row(std::integral_constant<int, 5>{}, g + 5);
-    FF_NMS(nrows - 1, T2, U1, C1, 0u)
+    if (g < nrows) ff_row(std::integral_constant<int, 0>{}, g, g9);
+    if (g + 1 < nrows) ff_row(std::integral_constant<int, 1>{}, g, g9);
+    if (g + 2 < nrows) ff_row(std::integral_constant<int, 2>{}, g, g9);
+    if (g + 3 < nrows) ff_row(std::integral_constant<int, 3>{}, g, g9);
+    if (g + 4 < nrows) ff_row(std::integral_constant<int, 4>{}, g, g9);
+    if (g + 5 < nrows) ff_row(std::integral_constant<int, 5>{}, g, g9);
+    FF_NMS((unsigned)(nrows - 1) << 9, T2, U1, C1, 0u)
 #undef FF_LOAD
 #undef FF_NMS
     __syncwarp();
     // ---- threshold choice per cell (:812-816) and emission
     const int ini = P->ini_th, mn = P->min_th;
-    const int nmax = __reduce_max_sync(0xffffffffu, nl);
     const int s_ini = ini - th_store + 1;                              // S' >= s_ini  <=>  score >= iniThFAST
-    int strong0 = 0, strong1 = 0, weak0 = 0, weak1 = 0;
-    for (int i = 0; i < nmax; ++i) {
-        if (i < nl) {
-            const uint32_t en = mylist[i * lstride];
-            const int sa = en & 0x1ffu, sb = (en >> 9) & 0x1ffu;
-            const bool a = sa >= s_ini, b = sb >= s_ini, wa = sa > 0 && !a, wb = sb > 0 && !b;
-            strong0 += (a && !c0) + (b && !c1); strong1 += (a && c0) + (b && c1);
-            weak0 += (wa && !c0) + (wb && !c1); weak1 += (wa && c0) + (wb && c1);
-        }
+    // the lane's survivors at iniThFAST and at all, counted on both pixels at once (pixel 0 | pixel 1 << 16)
+    const unsigned k_ini = 0x00010001u * (unsigned)((1 - s_ini) & 0xffff);
+    unsigned n_str = 0, n_pos = 0;
+    for (unsigned q = lp0; q != lp; q += lstride4) {
+        const unsigned e2 = lds_u32(q) & 0x01ff01ffu;
+        n_pos += __vminu2(e2, 0x00010001u);
+        n_str += __viaddmin_s16x2_relu(e2, k_ini, 0x00010001u);
     }
+    const int strA = n_str & 0xffffu, strB = n_str >> 16, weakA = (int)(n_pos & 0xffffu) - strA, weakB = (int)(n_pos >> 16) - strB;
+    const int strong0 = (c0 ? 0 : strA) + (c1 ? 0 : strB), strong1 = (c0 ? strA : 0) + (c1 ? strB : 0);
+    const int weak0 = (c0 ? 0 : weakA) + (c1 ? 0 : weakB), weak1 = (c0 ? weakA : 0) + (c1 ? weakB : 0);
     const bool has0 = __any_sync(0xffffffffu, strong0 > 0), has1 = __any_sync(0xffffffffu, strong1 > 0);
     // a cell with a corner at iniThFAST keeps only those; an empty one falls back to minThFAST (when that is lower)
     const int s0c = has0 ? s_ini : (mn < ini ? 1 : 0x7fffffff), s1c = has1 ? s_ini : (mn < ini ? 1 : 0x7fffffff);
@@ -894,18 +924,20 @@ __device__ __forceinline__ void ff_process(const DevParams *__restrict__ P, cons
     int base = 0;
     if (lane == 0) base = (int)atomicAdd(P->cand_count + frame * P->nlevels + level, (unsigned)total);
     int at = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
-    const uint32_t yx0 = (uint32_t)(x0 + dx0 - kMinBorder) | (uint32_t)(y0 - kMinBorder) << 12;
-    const int thr0 = c0 ? s1c : s0c, thr1 = c1 ? s1c : s0c;
-    for (int i = 0; i < nl; ++i) {
-        const uint32_t en = mylist[i * lstride];
-        const int sa = en & 0x1ffu, sb = (en >> 9) & 0x1ffu;
-        const uint32_t yx = yx0 + ((en >> 18) << 12);
-        if (sa > 0 && sa >= thr0) {
-            if (at < G.cand_cap) cand[at] = yx + ((uint32_t)(sa + th_store - 1) << 24);
+    // candidate = x | y << 12 | score << 24, score = S' + th_store - 1
+    const uint32_t yx0 = ((uint32_t)(x0 + dx0 - kMinBorder) | (uint32_t)(y0 - kMinBorder) << 12) + ((uint32_t)(th_store - 1) << 24);
+    const int thr0 = max(1, c0 ? s1c : s0c), thr1 = max(1, c1 ? s1c : s0c);
+    const int cap = G.cand_cap;
+    for (unsigned q = lp0; q != lp; q += lstride4) {
+        const uint32_t en = lds_u32(q);
+        const uint32_t yx = yx0 + ((en & 0xfe00u) << 3);               // + row << 12
+        const int sa = en & 0x1ffu, sb = en >> 16;
+        if (sa >= thr0) {
+            if (at < cap) cand[at] = yx + ((uint32_t)sa << 24);
             ++at;
         }
-        if (sb > 0 && sb >= thr1) {
-            if (at < G.cand_cap) cand[at] = yx + 1u + ((uint32_t)(sb + th_store - 1) << 24);
+        if (sb >= thr1) {
+            if (at < cap) cand[at] = yx + 1u + ((uint32_t)sb << 24);
             ++at;
         }
     }

@@ -23,5 +23,5 @@ except Exception as e:
 P
 }
 one k1 new 1 1000; one k1 prev 1 1000; one k1 new4 1 1000; one k1 new 2 1000; one k1 prev 2 1000
-one k2 new 1 200; one k2 prev 1 200
+one k2 new 1 200
 cat $S
