@@ -414,7 +414,7 @@ def main():
     # dram__bytes_read + write of that kernel per launch: NOT measured in this run (a run under ncu is never a bench run); read from
     # the committed `ncu --set full` capture of this same command, when there is one for the workload
     traffic, traffic_src = None, None
-    for tf in ("r2_traffic.json", "r1_traffic.json"):
+    for tf in ("r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):   # newest capture that holds this workload
         tp = os.path.join(ROOT, "profiles", tf)
         if os.path.exists(tp):
             v = json.load(open(tp)).get(args.workload, {}).get(kname)

@@ -17,8 +17,9 @@ for src, dst in (("bench_%s_k1.json", "%s_bench_k1.json"), ("bench_%s_k1_20steps
     if os.path.exists(os.path.join(G, src % tag)):
         shutil.copy(os.path.join(G, src % tag), os.path.join(P, dst % tag))
 
-# ---- launch shares of the default bench command
-rows = list(csv.reader(open(os.path.join(G, "launches_%s.csv" % tag))))
+# ---- launch shares of the default bench command (scripts/gpu_final.sh runs, e.g. tag r2b, have no launch list: skipped)
+have_launches = os.path.exists(os.path.join(G, "launches_%s.csv" % tag))
+rows = list(csv.reader(open(os.path.join(G, "launches_%s.csv" % tag)))) if have_launches else [["Kernel Name", "Metric Value", "Metric Unit"]]
 start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[start]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -33,8 +34,8 @@ for k, us in steady:
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += us
 step_kernels = ("k_fast", "k_octree", "k_resize", "k_orient", "k_blur", "k_repack", "k_pyramid")
 is_step = lambda k: any(t in k for t in step_kernels)
-tot = sum(a[1] for k, a in agg.items() if is_step(k))
-with open(os.path.join(P, "%s_launch_shares.txt" % tag), "w") as f:
+tot = sum(a[1] for k, a in agg.items() if is_step(k)) or 1.0
+with open(os.path.join(P, "%s_launch_shares.txt" % tag) if have_launches else os.devnull, "w") as f:
     f.write("# ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras` (round 2 kernels)\n"
             "# gpu__time_duration.sum per launch, --clock-control none; cold-cache and serialised: compare SHARES, not absolutes\n"
             "# last two thirds of the %d captured launches; source: %s_launches_bench_k1.csv\n\n" % (len(launches), tag))
@@ -104,4 +105,5 @@ open(os.path.join(P, "%s_kernel_table.txt" % tag), "w").write(
     "# l2hit% = lts__t_sector_hit_rate; alu% = integer ALU pipe, fma% = FMA pipe (IMAD, IDP), xu% = XU pipe (POPC), all as % of peak while the SM was active" + "\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
 print(open(os.path.join(P, "%s_kernel_table.txt" % tag)).read())
-print(open(os.path.join(P, "%s_launch_shares.txt" % tag)).read())
+if have_launches:
+    print(open(os.path.join(P, "%s_launch_shares.txt" % tag)).read())
