@@ -25,7 +25,8 @@ BASE_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 @pytest.mark.parametrize("name", ["r1_bench_k1.json", "r1_bench_k2.json", "r1_bench_k4.json", "r1_bench_k1_8gpu.json",
                                   "r2_bench_k1.json", "r2_bench_k1_20steps.json", "r2_bench_k2.json", "r2_bench_k4.json", "r2_bench_k1_8gpu.json",
-                                  "r2_bench_k1_2gpu.json", "r2_bench_k1_4gpu_20steps.json", "r2_bench_k4_2gpu.json", "r2_bench_k4_4gpu.json", "r2_bench_k4_8gpu.json"])
+                                  "r2_bench_k1_2gpu.json", "r2_bench_k1_4gpu_20steps.json", "r2_bench_k4_2gpu.json", "r2_bench_k4_4gpu.json", "r2_bench_k4_8gpu.json",
+                                  "r2b_bench_k1.json", "r2b_bench_k1_20steps.json", "r2b_bench_k2.json", "r2b_bench_k4.json"])
 def test_our_arm_line(name):
     d = _line(name)
     for k in BASE_KEYS + ("clocks", "gpu_launches", "roofline"):
@@ -49,7 +50,7 @@ def test_our_arm_line(name):
         for k in ("value", "unit", "cores", "kind", "sample"):
             assert k in c, k
         assert c["kind"] in ("reference", "port")
-    if name.startswith("r2_"):
+    if name.startswith("r2"):
         assert d["parity_checked"] is True and d["parity"]["frames_with_keypoint_mismatch"] == 0 and d["parity"]["descriptor_bits_differing"] == 0
         if d["n_gpus"] == 1 and d.get("cpu_baseline"):
             legs = d["cpu_baseline"]["legs"]                       # both CPU legs, the faster one named
