@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--cpu-bind", default="none", choices=["auto", "none"], help="multi-rank runs: pin each rank to its own slice of the GPU's CPUs")
     ap.add_argument("--handles", type=int, default=6, help="batches in flight per GPU (depth of the native dispatcher)")
     ap.add_argument("--batch", type=int, default=0, help="experiment: another batch size for the named shape")
+    ap.add_argument("--fast-tma", action="store_true", help="experiment: the persistent TMA-staged variant of the FAST kernel (ORBX_OPT_FAST_TMA); named in config")
     ap.add_argument("--full-records", action="store_true", help="device-resident loop with 28-byte cv::KeyPoint records instead of the 12-byte compact ones")
     ap.add_argument("--lanes", type=int, default=0, help="dispatcher workers per GPU: a batch is split into that many contiguous sub-batches, each with its own "
                                                           "worker thread, handles and streams (0 = the workload's default)")
@@ -252,6 +253,8 @@ def main():
     xpool = orb.ExtractorPool(*params, devices=[local] * lanes, depth=depth, max_width=W, max_height=H, max_batch=max(hi - lo for lo, hi in sub))
     OPT_COMPACT = orb.ORBextractor.OPT_COMPACT_KEYPOINTS
     compact = not args.full_records
+    if args.fast_tma:
+        xpool.set_option(orb.ORBextractor.OPT_FAST_TMA, 1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -516,6 +519,7 @@ def main():
                            "dispatcher": "orbx_pool: %d native worker thread(s) per GPU, each batch split into %d contiguous sub-batch(es), %d batches in flight" % (lanes, lanes, depth),
                            "l2": "inputs larger than L2: %d frame slots = %.0f MB in HBM, walked cyclically" % (nslots, nslots * H * pitch / 2 ** 20),
                            "input_row_pitch": pitch, "keypoints_per_step": kp_dev / max(1, args.steps),
+                           "fast_kernel": "k_fast_fused_tma (ORBX_OPT_FAST_TMA, experiment)" if args.fast_tma else "k_fast_fused (default)",
                            "result_records": ("orbx_keypoint_compact (12 B, lossless) + descriptor (32 B) per keypoint, %d B D2H per step" % (batch * (cap * 44 + 4))) if compact
                                              else "cv::KeyPoint (28 B) + descriptor (32 B) per keypoint, %d B D2H per step" % (batch * (cap * 60 + 4))},
                 "clocks": clocks,
